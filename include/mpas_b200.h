@@ -1,0 +1,226 @@
+/* mpas_b200.h -- C ABI of libmpas_b200.so
+ *
+ * Drop-in boundary for the RK3 dynamics hot path of alexaiken/mpas-regent.
+ * Every Regent leaf task on the path keeps its signature, privileges and call site
+ * (dynamics/rk_timestep.rg:404-481, atm_core.rg:31); its *body* becomes one call of
+ * the matching entry point below, made from a Terra shim written to the only FFI
+ * pattern the reference has (fortran/examples.rg:14-69: __physical/__fields ->
+ * legion_accessor_array_*_raw_rect_ptr -> extern call).  INTEGRATION.md shows the shim.
+ *
+ * Conventions
+ *   - plain C, POD structs, no C++/torch types cross this line;
+ *   - every entry returns 0 on success and a negative MPASB200_E* code otherwise, the
+ *     message is available from mpasb200_last_error(); nothing here exit()s or throws
+ *     (the reference's own convention is "retval == 1 + printf", netcdf_tasks.rg:13-18);
+ *   - state is DEVICE-RESIDENT between calls: the library owns a structure-of-arrays
+ *     mirror of the hot-path fields (mpas_b200_fields.def); host regions are touched
+ *     only by upload_field / download_field;
+ *   - task entries enqueue work on the handle's stream and return (asynchronous);
+ *     mpasb200_sync() is the host-visible point;
+ *   - pointers passed in are borrowed for the duration of the call only;
+ *   - there is no CPU fallback: with no usable CUDA device mpasb200_create fails.
+ */
+#ifndef MPAS_B200_H
+#define MPAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpasb200 mpasb200_t;
+
+/* ---- error codes ------------------------------------------------------------ */
+enum {
+  MPASB200_OK        =  0,
+  MPASB200_EINVAL    = -1,  /* bad argument (null pointer, id out of range, bad enum) */
+  MPASB200_ECUDA     = -2,  /* a CUDA runtime call failed; text in last_error          */
+  MPASB200_ENODEVICE = -3,  /* no CUDA device: the library never computes on the host  */
+  MPASB200_ESTATE    = -4,  /* call order violated (e.g. task before upload_mesh)      */
+  MPASB200_ENOMEM    = -5
+};
+
+/* ---- field ids (one per line of mpas_b200_fields.def) -------------------------- */
+typedef enum {
+#define MPASB200_FIELD(name, entity, slots) MPASB200_F_##name,
+#define MPASB200_VFIELD(name)               MPASB200_F_##name,
+#include "mpas_b200_fields.def"
+#undef MPASB200_FIELD
+#undef MPASB200_VFIELD
+  MPASB200_F_COUNT
+} mpasb200_field_t;
+
+typedef enum { MPASB200_CELL = 0, MPASB200_EDGE = 1, MPASB200_VERTEX = 2, MPASB200_VERTICAL = 3 } mpasb200_entity_t;
+
+/* How a stored mesh id becomes an array index (rule M2).
+ * LITERAL   : what the reference does -- the 1-based id read from the grid file
+ *             (mesh_loading.rg:228-230,268-269,294-295) is used as a 0-based index
+ *             (dynamics_tasks.rg:347-350 ...); id == N addresses a zero pad entity.
+ * CORRECTED : id-1; id 0 (absent neighbour) addresses the pad entity.             */
+typedef enum { MPASB200_INDEX_LITERAL = 0, MPASB200_INDEX_CORRECTED = 1 } mpasb200_index_policy_t;
+
+/* config_horiz_mixing (constants.rg:63).  An enum, because the reference compares
+ * rawstring *pointers* (dynamics_tasks.rg:861,892), which is toolchain-dependent.     */
+typedef enum { MPASB200_MIX_2D_SMAGORINSKY = 0, MPASB200_MIX_2D_FIXED = 1, MPASB200_MIX_OTHER = 2 } mpasb200_horiz_mixing_t;
+
+/* What atm_srk3 passes as atm_compute_dyn_tend's `rk_step : int`.
+ * SUBSTEP_TRUNC : literal -- rk_timestep.rg:437 passes rk_sub_timestep[rk_step] (a
+ *                 double) which narrows to int, so the rk_step==0 branches run only
+ *                 when the sub-timestep truncates to 0.
+ * STAGE_INDEX   : the RK stage index 0,1,2 (what MPAS does).                          */
+typedef enum { MPASB200_RKARG_SUBSTEP_TRUNC = 0, MPASB200_RKARG_STAGE_INDEX = 1 } mpasb200_rkarg_policy_t;
+
+/* ---- dimensions (constants.rg:18-26) ------------------------------------------- */
+typedef struct {
+  int32_t nCells, nEdges, nVertices;  /* entities in the regions handed to the tasks  */
+  int32_t nVertLevels;                /* regions hold nVertLevels+1 levels (main.rg:21-24) */
+  int32_t maxEdges;                   /* 10 */
+  int32_t maxEdges2;                  /* 20 */
+  int32_t vertexDegree;               /* 3  */
+  int32_t nAdvCells;                  /* FIFTEEN = 15 */
+} MpasDims;
+
+/* ---- configuration (constants.rg:27-69,99-104; rk_timestep.rg:378-382) ----------- */
+typedef struct {
+  double gravity, rgas, cp, cv, omega, sphere_radius, prandtl;
+  double config_epssm, config_smdiv, config_len_disp;
+  double config_smagorinsky_coef, config_visc4_2dsmag, config_del4u_div_factor;
+  double config_v_mom_eddy_visc2, config_v_theta_eddy_visc2;
+  double config_h_mom_eddy_visc4, config_h_theta_eddy_visc4;
+  double config_rayleigh_damp_u_timescale_days;
+  double config_mpas_cam_coef;
+  int32_t config_number_rayleigh_damp_u_levels;
+  int32_t config_horiz_mixing;        /* mpasb200_horiz_mixing_t */
+  int32_t config_mix_full, config_rayleigh_damp_u;
+  int32_t nRelaxZone;
+  int32_t number_of_sub_steps;        /* 2, rk_timestep.rg:378 */
+  int32_t config_dynamics_split_steps;/* 1, constants.rg:60    */
+  int32_t index_policy;               /* mpasb200_index_policy_t */
+  int32_t rkarg_policy;               /* mpasb200_rkarg_policy_t */
+  int32_t sfc_renumber;               /* 1: renumber cells/edges/vertices along a space-filling curve on the device */
+  int32_t device;                     /* CUDA ordinal; -1 = the calling thread's current device */
+  int32_t use_graph;                  /* 1: mpasb200_srk3 replays a captured CUDA graph */
+} MpasConfig;
+
+/* ---- level-0 ("static") region data -------------------------------------------- *
+ * Host pointers, each array row-major [entity][slot] exactly like the array-typed
+ * region fields (int[maxEdges] ...).  Ids are the RAW stored values; index_policy says
+ * how to resolve them.  A null pointer means "never written": the field is all zero
+ * (memory-model rule M1 of SURVEY.md 8c).                                           */
+typedef struct {
+  /* cell_fs */
+  const int32_t *nEdgesOnCell;      /* [nCells]                                      */
+  const int32_t *edgesOnCell;       /* [nCells][maxEdges]                            */
+  const int32_t *verticesOnCell;    /* [nCells][maxEdges]                            */
+  const int32_t *kiteForCell;       /* [nCells][maxEdges]   (atm_compute_signs)      */
+  const double  *edgesOnCellSign;   /* [nCells][maxEdges]   (atm_compute_signs)      */
+  const double  *edgesOnCell_sign;  /* [nCells][maxEdges]   never written upstream   */
+  const double  *invAreaCell;       /* [nCells]             never written upstream   */
+  const double  *latCell;           /* [nCells]                                      */
+  const double  *defc_a, *defc_b;   /* [nCells][maxEdges]   never written upstream   */
+  const int32_t *bdyMaskCell;       /* [nCells]             never written upstream   */
+  const double  *specZoneMaskCell;  /* [nCells]             never written upstream   */
+  const uint8_t *isShared;          /* [nCells]  mark_shared_cells, main.rg:48-52    */
+  const uint8_t *inCpr;             /* [nCells]  1 if the cell belongs to `cpr` (private_1[i], main.rg:57-66); null = all */
+  /* edge_fs */
+  const int32_t *cellsOnEdge;       /* [nEdges][2]  (also cellOne/cellTwo .lo.x)     */
+  const int32_t *verticesOnEdge;    /* [nEdges][2]                                   */
+  const int32_t *nEdgesOnEdge;      /* [nEdges]                                      */
+  const int32_t *edgesOnEdge_ECP;   /* [nEdges][maxEdges2]  the field load_mesh fills */
+  const int32_t *edgesOnEdge;       /* [nEdges][maxEdges2]  never written upstream   */
+  const double  *weightsOnEdge;     /* [nEdges][maxEdges2]                           */
+  const double  *dcEdge, *dvEdge;   /* [nEdges]                                      */
+  const double  *invDcEdge, *invDvEdge; /* [nEdges]         never written upstream   */
+  const double  *angleEdge, *latEdge;   /* [nEdges]                                  */
+  const int32_t *nAdvCellsForEdge;  /* [nEdges]             atm_adv_coef_compression */
+  const int32_t *advCellsForEdge;   /* [nEdges][nAdvCells]                           */
+  const double  *adv_coefs, *adv_coefs_3rd; /* [nEdges][nAdvCells]                   */
+  const double  *meshScalingDel2, *meshScalingDel4; /* [nEdges]                      */
+  const double  *specZoneMaskEdge;  /* [nEdges]             never written upstream   */
+  /* vertex_fs */
+  const int32_t *edgesOnVertex;     /* [nVertices][vertexDegree]                     */
+  const double  *edgesOnVertexSign; /* [nVertices][vertexDegree] (atm_compute_signs) */
+  const double  *edgesOnVertex_sign;/* [nVertices][vertexDegree] never written upstream */
+  const double  *kiteAreasOnVertex; /* [nVertices][vertexDegree]                     */
+  const double  *fVertex;           /* [nVertices]                                   */
+  const double  *invAreaTriangle;   /* [nVertices]          never written upstream   */
+  /* coordinates used only to build the space-filling-curve order (may be null: no renumbering) */
+  const double  *xCell, *yCell, *zCell;
+} MpasMeshPtrs;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+void mpasb200_default_config(MpasConfig *cfg);   /* the values of constants.rg */
+int  mpasb200_create(const MpasDims *dims, const MpasConfig *cfg, mpasb200_t **out);
+int  mpasb200_destroy(mpasb200_t *h);
+const char *mpasb200_last_error(const mpasb200_t *h);   /* h may be null: last create error */
+int  mpasb200_upload_mesh(mpasb200_t *h, const MpasMeshPtrs *mesh);
+
+/* ---- region <-> device mirror ---------------------------------------------------- *
+ * `base` addresses element (x=0, level=0, slot=0) of the field instance; stride_x /
+ * stride_k are BYTE strides in x and level exactly as legion_accessor_array_2d_raw_rect_ptr
+ * reports them in offsets[0..1]; array-typed fields have their slots contiguous.
+ * Levels 0..nVertLevels are transferred.  Vertical fields use stride_k only.
+ * Both calls are synchronous with respect to the host buffer.                          */
+int  mpasb200_upload_field(mpasb200_t *h, int field, const void *base, int64_t stride_x, int64_t stride_k);
+int  mpasb200_download_field(mpasb200_t *h, int field, void *base, int64_t stride_x, int64_t stride_k);
+int  mpasb200_zero_field(mpasb200_t *h, int field);
+int  mpasb200_sync(mpasb200_t *h);
+
+/* ---- one entry per hot-path task: scalars only -------------------------------------- */
+/* atm_rk_integration_setup            dynamics_tasks.rg:747-778   */
+int  mpasb200_rk_integration_setup(mpasb200_t *h);
+/* atm_compute_moist_coefficients      dynamics_tasks.rg:460-502   */
+int  mpasb200_compute_moist_coefficients(mpasb200_t *h);
+/* atm_compute_vert_imp_coefs          dynamics_tasks.rg:513-592   */
+int  mpasb200_compute_vert_imp_coefs(mpasb200_t *h, double dts);
+/* atm_compute_dyn_tend(_work)         dynamics_tasks.rg:814-1500  */
+int  mpasb200_compute_dyn_tend(mpasb200_t *h, int rk_step, double dt, int config_horiz_mixing,
+                               double config_mpas_cam_coef, int config_mix_full, int config_rayleigh_damp_u);
+/* atm_set_smlstep_pert_variables      dynamics_tasks.rg:1503-1538 */
+int  mpasb200_set_smlstep_pert_variables(mpasb200_t *h);
+/* atm_advance_acoustic_step           dynamics_tasks.rg:1546-1719 */
+int  mpasb200_advance_acoustic_step(mpasb200_t *h, double dts, int small_step);
+/* atm_divergence_damping_3d           dynamics_tasks.rg:1726-1763 */
+int  mpasb200_divergence_damping_3d(mpasb200_t *h, double dts);
+/* atm_recover_large_step_variables    dynamics_tasks.rg:1766-1887 (call commented out at rk_timestep.rg:460) */
+int  mpasb200_recover_large_step_variables(mpasb200_t *h, int ns, int rk_step, double dt);
+/* atm_compute_solve_diagnostics       dynamics_tasks.rg:328-454   */
+int  mpasb200_compute_solve_diagnostics(mpasb200_t *h, int hollingsworth, int rk_step);
+/* atm_rk_dynamics_substep_finish      dynamics_tasks.rg:1951-2007 */
+int  mpasb200_rk_dynamics_substep_finish(mpasb200_t *h, int dynamics_substep, int dynamics_split);
+
+/* ---- the driver: atm_srk3 / atm_timestep  rk_timestep.rg:361-519 ------------------------- *
+ * Replays the reference's call sequence on the device (control flow + scalars only).    */
+int  mpasb200_srk3(mpasb200_t *h, double dt);
+int  mpasb200_timestep(mpasb200_t *h, double dt);
+
+/* ---- halo exchange building blocks (one process per GPU; the wire is the host's job) ------ *
+ * Lists are LOCAL entity indices in the caller's (un-renumbered) numbering.  pack gathers
+ * `nfields` fields x `n` columns x (nVertLevels+1) levels into the contiguous device
+ * buffer `d_buf` laid out [field][i][level]; unpack scatters the same layout back.
+ * A list is registered once and referred to by the returned id.                         */
+int  mpasb200_register_list(mpasb200_t *h, int entity, const int32_t *idx, int32_t n, int32_t *list_id);
+int  mpasb200_pack(mpasb200_t *h, int list_id, const int32_t *fields, int32_t nfields, void *d_buf);
+int  mpasb200_unpack(mpasb200_t *h, int list_id, const int32_t *fields, int32_t nfields, const void *d_buf);
+/* Restrict compute to a sub-range of entities (interior / boundary split for overlap):
+ * tasks then run on [begin,end) of each entity type in the library's internal order.  */
+int  mpasb200_set_stream(mpasb200_t *h, void *cuda_stream);  /* null = the handle's own stream */
+
+/* ---- introspection --------------------------------------------------------------------- */
+int64_t mpasb200_launch_count(const mpasb200_t *h);   /* kernels launched so far by this handle */
+int64_t mpasb200_device_bytes(const mpasb200_t *h);   /* bytes of HBM held by the mirror */
+int  mpasb200_field_info(int field, int *entity, int *slots, const char **name);
+int  mpasb200_field_by_name(const char *name);        /* -1 if unknown */
+/* Per-task CUDA-event timing: when enabled every task entry is bracketed by events on the
+ * handle's stream; task_ms returns the accumulated milliseconds and call count per entry. */
+int  mpasb200_enable_timing(mpasb200_t *h, int on);
+int  mpasb200_task_time(mpasb200_t *h, int task, double *ms, int64_t *calls, const char **name);
+int  mpasb200_reset_timing(mpasb200_t *h);
+enum { MPASB200_T_SETUP = 0, MPASB200_T_MOIST, MPASB200_T_VERT_IMP, MPASB200_T_DYN_TEND, MPASB200_T_SMLSTEP,
+       MPASB200_T_ACOUSTIC, MPASB200_T_DIVDAMP, MPASB200_T_RECOVER, MPASB200_T_DIAG, MPASB200_T_FINISH, MPASB200_T_COUNT };
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPAS_B200_H */

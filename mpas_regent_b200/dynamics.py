@@ -1,0 +1,303 @@
+"""Host-side mirror of the reference's task interface for the RK3 dynamics hot path.
+
+``Dynamics`` owns one ``mpasb200_t`` handle of libmpas_b200.so and exposes the hot-path
+leaf tasks under the reference's own names and argument meaning (reference:
+dynamics/dynamics_tasks.rg signatures at :328-337, 460-466, 513-520, 747-752, 1484-1496,
+1530-1535, 1707-1715, 1726-1732, 1875-1883, 1951-1959), and the driver ``atm_srk3`` /
+``atm_timestep`` (dynamics/rk_timestep.rg:361-519).  Regions are replaced by the device-
+resident mirror behind the handle; ``upload_field`` / ``download_field`` are the only
+calls that touch host memory.
+
+There is no CPU fallback: if libmpas_b200.so is missing, or no CUDA device is usable,
+construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._abi import (CELL, EDGE, FIELD_ENTITY, FIELD_ID, FIELD_SLOTS, FIELDS, VERTEX, VERTICAL, MpasConfig, MpasDims,
+                   MpasMeshPtrs)
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libmpas_b200.so")
+_lib = None
+
+
+class MpasB200Error(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen libmpas_b200.so (built in-tree by __graft_entry__.build / csrc/Makefile)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or _LIB_PATH
+    if not os.path.exists(p):
+        raise MpasB200Error(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            f"(there is no CPU fallback)")
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    _declare(lib, "mpasb200_")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _declare(lib, prefix: str, handle_t=C.c_void_p):
+    H, I, D = handle_t, C.c_int, C.c_double
+    sig = {
+        "create": ([C.POINTER(MpasDims), C.POINTER(MpasConfig), C.POINTER(H)], I),
+        "destroy": ([H], I),
+        "upload_mesh": ([H, C.POINTER(MpasMeshPtrs)], I),
+        "rk_integration_setup": ([H], I),
+        "compute_moist_coefficients": ([H], I),
+        "compute_vert_imp_coefs": ([H, D], I),
+        "compute_dyn_tend": ([H, I, D, I, D, I, I], I),
+        "set_smlstep_pert_variables": ([H], I),
+        "advance_acoustic_step": ([H, D, I], I),
+        "divergence_damping_3d": ([H, D], I),
+        "recover_large_step_variables": ([H, I, I, D], I),
+        "compute_solve_diagnostics": ([H, I, I], I),
+        "rk_dynamics_substep_finish": ([H, I, I], I),
+        "srk3": ([H, D], I),
+        "timestep": ([H, D], I),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(lib, prefix + name)
+        fn.argtypes, fn.restype = args, res
+    if prefix == "mpasb200_":
+        lib.mpasb200_default_config.argtypes, lib.mpasb200_default_config.restype = [C.POINTER(MpasConfig)], None
+        lib.mpasb200_last_error.argtypes, lib.mpasb200_last_error.restype = [H], C.c_char_p
+        lib.mpasb200_upload_field.argtypes = [H, I, C.c_void_p, C.c_int64, C.c_int64]
+        lib.mpasb200_download_field.argtypes = [H, I, C.c_void_p, C.c_int64, C.c_int64]
+        lib.mpasb200_zero_field.argtypes = [H, I]
+        lib.mpasb200_sync.argtypes = [H]
+        lib.mpasb200_register_list.argtypes = [H, I, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        lib.mpasb200_pack.argtypes = [H, I, C.c_void_p, C.c_int32, C.c_void_p]
+        lib.mpasb200_unpack.argtypes = [H, I, C.c_void_p, C.c_int32, C.c_void_p]
+        lib.mpasb200_set_stream.argtypes = [H, C.c_void_p]
+        lib.mpasb200_launch_count.argtypes, lib.mpasb200_launch_count.restype = [H], C.c_int64
+        lib.mpasb200_device_bytes.argtypes, lib.mpasb200_device_bytes.restype = [H], C.c_int64
+        lib.mpasb200_field_info.argtypes = [I, C.POINTER(I), C.POINTER(I), C.POINTER(C.c_char_p)]
+        lib.mpasb200_field_by_name.argtypes, lib.mpasb200_field_by_name.restype = [C.c_char_p], I
+        lib.mpasb200_enable_timing.argtypes = [H, I]
+        lib.mpasb200_task_time.argtypes = [H, I, C.POINTER(D), C.POINTER(C.c_int64), C.POINTER(C.c_char_p)]
+        lib.mpasb200_reset_timing.argtypes = [H]
+        for n in ("upload_field", "download_field", "zero_field", "sync", "register_list", "pack", "unpack", "set_stream",
+                  "field_info", "enable_timing", "task_time", "reset_timing"):
+            getattr(lib, "mpasb200_" + n).restype = I
+
+
+class TaskAPI:
+    """The task-level interface shared by the CUDA library wrapper and the CPU oracle wrapper
+    (so parity tests drive both with the same code).  Subclasses provide _call and the field I/O."""
+
+    dims: MpasDims
+    cfg: MpasConfig
+
+    # ---- shape helpers -----------------------------------------------------------------------
+    def entity_count(self, ent: int) -> int:
+        return {CELL: self.dims.nCells, EDGE: self.dims.nEdges, VERTEX: self.dims.nVertices, VERTICAL: 1}[ent]
+
+    def field_shape(self, name: str):
+        ent, s, L1 = FIELD_ENTITY[name], FIELD_SLOTS[name], self.dims.nVertLevels + 1
+        if ent == VERTICAL:
+            return (L1,)
+        n = self.entity_count(ent)
+        return (n, L1) if s == 1 else (n, L1, s)
+
+    # ---- bulk helpers ------------------------------------------------------------------------
+    def upload_state(self, fields: Dict[str, np.ndarray], vert: Optional[Dict[str, np.ndarray]] = None):
+        for k, a in fields.items():
+            if k in FIELD_ID:
+                self.upload_field(k, a)
+        for k, a in (vert or {}).items():
+            if k in FIELD_ID:
+                self.upload_field(k, a)
+
+    def download_all(self, names: Optional[Iterable[str]] = None) -> Dict[str, np.ndarray]:
+        names = list(names) if names is not None else [n for (n, _, _) in FIELDS]
+        return {n: self.download_field(n) for n in names}
+
+    # ---- the reference's task names -----------------------------------------------------------
+    def atm_rk_integration_setup(self):
+        self._call("rk_integration_setup")
+
+    def atm_compute_moist_coefficients(self):
+        self._call("compute_moist_coefficients")
+
+    def atm_compute_vert_imp_coefs(self, dts: float):
+        self._call("compute_vert_imp_coefs", float(dts))
+
+    def atm_compute_dyn_tend(self, rk_step: int, dt: float, config_horiz_mixing: Optional[int] = None,
+                             config_mpas_cam_coef: Optional[float] = None, config_mix_full: Optional[bool] = None,
+                             config_rayleigh_damp_u: Optional[bool] = None):
+        c = self.cfg
+        self._call("compute_dyn_tend", int(rk_step), float(dt),
+                   int(c.config_horiz_mixing if config_horiz_mixing is None else config_horiz_mixing),
+                   float(c.config_mpas_cam_coef if config_mpas_cam_coef is None else config_mpas_cam_coef),
+                   int(c.config_mix_full if config_mix_full is None else config_mix_full),
+                   int(c.config_rayleigh_damp_u if config_rayleigh_damp_u is None else config_rayleigh_damp_u))
+
+    def atm_set_smlstep_pert_variables(self):
+        self._call("set_smlstep_pert_variables")
+
+    def atm_advance_acoustic_step(self, dts: float, small_step: int):
+        self._call("advance_acoustic_step", float(dts), int(small_step))
+
+    def atm_divergence_damping_3d(self, dts: float):
+        self._call("divergence_damping_3d", float(dts))
+
+    def atm_recover_large_step_variables(self, ns: int, rk_step: int, dt: float):
+        self._call("recover_large_step_variables", int(ns), int(rk_step), float(dt))
+
+    def atm_compute_solve_diagnostics(self, hollingsworth: bool, rk_step: int):
+        self._call("compute_solve_diagnostics", int(bool(hollingsworth)), int(rk_step))
+
+    def atm_rk_dynamics_substep_finish(self, dynamics_substep: int, dynamics_split: int):
+        self._call("rk_dynamics_substep_finish", int(dynamics_substep), int(dynamics_split))
+
+    def atm_srk3(self, dt: float):
+        """The library's own replay of rk_timestep.rg:361-500 (one call, optionally a CUDA graph)."""
+        self._call("srk3", float(dt))
+
+    def atm_timestep(self, dt: float):
+        self._call("timestep", float(dt))
+
+    def atm_srk3_by_tasks(self, dt: float, hook=None):
+        """atm_srk3 replayed task by task from the host, exactly in the reference's order
+        (rk_timestep.rg:378-481).  ``hook(name)`` is called after every task (halo exchange point)."""
+        c = self.cfg
+        number_of_sub_steps = c.number_of_sub_steps
+        dynamics_split = c.config_dynamics_split_steps
+        rk_sub_timestep = [dt / 3, dt / number_of_sub_steps, dt / number_of_sub_steps]
+        number_sub_steps = [max(1, number_of_sub_steps // 2), max(1, number_of_sub_steps // 2), number_of_sub_steps]
+        h = hook or (lambda name: None)
+        self.atm_rk_integration_setup(); h("rk_integration_setup")
+        self.atm_compute_moist_coefficients(); h("compute_moist_coefficients")
+        self.atm_compute_vert_imp_coefs(rk_sub_timestep[0]); h("compute_vert_imp_coefs")
+        for rk_step in range(3):
+            if rk_step == 1:
+                self.atm_compute_vert_imp_coefs(rk_sub_timestep[rk_step]); h("compute_vert_imp_coefs")
+            rk_arg = int(rk_sub_timestep[rk_step]) if c.rkarg_policy == _abi.RKARG_SUBSTEP_TRUNC else rk_step
+            self.atm_compute_dyn_tend(rk_arg, dt); h("compute_dyn_tend")
+            self.atm_set_smlstep_pert_variables(); h("set_smlstep_pert_variables")
+            for small_step in range(number_sub_steps[rk_step] + 1):
+                self.atm_advance_acoustic_step(rk_sub_timestep[rk_step], small_step); h("advance_acoustic_step")
+                self.atm_divergence_damping_3d(rk_sub_timestep[rk_step]); h("divergence_damping_3d")
+            self.atm_compute_solve_diagnostics(False, rk_step); h("compute_solve_diagnostics")
+        self.atm_rk_dynamics_substep_finish(1, dynamics_split); h("rk_dynamics_substep_finish")
+
+
+class Dynamics(TaskAPI):
+    """One device-resident mirror (one GPU).  See module docstring."""
+
+    def __init__(self, dims: MpasDims, cfg: Optional[MpasConfig] = None, lib_path: Optional[str] = None):
+        self._lib = load_library(lib_path)
+        self.dims = dims
+        self.cfg = cfg if cfg is not None else _abi.default_config()
+        self._h = C.c_void_p()
+        rc = self._lib.mpasb200_create(C.byref(self.dims), C.byref(self.cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.mpasb200_last_error(None)
+            raise MpasB200Error(f"mpasb200_create failed ({rc}): {msg.decode() if msg else ''}")
+        self._keep = []
+
+    # ---- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self._lib.mpasb200_last_error(self._h)
+            raise MpasB200Error(f"mpasb200_{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def _call(self, name: str, *args):
+        self._check(getattr(self._lib, "mpasb200_" + name)(self._h, *args), name)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.mpasb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- mesh + fields ---------------------------------------------------------------------------
+    def upload_mesh(self, static: Dict[str, np.ndarray]):
+        m, keep = _abi.mesh_ptrs(static, self.dims)
+        self._check(self._lib.mpasb200_upload_mesh(self._h, C.byref(m)), "upload_mesh")
+        del keep
+
+    def upload_field(self, name: str, a: np.ndarray):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        shp = self.field_shape(name)
+        if a.shape != shp:
+            raise ValueError(f"{name}: shape {a.shape}, expected {shp}")
+        s = FIELD_SLOTS[name]
+        L1 = self.dims.nVertLevels + 1
+        self._check(self._lib.mpasb200_upload_field(self._h, FIELD_ID[name], a.ctypes.data, 8 * L1 * s, 8 * s), "upload_field")
+
+    def download_field(self, name: str, out: Optional[np.ndarray] = None) -> np.ndarray:
+        shp = self.field_shape(name)
+        a = out if out is not None else np.empty(shp, dtype=np.float64)
+        assert a.shape == shp and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        s = FIELD_SLOTS[name]
+        L1 = self.dims.nVertLevels + 1
+        self._check(self._lib.mpasb200_download_field(self._h, FIELD_ID[name], a.ctypes.data, 8 * L1 * s, 8 * s), "download_field")
+        return a
+
+    def zero_field(self, name: str):
+        self._check(self._lib.mpasb200_zero_field(self._h, FIELD_ID[name]), "zero_field")
+
+    def sync(self):
+        self._check(self._lib.mpasb200_sync(self._h), "sync")
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.mpasb200_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")
+
+    # ---- halo building blocks ------------------------------------------------------------------------
+    def register_list(self, entity: int, idx: np.ndarray) -> int:
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        lid = C.c_int32(-1)
+        self._check(self._lib.mpasb200_register_list(self._h, entity, idx.ctypes.data, idx.shape[0], C.byref(lid)), "register_list")
+        return int(lid.value)
+
+    def pack(self, list_id: int, fields: Sequence[str], d_buf_ptr: int):
+        ids = np.asarray([FIELD_ID[f] for f in fields], dtype=np.int32)
+        self._check(self._lib.mpasb200_pack(self._h, list_id, ids.ctypes.data, len(ids), C.c_void_p(d_buf_ptr)), "pack")
+
+    def unpack(self, list_id: int, fields: Sequence[str], d_buf_ptr: int):
+        ids = np.asarray([FIELD_ID[f] for f in fields], dtype=np.int32)
+        self._check(self._lib.mpasb200_unpack(self._h, list_id, ids.ctypes.data, len(ids), C.c_void_p(d_buf_ptr)), "unpack")
+
+    # ---- introspection ------------------------------------------------------------------------------------
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mpasb200_launch_count(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.mpasb200_device_bytes(self._h))
+
+    def enable_timing(self, on: bool = True):
+        self._check(self._lib.mpasb200_enable_timing(self._h, int(on)), "enable_timing")
+
+    def reset_timing(self):
+        self._check(self._lib.mpasb200_reset_timing(self._h), "reset_timing")
+
+    def task_times(self) -> Dict[str, tuple]:
+        out = {}
+        for t in range(len(_abi.TASK_NAMES)):
+            ms, calls, nm = C.c_double(), C.c_int64(), C.c_char_p()
+            self._check(self._lib.mpasb200_task_time(self._h, t, C.byref(ms), C.byref(calls), C.byref(nm)), "task_time")
+            out[nm.value.decode()] = (ms.value, calls.value)
+        return out
+
+
+def dims_of(mesh, nVertLevels: int) -> MpasDims:
+    return _abi.make_dims(mesh.nCells, mesh.nEdges, mesh.nVertices, nVertLevels)
