@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- RK3 dynamics step throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mesh CELLS] [--levels L] [--impl reference]
+
+One "step" = one atm_srk3 (reference: dynamics/rk_timestep.rg:361-500) over the whole synthetic
+icosahedral mesh.  metric = cell-level updates/s = nCells * nVertLevels * steps / seconds (whole job).
+Under torchrun (N > 1) the mesh is partitioned across ranks (strong scaling: the global mesh is fixed).
+
+Timed with CUDA events on the stream the kernels are launched on, max over ranks, barrier +
+synchronize on both sides.  Extra objects on the JSON line: roofline (dominant kernel, algorithmic
+bytes / CUDA-event duration / measured HBM peak), cpu_baseline (the CPU oracle on a bounded sample,
+rank 0, N=1), e2e (same metric through the C ABI with host buffers: H2D of the prognostic state from
+pinned memory + step + D2H, every step), clocks, gpu_launches.
+
+--impl reference times the reference's CPU implementation of the path.  The reference is Regent and
+cannot be built here, so this arm runs the oracle port (oracle/, a literal C++ restatement) with all
+host threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cell_level_updates_per_s"
+UNIT = "cell-levels/s"
+DT_REF = 720.0           # constants.rg:99, scaled with resolution to keep the CFL number
+E2E_FIELDS = ("u", "ru", "w", "theta_m", "rho_zz", "rw", "rho_p", "rtheta_p", "exner", "pressure_p")
+
+
+def dt_for(n_cells: int) -> float:
+    return DT_REF * (2562.0 / n_cells) ** 0.5
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and "Active" in r[col] and "Not" not in r[col]:
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_inputs(n_cells: int, L: int):
+    from mpas_regent_b200 import _abi, icosa, init_jw
+    t0 = time.time()
+    mesh = icosa.make_icosahedral_mesh(n_cells)
+    st = init_jw.make_state(mesh, L, _abi.INDEX_CORRECTED, m5=True, diag_on_host=False)
+    return mesh, st, time.time() - t0
+
+
+def cpu_baseline(sample_cells: int, L: int, steps: int, warmup: int, threads: int):
+    """The oracle (a port: the Regent reference cannot run here) on a bounded sample of the workload."""
+    from mpas_regent_b200 import _abi, dynamics, icosa, init_jw
+    from oracle.oracle import Oracle
+    mesh = icosa.make_icosahedral_mesh(sample_cells)
+    st = init_jw.make_state(mesh, L, _abi.INDEX_CORRECTED, m5=True, diag_on_host=False)
+    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX)
+    o = Oracle(dynamics.dims_of(mesh, L), cfg, threads=threads)
+    o.upload_mesh(st.static); o.upload_state(st.f, st.vert)
+    o.atm_compute_solve_diagnostics(False, -1)
+    dt = dt_for(sample_cells)
+    for _ in range(warmup):
+        o.atm_srk3(dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.atm_srk3(dt)
+    sec = time.perf_counter() - t0
+    o.close()
+    return sample_cells * L * steps / sec, sec / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import Oracle
+    threads = Oracle.max_threads()
+    val, sec = cpu_baseline(args.cpu_sample_cells, args.levels, max(1, args.steps), max(0, args.warmup), threads)
+    sample = (f"oracle port (literal C++ restatement, OpenMP over the outer entity loop), x1.{args.cpu_sample_cells} "
+              f"icosahedral mesh x {args.levels} levels, {args.steps} RK3 steps after {args.warmup} warm-up")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"x1.{args.mesh} synthetic icosahedral Voronoi mesh, {args.levels} levels, JW-style state, "
+                               f"one atm_srk3 per step (canonical stage-index sequence)", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--mesh", type=int, default=int(os.environ.get("MPAS_BENCH_CELLS", "655362")))
+    ap.add_argument("--levels", type=int, default=55)
+    ap.add_argument("--cpu-sample-cells", type=int, default=10242)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from mpas_regent_b200 import _abi, dynamics, traffic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    L, nC = args.levels, args.mesh
+    dt = dt_for(nC)
+    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, device=local_rank, use_graph=args.graph)
+    stream = torch.cuda.Stream()
+
+    if world == 1:
+        mesh, st, t_init = build_inputs(nC, L)
+        g = dynamics.Dynamics(dynamics.dims_of(mesh, L), cfg)
+        g.set_stream(stream.cuda_stream)
+        g.upload_mesh(st.static)
+        g.upload_state(st.f, st.vert)
+        # pinned host images of the prognostic state for the end-to-end leg
+        host = {}
+        if not args.no_e2e:
+            for n in E2E_FIELDS:
+                t = torch.from_numpy(st.f[n]).pin_memory()
+                host[n] = t
+        del st
+        g.atm_compute_solve_diagnostics(False, -1)       # atm_core_init, atm_core.rg:31
+        step = lambda: g.atm_srk3(dt)
+        n_owned_total = nC
+        parallelism = "single partition"
+    else:
+        from mpas_regent_b200 import parallel
+        run = parallel.DistributedDynamics.for_bench(nC, L, cfg, stream, rank, world)
+        g = run.dyn
+        host = {}
+        step = lambda: run.step(dt)
+        n_owned_total = nC
+        parallelism = f"{world}-way cell partition (SFC chunks), 2-ring halo exchange over NCCL send/recv"
+        t_init = run.t_init
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step()
+        g.sync()
+        g.reset_kernel_timing(); g.enable_kernel_timing(True)
+        launches0 = g.launch_count
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        torch.cuda.synchronize(); barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else {}
+        launches = g.launch_count - launches0
+        ktimes = g.kernel_times()
+        g.enable_kernel_timing(False)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tl = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+        launches = int(tl.item())
+    value = n_owned_total * L * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (rank 0's kernels; cells of this rank) ----
+    peak, peak_src = peaks()
+    n_local = g.dims.nCells
+    roof = None
+    if ktimes:
+        name, (kms, kn) = max(ktimes.items(), key=lambda kv: kv[1][0])
+        key = name if name in traffic.K else None
+        if key is not None and kn > 0:
+            u = traffic.units(key, scratch=False)
+            bytes_per_launch = u * 8.0 * n_local * L
+            achieved = bytes_per_launch / (kms / kn * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "avg_launch_ms": kms / kn, "launches_timed": kn, "share_of_step": kms / ms}
+    step_bytes = traffic.SURVEY_STEP_UNITS_CANONICAL * 8.0 * nC * L
+    step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        k_e = max(2, min(args.steps, 3))
+        h2d = sum(t.numel() * 8 for t in host.values())
+        outs = {n: torch.empty_like(t).pin_memory() for n, t in host.items()}
+        with torch.cuda.stream(stream):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(k_e):
+                for n, t in host.items():
+                    g.upload_field(n, t.numpy())
+                g.atm_srk3(dt)
+                for n, t in outs.items():
+                    g.download_field(n, t.numpy())
+            torch.cuda.synchronize()
+            sec = time.perf_counter() - t0
+        e2e = {"value": nC * L * k_e / sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
+               "steps": k_e, "fields": list(E2E_FIELDS), "ms_per_step": sec / k_e * 1e3}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle.oracle import Oracle
+        thr = Oracle.max_threads()
+        v1, s1 = cpu_baseline(args.cpu_sample_cells, L, 1, 0, 1)
+        vN, sN = cpu_baseline(args.cpu_sample_cells, L, 2, 1, thr)
+        cpu = {"value": vN, "unit": UNIT, "cores": thr, "kind": "port",
+               "sample": f"oracle port on x1.{args.cpu_sample_cells} x {L} levels: 2 RK3 steps with {thr} OpenMP threads "
+                         f"({sN:.2f} s/step); 1 thread: {v1:.4g} {UNIT} ({s1:.2f} s/step)",
+               "single_thread_value": v1}
+
+    if rank == 0:
+        top = sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:8]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"x1.{nC} synthetic icosahedral Voronoi mesh, {L} levels, JW-style analytic state, dt={dt:.2f}s, "
+                                   f"one atm_srk3 per step (canonical stage-index sequence: stage 0 takes the rk_step==0 branches)",
+                       "parallelism": parallelism, "l2": "working set (tens of GB) >> 126 MB L2; no flush needed",
+                       "host_init_s": round(t_init, 1), "device_bytes": g.device_bytes, "cuda_graph": bool(args.graph)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "step_hbm": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs_per_gpu": step_gbs / world,
+                         "frac_of_peak": step_gbs / world / peak},
+            "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in top},
+            "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -217,6 +217,11 @@ int  mpasb200_field_by_name(const char *name);        /* -1 if unknown */
 int  mpasb200_enable_timing(mpasb200_t *h, int on);
 int  mpasb200_task_time(mpasb200_t *h, int task, double *ms, int64_t *calls, const char **name);
 int  mpasb200_reset_timing(mpasb200_t *h);
+/* Per-KERNEL CUDA-event timing: every launch is bracketed by an event pair on the handle's stream.
+ * kernel_time(idx) walks the table (returns MPASB200_EINVAL past the end).                       */
+int  mpasb200_enable_kernel_timing(mpasb200_t *h, int on);
+int  mpasb200_reset_kernel_timing(mpasb200_t *h);
+int  mpasb200_kernel_time(mpasb200_t *h, int idx, const char **name, double *ms, int64_t *launches);
 enum { MPASB200_T_SETUP = 0, MPASB200_T_MOIST, MPASB200_T_VERT_IMP, MPASB200_T_DYN_TEND, MPASB200_T_SMLSTEP,
        MPASB200_T_ACOUSTIC, MPASB200_T_DIVDAMP, MPASB200_T_RECOVER, MPASB200_T_DIAG, MPASB200_T_FINISH, MPASB200_T_COUNT };
 

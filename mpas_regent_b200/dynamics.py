@@ -87,6 +87,11 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         lib.mpasb200_enable_timing.argtypes = [H, I]
         lib.mpasb200_task_time.argtypes = [H, I, C.POINTER(D), C.POINTER(C.c_int64), C.POINTER(C.c_char_p)]
         lib.mpasb200_reset_timing.argtypes = [H]
+        lib.mpasb200_enable_kernel_timing.argtypes = [H, I]
+        lib.mpasb200_reset_kernel_timing.argtypes = [H]
+        lib.mpasb200_kernel_time.argtypes = [H, I, C.POINTER(C.c_char_p), C.POINTER(D), C.POINTER(C.c_int64)]
+        for n in ("enable_kernel_timing", "reset_kernel_timing", "kernel_time"):
+            getattr(lib, "mpasb200_" + n).restype = I
         for n in ("upload_field", "download_field", "zero_field", "sync", "register_list", "pack", "unpack", "set_stream",
                   "field_info", "enable_timing", "task_time", "reset_timing"):
             getattr(lib, "mpasb200_" + n).restype = I
@@ -289,6 +294,22 @@ class Dynamics(TaskAPI):
 
     def reset_timing(self):
         self._check(self._lib.mpasb200_reset_timing(self._h), "reset_timing")
+
+    def enable_kernel_timing(self, on: bool = True):
+        self._check(self._lib.mpasb200_enable_kernel_timing(self._h, int(on)), "enable_kernel_timing")
+
+    def reset_kernel_timing(self):
+        self._check(self._lib.mpasb200_reset_kernel_timing(self._h), "reset_kernel_timing")
+
+    def kernel_times(self) -> Dict[str, tuple]:
+        """{kernel name: (total ms, launches)} measured with CUDA events on the launching stream."""
+        out, i = {}, 0
+        while True:
+            nm, ms, n = C.c_char_p(), C.c_double(), C.c_int64()
+            if self._lib.mpasb200_kernel_time(self._h, i, C.byref(nm), C.byref(ms), C.byref(n)) != 0:
+                return out
+            out[nm.value.decode()] = (ms.value, n.value)
+            i += 1
 
     def task_times(self) -> Dict[str, tuple]:
         out = {}

@@ -159,7 +159,7 @@ def make_icosahedral_mesh(n_cells: int) -> Mesh:
     first = np.searchsorted(a_s, np.arange(nC))           # first half-edge leaving each cell
     deg = np.searchsorted(a_s, np.arange(nC), side="right") - first
     nEdgesOnCell = deg.astype(np.int32)
-    assert deg.min() == 5 and deg.max() == 6 and int((deg == 5).sum()) == 12
+    assert deg.min() == 5 and deg.max() <= 6 and int((deg == 5).sum()) == 12
     cellsOnCell = np.zeros((nC, MAX_EDGES), dtype=np.int64)
     triAfter = np.zeros((nC, MAX_EDGES), dtype=np.int64)   # triangle between neighbour i and i+1
     cur = b_s[first]

@@ -1,0 +1,188 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle -- the parity tests proper.
+
+Reference: every hot-path task of dynamics/dynamics_tasks.rg and the driver rk_timestep.rg:361-500.
+Tolerance per BASELINE.json: 1e-12 relative per field, identical NaN/Inf positions; integer
+connectivity handling is exercised under both index policies.
+"""
+import numpy as np
+import pytest
+
+from mpas_regent_b200 import _abi
+from tests.util import build_pair, compare, copy_state
+
+pytestmark = pytest.mark.gpu
+
+L_SMALL = 26
+DT = 720.0
+
+
+def _warm(ora, g, dt=DT):
+    """populate every intermediate field with one oracle step, then mirror it onto the GPU."""
+    ora.atm_compute_solve_diagnostics(False, -1)
+    ora.atm_srk3(dt)
+    copy_state(ora, g)
+
+
+TASKS = [
+    ("rk_integration_setup", lambda b: b.atm_rk_integration_setup()),
+    ("compute_moist_coefficients", lambda b: b.atm_compute_moist_coefficients()),
+    ("compute_vert_imp_coefs", lambda b: b.atm_compute_vert_imp_coefs(240.0)),
+    ("compute_vert_imp_coefs_again", lambda b: (b.atm_compute_vert_imp_coefs(240.0), b.atm_compute_vert_imp_coefs(360.0))),
+    ("dyn_tend_rk0", lambda b: b.atm_compute_dyn_tend(0, DT)),
+    ("dyn_tend_rk1", lambda b: b.atm_compute_dyn_tend(1, DT)),
+    ("dyn_tend_rk2", lambda b: b.atm_compute_dyn_tend(2, DT)),
+    ("dyn_tend_neg", lambda b: b.atm_compute_dyn_tend(-1, DT)),
+    ("dyn_tend_fixed", lambda b: b.atm_compute_dyn_tend(0, DT, config_horiz_mixing=_abi.MIX_2D_FIXED)),
+    ("dyn_tend_other", lambda b: b.atm_compute_dyn_tend(0, DT, config_horiz_mixing=_abi.MIX_OTHER)),
+    ("dyn_tend_cam", lambda b: b.atm_compute_dyn_tend(0, DT, config_mpas_cam_coef=0.2)),
+    ("dyn_tend_rayleigh", lambda b: b.atm_compute_dyn_tend(1, DT, config_rayleigh_damp_u=True)),
+    ("set_smlstep_pert_variables", lambda b: b.atm_set_smlstep_pert_variables()),
+    ("acoustic_step0", lambda b: b.atm_advance_acoustic_step(240.0, 0)),
+    ("acoustic_step1", lambda b: b.atm_advance_acoustic_step(360.0, 1)),
+    ("acoustic_pair", lambda b: (b.atm_advance_acoustic_step(360.0, 0), b.atm_divergence_damping_3d(360.0),
+                                 b.atm_advance_acoustic_step(360.0, 1), b.atm_divergence_damping_3d(360.0),
+                                 b.atm_advance_acoustic_step(360.0, 2))),
+    ("divergence_damping_3d", lambda b: b.atm_divergence_damping_3d(360.0)),
+    ("recover_rk0", lambda b: b.atm_recover_large_step_variables(1, 0, DT)),
+    ("recover_rk2", lambda b: b.atm_recover_large_step_variables(2, 2, DT)),
+    ("solve_diagnostics_rk0", lambda b: b.atm_compute_solve_diagnostics(False, 0)),
+    ("solve_diagnostics_rk2", lambda b: b.atm_compute_solve_diagnostics(False, 2)),
+    ("solve_diagnostics_init", lambda b: b.atm_compute_solve_diagnostics(False, -1)),
+    ("solve_diagnostics_hollingsworth", lambda b: b.atm_compute_solve_diagnostics(True, 2)),
+    ("substep_finish_1_1", lambda b: b.atm_rk_dynamics_substep_finish(1, 1)),
+    ("substep_finish_1_3", lambda b: b.atm_rk_dynamics_substep_finish(1, 3)),
+    ("substep_finish_2_3", lambda b: b.atm_rk_dynamics_substep_finish(2, 3)),
+    ("substep_finish_3_3", lambda b: b.atm_rk_dynamics_substep_finish(3, 3)),
+]
+
+
+@pytest.fixture(scope="module", params=[_abi.INDEX_CORRECTED, _abi.INDEX_LITERAL], ids=["corrected", "literal"])
+def warmed(request, grid2562):
+    st, ora, g = build_pair(grid2562, L_SMALL, request.param, m5=True)
+    _warm(ora, g)
+    snap = {n: ora.download_field(n) for (n, _, _) in _abi.FIELDS}
+    yield ora, g, snap
+    g.close(); ora.close()
+
+
+@pytest.mark.parametrize("name,fn", TASKS, ids=[t[0] for t in TASKS])
+def test_task_parity(warmed, name, fn):
+    ora, g, snap = warmed
+    for n, a in snap.items():          # same starting state for every task
+        ora.upload_field(n, a); g.upload_field(n, a)
+    fn(ora); fn(g)
+    compare(g, ora, what=name)
+
+
+@pytest.mark.parametrize("policy", [_abi.INDEX_CORRECTED, _abi.INDEX_LITERAL], ids=["corrected", "literal"])
+@pytest.mark.parametrize("rkarg", [_abi.RKARG_STAGE_INDEX, _abi.RKARG_SUBSTEP_TRUNC], ids=["stage_index", "substep_trunc"])
+def test_full_step_parity(grid2562, policy, rkarg):
+    """one RK3 step after init (atm_core.rg:31 diagnostics + rk_timestep.rg:361-500), then 3 more."""
+    st, ora, g = build_pair(grid2562, L_SMALL, policy, m5=True, rkarg=rkarg)
+    for b in (ora, g):
+        b.atm_compute_solve_diagnostics(False, -1)
+        b.atm_srk3(DT)
+    compare(g, ora, what="after 1 step")
+    for b in (ora, g):
+        for _ in range(3):
+            b.atm_srk3(DT)
+    compare(g, ora, what="after 4 steps")
+    g.close(); ora.close()
+
+
+def test_full_step_memory_model_m1(grid2562):
+    """the literal reading: never-written fields are zero (rule M1), literal index policy, literal driver."""
+    st, ora, g = build_pair(grid2562, L_SMALL, _abi.INDEX_LITERAL, m5=False, rkarg=_abi.RKARG_SUBSTEP_TRUNC)
+    for b in (ora, g):
+        b.atm_compute_solve_diagnostics(False, -1)
+        b.atm_srk3(DT)
+    compare(g, ora, what="M1 literal step")
+    g.close(); ora.close()
+
+
+def test_literal_driver_dt_zero_nan_masks(grid2562):
+    """main.rg:66 passes the loop index as dt (Q1): the first step has dts = 0, coef_divdamp = inf,
+    inf*0 = NaN in ru_p (dynamics_tasks.rg:1737-1759).  NaN masks must coincide."""
+    st, ora, g = build_pair(grid2562, L_SMALL, _abi.INDEX_CORRECTED, m5=True, rkarg=_abi.RKARG_SUBSTEP_TRUNC)
+    for b in (ora, g):
+        b.atm_compute_solve_diagnostics(False, -1)
+        b.atm_srk3(0.0)
+        b.atm_srk3(1.0)
+    assert np.isnan(ora.download_field("ru_p")).any()
+    compare(g, ora, what="dt=0 then dt=1")
+    g.close(); ora.close()
+
+
+def test_by_tasks_equals_driver_and_graph(grid642):
+    """the host replay of atm_srk3, the library's driver and its CUDA-graph replay are bit-identical."""
+    from mpas_regent_b200 import dynamics, init_jw
+    st = init_jw.make_state(grid642, 10, _abi.INDEX_CORRECTED)
+    outs = []
+    for mode in ("tasks", "driver", "graph"):
+        cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, use_graph=int(mode == "graph"))
+        g = dynamics.Dynamics(dynamics.dims_of(grid642, 10), cfg)
+        g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
+        g.atm_compute_solve_diagnostics(False, -1)
+        for _ in range(3):
+            g.atm_srk3_by_tasks(600.0) if mode == "tasks" else g.atm_srk3(600.0)
+        outs.append(g.download_all())
+        assert g.launch_count > 0
+        g.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
+        assert np.array_equal(outs[0][n], outs[2][n], equal_nan=True), n
+
+
+def test_sfc_renumbering_is_transparent(grid642):
+    """results must not depend on the internal space-filling-curve numbering (bitwise)."""
+    from mpas_regent_b200 import dynamics, init_jw
+    st = init_jw.make_state(grid642, 10, _abi.INDEX_CORRECTED)
+    outs = []
+    for sfc in (0, 1):
+        g = dynamics.Dynamics(dynamics.dims_of(grid642, 10), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, sfc_renumber=sfc))
+        g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
+        g.atm_compute_solve_diagnostics(False, -1)
+        g.atm_srk3(600.0); g.atm_srk3(600.0)
+        outs.append(g.download_all()); g.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
+
+
+def test_vertical_mixing_branches(grid642):
+    """config_v_mom_eddy_visc2 / config_v_theta_eddy_visc2 > 0 (dead with the shipped constants,
+    dynamics_tasks.rg:1094-1146,1304-1314,1432-1473), both mix_full settings."""
+    for mix_full in (0, 1):
+        st, ora, g = build_pair(grid642, 12, _abi.INDEX_CORRECTED, config_v_mom_eddy_visc2=30.0,
+                                config_v_theta_eddy_visc2=20.0, config_mix_full=mix_full)
+        for b in (ora, g):
+            b.atm_compute_solve_diagnostics(False, -1)
+            b.atm_srk3(600.0)
+        compare(g, ora, what=f"vertical mixing, mix_full={mix_full}")
+        g.close(); ora.close()
+
+
+def test_strided_region_layout(grid642):
+    """upload/download with Legion-style byte strides (x-fastest instance): stride_x = 8, stride_k = 8*n."""
+    import ctypes as C
+    from mpas_regent_b200 import dynamics, init_jw
+    st = init_jw.make_state(grid642, 10, _abi.INDEX_CORRECTED)
+    g = dynamics.Dynamics(dynamics.dims_of(grid642, 10), _abi.default_config())
+    g.upload_mesh(st.static)
+    a = st.f["theta_m"]                      # [n, L1]
+    at = np.ascontiguousarray(a.T)           # [L1, n]: x fastest
+    n = a.shape[0]
+    rc = g._lib.mpasb200_upload_field(g._h, _abi.FIELD_ID["theta_m"], at.ctypes.data, 8, 8 * n)
+    assert rc == 0
+    assert np.array_equal(g.download_field("theta_m"), a)
+    back = np.zeros_like(at)
+    rc = g._lib.mpasb200_download_field(g._h, _abi.FIELD_ID["theta_m"], back.ctypes.data, 8, 8 * n)
+    assert rc == 0 and np.array_equal(back, at)
+    g.close()
+
+
+def test_error_paths(grid642):
+    from mpas_regent_b200 import dynamics
+    g = dynamics.Dynamics(dynamics.dims_of(grid642, 10), _abi.default_config())
+    with pytest.raises(dynamics.MpasB200Error, match="upload_mesh"):
+        g.atm_rk_integration_setup()
+    g.close()
