@@ -101,6 +101,8 @@ typedef struct {
   int32_t sfc_renumber;               /* 1: renumber cells/edges/vertices along a space-filling curve on the device */
   int32_t device;                     /* CUDA ordinal; -1 = the calling thread's current device */
   int32_t use_graph;                  /* 1: mpasb200_srk3 replays a captured CUDA graph */
+  int32_t acoustic_exact;             /* 1: evaluate the acoustic column sweep strictly left-to-right (two kernels, one
+                                         thread per column); 0 (default): fused kernel, affine sweep (a few ulp apart) */
 } MpasConfig;
 
 /* ---- level-0 ("static") region data -------------------------------------------- *

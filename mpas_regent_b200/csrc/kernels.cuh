@@ -693,6 +693,111 @@ __global__ void k_acoustic_column(const View V, double dts, int small_step, doub
   }
 }
 
+// Fused single-kernel form of the acoustic step (default).  lane = level, a block owns whole columns.
+// Everything except the dependence of rw_p(k) on the freshly updated level k-1 is evaluated in
+// parallel exactly as written in the reference.  That dependence is affine: with x = rw_p_new,
+//     rho_pp_new(k-1)    = rp0 + rp1 * x(k-1)          (:1694)
+//     rtheta_pp_new(k-1) = rt0 + rt1 * x(k-1)          (:1695-1696)
+//     x(k) = P(k) + Q(k) * x(k-1)                      (:1662-1686 collected in x(k-1))
+// so every thread computes its (P, Q) and ONE thread per column runs the 1-multiply-add-per-level
+// sweep out of shared memory; rho_pp / rtheta_pp / wwAvg then follow in parallel from x with the
+// reference's own expressions.  Differs from the literal left-to-right evaluation only by the
+// regrouping of terms inside one level (a few ulp; checked against the oracle at 1e-12).
+template <bool S0>
+__global__ void k_acoustic(const View V, double dts, double epssm, double resm) {
+  extern __shared__ double sm[];
+  COLUMN_THREAD(V.nCells)
+  const int TS = LP + 1;
+  double* s_rp0 = sm + (size_t)threadIdx.y * TS;
+  double* s_rt0 = sm + (size_t)(blockDim.y + threadIdx.y) * TS;
+  double* s_P = sm + (size_t)(2 * blockDim.y + threadIdx.y) * TS;
+  double* s_Q = sm + (size_t)(3 * blockDim.y + threadIdx.y) * TS;
+  const bool act = inx && k < L;
+  const bool spec = inx ? (V.specZoneMaskCell[x] != 0.0) : false;
+  if (inx && k == L && S0) { FLD(wwAvg)[ix] = 0; FLD(rw_p)[ix] = 0; }                                // :1625-1630, level L
+  double rs = 0, ts = 0, rw_old_k = 0, rw_old_p = 0, rho_old = 0, rt_old = 0, ww_old = 0;
+  double coftz_k = 0, coftz_p = 0, cofrz_k = 0, rdzw_k = 0, w_k = 0, tr_k = 0, tm_k = 0;
+  if (act) {
+    const double* tm = FLD(theta_m);
+    cofrz_k = FLD(cofrz)[k]; rdzw_k = FLD(rdzw)[k];
+    if (!S0) {
+      rw_old_k = FLD(rw_p)[ix]; rw_old_p = FLD(rw_p)[ix + 1];
+      rho_old = FLD(rho_pp)[ix]; rt_old = FLD(rtheta_pp)[ix]; ww_old = FLD(wwAvg)[ix];
+    }
+    FLD(rtheta_pp_old)[ix] = S0 ? 0.0 : rt_old;                                                       // :1615-1623
+    w_k = FLD(w)[ix]; tr_k = FLD(tend_rho)[ix]; tm_k = tm[ix];
+    if (!spec) {
+      const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
+      const double* ru_p = FLD(ru_p);
+      const double inva = V.invAreaCell[x];
+      for (int i = 0; i < n; ++i) {                                                                   // :1644-1652
+        const int e = V.edgesOnCell[x * ME + i];
+        const int c1 = V.cellsOnEdge[e * 2], c2 = V.cellsOnEdge[e * 2 + 1];
+        const double flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvEdge[e] * AT(ru_p, e, k) * inva;
+        rs -= flux;
+        ts -= flux * 0.5 * (AT(tm, c2, k) + AT(tm, c1, k));
+      }
+      coftz_k = FLD(coftz)[ix]; coftz_p = FLD(coftz)[ix + 1];
+      rs = rho_old + dts * tr_k + rs - cofrz_k * resm * (rw_old_p - rw_old_k);                        // :1657
+      ts = rt_old + dts * tm_k + ts - resm * rdzw_k * (coftz_p * rw_old_p - coftz_k * rw_old_k);      // :1658
+      // new rho_pp / rtheta_pp of THIS level as affine functions of x(k):  rp0 + cofrz*x,  rt0 + rdzw*coftz*x
+      s_rp0[k] = rs - cofrz_k * rw_old_p;
+      s_rt0[k] = ts - rdzw_k * (coftz_p * rw_old_p);
+    }
+  }
+  __syncthreads();
+  double r3 = 0, r2 = 1, cofwt_k = 0, zz_k = 0;
+  if (act && !spec) {
+    zz_k = FLD(zz)[ix]; cofwt_k = FLD(cofwt)[ix];
+    if (k == 0) { s_P[0] = rw_old_k; s_Q[0] = 0.0; }
+    else {
+      const double zz_m = FLD(zz)[ix - 1], cofwt_m = FLD(cofwt)[ix - 1], rz_k = FLD(rho_zz)[ix], rz_m = FLD(rho_zz)[ix - 1];
+      const double cofwz_k = FLD(cofwz)[ix], cofwr_k = FLD(cofwr)[ix];
+      const double fm = FLD(fzm)[k], fp = FLD(fzp)[k];
+      const double dsk = FLD(dss)[ix];
+      r3 = FLD(rw_save)[ix] - FLD(rw)[ix];
+      const double r1 = r3 - dts * dsk * (fm * zz_k + fp * zz_m) * (fm * rz_k + fp * rz_m) * w_k;      // :1682-1684
+      r2 = 1.0 + dts * dsk;                                                                           // :1685
+      // terms of :1662-1667 that do not involve level k-1's new values
+      const double A0 = rw_old_k + (dts * w_k - cofwz_k * ((zz_k * ts - zz_m * 0.0) + resm * (zz_k * rt_old))
+                                    - cofwr_k * ((rs + 0.0) + resm * rho_old) + cofwt_k * (ts + resm * rt_old));
+      const double A1 = resm * (cofwz_k * zz_m + cofwt_m);        // coefficient of rtheta_pp_new(k-1)
+      const double A2 = resm * cofwr_k;                           // coefficient of -rho_pp_new(k-1)
+      const double rp0 = s_rp0[k - 1], rt0 = s_rt0[k - 1];
+      const double rp1 = FLD(cofrz)[k - 1], rt1 = FLD(rdzw)[k - 1] * FLD(coftz)[ix - 1];
+      const double B0 = A0 + A1 * rt0 - A2 * rp0;
+      const double B1 = A1 * rt1 - A2 * rp1 - FLD(a_tri)[ix];                                          // :1670
+      const double al = FLD(alpha_tri)[ix];                                                            // :1671
+      s_P[k] = (B0 * al + r1) / r2 - r3;                                                               // :1682-1686
+      s_Q[k] = B1 * al / r2;
+    }
+  }
+  __syncthreads();
+  if (inx && !spec && k == 0) {             // the sweep: one multiply-add per level, levels ascending (M4)
+    double xv = s_P[0];
+    for (int kk = 1; kk < L; ++kk) { xv = s_P[kk] + s_Q[kk] * xv; s_P[kk] = xv; }
+  }
+  __syncthreads();
+  if (!act) return;
+  double rw_new, rho_new, rt_new, ww_new = ww_old;
+  if (!spec) {
+    rw_new = s_P[k];
+    if (k > 0) {
+      ww_new += 0.5 * (1.0 - epssm) * rw_old_k;                                                        // :1661
+      ww_new += 0.5 * (1.0 + epssm) * rw_new;                                                          // :1689
+    }
+    rho_new = rs - cofrz_k * (rw_old_p - rw_new);                                                      // :1694
+    rt_new = ts - rdzw_k * (coftz_p * rw_old_p - coftz_k * rw_new);                                    // :1695-1696
+  } else {                                                                                             // :1698-1703
+    rho_new = rho_old + dts * tr_k;
+    rt_new = rt_old + dts * tm_k;
+    rw_new = rw_old_k + dts * w_k;
+    ww_new = ww_old + 0.5 * (1.0 + epssm) * rw_new;
+  }
+  FLD(rho_pp)[ix] = rho_new; FLD(rtheta_pp)[ix] = rt_new;
+  if (S0 || spec || k > 0) { FLD(rw_p)[ix] = rw_new; FLD(wwAvg)[ix] = ww_new; }
+}
+
 // ============================================================================================
 // atm_divergence_damping_3d  :1726-1763
 __global__ void k_divdamp(const View V, double coef_divdamp) {

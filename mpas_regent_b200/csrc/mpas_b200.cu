@@ -290,6 +290,11 @@ int t_smlstep(mpasb200_t* h) { LAUNCH(k_smlstep, h->nCells, 0, h->V, h->c.nRelax
 int t_acoustic(mpasb200_t* h, double dts, int small_step) {
   const double epssm = h->c.config_epssm;
   const double resm = (1.0 - epssm) / (1.0 + epssm);
+  if (!h->c.acoustic_exact) {
+    if (small_step == 0) LAUNCH(k_acoustic<true>, h->nCells, tile_bytes(h, 4), h->V, dts, epssm, resm);
+    else LAUNCH(k_acoustic<false>, h->nCells, tile_bytes(h, 4), h->V, dts, epssm, resm);
+    return post_launch(h);
+  }
   LAUNCH(k_acoustic_flux, h->nCells, 0, h->V, dts, small_step);
   if (h->nCells > 0) {
     const int tb = 64;
@@ -420,7 +425,7 @@ void mpasb200_default_config(MpasConfig* c) {
   c->config_horiz_mixing = MPASB200_MIX_2D_SMAGORINSKY;
   c->nRelaxZone = 5; c->number_of_sub_steps = 2; c->config_dynamics_split_steps = 1;
   c->index_policy = MPASB200_INDEX_CORRECTED; c->rkarg_policy = MPASB200_RKARG_SUBSTEP_TRUNC;
-  c->sfc_renumber = 1; c->device = -1; c->use_graph = 0;
+  c->sfc_renumber = 1; c->device = -1; c->use_graph = 0; c->acoustic_exact = 0;
 }
 
 const char* mpasb200_last_error(const mpasb200_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }

@@ -1,0 +1,34 @@
+"""The per-kernel field lists (mpas_regent_b200/traffic.py) regenerate SURVEY.md 8(d)'s table; a
+kernel's declared algorithmic bytes may not drop below the contract figures."""
+import re
+
+from mpas_regent_b200 import _abi, traffic as T
+
+
+def test_every_declared_field_exists():
+    for k, (r, w) in T.K.items():
+        for n in r + w:
+            assert n == "scr" or n in _abi.FIELD_ID, (k, n)
+
+
+def test_task_units_not_below_survey():
+    for task, want in T.SURVEY_TASK_UNITS.items():
+        assert T.task_units(task) >= want, (task, T.task_units(task), want)
+    # tasks whose kernels move exactly the contract figure
+    for task in ("rk_integration_setup", "compute_moist_coefficients", "compute_vert_imp_coefs", "set_smlstep_pert_variables",
+                 "advance_acoustic_step:s0", "advance_acoustic_step", "divergence_damping_3d", "rk_dynamics_substep_finish"):
+        assert T.task_units(task) == T.SURVEY_TASK_UNITS[task], task
+
+
+def test_step_units():
+    assert T.step_units(True, scratch=False) >= T.SURVEY_STEP_UNITS_CANONICAL
+    assert T.step_units(False, scratch=False) >= T.SURVEY_STEP_UNITS_LITERAL
+    assert len(T.step_launches(True)) == 47 and len(T.step_launches(False)) == 42
+
+
+def test_every_kernel_in_the_library_is_declared():
+    src = open(_abi.REPO_ROOT + "/mpas_regent_b200/csrc/mpas_b200.cu").read()
+    names = set(re.findall(r"LAUNCH\((k_\w+(?:<\w+>)?)", src))
+    assert names, "no launches found"
+    for n in names:
+        assert n in T.K, n
