@@ -1,13 +1,15 @@
 // kernels.cuh -- hand-written sm_100a kernels for the RK3 dynamics hot path.
 //
-// Thread mapping (all stencil kernels): blockDim = (LP, CPB): threadIdx.x = level k (levels
-// contiguous in memory -> every warp request is a run of consecutive doubles of one or two
-// columns), threadIdx.y = column within the block, CPB chosen so LP*CPB is a multiple of 32.
-// A block therefore owns CPB whole columns, so column neighbours (k-2..k+1) computed in the
-// same kernel are exchanged through shared memory; neighbour columns (edgesOnCell,
-// cellsOnEdge, advCellsForEdge ...) are gathered straight from L2/HBM as contiguous level
-// strips.  Flux divergences are cell-centric gathers over edgesOnCell in slot order: no
-// atomics, bit-reproducible.  Every kernel is HBM-bound (fp64, ~0.3 flop/B).
+// Thread mapping (all stencil kernels): blockDim = (LP/2, CPB).  threadIdx.x owns the level PAIR
+// (2*tx, 2*tx+1) of one column -- levels are contiguous in memory and LP is a multiple of 4, so
+// every access to a 3-D field is one aligned 128-bit load/store and a column is a run of
+// consecutive 16-byte words across the lanes; threadIdx.y = column within the block, CPB chosen so
+// the block is a multiple of 32 threads.  A block owns CPB whole columns, so column neighbours
+// (k-2..k+1) produced inside a kernel are exchanged through shared memory; neighbour columns
+// (edgesOnCell, cellsOnEdge, advCellsForEdge ...) are gathered from L2/HBM as contiguous level strips
+// after ONE level of index loads (per-(cell,slot) copies of the edge statics, view.h).  Flux
+// divergences are cell-centric gathers over edgesOnCell in slot order: no atomics, bit-reproducible.
+// Every kernel is HBM-bound (fp64, ~0.3 flop/B); the design goal is bytes in flight per thread.
 //
 // Arithmetic follows the reference's expression order (compiled with --fmad=false) so that
 // results agree with the CPU oracle to the last bit wherever no libm call is involved.
@@ -15,47 +17,92 @@
 #pragma once
 #include "view.h"
 
+#define DI __device__ __forceinline__
+typedef double2 D2;
+
+DI D2 mk(double a, double b) { return make_double2(a, b); }
+DI D2 bc(double a) { return make_double2(a, a); }
+DI D2 operator+(D2 a, D2 b) { return mk(a.x + b.x, a.y + b.y); }
+DI D2 operator-(D2 a, D2 b) { return mk(a.x - b.x, a.y - b.y); }
+DI D2 operator*(D2 a, D2 b) { return mk(a.x * b.x, a.y * b.y); }
+DI D2 operator/(D2 a, D2 b) { return mk(a.x / b.x, a.y / b.y); }
+DI D2 operator+(D2 a, double b) { return mk(a.x + b, a.y + b); }
+DI D2 operator-(D2 a, double b) { return mk(a.x - b, a.y - b); }
+DI D2 operator*(D2 a, double b) { return mk(a.x * b, a.y * b); }
+DI D2 operator/(D2 a, double b) { return mk(a.x / b, a.y / b); }
+DI D2 operator+(double a, D2 b) { return mk(a + b.x, a + b.y); }
+DI D2 operator-(double a, D2 b) { return mk(a - b.x, a - b.y); }
+DI D2 operator*(double a, D2 b) { return mk(a * b.x, a * b.y); }
+DI D2 operator/(double a, D2 b) { return mk(a / b.x, a / b.y); }
+DI D2 operator-(D2 a) { return mk(-a.x, -a.y); }
+DI D2& operator+=(D2& a, D2 b) { a.x += b.x; a.y += b.y; return a; }
+DI D2& operator-=(D2& a, D2 b) { a.x -= b.x; a.y -= b.y; return a; }
+DI D2& operator*=(D2& a, D2 b) { a.x *= b.x; a.y *= b.y; return a; }
+DI D2& operator*=(D2& a, double b) { a.x *= b; a.y *= b; return a; }
+DI D2& operator/=(D2& a, D2 b) { a.x /= b.x; a.y /= b.y; return a; }
+DI D2 sgn1(D2 v) { return mk(copysign(1.0, v.x), copysign(1.0, v.y)); }
+DI double dmin(double a, double b) { return (b < a) ? b : a; }     // std::min
+DI double dmax(double a, double b) { return (a < b) ? b : a; }     // std::max
+DI D2 sel(bool c0, bool c1, D2 a, D2 b) { return mk(c0 ? a.x : b.x, c1 ? a.y : b.y); }
+DI D2 ld2(const double* p, size_t i) { return *reinterpret_cast<const D2*>(p + i); }
+DI void st2(double* p, size_t i, D2 v) { *reinterpret_cast<D2*>(p + i) = v; }
+// store the components whose mask is set (a pair that straddles the top level stores one double)
+DI void st2m(double* p, size_t i, D2 v, bool m0, bool m1) {
+  if (m0 && m1) st2(p, i, v);
+  else { if (m0) p[i] = v.x; if (m1) p[i + 1] = v.y; }
+}
+
 #define FLD(name) (V.f[MPASB200_F_##name])
-#define COLUMN_THREAD(n)                                        \
-  const int k = threadIdx.x;                                    \
+#define PAIR_THREAD(n)                                          \
+  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;             \
   const int x = blockIdx.x * blockDim.y + threadIdx.y;          \
   const bool inx = x < (n);                                     \
   const int LP = V.LP; const int L = V.L;                       \
-  const size_t ix = (size_t)(inx ? x : 0) * LP + k;             \
-  (void)L; (void)ix;
-#define AT(p, x_, k_) ((p)[(size_t)(x_) * LP + (k_)])
+  const size_t ix = (size_t)(inx ? x : 0) * LP + k0;            \
+  const bool m0 = inx && k0 < L, m1 = inx && k1 < L;            \
+  (void)ix; (void)m1; (void)k1;
+#define G2(p, e) ld2((p), (size_t)(e) * LP + k0)                 /* the level pair of neighbour column e */
+#define G1(p, e, k_) ((p)[(size_t)(e) * LP + (k_)])
+// values one level below / above the pair: (f[k0-1], f[k0]) and (f[k1], f[k1+1])
+DI D2 below(const double* p, size_t ix, int k0, D2 cur) { return mk(k0 > 0 ? p[ix - 1] : 0.0, cur.x); }
+DI D2 above(const double* p, size_t ix, int k0, int L, D2 cur) { return mk(cur.y, (k0 + 2 <= L) ? p[ix + 2] : 0.0); }
 
-__device__ __forceinline__ double flux4(double q_im2, double q_im1, double q_i, double q_ip1, double ua) {
+DI double flux4(double q_im2, double q_im1, double q_i, double q_ip1, double ua) {
   return ua * (7. * (q_i + q_im1) - (q_ip1 + q_im2)) / 12.0;                       // :781-783
 }
-__device__ __forceinline__ double flux3(double q_im2, double q_im1, double q_i, double q_ip1, double ua, double coef3) {
+DI double flux3(double q_im2, double q_im1, double q_i, double q_ip1, double ua, double coef3) {
   return flux4(q_im2, q_im1, q_i, q_ip1, ua) + coef3 * fabs(ua) * ((q_ip1 - q_im2) - 3. * (q_i - q_im1)) / 12.0;   // :786-789
 }
-__device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
-__device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }
 
 // ============================================================================================
 // atm_rk_integration_setup  :747-778
 __global__ void k_setup_cell(const View V) {
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
-  FLD(rw_save)[ix] = FLD(rw)[ix]; FLD(rtheta_p_save)[ix] = FLD(rtheta_p)[ix]; FLD(rho_p_save)[ix] = FLD(rho_p)[ix];
-  FLD(w_2)[ix] = FLD(w)[ix]; FLD(theta_m_2)[ix] = FLD(theta_m)[ix];
-  const double r = FLD(rho_zz)[ix]; FLD(rho_zz_2)[ix] = r; FLD(rho_zz_old_split)[ix] = r;
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
+  st2m(FLD(rw_save), ix, ld2(FLD(rw), ix), m0, m1);
+  st2m(FLD(rtheta_p_save), ix, ld2(FLD(rtheta_p), ix), m0, m1);
+  st2m(FLD(rho_p_save), ix, ld2(FLD(rho_p), ix), m0, m1);
+  st2m(FLD(w_2), ix, ld2(FLD(w), ix), m0, m1);
+  st2m(FLD(theta_m_2), ix, ld2(FLD(theta_m), ix), m0, m1);
+  const D2 r = ld2(FLD(rho_zz), ix);
+  st2m(FLD(rho_zz_2), ix, r, m0, m1);
+  st2m(FLD(rho_zz_old_split), ix, r, m0, m1);
 }
 __global__ void k_setup_edge(const View V) {
-  COLUMN_THREAD(V.nEdges)
-  if (!inx || k >= L) return;
-  FLD(ru_save)[ix] = FLD(ru)[ix]; FLD(u_2)[ix] = FLD(u)[ix];
+  PAIR_THREAD(V.nEdges)
+  if (!m0) return;
+  st2m(FLD(ru_save), ix, ld2(FLD(ru), ix), m0, m1);
+  st2m(FLD(u_2), ix, ld2(FLD(u), ix), m0, m1);
 }
 
 // atm_compute_moist_coefficients  :460-502   (qtot = 0; cqw from it for k > 0; cqu never written)
 __global__ void k_moist(const View V) {
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
   const double qz = 0.0;
-  FLD(qtot)[ix] = qz;
-  if (k > 0) { const double qtotal = 0.5 * (qz + qz); FLD(cqw)[ix] = 1.0 / (1.0 + qtotal); }
+  st2m(FLD(qtot), ix, bc(qz), m0, m1);
+  const double qtotal = 0.5 * (qz + qz);
+  st2m(FLD(cqw), ix, bc(1.0 / (1.0 + qtotal)), m0 && k0 > 0, m1);
 }
 
 // atm_compute_vert_imp_coefs  :513-592
@@ -63,126 +110,140 @@ __global__ void k_moist(const View V) {
 // before the barrier, everything this call produces for neighbours (coftz, cofwt) goes through smem.
 __global__ void k_vert_imp(const View V, double dtseps, double c2, double rcv, double gravity) {
   extern __shared__ double sm[];
-  COLUMN_THREAD(V.nCells)
-  const int TS = LP + 1;
+  PAIR_THREAD(V.nCells)
+  const int TS = LP + 2;
   double* s_coftz = sm + (size_t)threadIdx.y * TS;
   double* s_cofwt = sm + (size_t)(blockDim.y + threadIdx.y) * TS;
-  const double* rdzw = FLD(rdzw); const double* rdzu = FLD(rdzu); const double* fzm = FLD(fzm); const double* fzp = FLD(fzp);
-  const bool act = inx && k < L;
-  double zz_k = 0, zz_m = 0, coftz_k = 0, cofwt_k = 0, cofwr_k = 0, cofwz_k = 0, gamma_prev = 0;
-  if (blockIdx.x == 0 && threadIdx.y == 0 && k < L) FLD(cofrz)[k] = dtseps * rdzw[k];          // :537-539
-  if (act) {
-    zz_k = FLD(zz)[ix];
-    const double ex_k = FLD(exner)[ix], th_k = FLD(theta_m)[ix];
-    if (k > 0) {
-      zz_m = FLD(zz)[ix - 1];
-      const double zf = fzm[k] * zz_k + fzp[k] * zz_m;
-      cofwr_k = .5 * dtseps * gravity * zf;                                                      // :552
-      cofwz_k = dtseps * c2 * zf * rdzu[k] * FLD(cqw)[ix] * (fzm[k] * ex_k + fzp[k] * FLD(exner)[ix - 1]);   // :557
-      coftz_k = dtseps * (fzm[k] * th_k + fzp[k] * FLD(theta_m)[ix - 1]);                        // :558
-      gamma_prev = (k == 1) ? 0.0 : FLD(gamma_tri)[ix - 1];                                      // :545, :583 (previous call's gamma)
-    }
-    const double qtotal = FLD(qtot)[ix];
-    cofwt_k = .5 * dtseps * rcv * zz_k * gravity * FLD(rho_base)[ix] / (1.0 + qtotal) * ex_k
-              / ((FLD(rtheta_base)[ix] + FLD(rtheta_p)[ix]) * FLD(exner_base)[ix]);             // :563
-    s_coftz[k] = coftz_k; s_cofwt[k] = cofwt_k;
+  if (blockIdx.x == 0 && threadIdx.y == 0) {                                                         // :537-539
+    if (k0 < L) FLD(cofrz)[k0] = dtseps * FLD(rdzw)[k0];
+    if (k1 < L) FLD(cofrz)[k1] = dtseps * FLD(rdzw)[k1];
   }
-  if (inx && k == L) s_coftz[L] = FLD(coftz)[ix];     // level L is never written: whatever the mirror holds
+  D2 zz = bc(0), zzm = bc(0), coftz = bc(0), cofwt = bc(0), cofwr = bc(0), cofwz = bc(0), gprev = bc(0);
+  D2 rdzw2 = bc(0), rdzwm = bc(0);
+  if (m0) {
+    const D2 fzm = ld2(FLD(fzm), k0), fzp = ld2(FLD(fzp), k0), rdzu = ld2(FLD(rdzu), k0);
+    rdzw2 = ld2(FLD(rdzw), k0); rdzwm = below(FLD(rdzw), k0, k0, rdzw2);
+    zz = ld2(FLD(zz), ix); zzm = below(FLD(zz), ix, k0, zz);
+    const D2 ex = ld2(FLD(exner), ix), exm = below(FLD(exner), ix, k0, ex);
+    const D2 th = ld2(FLD(theta_m), ix), thm = below(FLD(theta_m), ix, k0, th);
+    const D2 zf = fzm * zz + fzp * zzm;
+    cofwr = .5 * dtseps * gravity * zf;                                                               // :552
+    cofwz = dtseps * c2 * zf * rdzu * ld2(FLD(cqw), ix) * (fzm * ex + fzp * exm);                     // :557
+    coftz = dtseps * (fzm * th + fzp * thm);                                                          // :558
+    if (k0 == 0) coftz.x = 0.0;                                                                       // :555
+    const D2 g = ld2(FLD(gamma_tri), ix);                      // previous call's gamma (:583)
+    gprev = mk(k0 > 1 ? FLD(gamma_tri)[ix - 1] : 0.0, k0 > 0 ? g.x : 0.0);                            // gamma(0) = 0 (:545)
+    const D2 qtotal = ld2(FLD(qtot), ix);
+    cofwt = .5 * dtseps * rcv * zz * gravity * ld2(FLD(rho_base), ix) / (1.0 + qtotal) * ex
+            / ((ld2(FLD(rtheta_base), ix) + ld2(FLD(rtheta_p), ix)) * ld2(FLD(exner_base), ix));      // :563
+    s_coftz[k0] = coftz.x; s_cofwt[k0] = cofwt.x;
+    if (m1) { s_coftz[k1] = coftz.y; s_cofwt[k1] = cofwt.y; }
+  }
+  // level L is never written: whatever the mirror holds
+  if (inx && k0 == L) s_coftz[L] = FLD(coftz)[ix];
+  if (inx && k1 == L) s_coftz[L] = FLD(coftz)[ix + 1];
   __syncthreads();
-  if (!act) return;
-  FLD(coftz)[ix] = coftz_k; FLD(cofwt)[ix] = cofwt_k;
-  if (k == 0) { FLD(gamma_tri)[ix] = 0.0; return; }
-  FLD(cofwr)[ix] = cofwr_k; FLD(cofwz)[ix] = cofwz_k;
-  const double coftz_m = s_coftz[k - 1], coftz_p = s_coftz[k + 1], cofwt_m = s_cofwt[k - 1];
-  const double cofrz_k = dtseps * rdzw[k], cofrz_m = dtseps * rdzw[k - 1];
-  const double a = -1.0 * cofwz_k * coftz_m * rdzw[k - 1] * zz_m + cofwr_k * cofrz_m - cofwt_m * coftz_m * rdzw[k - 1];   // :568-569
-  const double b = 1.0 + cofwz_k * (coftz_k * rdzw[k] * zz_k + coftz_k * rdzw[k - 1] * zz_m)
-                   - coftz_k * (cofwt_k * rdzw[k] - cofwt_k * rdzw[k - 1]) + cofwr_k * ((cofrz_k - cofrz_m));           // :571-573
-  const double c = -1.0 * cofwz_k * coftz_p * rdzw[k] * zz_k - cofwr_k * cofrz_k + cofwt_k * coftz_p * rdzw[k];          // :575-576
-  const double alpha = 1.0 / (b - a * gamma_prev);                                                                      // :583
-  FLD(a_tri)[ix] = a; FLD(b_tri)[ix] = b; FLD(c_tri)[ix] = c; FLD(alpha_tri)[ix] = alpha;
-  FLD(gamma_tri)[ix] = c * alpha;                                                                                       // :589
+  if (!m0) return;
+  st2m(FLD(coftz), ix, coftz, m0, m1); st2m(FLD(cofwt), ix, cofwt, m0, m1);
+  const bool w0 = k0 > 0, w1 = m1;
+  st2m(FLD(cofwr), ix, cofwr, w0, w1); st2m(FLD(cofwz), ix, cofwz, w0, w1);
+  const D2 coftz_m = mk(k0 > 0 ? s_coftz[k0 - 1] : 0.0, coftz.x);
+  const D2 coftz_p = mk(m1 ? s_coftz[k1] : s_coftz[L], m1 ? s_coftz[k1 + 1] : 0.0);
+  const D2 cofwt_m = mk(k0 > 0 ? s_cofwt[k0 - 1] : 0.0, cofwt.x);
+  const D2 cofrz = dtseps * rdzw2, cofrz_m = dtseps * rdzwm;
+  const D2 a = -1.0 * cofwz * coftz_m * rdzwm * zzm + cofwr * cofrz_m - cofwt_m * coftz_m * rdzwm;    // :568-569
+  const D2 b = 1.0 + cofwz * (coftz * rdzw2 * zz + coftz * rdzwm * zzm)
+               - coftz * (cofwt * rdzw2 - cofwt * rdzwm) + cofwr * ((cofrz - cofrz_m));               // :571-573
+  const D2 c = -1.0 * cofwz * coftz_p * rdzw2 * zz - cofwr * cofrz + cofwt * coftz_p * rdzw2;          // :575-576
+  const D2 alpha = 1.0 / (b - a * gprev);                                                             // :583
+  st2m(FLD(a_tri), ix, a, w0, w1); st2m(FLD(b_tri), ix, b, w0, w1); st2m(FLD(c_tri), ix, c, w0, w1);
+  st2m(FLD(alpha_tri), ix, alpha, w0, w1);
+  D2 gam = c * alpha;                                                                                 // :589
+  if (k0 == 0) gam.x = 0.0;                                                                           // :545
+  st2m(FLD(gamma_tri), ix, gam, m0, m1);
 }
 
 // ============================================================================================
 // atm_compute_solve_diagnostics  :328-454
 __global__ void k_diag_vertex(const View V) {      // vorticity :356-366, pv_vertex :443-445
-  COLUMN_THREAD(V.nVertices)
-  if (!inx || k >= L) return;
-  const int VD = V.vertexDegree;
+  PAIR_THREAD(V.nVertices)
+  if (!m0) return;
   const double* u = FLD(u);
-  double vort = 0.0;
-  for (int i = 0; i < VD; ++i) {
-    const int e = V.edgesOnVertex[x * VD + i];
-    const double s = V.edgesOnVertexSign[x * VD + i] * V.dcEdge[e];
-    vort += s * AT(u, e, k);
-  }
+  const int e0 = V.edgesOnVertex[x * 3], e1 = V.edgesOnVertex[x * 3 + 1], e2 = V.edgesOnVertex[x * 3 + 2];
+  const D2 u0 = G2(u, e0), u1 = G2(u, e1), u2 = G2(u, e2);
+  D2 vort = bc(0.0);
+  vort += (V.edgesOnVertexSign[x * 3] * V.dcOnVertex[x * 3]) * u0;
+  vort += (V.edgesOnVertexSign[x * 3 + 1] * V.dcOnVertex[x * 3 + 1]) * u1;
+  vort += (V.edgesOnVertexSign[x * 3 + 2] * V.dcOnVertex[x * 3 + 2]) * u2;
   vort *= V.invAreaTriangle[x];
-  FLD(vorticity)[ix] = vort;
-  FLD(pv_vertex)[ix] = V.fVertex[x] + vort;
+  st2m(FLD(vorticity), ix, vort, m0, m1);
+  st2m(FLD(pv_vertex), ix, V.fVertex[x] + vort, m0, m1);
 }
 __global__ void k_diag_cell(const View V) {        // divergence :369-379 (s + u), ke :382-390
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
   const double* u = FLD(u);
-  double div = 0.0, kec = 0.0;
+  D2 div = bc(0.0), kec = bc(0.0);
+#pragma unroll 2
   for (int i = 0; i < n; ++i) {
-    const int e = V.edgesOnCell[x * ME + i];
-    const double s = V.edgesOnCellSign[x * ME + i] * V.dvEdge[e];
-    const double ue = AT(u, e, k);
+    const int e = V.edgesOnCell[x * V.MEP + i];
+    const double dv = V.dvOnCell[x * ME + i];
+    const double s = V.edgesOnCellSign[x * ME + i] * dv;
+    const D2 ue = G2(u, e);
     div += s + ue;
-    const double efac = V.dcEdge[e] * V.dvEdge[e];
+    const double efac = V.dcEdge[e] * dv;
     kec += 0.25 * (efac * (ue * ue));               // ke_edge recomputed from u: same value as the stored field
   }
   const double r = V.invAreaCell[x];
-  FLD(divergence)[ix] = div * r;
-  FLD(ke)[ix] = kec * r;
+  st2m(FLD(divergence), ix, div * r, m0, m1);
+  st2m(FLD(ke), ix, kec * r, m0, m1);
 }
 template <bool RECON_V>
 __global__ void k_diag_edge(const View V) {        // h_edge, ke_edge :346-353; v :431-438; pv_edge :449-451
-  COLUMN_THREAD(V.nEdges)
-  if (!inx || k >= L) return;
-  const int c1 = V.cellsOnEdge[x * 2], c2 = V.cellsOnEdge[x * 2 + 1];
+  PAIR_THREAD(V.nEdges)
+  if (!m0) return;
+  const int4 cv = V.ecv[x];
   const double* u = FLD(u); const double* h = FLD(h); const double* pvv = FLD(pv_vertex);
-  FLD(h_edge)[ix] = 0.5 * (AT(h, c1, k) + AT(h, c2, k));
+  const D2 h1 = G2(h, cv.x), h2 = G2(h, cv.y), p1 = G2(pvv, cv.z), p2 = G2(pvv, cv.w);
+  const D2 ue = ld2(u, ix);
+  st2m(FLD(h_edge), ix, 0.5 * (h1 + h2), m0, m1);
   const double efac = V.dcEdge[x] * V.dvEdge[x];
-  const double ue = u[ix];
-  FLD(ke_edge)[ix] = efac * (ue * ue);
+  st2m(FLD(ke_edge), ix, efac * (ue * ue), m0, m1);
   if (RECON_V) {
     const int ME2 = V.maxEdges2, n = V.nEdgesOnEdge[x];
-    double vv = 0;
+    D2 vv = bc(0.0);
+#pragma unroll 2
     for (int i = 1; i < n; ++i) {                   // starts at 1 (Q7)
       const int eoe = V.edgesOnEdge_ECP[x * ME2 + i];
-      vv += V.weightsOnEdge[x * ME2 + i] * AT(u, eoe, k);
+      vv += V.weightsOnEdge[x * ME2 + i] * G2(u, eoe);
     }
-    FLD(v)[ix] = vv;
+    st2m(FLD(v), ix, vv, m0, m1);
   }
-  FLD(pv_edge)[ix] = 0.5 * (AT(pvv, V.verticesOnEdge[x * 2], k) + AT(pvv, V.verticesOnEdge[x * 2 + 1], k));
+  st2m(FLD(pv_edge), ix, 0.5 * (p1 + p2), m0, m1);
 }
 __global__ void k_diag_ke_vertex(const View V) {   // hollingsworth part 1 :395-400
-  COLUMN_THREAD(V.nVertices)
-  if (!inx || k >= L) return;
-  const int VD = V.vertexDegree;
+  PAIR_THREAD(V.nVertices)
+  if (!m0) return;
   const double* ke_edge = FLD(ke_edge);
   const double r = 0.25 * V.invAreaTriangle[x];
-  FLD(ke_vertex)[ix] = (AT(ke_edge, V.edgesOnVertex[x * VD], k) + AT(ke_edge, V.edgesOnVertex[x * VD + 1], k)
-                        + AT(ke_edge, V.edgesOnVertex[x * VD + 2], k)) * r;
+  st2m(FLD(ke_vertex), ix, (G2(ke_edge, V.edgesOnVertex[x * 3]) + G2(ke_edge, V.edgesOnVertex[x * 3 + 1])
+                            + G2(ke_edge, V.edgesOnVertex[x * 3 + 2])) * r, m0, m1);
 }
 __global__ void k_diag_ke_holl(const View V) {     // hollingsworth part 2 :403-417
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
-  const int ME = V.maxEdges, VD = V.vertexDegree, n = V.nEdgesOnCell[x];
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
+  const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
   const double ke_fact = 1.0 - 0.375;
   const double* kev = FLD(ke_vertex);
-  double kec = FLD(ke)[ix] * ke_fact;
+  D2 kec = ld2(FLD(ke), ix) * ke_fact;
   const double r = V.invAreaCell[x];
   for (int i = 0; i < n; ++i) {
     const int iv = V.verticesOnCell[x * ME + i];
     const int j = V.kiteForCell[x * ME + i];
-    kec += (1.0 - ke_fact) * V.kiteAreasOnVertex[iv * VD + j] * AT(kev, iv, k) * r;
+    kec += (1.0 - ke_fact) * V.kiteAreasOnVertex[iv * 3 + j] * G2(kev, iv) * r;
   }
-  FLD(ke)[ix] = kec;
+  st2m(FLD(ke), ix, kec, m0, m1);
 }
 
 // ============================================================================================
@@ -190,429 +251,639 @@ __global__ void k_diag_ke_holl(const View V) {     // hollingsworth part 2 :403-
 // cell pre-pass: kdiff (:858-917), h_divergence (:924-938), tend_rho + dpdz (:942-951)
 template <bool RK0>
 __global__ void k_dt_cell0(const View V, const DynTendParams P, double len_disp, double cam_coef) {
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
   const double* ru = FLD(ru);
-  double hdiv = 0.0;
-  if (RK0 && P.mixing == MPASB200_MIX_2D_SMAGORINSKY) {
+  D2 hdiv = bc(0.0);
+  const bool smag = RK0 && P.mixing == MPASB200_MIX_2D_SMAGORINSKY;
+  if (smag) {
     const double* u = FLD(u); const double* v = FLD(v);
-    double d_diag = 0.0, d_off = 0.0;
+    D2 d_diag = bc(0.0), d_off = bc(0.0);
+#pragma unroll 2
     for (int i = 0; i < n; ++i) {
-      const int e = V.edgesOnCell[x * ME + i];
+      const int e = V.edgesOnCell[x * V.MEP + i];
       const double a = V.defc_a[x * ME + i], b = V.defc_b[x * ME + i];
-      const double ue = AT(u, e, k), ve = AT(v, e, k);
+      const D2 ue = G2(u, e), ve = G2(v, e), rue = G2(ru, e);
       d_diag += a * ue - b * ve;
       d_off += b * ue + a * ve;
-      hdiv += (V.edgesOnCell_sign[x * ME + i] * V.dvEdge[e]) * AT(ru, e, k);
+      hdiv += (V.edgesOnCell_sign[x * ME + i] * V.dvOnCell[x * ME + i]) * rue;
     }
-    double kd = dmin(P.kdiff_scale * sqrt(d_diag * d_diag + d_off * d_off), P.kdiff_cap);      // :884-886
-    if (P.cam_on && k >= L - 2) kd = dmax(kd, pow(2.0, (double)(k - (L - 2))) * 2.0833 * len_disp * cam_coef);   // :911-914
-    FLD(kdiff)[ix] = kd;
+    const D2 mag = d_diag * d_diag + d_off * d_off;
+    D2 kd = mk(dmin(P.kdiff_scale * sqrt(mag.x), P.kdiff_cap), dmin(P.kdiff_scale * sqrt(mag.y), P.kdiff_cap));   // :884-886
+    if (P.cam_on) {                                                                                                // :911-914
+      if (k0 >= L - 2) kd.x = dmax(kd.x, pow(2.0, (double)(k0 - (L - 2))) * 2.0833 * len_disp * cam_coef);
+      if (k1 >= L - 2) kd.y = dmax(kd.y, pow(2.0, (double)(k1 - (L - 2))) * 2.0833 * len_disp * cam_coef);
+    }
+    st2m(FLD(kdiff), ix, kd, m0, m1);
   } else {
+#pragma unroll 2
     for (int i = 0; i < n; ++i) {
-      const int e = V.edgesOnCell[x * ME + i];
-      hdiv += (V.edgesOnCell_sign[x * ME + i] * V.dvEdge[e]) * AT(ru, e, k);
+      const int e = V.edgesOnCell[x * V.MEP + i];
+      hdiv += (V.edgesOnCell_sign[x * ME + i] * V.dvOnCell[x * ME + i]) * G2(ru, e);
     }
     if (RK0 && (P.mixing == MPASB200_MIX_2D_FIXED || P.cam_on)) {
-      double kd = (P.mixing == MPASB200_MIX_2D_FIXED) ? 0.0 : FLD(kdiff)[ix];
-      if (P.cam_on && k >= L - 2) kd = dmax(kd, pow(2.0, (double)(k - (L - 2))) * 2.0833 * len_disp * cam_coef);
-      FLD(kdiff)[ix] = kd;
+      D2 kd = (P.mixing == MPASB200_MIX_2D_FIXED) ? bc(0.0) : ld2(FLD(kdiff), ix);
+      if (P.cam_on) {
+        if (k0 >= L - 2) kd.x = dmax(kd.x, pow(2.0, (double)(k0 - (L - 2))) * 2.0833 * len_disp * cam_coef);
+        if (k1 >= L - 2) kd.y = dmax(kd.y, pow(2.0, (double)(k1 - (L - 2))) * 2.0833 * len_disp * cam_coef);
+      }
+      st2m(FLD(kdiff), ix, kd, m0, m1);
     }
   }
   hdiv *= V.invAreaCell[x];
-  FLD(h_divergence)[ix] = hdiv;
+  st2m(FLD(h_divergence), ix, hdiv, m0, m1);
   if (RK0) {
     const double* rw = FLD(rw);
-    const double qt = FLD(qtot)[ix];
-    FLD(tend_rho)[ix] = -hdiv - FLD(rdzw)[k] * (rw[ix + 1] - rw[ix] + FLD(tend_rho_physics)[ix]);   // :947
-    FLD(dpdz)[ix] = -P.gravity * (FLD(rho_base)[ix] * (qt) + FLD(rho_p_save)[ix] * (1.0 + qt));   // :949
+    const D2 rw2 = ld2(rw, ix), rwp = above(rw, ix, k0, L, rw2);
+    const D2 qt = ld2(FLD(qtot), ix);
+    st2m(FLD(tend_rho), ix, -hdiv - ld2(FLD(rdzw), k0) * (rwp - rw2 + ld2(FLD(tend_rho_physics), ix)), m0, m1);   // :947
+    st2m(FLD(dpdz), ix, -P.gravity * (ld2(FLD(rho_base), ix) * (qt) + ld2(FLD(rho_p_save), ix) * (1.0 + qt)), m0, m1);   // :949
   }
 }
 
 // first del^2 of u  :1030-1043  (only delsq_u; the tend_u_euler contribution is added in k_dt_edge)
-__global__ void k_dt_edge_delsq(const View V) {
-  COLUMN_THREAD(V.nEdges)
-  if (!inx || k >= L) return;
-  const int c1 = V.cellsOnEdge[x * 2], c2 = V.cellsOnEdge[x * 2 + 1];
-  const int v1 = V.verticesOnEdge[x * 2], v2 = V.verticesOnEdge[x * 2 + 1];
+DI D2 u_diffusion2(const View& V, int x, int4 cv, int k0, int LP) {
   const double* dv = FLD(divergence); const double* vo = FLD(vorticity);
   const double r_dc = V.invDcEdge[x];
   const double r_dv = dmin(V.invDvEdge[x], 4 * r_dc);
-  const double u_diffusion = (AT(dv, c2, k) - AT(dv, c1, k)) * r_dc - (AT(vo, v2, k) - AT(vo, v1, k)) * r_dv;
-  FLD(delsq_u)[ix] = 0.0 + u_diffusion;
+  const D2 d2 = G2(dv, cv.y), d1 = G2(dv, cv.x), o2 = G2(vo, cv.w), o1 = G2(vo, cv.z);
+  return (d2 - d1) * r_dc - (o2 - o1) * r_dv;                                                         // :1041-1042
+}
+__global__ void k_dt_edge_delsq(const View V) {
+  PAIR_THREAD(V.nEdges)
+  if (!m0) return;
+  st2m(FLD(delsq_u), ix, 0.0 + u_diffusion2(V, x, V.ecv[x], k0, LP), m0, m1);
 }
 __global__ void k_dt_vertex_delsq(const View V) {   // delsq_vorticity :1052-1060
-  COLUMN_THREAD(V.nVertices)
-  if (!inx || k >= L) return;
-  const int VD = V.vertexDegree;
+  PAIR_THREAD(V.nVertices)
+  if (!m0) return;
   const double* dsu = FLD(delsq_u);
-  double acc = 0.0;
-  for (int i = 0; i < VD; ++i) {
-    const int e = V.edgesOnVertex[x * VD + i];
-    const double edge_sign = V.invAreaTriangle[x] * V.dcEdge[e] * V.edgesOnVertex_sign[x * VD + i];
-    acc += edge_sign * AT(dsu, e, k);
-  }
-  FLD(delsq_vorticity)[ix] = acc;
+  const D2 a0 = G2(dsu, V.edgesOnVertex[x * 3]), a1 = G2(dsu, V.edgesOnVertex[x * 3 + 1]), a2 = G2(dsu, V.edgesOnVertex[x * 3 + 2]);
+  const double iat = V.invAreaTriangle[x];
+  D2 acc = bc(0.0);
+  acc += (iat * V.dcOnVertex[x * 3] * V.edgesOnVertex_sign[x * 3]) * a0;
+  acc += (iat * V.dcOnVertex[x * 3 + 1] * V.edgesOnVertex_sign[x * 3 + 1]) * a1;
+  acc += (iat * V.dcOnVertex[x * 3 + 2] * V.edgesOnVertex_sign[x * 3 + 2]) * a2;
+  st2m(FLD(delsq_vorticity), ix, acc, m0, m1);
 }
 __global__ void k_dt_cell_delsq(const View V) {     // delsq_divergence :1062-1070
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
   const double* dsu = FLD(delsq_u);
   const double r = V.invAreaCell[x];
-  double acc = 0.0;
+  D2 acc = bc(0.0);
+#pragma unroll 2
   for (int i = 0; i < n; ++i) {
-    const int e = V.edgesOnCell[x * ME + i];
-    const double edge_sign = r * V.dvEdge[e] * V.edgesOnCell_sign[x * ME + i];
-    acc += edge_sign * AT(dsu, e, k);
+    const int e = V.edgesOnCell[x * V.MEP + i];
+    const double edge_sign = r * V.dvOnCell[x * ME + i] * V.edgesOnCell_sign[x * ME + i];
+    acc += edge_sign * G2(dsu, e);
   }
-  FLD(delsq_divergence)[ix] = acc;
+  st2m(FLD(delsq_divergence), ix, acc, m0, m1);
+}
+
+// vertical transport of u at one level  :973-980
+DI double wduz_at(int k, int L, double rwavg, double fzm, double fzp, double um2, double um1, double u0, double up1) {
+  double r = 0.0;
+  if (k == 1 || k == L - 1) r = rwavg * (fzm * u0 + fzp * um1);
+  if (k > 1 && k < L - 1) r = flux3(um2, um1, u0, up1, rwavg, 1.0);
+  return r;
+}
+DI double vmix_u_at(double rho_e, double visc, double up, double uc, double um, double z1, double z2, double z3, double z4) {
+  const double zm = 0.5 * (z1 + z2), z0 = 0.5 * (z2 + z3), zp = 0.5 * (z3 + z4);
+  return rho_e * visc * ((up - uc) / (zp - z0) - (uc - um) / (z0 - zm)) / (0.5 * (zp - zm));
 }
 
 // u tendency  :958-1163
 template <bool RK0>
 __global__ void k_dt_edge(const View V, const DynTendParams P) {
   extern __shared__ double sm[];
-  COLUMN_THREAD(V.nEdges)
-  const int TS = LP + 1;
+  PAIR_THREAD(V.nEdges)
+  const int TS = LP + 2;
   double* s_wduz = sm + (size_t)threadIdx.y * TS;
   double* s_um = sm + (size_t)(blockDim.y + threadIdx.y) * TS;      // u_mix (vertical mixing of the perturbation)
-  const bool act = inx && k < L;
   const double* u = FLD(u);
-  int c1 = 0, c2 = 0;
-  double u_k = 0, wduz_k = 0.0;
-  if (act) {
-    c1 = V.cellsOnEdge[x * 2]; c2 = V.cellsOnEdge[x * 2 + 1];
-    u_k = u[ix];
+  int4 cv = make_int4(0, 0, 0, 0);
+  D2 u2 = bc(0.0), wduz = bc(0.0);
+  if (m0) {
+    cv = V.ecv[x];
+    u2 = ld2(u, ix);
     const double* rw = FLD(rw);
-    const double* fzm = FLD(fzm); const double* fzp = FLD(fzp);
-    if (k == 1 || k == L - 1)                                                                       // :974-976
-      wduz_k = 0.5 * (AT(rw, c1, k) + AT(rw, c2, k)) * (fzm[k] * u_k + fzp[k] * u[ix - 1]);
-    if (k > 1 && k < L - 1)                                                                         // :977-980
-      wduz_k = flux3(u[ix - 2], u[ix - 1], u_k, u[ix + 1], 0.5 * (AT(rw, c1, k) + AT(rw, c2, k)), 1.0);
-    s_wduz[k] = wduz_k;
-    FLD(wduz)[ix] = wduz_k;
+    const D2 rwavg = 0.5 * (G2(rw, cv.x) + G2(rw, cv.y));
+    const D2 fzm = ld2(FLD(fzm), k0), fzp = ld2(FLD(fzp), k0);
+    const D2 um = (k0 >= 2) ? ld2(u, ix - 2) : bc(0.0);            // (u[k0-2], u[k0-1])
+    const double up = (k0 + 2 <= L) ? u[ix + 2] : 0.0;             // u[k1+1]
+    wduz.x = wduz_at(k0, L, rwavg.x, fzm.x, fzp.x, um.x, um.y, u2.x, u2.y);
+    if (m1) wduz.y = wduz_at(k1, L, rwavg.y, fzm.y, fzp.y, um.y, u2.x, u2.y, up);
+    s_wduz[k0] = wduz.x; if (m1) s_wduz[k1] = wduz.y;
+    st2m(FLD(wduz), ix, wduz, m0, m1);
     if (RK0 && P.vmix_u_on && !P.mix_full) {                                                        // :1120-1123
-      const double um = u_k - FLD(u_init)[k] * V.cosAngleEdge[x] - FLD(v_init)[k] * V.sinAngleEdge[x];
-      s_um[k] = um; FLD(u_mix)[ix] = um;
+      const D2 umix = u2 - ld2(FLD(u_init), k0) * V.cosAngleEdge[x] - ld2(FLD(v_init), k0) * V.sinAngleEdge[x];
+      s_um[k0] = umix.x; if (m1) s_um[k1] = umix.y;
+      st2m(FLD(u_mix), ix, umix, m0, m1);
     }
   }
-  if (inx && k == L) s_wduz[L] = FLD(wduz)[ix];          // level L: never written, read as stored
+  if (inx && k0 == L) s_wduz[L] = FLD(wduz)[ix];          // level L: never written, read as stored
+  if (inx && k1 == L) s_wduz[L] = FLD(wduz)[ix + 1];
   __syncthreads();
-  if (!act) return;
-  const double rho_e = FLD(rho_edge)[ix];
+  if (!m0) return;
+  const D2 rho_e = ld2(FLD(rho_edge), ix);
   const double invDc = V.invDcEdge[x];
-  double tend_u = -FLD(rdzw)[k] * (s_wduz[k + 1] - wduz_k);                                         // :987
+  const D2 wduz_p = mk(s_wduz[k1], m1 ? s_wduz[k1 + 1] : 0.0);
+  D2 tend_u = -ld2(FLD(rdzw), k0) * (wduz_p - wduz);                                                // :987
   // nonlinear Coriolis term :991-1001.  The reference adds each term nVertLevels times in a row
   // (Q14); here it is added once, multiplied by nVertLevels (same value to O(L) ulp).
-  double q = 0.0;
+  D2 q = bc(0.0);
   {
     const int ME2 = V.maxEdges2, n = V.nEdgesOnEdge[x];
     const double* pv = FLD(pv_edge);
-    const double pv_k = pv[ix];
+    const D2 pv_k = ld2(pv, ix);
     const double Ld = (double)L;
+#pragma unroll 2
     for (int j = 0; j < n; ++j) {
       const int eoe = V.edgesOnEdge[x * ME2 + j];
-      const double workpv = 0.5 * (pv_k + AT(pv, eoe, k));
-      q += Ld * (V.weightsOnEdge[x * ME2 + j] * AT(u, eoe, k) * workpv);
+      const D2 workpv = 0.5 * (pv_k + G2(pv, eoe));
+      q += Ld * (V.weightsOnEdge[x * ME2 + j] * G2(u, eoe) * workpv);
     }
   }
-  FLD(q)[ix] = q;
+  st2m(FLD(q), ix, q, m0, m1);
   const double* ke = FLD(ke); const double* hd = FLD(h_divergence); const double* w = FLD(w);
-  tend_u += rho_e * (q - (AT(ke, c2, k) - AT(ke, c1, k)) * invDc) - u_k * 0.5 * (AT(hd, c1, k) + AT(hd, c2, k));   // :1005-1007
+  tend_u += rho_e * (q - (G2(ke, cv.y) - G2(ke, cv.x)) * invDc) - u2 * 0.5 * (G2(hd, cv.x) + G2(hd, cv.y));   // :1005-1007
   {
-    const double wsum = AT(w, c1, k) + AT(w, c1, k + 1) + AT(w, c2, k) + AT(w, c2, k + 1);
+    const D2 w1 = G2(w, cv.x), w2 = G2(w, cv.y);
+    const D2 w1p = mk(w1.y, m1 ? G1(w, cv.x, k0 + 2) : 0.0), w2p = mk(w2.y, m1 ? G1(w, cv.y, k0 + 2) : 0.0);
+    const D2 wsum = w1 + w1p + w2 + w2p;
     tend_u -= (P.omega2 * V.cosAngleEdge[x] * V.cosLatEdge[x] * rho_e * 0.25 * wsum)
-              - (u_k * 0.25 * wsum * rho_e * P.inv_r_earth);                                       // :1011-1017
+              - (u2 * 0.25 * wsum * rho_e * P.inv_r_earth);                                        // :1011-1017
   }
-  double tue;
+  D2 tue;
   if (RK0) {
     const double* pp = FLD(pressure_p); const double* zz = FLD(zz); const double* dpdz = FLD(dpdz);
-    tue = -FLD(cqu)[ix] * ((AT(pp, c2, k) - AT(pp, c1, k)) * invDc / (0.5 * (AT(zz, c2, k) + AT(zz, c1, k)))
-                           - 0.5 * FLD(zxu)[ix] * (AT(dpdz, c1, k) + AT(dpdz, c2, k)));             // :967-969
-    const int v1 = V.verticesOnEdge[x * 2], v2 = V.verticesOnEdge[x * 2 + 1];
-    const double* dv = FLD(divergence); const double* vo = FLD(vorticity); const double* kd = FLD(kdiff);
-    const double r_dc = invDc;
-    const double r_dv = dmin(V.invDvEdge[x], 4 * r_dc);
-    const double u_diffusion = (AT(dv, c2, k) - AT(dv, c1, k)) * r_dc - (AT(vo, v2, k) - AT(vo, v1, k)) * r_dv;   // :1041-1042
-    const double kdiffu = 0.5 * (AT(kd, c1, k) + AT(kd, c2, k));
+    tue = -ld2(FLD(cqu), ix) * ((G2(pp, cv.y) - G2(pp, cv.x)) * invDc / (0.5 * (G2(zz, cv.y) + G2(zz, cv.x)))
+                                - 0.5 * ld2(FLD(zxu), ix) * (G2(dpdz, cv.x) + G2(dpdz, cv.y)));      // :967-969
+    const double* kd = FLD(kdiff);
+    const D2 u_diffusion = u_diffusion2(V, x, cv, k0, LP);
+    const D2 kdiffu = 0.5 * (G2(kd, cv.x) + G2(kd, cv.y));
     tue += rho_e * kdiffu * u_diffusion * V.meshScalingDel2[x];                                     // :1046-1047
     if (P.visc4_on) {                                                                               // :1072-1090
       const double* dd = FLD(delsq_divergence); const double* dvo = FLD(delsq_vorticity);
       const double u_mix_scale = V.meshScalingDel4[x] * P.h_mom_eddy_visc4;
       const double r_dc4 = u_mix_scale * P.del4u_div_factor * invDc;
       const double r_dv4 = u_mix_scale * dmin(V.invDvEdge[x], 4 * invDc);
-      const double ud4 = rho_e * ((AT(dd, c2, k) - AT(dd, c1, k)) * r_dc4 - (AT(dvo, v2, k) - AT(dvo, v1, k)) * r_dv4);
+      const D2 ud4 = rho_e * ((G2(dd, cv.y) - G2(dd, cv.x)) * r_dc4 - (G2(dvo, cv.w) - G2(dvo, cv.z)) * r_dv4);
       tue -= ud4;
     }
-    if (P.vmix_u_on && k > 0 && k < L - 1) {                                                        // :1094-1146
+    if (P.vmix_u_on) {                                                                              // :1094-1146
       const double* zg = FLD(zgrid);
-      const double z1 = 0.5 * (AT(zg, c1, k - 1) + AT(zg, c2, k - 1)), z2 = 0.5 * (AT(zg, c1, k) + AT(zg, c2, k));
-      const double z3 = 0.5 * (AT(zg, c1, k + 1) + AT(zg, c2, k + 1)), z4 = 0.5 * (AT(zg, c1, k + 2) + AT(zg, c2, k + 2));
-      const double zm = 0.5 * (z1 + z2), z0 = 0.5 * (z2 + z3), zp = 0.5 * (z3 + z4);
-      double up, uc, um;
-      if (P.mix_full) { up = u[ix + 1]; uc = u_k; um = u[ix - 1]; }
-      else { up = s_um[k + 1]; uc = s_um[k]; um = s_um[k - 1]; }
-      tue += rho_e * P.v_mom_eddy_visc2 * ((up - uc) / (zp - z0) - (uc - um) / (z0 - zm)) / (0.5 * (zp - zm));
+      for (int c = 0; c < 2; ++c) {
+        const int k = k0 + c;
+        if (!(k > 0 && k < L - 1)) continue;
+        const double z1 = 0.5 * (G1(zg, cv.x, k - 1) + G1(zg, cv.y, k - 1)), z2 = 0.5 * (G1(zg, cv.x, k) + G1(zg, cv.y, k));
+        const double z3 = 0.5 * (G1(zg, cv.x, k + 1) + G1(zg, cv.y, k + 1)), z4 = 0.5 * (G1(zg, cv.x, k + 2) + G1(zg, cv.y, k + 2));
+        double up, uc, um;
+        if (P.mix_full) { up = G1(u, x, k + 1); uc = G1(u, x, k); um = G1(u, x, k - 1); }
+        else { up = s_um[k + 1]; uc = s_um[k]; um = s_um[k - 1]; }
+        const double add = vmix_u_at(c ? rho_e.y : rho_e.x, P.v_mom_eddy_visc2, up, uc, um, z1, z2, z3, z4);
+        if (c) tue.y += add; else tue.x += add;
+      }
     }
-    FLD(tend_u_euler)[ix] = tue;
+    st2m(FLD(tend_u_euler), ix, tue, m0, m1);
   } else {
-    tue = FLD(tend_u_euler)[ix];
+    tue = ld2(FLD(tend_u_euler), ix);
   }
-  if (P.rayleigh_u && k > L - P.rayleigh_levels + 1) {                                              // :1152-1159
-    const double coef = (double)((double)k - (L - P.rayleigh_levels)) * P.rayleigh_coef_inverse;
-    tend_u -= rho_e * u_k * coef;
+  if (P.rayleigh_u) {                                                                               // :1152-1159
+    const int lim = L - P.rayleigh_levels + 1;
+    if (k0 > lim) tend_u.x -= rho_e.x * u2.x * ((double)((double)k0 - (L - P.rayleigh_levels)) * P.rayleigh_coef_inverse);
+    if (k1 > lim) tend_u.y -= rho_e.y * u2.y * ((double)((double)k1 - (L - P.rayleigh_levels)) * P.rayleigh_coef_inverse);
   }
-  tend_u += tue + FLD(tend_ru_physics)[ix];                                                         // :1162
-  FLD(tend_u)[ix] = tend_u;
+  tend_u += tue + ld2(FLD(tend_ru_physics), ix);                                                    // :1162
+  st2m(FLD(tend_u), ix, tend_u, m0, m1);
 }
 
-// helper: horizontal advection + curvature part of the w tendency  :1170-1218  (value of cr.w before mixing)
-__device__ __forceinline__ double w_adv_curv(const View& V, const DynTendParams& P, int x, int k, size_t ix, int LP) {
-  if (k == 0) return 0.0;
-  const int ME = V.maxEdges, NA = V.nAdv, n = V.nEdgesOnCell[x];
-  const double* fzm = FLD(fzm); const double* fzp = FLD(fzp);
-  const double fm = fzm[k], fp = fzp[k];
-  double wv = 0.0;
+// horizontal advection + curvature part of the w tendency  :1170-1218  (value of cr.w before mixing);
+// level 0 stays 0.  Also writes ru_edge_w for levels > 0.
+DI D2 w_adv_curv(const View& V, const DynTendParams& P, int x, int k0, size_t ix, int LP, bool m0, bool m1) {
+  const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
+  const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0);
+  D2 wv = bc(0.0);
   if (n > 0) {
     // ru_edge_w / flux_arr are per-point fields overwritten for every edge (Q18): only the LAST
     // edge's values survive, and the second loop multiplies them by every edge's sign.
     const double* ru = FLD(ru);
-    const int e = V.edgesOnCell[x * ME + (n - 1)];
-    const double rew = fm * AT(ru, e, k) + fp * AT(ru, e, k - 1);
-    double fa = 0.0;
-    const int na = V.nAdvCellsForEdge[e];
+    const int e = V.edgesOnCell[x * V.MEP + (n - 1)];
+    const D2 ru2 = G2(ru, e);
+    const D2 rew = fm * ru2 + fp * below(ru, (size_t)e * LP + k0, k0, ru2);
+    D2 fa = bc(0.0);
+    const int na = V.nAdvOnCell[x * ME + (n - 1)];
+    const size_t ab = ((size_t)x * ME + (n - 1)) * V.NAP;
     for (int j = 0; j < na; ++j) {
-      const double sw = V.adv_coefs[e * NA + j] + copysign(1.0, rew) * V.adv_coefs_3rd[e * NA + j];
+      const D2 sw = V.advCoefOnCell[ab + j] + sgn1(rew) * V.adv3OnCell[ab + j];
       fa += sw * 0.0;          // cr.w was zeroed on levels < L just before (:1170-1172); the pad cell is zero too
     }
-    FLD(ru_edge_w)[ix] = rew;
-    for (int i = 0; i < n; ++i) wv -= V.edgesOnCell_sign[x * ME + i] * rew * fa;                   // :1202
+    st2m(FLD(ru_edge_w), ix, rew, m0 && k0 > 0, m1);
+    for (int i = 0; i < n; ++i) wv -= V.edgesOnCell_sign[x * ME + i] * rew * fa;                    // :1202
   }
   const double* rz = FLD(rho_zz); const double* uz = FLD(uReconstructZonal); const double* um = FLD(uReconstructMeridional);
-  const double rzf = rz[ix] * fm + rz[ix - 1] * fp;
-  const double uzf = fm * uz[ix] + fp * uz[ix - 1];
-  const double umf = fm * um[ix] + fp * um[ix - 1];
-  wv += rzf * (uzf * uzf + umf * umf) / P.r_earth + P.omega2 * V.cosLatCell[x] * uzf * rzf;       // :1210-1216
+  const D2 rz2 = ld2(rz, ix), uz2 = ld2(uz, ix), um2 = ld2(um, ix);
+  const D2 rzf = rz2 * fm + below(rz, ix, k0, rz2) * fp;
+  const D2 uzf = fm * uz2 + fp * below(uz, ix, k0, uz2);
+  const D2 umf = fm * um2 + fp * below(um, ix, k0, um2);
+  wv += rzf * (uzf * uzf + umf * umf) / P.r_earth + P.omega2 * V.cosLatCell[x] * uzf * rzf;         // :1210-1216
+  if (k0 == 0) wv.x = 0.0;
   return wv;
 }
 
 // rk_step == 0, cell pass A: w after advection+curvature (:1170-1218) and the first del^2 of theta (:1365-1382)
 __global__ void k_dt_cellA(const View V, const DynTendParams P) {
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
-  FLD(w)[ix] = w_adv_curv(V, P, x, k, ix, LP);
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
+  st2m(FLD(w), ix, w_adv_curv(V, P, x, k0, ix, LP, m0, m1), m0, m1);
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
   const double* tm = FLD(theta_m); const double* kd = FLD(kdiff); const double* re = FLD(rho_edge);
   const double r_areaCell = V.invAreaCell[x];
-  double dsq = 0.0, tte = 0.0;
+  D2 dsq = bc(0.0), tte = bc(0.0);
+#pragma unroll 2
   for (int i = 0; i < n; ++i) {
-    const int e = V.edgesOnCell[x * ME + i];
-    const double edge_sign = r_areaCell * V.edgesOnCell_sign[x * ME + i] * V.dvEdge[e] * V.invDcEdge[e];
-    const double pr_scale = P.prandtl_inv * V.meshScalingDel2[e];
-    const int c1 = V.cellsOnEdge[e * 2], c2 = V.cellsOnEdge[e * 2 + 1];
-    double flux = edge_sign * (AT(tm, c2, k) - AT(tm, c1, k)) * AT(re, e, k);
+    const int e = V.edgesOnCell[x * V.MEP + i];
+    const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+    const double edge_sign = r_areaCell * V.edgesOnCell_sign[x * ME + i] * V.dvOnCell[x * ME + i] * V.invDcOnCell[x * ME + i];
+    const double pr_scale = P.prandtl_inv * V.ms2OnCell[x * ME + i];
+    D2 flux = edge_sign * (G2(tm, c2) - G2(tm, c1)) * G2(re, e);
     dsq += flux;
-    flux *= 0.5 * (AT(kd, c1, k) + AT(kd, c2, k)) * pr_scale;
+    flux *= 0.5 * (G2(kd, c1) + G2(kd, c2)) * pr_scale;
     tte += flux;
   }
-  FLD(delsq_theta)[ix] = dsq;
-  FLD(tend_theta_euler)[ix] = tte;
+  st2m(FLD(delsq_theta), ix, dsq, m0, m1);
+  st2m(FLD(tend_theta_euler), ix, tte, m0, m1);
 }
 // rk_step == 0, cell pass B: first del^2 of w  :1231-1254  (needs pass A's w on neighbour cells)
 __global__ void k_dt_cellB(const View V, const DynTendParams P) {
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
-  double dsq = 0.0, twe = 0.0;
-  if (k > 0) {
-    const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
-    const double* w = FLD(w); const double* kd = FLD(kdiff); const double* re = FLD(rho_edge);
-    const double r_areaCell = V.invAreaCell[x];
-    for (int i = 0; i < n; ++i) {
-      const int e = V.edgesOnCell[x * ME + i];
-      const double edge_sign = 0.5 * r_areaCell * V.edgesOnCell_sign[x * ME + i] * V.dvEdge[e] * V.invDcEdge[e];
-      const int c1 = V.cellsOnEdge[e * 2], c2 = V.cellsOnEdge[e * 2 + 1];
-      double flux = edge_sign * (AT(re, e, k) + AT(re, e, k - 1)) * (AT(w, c2, k) - AT(w, c1, k));
-      dsq += flux;
-      flux *= V.meshScalingDel2[e] * 0.25 * (AT(kd, c1, k) + AT(kd, c2, k) + AT(kd, c1, k - 1) + AT(kd, c2, k - 1));
-      twe += flux;
-    }
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
+  const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
+  const double* w = FLD(w); const double* kd = FLD(kdiff); const double* re = FLD(rho_edge);
+  const double r_areaCell = V.invAreaCell[x];
+  D2 dsq = bc(0.0), twe = bc(0.0);
+#pragma unroll 2
+  for (int i = 0; i < n; ++i) {
+    const int e = V.edgesOnCell[x * V.MEP + i];
+    const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+    const double edge_sign = 0.5 * r_areaCell * V.edgesOnCell_sign[x * ME + i] * V.dvOnCell[x * ME + i] * V.invDcOnCell[x * ME + i];
+    const D2 re2 = G2(re, e), k1v = G2(kd, c1), k2v = G2(kd, c2);
+    const D2 rem = below(re, (size_t)e * LP + k0, k0, re2);
+    const D2 k1m = below(kd, (size_t)c1 * LP + k0, k0, k1v), k2m = below(kd, (size_t)c2 * LP + k0, k0, k2v);
+    D2 flux = edge_sign * (re2 + rem) * (G2(w, c2) - G2(w, c1));
+    dsq += flux;
+    flux *= V.ms2OnCell[x * ME + i] * 0.25 * (k1v + k2v + k1m + k2m);
+    twe += flux;
   }
-  FLD(delsq_w)[ix] = dsq;
-  FLD(tend_w_euler)[ix] = twe;
+  if (k0 == 0) { dsq.x = 0.0; twe.x = 0.0; }           // only k > 0 accumulates (:1244)
+  st2m(FLD(delsq_w), ix, dsq, m0, m1);
+  st2m(FLD(tend_w_euler), ix, twe, m0, m1);
 }
+
+DI double wdwz_at(int k, int L, double rw_k, double rw_m, const double* s) {      // :1277-1287, s = w of the column in smem
+  double r = 0.0;
+  if (k == 1 || k == L - 1) r = 0.25 * (rw_k + rw_m) * (s[k] + s[k - 1]);
+  if (k > 1 && k < L - 1) r = flux3(s[k - 2], s[k - 1], s[k], s[k + 1], 0.5 * (rw_k + rw_m), 1.0);
+  return r;
+}
+DI double wdtz_at(int k, int L, double rws, double rw, double fzm, double fzp, double tms_k, double tms_m, double tm_k, double tm_m) {
+  double r = 0.0;                                                                 // :1406-1420
+  if (k > 0 && k < L - 1) r = ((rws - rw) * (fzm * tms_k + fzp * tms_m));
+  if (k == 1) r += rw * (fzm * tm_k + fzp * tm_m);
+  if (k == L - 1) r = rws * (fzm * tms_k + fzp * tms_m);
+  return r;
+}
+
 // final cell pass: w (:1256-1322) and theta (:1328-1479)
 template <bool RK0>
 __global__ void k_dt_cellC(const View V, const DynTendParams P) {
   extern __shared__ double sm[];
-  COLUMN_THREAD(V.nCells)
-  const int TS = LP + 1;
+  PAIR_THREAD(V.nCells)
+  const int TS = LP + 2;
   double* s_a = sm + (size_t)threadIdx.y * TS;                       // w, later wdtz
   double* s_b = sm + (size_t)(blockDim.y + threadIdx.y) * TS;        // wdwz, later post-multiply w
-  const bool act = inx && k < L;
-  const int ME = V.maxEdges, NA = V.nAdv;
+  const int ME = V.maxEdges;
   const int n = inx ? V.nEdgesOnCell[x] : 0;
-  const double* fzm = FLD(fzm); const double* fzp = FLD(fzp); const double* rdzu = FLD(rdzu); const double* rdzw = FLD(rdzw);
   const double* rw = FLD(rw);
-  double w_k = 0.0, twe = 0.0;
-  if (act) {
+  D2 w2 = bc(0.0), twe = bc(0.0), fzm = bc(0.0), fzp = bc(0.0), rdzu = bc(0.0), rdzw = bc(0.0), rw2 = bc(0.0), rwm = bc(0.0);
+  if (m0) {
+    fzm = ld2(FLD(fzm), k0); fzp = ld2(FLD(fzp), k0); rdzu = ld2(FLD(rdzu), k0); rdzw = ld2(FLD(rdzw), k0);
+    rw2 = ld2(rw, ix); rwm = below(rw, ix, k0, rw2);
     if (RK0) {
-      w_k = FLD(w)[ix];
-      twe = FLD(tend_w_euler)[ix];
-      if (P.visc4_on && k > 0) {                                                                     // :1256-1272
+      w2 = ld2(FLD(w), ix);
+      twe = ld2(FLD(tend_w_euler), ix);
+      if (P.visc4_on) {                                                                             // :1256-1272
         const double* dsw = FLD(delsq_w);
         const double r_areaCell = P.h_mom_eddy_visc4 * V.invAreaCell[x];
+        D2 acc = twe;
+#pragma unroll 2
         for (int i = 0; i < n; ++i) {
-          const int e = V.edgesOnCell[x * ME + i];
-          const int c1 = V.cellsOnEdge[e * 2], c2 = V.cellsOnEdge[e * 2 + 1];
-          const double edge_sign = V.meshScalingDel4[e] * r_areaCell * V.dvEdge[e] * V.edgesOnCell_sign[x * ME + i] * V.invDcEdge[e];
-          twe -= edge_sign * (AT(dsw, c2, k) - AT(dsw, c1, k));
+          const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+          const double edge_sign = V.ms4OnCell[x * ME + i] * r_areaCell * V.dvOnCell[x * ME + i] * V.edgesOnCell_sign[x * ME + i] * V.invDcOnCell[x * ME + i];
+          acc -= edge_sign * (G2(dsw, c2) - G2(dsw, c1));
         }
+        twe = mk(k0 > 0 ? acc.x : twe.x, acc.y);
       }
     } else {
-      w_k = w_adv_curv(V, P, x, k, ix, LP);
+      w2 = w_adv_curv(V, P, x, k0, ix, LP, m0, m1);
     }
-    s_a[k] = w_k;
+    s_a[k0] = w2.x; if (m1) s_a[k1] = w2.y;
   }
-  if (inx && k == L) { s_a[L] = FLD(w)[ix]; s_b[L] = FLD(wdwz)[ix]; }   // level L keeps its stored value
+  if (inx && k0 == L) { s_a[L] = FLD(w)[ix]; s_b[L] = FLD(wdwz)[ix]; }          // level L keeps its stored value
+  if (inx && k1 == L) { s_a[L] = FLD(w)[ix + 1]; s_b[L] = FLD(wdwz)[ix + 1]; }
   __syncthreads();
-  double wdwz_k = 0.0;
-  if (act) {                                                                                          // :1277-1287
-    if (k == 1 || k == L - 1) wdwz_k = 0.25 * (rw[ix] + rw[ix - 1]) * (s_a[k] + s_a[k - 1]);
-    if (k > 1 && k < L - 1) wdwz_k = flux3(s_a[k - 2], s_a[k - 1], s_a[k], s_a[k + 1], 0.5 * (rw[ix] + rw[ix - 1]), 1.0);
-    s_b[k] = wdwz_k;
-    FLD(wdwz)[ix] = wdwz_k;
+  D2 wdwz = bc(0.0);
+  if (m0) {
+    wdwz.x = wdwz_at(k0, L, rw2.x, rwm.x, s_a);
+    if (m1) wdwz.y = wdwz_at(k1, L, rw2.y, rwm.y, s_a);
+    s_b[k0] = wdwz.x; if (m1) s_b[k1] = wdwz.y;
+    st2m(FLD(wdwz), ix, wdwz, m0, m1);
   }
   __syncthreads();
-  double wdwz_p = 0.0;
-  if (act) wdwz_p = s_b[k + 1];
+  D2 wdwz_p = bc(0.0);
+  if (m0) wdwz_p = mk(s_b[k1], m1 ? s_b[k1 + 1] : 0.0);
   __syncthreads();
-  if (act) {
-    if (k > 0) w_k *= V.invAreaCell[x] - rdzu[k] * (wdwz_p - wdwz_k);                                // :1292
-    if (RK0 && k > 0) {                                                                               // :1297-1299
+  if (m0) {
+    const D2 wmul = w2 * (V.invAreaCell[x] - rdzu * (wdwz_p - wdwz));                                // :1292
+    w2 = mk(k0 > 0 ? wmul.x : w2.x, wmul.y);
+    if (RK0) {                                                                                       // :1297-1299
       const double* pp = FLD(pressure_p); const double* dpdz = FLD(dpdz);
-      twe -= FLD(cqw)[ix] * (rdzu[k] * (pp[ix] - pp[ix - 1]) - (fzm[k] * dpdz[ix] + fzp[k] * dpdz[ix - 1]));
+      const D2 pp2 = ld2(pp, ix), dp2 = ld2(dpdz, ix);
+      const D2 t = twe - ld2(FLD(cqw), ix) * (rdzu * (pp2 - below(pp, ix, k0, pp2)) - (fzm * dp2 + fzp * below(dpdz, ix, k0, dp2)));
+      twe = mk(k0 > 0 ? t.x : twe.x, t.y);
     }
-    s_b[k] = w_k;                                                    // post-multiply w, for the vertical mixing of w
+    s_b[k0] = w2.x; if (m1) s_b[k1] = w2.y;                         // post-multiply w, for the vertical mixing of w
   }
-  if (inx && k == L) s_b[L] = s_a[L];
+  if (inx && (k0 == L || k1 == L)) s_b[L] = s_a[L];
   __syncthreads();
-  if (act) {
-    if (RK0 && P.vmix_u_on && k > 0) {                                                                // :1304-1314
+  if (m0) {
+    if (RK0 && P.vmix_u_on) {                                                                        // :1304-1314
       const double* rz = FLD(rho_zz);
-      twe += P.v_mom_eddy_visc2 * (rz[ix] + rz[ix - 1]) * 0.5
-             * ((s_b[k + 1] - s_b[k]) * rdzw[k] - (s_b[k] - s_b[k - 1]) * rdzw[k - 1]) * rdzu[k];
+      const double* rdzw_ = FLD(rdzw);
+      for (int c = 0; c < 2; ++c) {
+        const int k = k0 + c;
+        if (k == 0 || k >= L) continue;
+        const double add = P.v_mom_eddy_visc2 * (rz[ix + c] + rz[ix + c - 1]) * 0.5
+                           * ((s_b[k + 1] - s_b[k]) * rdzw_[k] - (s_b[k] - s_b[k - 1]) * rdzw_[k - 1]) * (c ? rdzu.y : rdzu.x);
+        if (c) twe.y += add; else twe.x += add;
+      }
     }
-    if (!RK0 && k > 0) twe = FLD(tend_w_euler)[ix];
-    if (RK0) FLD(tend_w_euler)[ix] = twe;
-    if (k > 0) w_k += twe;                                                                            // :1320
-    FLD(w)[ix] = w_k;
+    if (!RK0) { const D2 t = ld2(FLD(tend_w_euler), ix); twe = mk(k0 > 0 ? t.x : 0.0, t.y); }
+    if (RK0) st2m(FLD(tend_w_euler), ix, twe, m0, m1);
+    w2 = mk(k0 > 0 ? w2.x + twe.x : w2.x, w2.y + twe.y);                                            // :1320
+    st2m(FLD(w), ix, w2, m0, m1);
   }
   // ---------------- theta ----------------
-  const double* tm = FLD(theta_m); const double* tms = FLD(theta_m_save); const double* rws = FLD(rw_save);
-  double tt = 0.0, wdtz_k = 0.0;
-  if (act) {
+  const double* tm = FLD(theta_m); const double* tms = FLD(theta_m_save);
+  D2 tt = bc(0.0), wdtz = bc(0.0);
+  if (m0) {
     const double* ru = FLD(ru);
-    double fa_last = 0.0;
+    D2 fa_last = bc(0.0);
     for (int i = 0; i < n; ++i) {                                                                     // :1328-1344
-      const int e = V.edgesOnCell[x * ME + i];
-      const double ru_e = AT(ru, e, k);
-      const int na = V.nAdvCellsForEdge[e];
-      double fa = 0.0;
+      const int e = V.edgesOnCell[x * V.MEP + i];
+      const D2 ru_e = G2(ru, e);
+      const int na = V.nAdvOnCell[x * ME + i];
+      const size_t ab = ((size_t)x * ME + i) * V.NAP;
+      const D2 sg = sgn1(ru_e);
+      D2 fa = bc(0.0);
+#pragma unroll 4
       for (int j = 0; j < na; ++j) {
-        const int ac = V.advCellsForEdge[e * NA + j];
-        const double sw = V.adv_coefs[e * NA + j] + copysign(1.0, ru_e) * V.adv_coefs_3rd[e * NA + j];
-        fa += sw * AT(tm, ac, k);
+        const D2 sw = V.advCoefOnCell[ab + j] + sg * V.adv3OnCell[ab + j];
+        fa += sw * G2(tm, V.advCellOnCell[ab + j]);
       }
       tt -= V.edgesOnCell_sign[x * ME + i] * ru_e * fa;
       fa_last = fa;
     }
-    if (n > 0) FLD(flux_arr)[ix] = fa_last;
+    if (n > 0) st2m(FLD(flux_arr), ix, fa_last, m0, m1);
     if (P.rk_step > 0) {                                                                              // :1347-1360
       const double* rus = FLD(ru_save);
+#pragma unroll 2
       for (int i = 0; i < n; ++i) {
-        const int e = V.edgesOnCell[x * ME + i];
-        const int c1 = V.cellsOnEdge[e * 2], c2 = V.cellsOnEdge[e * 2 + 1];
-        const double flux = V.edgesOnCell_sign[x * ME + i] * V.dvEdge[e] * (AT(rus, e, k) - AT(ru, e, k)) * 0.5
-                            * (AT(tms, c2, k) + AT(tms, c1, k));
+        const int e = V.edgesOnCell[x * V.MEP + i];
+        const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+        const D2 flux = (V.edgesOnCell_sign[x * ME + i] * V.dvOnCell[x * ME + i]) * (G2(rus, e) - G2(ru, e)) * 0.5
+                        * (G2(tms, c2) + G2(tms, c1));
         tt -= flux;
       }
     }
-    if (k > 0 && k < L - 1) wdtz_k = ((rws[ix] - rw[ix]) * (fzm[k] * tms[ix] + fzp[k] * tms[ix - 1]));   // :1409-1412
-    if (k == 1) wdtz_k += rw[ix] * (fzm[k] * tm[ix] + fzp[k] * tm[ix - 1]);                           // :1413-1415
-    if (k == L - 1) wdtz_k = rws[ix] * (fzm[k] * tms[ix] + fzp[k] * tms[ix - 1]);                     // :1416-1419
-    s_a[k] = wdtz_k;
-    FLD(wdtz)[ix] = wdtz_k;
+    const D2 tm2 = ld2(tm, ix), tms2 = ld2(tms, ix), rws2 = ld2(FLD(rw_save), ix);
+    const D2 tmm = below(tm, ix, k0, tm2), tmsm = below(tms, ix, k0, tms2);
+    wdtz.x = wdtz_at(k0, L, rws2.x, rw2.x, fzm.x, fzp.x, tms2.x, tmsm.x, tm2.x, tmm.x);
+    if (m1) wdtz.y = wdtz_at(k1, L, rws2.y, rw2.y, fzm.y, fzp.y, tms2.y, tmsm.y, tm2.y, tmm.y);
+    s_a[k0] = wdtz.x; if (m1) s_a[k1] = wdtz.y;
+    st2m(FLD(wdtz), ix, wdtz, m0, m1);
   }
-  if (inx && k == L) s_a[L] = FLD(wdtz)[ix];
+  if (inx && k0 == L) s_a[L] = FLD(wdtz)[ix];
+  if (inx && k1 == L) s_a[L] = FLD(wdtz)[ix + 1];
   __syncthreads();
-  if (!act) return;
-  const double rz = FLD(rho_zz)[ix];
-  tt *= V.invAreaCell[x] - rdzw[k] * (s_a[k + 1] - wdtz_k);                                          // :1423
-  FLD(tend_rtheta_adv)[ix] = tt;
-  FLD(rthdynten)[ix] = tt / rz;
-  tt += rz * FLD(rt_diabatic_tend)[ix];
-  double tte = FLD(tend_theta_euler)[ix];
+  if (!m0) return;
+  const D2 rz = ld2(FLD(rho_zz), ix);
+  const D2 wdtz_p = mk(s_a[k1], m1 ? s_a[k1 + 1] : 0.0);
+  tt *= V.invAreaCell[x] - rdzw * (wdtz_p - wdtz);                                                   // :1423
+  st2m(FLD(tend_rtheta_adv), ix, tt, m0, m1);
+  st2m(FLD(rthdynten), ix, tt / rz, m0, m1);
+  tt += rz * ld2(FLD(rt_diabatic_tend), ix);
+  D2 tte = ld2(FLD(tend_theta_euler), ix);
   if (RK0) {
     if (P.visc4_on) {                                                                                 // :1384-1399
       const double* dst = FLD(delsq_theta);
       const double r_areaCell = P.h_theta_eddy_visc4 * P.prandtl_inv * V.invAreaCell[x];
+#pragma unroll 2
       for (int i = 0; i < n; ++i) {
-        const int e = V.edgesOnCell[x * ME + i];
-        const double edge_sign = V.meshScalingDel4[e] * r_areaCell * V.dvEdge[e] * V.edgesOnCell_sign[x * ME + i] * V.invDcEdge[e];
-        const int c1 = V.cellsOnEdge[e * 2], c2 = V.cellsOnEdge[e * 2 + 1];
-        tte -= edge_sign * (AT(dst, c2, k) - AT(dst, c1, k));
+        const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+        const double edge_sign = V.ms4OnCell[x * ME + i] * r_areaCell * V.dvOnCell[x * ME + i] * V.edgesOnCell_sign[x * ME + i] * V.invDcOnCell[x * ME + i];
+        tte -= edge_sign * (G2(dst, c2) - G2(dst, c1));
       }
     }
-    if (P.vmix_t_on && k > 0 && k < L - 1) {                                                          // :1432-1473
-      const double* zg = FLD(zgrid);
-      const double z1 = zg[ix - 1], z2 = zg[ix], z3 = zg[ix + 1], z4 = zg[ix + 2];
-      const double zm = 0.5 * (z1 + z2), z0 = 0.5 * (z2 + z3), zp = 0.5 * (z3 + z4);
-      if (P.mix_full) {
-        tte += P.v_theta_eddy_visc2 * P.prandtl_inv * rz * ((tm[ix + 1] - tm[ix]) / (zp - z0) - (tm[ix] - tm[ix - 1]) / (z0 - zm)) / (0.5 * (zp - zm));
-      } else {
-        const double* ti = FLD(t_init);
-        tte += P.v_theta_eddy_visc2 * P.prandtl_inv * rz
-               * (((tm[ix + 1] - ti[ix + 1]) - (tm[ix] - ti[ix])) / (zp - z0) - ((tm[ix] - ti[ix]) - (tm[ix - 1] - ti[ix - 1])) / (z0 - zm)) / (0.5 * (zp - zm));
+    if (P.vmix_t_on) {                                                                                // :1432-1473
+      const double* zg = FLD(zgrid); const double* ti = FLD(t_init);
+      for (int c = 0; c < 2; ++c) {
+        const int k = k0 + c;
+        if (!(k > 0 && k < L - 1)) continue;
+        const size_t i_ = ix + c;
+        const double z1 = zg[i_ - 1], z2 = zg[i_], z3 = zg[i_ + 1], z4 = zg[i_ + 2];
+        const double zm = 0.5 * (z1 + z2), z0 = 0.5 * (z2 + z3), zp = 0.5 * (z3 + z4);
+        const double rzc = c ? rz.y : rz.x;
+        double add;
+        if (P.mix_full)
+          add = P.v_theta_eddy_visc2 * P.prandtl_inv * rzc * ((tm[i_ + 1] - tm[i_]) / (zp - z0) - (tm[i_] - tm[i_ - 1]) / (z0 - zm)) / (0.5 * (zp - zm));
+        else
+          add = P.v_theta_eddy_visc2 * P.prandtl_inv * rzc
+                * (((tm[i_ + 1] - ti[i_ + 1]) - (tm[i_] - ti[i_])) / (zp - z0) - ((tm[i_] - ti[i_]) - (tm[i_ - 1] - ti[i_ - 1])) / (z0 - zm)) / (0.5 * (zp - zm));
+        if (c) tte.y += add; else tte.x += add;
       }
     }
-    FLD(tend_theta_euler)[ix] = tte;
+    st2m(FLD(tend_theta_euler), ix, tte, m0, m1);
   }
-  tt += tte + FLD(tend_rtheta_physics)[ix];                                                           // :1478
-  FLD(tend_theta)[ix] = tt;
+  tt += tte + ld2(FLD(tend_rtheta_physics), ix);                                                      // :1478
+  st2m(FLD(tend_theta), ix, tt, m0, m1);
 }
 
 // ============================================================================================
 // atm_set_smlstep_pert_variables_work  :1503-1528  (levels 0..L-1 of the cells of cpr; level -1 reads 0)
 __global__ void k_smlstep(const View V, int nRelaxZone) {
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
   if (!V.inCpr[x] || V.bdyMaskCell[x] > nRelaxZone) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
   const double* ut = FLD(u_tend); const double* zb = FLD(zb_cell); const double* zb3 = FLD(zb3_cell);
-  const double fm = FLD(fzm)[k], fp = FLD(fzp)[k];
-  double wv = FLD(w)[ix];
+  const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0);
+  D2 wv = ld2(FLD(w), ix);
+#pragma unroll 2
   for (int i = 0; i < n; ++i) {
-    const int e = V.edgesOnCell[x * ME + i];
-    const double ut_k = AT(ut, e, k);
-    const double ut_m = (k > 0) ? AT(ut, e, k - 1) : 0.0;
-    const double flux = V.edgesOnCell_sign[x * ME + i] * (fm * ut_k + fp * ut_m);
-    wv -= (zb[i * V.cellSlot + ix] + copysign(1.0, ut_k) * zb3[i * V.cellSlot + ix]) * flux;
+    const int e = V.edgesOnCell[x * V.MEP + i];
+    const D2 ut_k = G2(ut, e);
+    const D2 ut_m = below(ut, (size_t)e * LP + k0, k0, ut_k);
+    const D2 flux = V.edgesOnCell_sign[x * ME + i] * (fm * ut_k + fp * ut_m);
+    wv -= (ld2(zb, i * V.cellSlot + ix) + sgn1(ut_k) * ld2(zb3, i * V.cellSlot + ix)) * flux;
   }
-  const double zz_k = FLD(zz)[ix];
-  const double zz_m = (k > 0) ? FLD(zz)[ix - 1] : 0.0;
-  wv *= (fm * zz_k + fp * zz_m);
-  FLD(w)[ix] = wv;
+  const D2 zz2 = ld2(FLD(zz), ix);
+  wv *= (fm * zz2 + fp * below(FLD(zz), ix, k0, zz2));
+  st2m(FLD(w), ix, wv, m0, m1);
 }
 
 // ============================================================================================
 // atm_advance_acoustic_step_work  :1546-1705
-// phase 1 (all levels in parallel): rtheta_pp_old (:1615-1623), zeroing of level L (:1625-1630),
-// horizontal flux parts of rs/ts (:1644-1652) into scratch.
+// Fused single-kernel form of the acoustic step (default).  A block owns whole columns.
+// Everything except the dependence of rw_p(k) on the freshly updated level k-1 is evaluated in
+// parallel exactly as written in the reference.  That dependence is affine: with x = rw_p_new,
+//     rho_pp_new(k-1)    = rp0 + rp1 * x(k-1)          (:1694)
+//     rtheta_pp_new(k-1) = rt0 + rt1 * x(k-1)          (:1695-1696)
+//     x(k) = P(k) + Q(k) * x(k-1)                      (:1662-1686 collected in x(k-1))
+// so every thread computes its (P, Q) and ONE thread per column runs the 1-multiply-add-per-level
+// sweep out of shared memory; rho_pp / rtheta_pp / wwAvg then follow in parallel from x with the
+// reference's own expressions.  rs[k-1] and ts[k-1] are always 0 (the reference re-zeroes both arrays
+// at every point, Q25); the back-substitution is absent (Q28); cr.theta_m stands in for tend_rt and
+// cr.w for tend_rw (Q27).  Differs from the literal left-to-right evaluation only by the regrouping
+// of terms inside one level (a few ulp; checked against the oracle at 1e-12).
+struct AcLevel {   // per-level quantities of the affine form
+  double P, Q;
+};
+DI AcLevel ac_level(int k, double dts, double resm, double rw_old_k, double w_k, double ts, double rs, double rt_old, double rho_old,
+                    double zz_k, double zz_m, double cofwt_k, double cofwt_m, double rz_k, double rz_m, double cofwz_k, double cofwr_k,
+                    double fm, double fp, double dsk, double rws_k, double rw_k, double rp0m, double rt0m, double rp1m, double rt1m,
+                    double a_k, double al_k) {
+  AcLevel o;
+  if (k == 0) { o.P = rw_old_k; o.Q = 0.0; return o; }
+  const double r3 = rws_k - rw_k;
+  const double r1 = r3 - dts * dsk * (fm * zz_k + fp * zz_m) * (fm * rz_k + fp * rz_m) * w_k;       // :1682-1684
+  const double r2 = 1.0 + dts * dsk;                                                                // :1685
+  // terms of :1662-1667 that do not involve level k-1's new values
+  const double A0 = rw_old_k + (dts * w_k - cofwz_k * ((zz_k * ts - zz_m * 0.0) + resm * (zz_k * rt_old))
+                                - cofwr_k * ((rs + 0.0) + resm * rho_old) + cofwt_k * (ts + resm * rt_old));
+  const double A1 = resm * (cofwz_k * zz_m + cofwt_m);        // coefficient of rtheta_pp_new(k-1)
+  const double A2 = resm * cofwr_k;                           // coefficient of -rho_pp_new(k-1)
+  const double B0 = A0 + A1 * rt0m - A2 * rp0m;
+  const double B1 = A1 * rt1m - A2 * rp1m - a_k;                                                    // :1670
+  o.P = (B0 * al_k + r1) / r2 - r3;                                                                 // :1671, :1682-1686
+  o.Q = B1 * al_k / r2;
+  return o;
+}
+template <bool S0>
+__global__ void k_acoustic(const View V, double dts, double epssm, double resm) {
+  extern __shared__ double sm[];
+  PAIR_THREAD(V.nCells)
+  const int TS = LP + 2;
+  double* s_rp0 = sm + (size_t)threadIdx.y * TS;
+  double* s_rt0 = sm + (size_t)(blockDim.y + threadIdx.y) * TS;
+  double* s_P = sm + (size_t)(2 * blockDim.y + threadIdx.y) * TS;
+  double* s_Q = sm + (size_t)(3 * blockDim.y + threadIdx.y) * TS;
+  const bool spec = inx ? (V.specZoneMaskCell[x] != 0.0) : false;
+  if (S0 && inx) {                                                                                    // :1625-1630, level L
+    if (k0 == L) { FLD(wwAvg)[ix] = 0; FLD(rw_p)[ix] = 0; }
+    if (k1 == L) { FLD(wwAvg)[ix + 1] = 0; FLD(rw_p)[ix + 1] = 0; }
+  }
+  D2 rs = bc(0), ts = bc(0), rw_old = bc(0), rw_oldp = bc(0), rho_old = bc(0), rt_old = bc(0), ww_old = bc(0);
+  D2 coftz = bc(0), coftz_p = bc(0), cofrz = bc(0), rdzw = bc(0), w2 = bc(0), tr = bc(0), tm2 = bc(0);
+  if (m0) {
+    const double* tm = FLD(theta_m);
+    cofrz = ld2(FLD(cofrz), k0); rdzw = ld2(FLD(rdzw), k0);
+    if (!S0) {
+      rw_old = ld2(FLD(rw_p), ix); rw_oldp = above(FLD(rw_p), ix, k0, L, rw_old);
+      rho_old = ld2(FLD(rho_pp), ix); rt_old = ld2(FLD(rtheta_pp), ix); ww_old = ld2(FLD(wwAvg), ix);
+    }
+    st2m(FLD(rtheta_pp_old), ix, S0 ? bc(0.0) : rt_old, m0, m1);                                      // :1615-1623
+    w2 = ld2(FLD(w), ix); tr = ld2(FLD(tend_rho), ix); tm2 = ld2(tm, ix);
+    if (!spec) {
+      const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
+      const double* ru_p = FLD(ru_p);
+      const double inva = V.invAreaCell[x];
+#pragma unroll 2
+      for (int i = 0; i < n; ++i) {                                                                   // :1644-1652
+        const int e = V.edgesOnCell[x * V.MEP + i];
+        const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+        const D2 flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G2(ru_p, e) * inva;
+        rs -= flux;
+        ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
+      }
+      coftz = ld2(FLD(coftz), ix); coftz_p = above(FLD(coftz), ix, k0, L, coftz);
+      rs = rho_old + dts * tr + rs - cofrz * resm * (rw_oldp - rw_old);                               // :1657
+      ts = rt_old + dts * tm2 + ts - resm * rdzw * (coftz_p * rw_oldp - coftz * rw_old);              // :1658
+      // new rho_pp / rtheta_pp of THIS level as affine functions of x(k):  rp0 + cofrz*x,  rt0 + rdzw*coftz*x
+      const D2 rp0 = rs - cofrz * rw_oldp, rt0 = ts - rdzw * (coftz_p * rw_oldp);
+      s_rp0[k0] = rp0.x; s_rt0[k0] = rt0.x;
+      if (m1) { s_rp0[k1] = rp0.y; s_rt0[k1] = rt0.y; }
+    }
+  }
+  __syncthreads();
+  if (m0 && !spec) {
+    const D2 zz = ld2(FLD(zz), ix), zzm = below(FLD(zz), ix, k0, zz);
+    const D2 cwt = ld2(FLD(cofwt), ix), cwtm = below(FLD(cofwt), ix, k0, cwt);
+    const D2 rz = ld2(FLD(rho_zz), ix), rzm = below(FLD(rho_zz), ix, k0, rz);
+    const D2 cwz = ld2(FLD(cofwz), ix), cwr = ld2(FLD(cofwr), ix);
+    const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0);
+    const D2 ds = ld2(FLD(dss), ix), rws = ld2(FLD(rw_save), ix), rwv = ld2(FLD(rw), ix);
+    const D2 at = ld2(FLD(a_tri), ix), al = ld2(FLD(alpha_tri), ix);
+    // level k-1 partners: (rp0, rt0) from smem; rp1 = cofrz(k-1), rt1 = rdzw(k-1)*coftz(k-1)
+    const double cofrz_m = k0 > 0 ? FLD(cofrz)[k0 - 1] : 0.0, rdzw_m = k0 > 0 ? FLD(rdzw)[k0 - 1] : 0.0;
+    const double coftz_m = k0 > 0 ? FLD(coftz)[ix - 1] : 0.0;
+    const AcLevel l0 = ac_level(k0, dts, resm, rw_old.x, w2.x, ts.x, rs.x, rt_old.x, rho_old.x, zz.x, zzm.x, cwt.x, cwtm.x, rz.x, rzm.x,
+                                cwz.x, cwr.x, fm.x, fp.x, ds.x, rws.x, rwv.x, k0 > 0 ? s_rp0[k0 - 1] : 0.0, k0 > 0 ? s_rt0[k0 - 1] : 0.0,
+                                cofrz_m, rdzw_m * coftz_m, at.x, al.x);
+    s_P[k0] = l0.P; s_Q[k0] = l0.Q;
+    if (m1) {
+      const AcLevel l1 = ac_level(k1, dts, resm, rw_old.y, w2.y, ts.y, rs.y, rt_old.y, rho_old.y, zz.y, zzm.y, cwt.y, cwtm.y, rz.y, rzm.y,
+                                  cwz.y, cwr.y, fm.y, fp.y, ds.y, rws.y, rwv.y, s_rp0[k0], s_rt0[k0], cofrz.x, rdzw.x * coftz.x, at.y, al.y);
+      s_P[k1] = l1.P; s_Q[k1] = l1.Q;
+    }
+  }
+  __syncthreads();
+  if (inx && !spec && k0 == 0) {            // the sweep: one multiply-add per level, levels ascending (M4)
+    double xv = s_P[0];
+    for (int kk = 1; kk < L; ++kk) { xv = s_P[kk] + s_Q[kk] * xv; s_P[kk] = xv; }
+  }
+  __syncthreads();
+  if (!m0) return;
+  D2 rw_new, rho_new, rt_new, ww_new = ww_old;
+  if (!spec) {
+    rw_new = mk(s_P[k0], m1 ? s_P[k1] : 0.0);
+    const D2 wa = ww_old + 0.5 * (1.0 - epssm) * rw_old;                                              // :1661
+    const D2 wb = wa + 0.5 * (1.0 + epssm) * rw_new;                                                  // :1689
+    ww_new = mk(k0 > 0 ? wb.x : ww_old.x, wb.y);
+    rho_new = rs - cofrz * (rw_oldp - rw_new);                                                        // :1694
+    rt_new = ts - rdzw * (coftz_p * rw_oldp - coftz * rw_new);                                        // :1695-1696
+  } else {                                                                                            // :1698-1703
+    rho_new = rho_old + dts * tr;
+    rt_new = rt_old + dts * tm2;
+    rw_new = rw_old + dts * w2;
+    ww_new = ww_old + 0.5 * (1.0 + epssm) * rw_new;
+  }
+  st2m(FLD(rho_pp), ix, rho_new, m0, m1); st2m(FLD(rtheta_pp), ix, rt_new, m0, m1);
+  const bool wr0 = S0 || spec || k0 > 0;
+  st2m(FLD(rw_p), ix, rw_new, wr0, m1); st2m(FLD(wwAvg), ix, ww_new, wr0, m1);
+}
+
+// Two-kernel, strictly left-to-right form (MpasConfig.acoustic_exact = 1).  One thread per level in
+// phase 1, one thread per column in phase 2.
 __global__ void k_acoustic_flux(const View V, double dts, int small_step) {
-  COLUMN_THREAD(V.nCells)
-  if (!inx) return;
+  const int k = threadIdx.x;
+  const int x = blockIdx.x * blockDim.y + threadIdx.y;
+  if (x >= V.nCells) return;
+  const int LP = V.LP, L = V.L;
+  const size_t ix = (size_t)x * LP + k;
   if (k == L && small_step == 0) { FLD(wwAvg)[ix] = 0; FLD(rw_p)[ix] = 0; }
   if (k >= L) return;
   FLD(rtheta_pp_old)[ix] = (small_step == 0) ? 0.0 : FLD(rtheta_pp)[ix];
@@ -622,17 +893,14 @@ __global__ void k_acoustic_flux(const View V, double dts, int small_step) {
   const double inva = V.invAreaCell[x];
   double rs = 0, ts = 0;
   for (int i = 0; i < n; ++i) {
-    const int e = V.edgesOnCell[x * ME + i];
-    const int c1 = V.cellsOnEdge[e * 2], c2 = V.cellsOnEdge[e * 2 + 1];
-    const double flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvEdge[e] * AT(ru_p, e, k) * inva;
+    const int e = V.edgesOnCell[x * V.MEP + i];
+    const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+    const double flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G1(ru_p, e, k) * inva;
     rs -= flux;
-    ts -= flux * 0.5 * (AT(tm, c2, k) + AT(tm, c1, k));
+    ts -= flux * 0.5 * (G1(tm, c2, k) + G1(tm, c1, k));
   }
   V.scr_rs[ix] = rs; V.scr_ts[ix] = ts;
 }
-// phase 2 (one thread per column, levels ascending): the vertically implicit sweep  :1657-1703.
-// rs[k-1] and ts[k-1] are always 0 (the reference re-zeroes both arrays at every point, Q25); the
-// back-substitution is absent (Q28); cr.theta_m stands in for tend_rt and cr.w for tend_rw (Q27).
 __global__ void k_acoustic_column(const View V, double dts, int small_step, double epssm, double resm) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= V.nCells) return;
@@ -693,122 +961,19 @@ __global__ void k_acoustic_column(const View V, double dts, int small_step, doub
   }
 }
 
-// Fused single-kernel form of the acoustic step (default).  lane = level, a block owns whole columns.
-// Everything except the dependence of rw_p(k) on the freshly updated level k-1 is evaluated in
-// parallel exactly as written in the reference.  That dependence is affine: with x = rw_p_new,
-//     rho_pp_new(k-1)    = rp0 + rp1 * x(k-1)          (:1694)
-//     rtheta_pp_new(k-1) = rt0 + rt1 * x(k-1)          (:1695-1696)
-//     x(k) = P(k) + Q(k) * x(k-1)                      (:1662-1686 collected in x(k-1))
-// so every thread computes its (P, Q) and ONE thread per column runs the 1-multiply-add-per-level
-// sweep out of shared memory; rho_pp / rtheta_pp / wwAvg then follow in parallel from x with the
-// reference's own expressions.  Differs from the literal left-to-right evaluation only by the
-// regrouping of terms inside one level (a few ulp; checked against the oracle at 1e-12).
-template <bool S0>
-__global__ void k_acoustic(const View V, double dts, double epssm, double resm) {
-  extern __shared__ double sm[];
-  COLUMN_THREAD(V.nCells)
-  const int TS = LP + 1;
-  double* s_rp0 = sm + (size_t)threadIdx.y * TS;
-  double* s_rt0 = sm + (size_t)(blockDim.y + threadIdx.y) * TS;
-  double* s_P = sm + (size_t)(2 * blockDim.y + threadIdx.y) * TS;
-  double* s_Q = sm + (size_t)(3 * blockDim.y + threadIdx.y) * TS;
-  const bool act = inx && k < L;
-  const bool spec = inx ? (V.specZoneMaskCell[x] != 0.0) : false;
-  if (inx && k == L && S0) { FLD(wwAvg)[ix] = 0; FLD(rw_p)[ix] = 0; }                                // :1625-1630, level L
-  double rs = 0, ts = 0, rw_old_k = 0, rw_old_p = 0, rho_old = 0, rt_old = 0, ww_old = 0;
-  double coftz_k = 0, coftz_p = 0, cofrz_k = 0, rdzw_k = 0, w_k = 0, tr_k = 0, tm_k = 0;
-  if (act) {
-    const double* tm = FLD(theta_m);
-    cofrz_k = FLD(cofrz)[k]; rdzw_k = FLD(rdzw)[k];
-    if (!S0) {
-      rw_old_k = FLD(rw_p)[ix]; rw_old_p = FLD(rw_p)[ix + 1];
-      rho_old = FLD(rho_pp)[ix]; rt_old = FLD(rtheta_pp)[ix]; ww_old = FLD(wwAvg)[ix];
-    }
-    FLD(rtheta_pp_old)[ix] = S0 ? 0.0 : rt_old;                                                       // :1615-1623
-    w_k = FLD(w)[ix]; tr_k = FLD(tend_rho)[ix]; tm_k = tm[ix];
-    if (!spec) {
-      const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
-      const double* ru_p = FLD(ru_p);
-      const double inva = V.invAreaCell[x];
-      for (int i = 0; i < n; ++i) {                                                                   // :1644-1652
-        const int e = V.edgesOnCell[x * ME + i];
-        const int c1 = V.cellsOnEdge[e * 2], c2 = V.cellsOnEdge[e * 2 + 1];
-        const double flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvEdge[e] * AT(ru_p, e, k) * inva;
-        rs -= flux;
-        ts -= flux * 0.5 * (AT(tm, c2, k) + AT(tm, c1, k));
-      }
-      coftz_k = FLD(coftz)[ix]; coftz_p = FLD(coftz)[ix + 1];
-      rs = rho_old + dts * tr_k + rs - cofrz_k * resm * (rw_old_p - rw_old_k);                        // :1657
-      ts = rt_old + dts * tm_k + ts - resm * rdzw_k * (coftz_p * rw_old_p - coftz_k * rw_old_k);      // :1658
-      // new rho_pp / rtheta_pp of THIS level as affine functions of x(k):  rp0 + cofrz*x,  rt0 + rdzw*coftz*x
-      s_rp0[k] = rs - cofrz_k * rw_old_p;
-      s_rt0[k] = ts - rdzw_k * (coftz_p * rw_old_p);
-    }
-  }
-  __syncthreads();
-  double r3 = 0, r2 = 1, cofwt_k = 0, zz_k = 0;
-  if (act && !spec) {
-    zz_k = FLD(zz)[ix]; cofwt_k = FLD(cofwt)[ix];
-    if (k == 0) { s_P[0] = rw_old_k; s_Q[0] = 0.0; }
-    else {
-      const double zz_m = FLD(zz)[ix - 1], cofwt_m = FLD(cofwt)[ix - 1], rz_k = FLD(rho_zz)[ix], rz_m = FLD(rho_zz)[ix - 1];
-      const double cofwz_k = FLD(cofwz)[ix], cofwr_k = FLD(cofwr)[ix];
-      const double fm = FLD(fzm)[k], fp = FLD(fzp)[k];
-      const double dsk = FLD(dss)[ix];
-      r3 = FLD(rw_save)[ix] - FLD(rw)[ix];
-      const double r1 = r3 - dts * dsk * (fm * zz_k + fp * zz_m) * (fm * rz_k + fp * rz_m) * w_k;      // :1682-1684
-      r2 = 1.0 + dts * dsk;                                                                           // :1685
-      // terms of :1662-1667 that do not involve level k-1's new values
-      const double A0 = rw_old_k + (dts * w_k - cofwz_k * ((zz_k * ts - zz_m * 0.0) + resm * (zz_k * rt_old))
-                                    - cofwr_k * ((rs + 0.0) + resm * rho_old) + cofwt_k * (ts + resm * rt_old));
-      const double A1 = resm * (cofwz_k * zz_m + cofwt_m);        // coefficient of rtheta_pp_new(k-1)
-      const double A2 = resm * cofwr_k;                           // coefficient of -rho_pp_new(k-1)
-      const double rp0 = s_rp0[k - 1], rt0 = s_rt0[k - 1];
-      const double rp1 = FLD(cofrz)[k - 1], rt1 = FLD(rdzw)[k - 1] * FLD(coftz)[ix - 1];
-      const double B0 = A0 + A1 * rt0 - A2 * rp0;
-      const double B1 = A1 * rt1 - A2 * rp1 - FLD(a_tri)[ix];                                          // :1670
-      const double al = FLD(alpha_tri)[ix];                                                            // :1671
-      s_P[k] = (B0 * al + r1) / r2 - r3;                                                               // :1682-1686
-      s_Q[k] = B1 * al / r2;
-    }
-  }
-  __syncthreads();
-  if (inx && !spec && k == 0) {             // the sweep: one multiply-add per level, levels ascending (M4)
-    double xv = s_P[0];
-    for (int kk = 1; kk < L; ++kk) { xv = s_P[kk] + s_Q[kk] * xv; s_P[kk] = xv; }
-  }
-  __syncthreads();
-  if (!act) return;
-  double rw_new, rho_new, rt_new, ww_new = ww_old;
-  if (!spec) {
-    rw_new = s_P[k];
-    if (k > 0) {
-      ww_new += 0.5 * (1.0 - epssm) * rw_old_k;                                                        // :1661
-      ww_new += 0.5 * (1.0 + epssm) * rw_new;                                                          // :1689
-    }
-    rho_new = rs - cofrz_k * (rw_old_p - rw_new);                                                      // :1694
-    rt_new = ts - rdzw_k * (coftz_p * rw_old_p - coftz_k * rw_new);                                    // :1695-1696
-  } else {                                                                                             // :1698-1703
-    rho_new = rho_old + dts * tr_k;
-    rt_new = rt_old + dts * tm_k;
-    rw_new = rw_old_k + dts * w_k;
-    ww_new = ww_old + 0.5 * (1.0 + epssm) * rw_new;
-  }
-  FLD(rho_pp)[ix] = rho_new; FLD(rtheta_pp)[ix] = rt_new;
-  if (S0 || spec || k > 0) { FLD(rw_p)[ix] = rw_new; FLD(wwAvg)[ix] = ww_new; }
-}
-
 // ============================================================================================
 // atm_divergence_damping_3d  :1726-1763
 __global__ void k_divdamp(const View V, double coef_divdamp) {
-  COLUMN_THREAD(V.nEdges)
-  if (!inx || k >= L) return;
-  const int c1 = V.cellsOnEdge[x * 2], c2 = V.cellsOnEdge[x * 2 + 1];
-  if (V.isShared[c1] && V.isShared[c2]) return;
+  PAIR_THREAD(V.nEdges)
+  if (!m0) return;
+  if (V.divdampSkip[x]) return;
+  const int4 cv = V.ecv[x];
   const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
-  const double divCell1 = -(AT(rpp, c1, k) - AT(rppo, c1, k));
-  const double divCell2 = -(AT(rpp, c2, k) - AT(rppo, c2, k));
-  FLD(ru_p)[ix] += coef_divdamp * (divCell2 - divCell1) * (1.0 - V.specZoneMaskEdge[x]) / (AT(tm, c1, k) + AT(tm, c2, k));
+  const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
+  const D2 r = ld2(FLD(ru_p), ix);
+  const D2 divCell1 = -(a1 - b1);
+  const D2 divCell2 = -(a2 - b2);
+  st2m(FLD(ru_p), ix, r + coef_divdamp * (divCell2 - divCell1) * (1.0 - V.specZoneMaskEdge[x]) / (t1 + t2), m0, m1);
 }
 
 // ============================================================================================
@@ -818,101 +983,114 @@ __global__ void k_rec_pad(const View V) {           // :1792-1794: rho_zz = 1 on
   if (k < V.L) FLD(rho_zz)[(size_t)V.nCells * V.LP + k] = 1.0;
 }
 __global__ void k_rec_cell1(const View V, double invNs, int rk_step, double dt, double rgas, double rcv) {   // :1800-1826
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
-  const double rho_p = FLD(rho_p_save)[ix] + FLD(rho_pp)[ix];
-  const double rho_zz = rho_p + FLD(rho_base)[ix];
-  FLD(rho_p)[ix] = rho_p; FLD(rho_zz)[ix] = rho_zz;
-  double ww = FLD(wwAvg)[ix];
-  ww *= invNs; ww += FLD(rw_save)[ix];
-  FLD(wwAvg)[ix] = ww;
-  const double rwv = FLD(rw_save)[ix] + FLD(rw_p)[ix];
-  FLD(rw)[ix] = rwv;
-  const double zz_k = FLD(zz)[ix];
-  const double zz_m = (k > 0) ? FLD(zz)[ix - 1] : 0.0;
-  FLD(w)[ix] = rwv / (FLD(fzm)[k] * zz_k + FLD(fzp)[k] * zz_m);                                      // :1810
-  const double rtb = FLD(rtheta_base)[ix];
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
+  const D2 rws = ld2(FLD(rw_save), ix);
+  const D2 rho_p = ld2(FLD(rho_p_save), ix) + ld2(FLD(rho_pp), ix);
+  const D2 rho_zz = rho_p + ld2(FLD(rho_base), ix);
+  st2m(FLD(rho_p), ix, rho_p, m0, m1); st2m(FLD(rho_zz), ix, rho_zz, m0, m1);
+  D2 ww = ld2(FLD(wwAvg), ix);
+  ww *= invNs; ww += rws;
+  st2m(FLD(wwAvg), ix, ww, m0, m1);
+  const D2 rwv = rws + ld2(FLD(rw_p), ix);
+  st2m(FLD(rw), ix, rwv, m0, m1);
+  const D2 zz = ld2(FLD(zz), ix);
+  st2m(FLD(w), ix, rwv / (ld2(FLD(fzm), k0) * zz + ld2(FLD(fzp), k0) * below(FLD(zz), ix, k0, zz)), m0, m1);   // :1810
+  const D2 rtb = ld2(FLD(rtheta_base), ix);
   if (rk_step == 2) {
-    const double rtp = FLD(rtheta_p_save)[ix] + FLD(rtheta_pp)[ix] - dt * rho_zz * FLD(rt_diabatic_tend)[ix];
-    FLD(rtheta_p)[ix] = rtp;
-    FLD(theta_m)[ix] = (rtp + rtb) / rho_zz;
-    const double ex = zz_k * (rgas / 100000) * pow((rtp + rtb), rcv);                                 // :1819
-    FLD(exner)[ix] = ex;
-    FLD(pressure_p)[ix] = zz_k * rgas * (ex * rtp + rtb * (ex - FLD(exner_base)[ix]));               // :1821
+    const D2 rtp = ld2(FLD(rtheta_p_save), ix) + ld2(FLD(rtheta_pp), ix) - dt * rho_zz * ld2(FLD(rt_diabatic_tend), ix);
+    st2m(FLD(rtheta_p), ix, rtp, m0, m1);
+    st2m(FLD(theta_m), ix, (rtp + rtb) / rho_zz, m0, m1);
+    const D2 s = rtp + rtb;
+    const D2 ex = zz * (rgas / 100000) * mk(pow(s.x, rcv), pow(s.y, rcv));                              // :1819
+    st2m(FLD(exner), ix, ex, m0, m1);
+    st2m(FLD(pressure_p), ix, zz * rgas * (ex * rtp + rtb * (ex - ld2(FLD(exner_base), ix))), m0, m1);   // :1821
   } else {
-    const double rtp = FLD(rtheta_p_save)[ix] + FLD(rtheta_pp)[ix];
-    FLD(rtheta_p)[ix] = rtp;
-    FLD(theta_m)[ix] = (rtp + rtb) / rho_zz;
+    const D2 rtp = ld2(FLD(rtheta_p_save), ix) + ld2(FLD(rtheta_pp), ix);
+    st2m(FLD(rtheta_p), ix, rtp, m0, m1);
+    st2m(FLD(theta_m), ix, (rtp + rtb) / rho_zz, m0, m1);
   }
 }
 __global__ void k_rec_edge(const View V, double invNs) {                                               // :1835-1842
-  COLUMN_THREAD(V.nEdges)
-  if (!inx || k >= L) return;
-  const int c1 = V.cellsOnEdge[x * 2], c2 = V.cellsOnEdge[x * 2 + 1];
+  PAIR_THREAD(V.nEdges)
+  if (!m0) return;
+  const int4 cv = V.ecv[x];
   const double* rz = FLD(rho_zz);
-  double ra = FLD(ruAvg)[ix];
-  ra *= invNs; ra += FLD(ru_save)[ix];
-  FLD(ruAvg)[ix] = ra;
-  const double ruv = FLD(ru_save)[ix] * FLD(ru_p)[ix];                                                // a product, as written (:1840)
-  FLD(ru)[ix] = ruv;
-  FLD(u)[ix] = 2 * ruv / (AT(rz, c1, k) + AT(rz, c2, k));
+  const D2 rus = ld2(FLD(ru_save), ix);
+  D2 ra = ld2(FLD(ruAvg), ix);
+  ra *= invNs; ra += rus;
+  st2m(FLD(ruAvg), ix, ra, m0, m1);
+  const D2 ruv = rus * ld2(FLD(ru_p), ix);                                                            // a product, as written (:1840)
+  st2m(FLD(ru), ix, ruv, m0, m1);
+  st2m(FLD(u), ix, 2 * ruv / (G2(rz, cv.x) + G2(rz, cv.y)), m0, m1);
 }
 __global__ void k_rec_cell2(const View V, int nRelaxZone) {                                            // :1844-1871
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
   if (V.bdyMaskCell[x] > nRelaxZone) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
   const double* ru = FLD(ru); const double* zb = FLD(zb_cell); const double* zb3 = FLD(zb3_cell); const double* rz = FLD(rho_zz);
-  const double fm = FLD(fzm)[k], fp = FLD(fzp)[k];
+  const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0);
   const double cf1 = FLD(cf1)[0], cf2 = FLD(cf2)[0], cf3 = FLD(cf3)[0];
-  double wv = FLD(w)[ix];
-  if (k == 0) {
-    // the surface term is accumulated once per (cell, LEVEL) iteration: L times, interleaved with
-    // the level-0 flux2 term on the first pass (level -1 reads 0)
+  D2 wv = ld2(FLD(w), ix);
+  const D2 rz2 = ld2(rz, ix);
+  // levels k0 (if > 0) and k1: w += sign*(zb + sign(flux2)*zb3)*flux2, flux2 a PRODUCT as written (:1855)
+  for (int i = 0; i < n; ++i) {
+    const int e = V.edgesOnCell[x * V.MEP + i];
+    const D2 ru2 = G2(ru, e);
+    const D2 flux2 = fm * ru2 * (fp * below(ru, (size_t)e * LP + k0, k0, ru2));
+    const D2 add = V.edgesOnCell_sign[x * ME + i] * (ld2(zb, i * V.cellSlot + ix) + sgn1(flux2) * ld2(zb3, i * V.cellSlot + ix)) * flux2;
+    if (k0 > 0) wv.x += add.x;
+    wv.y += add.y;
+  }
+  if (k0 == 0) {
+    // level 0: the surface term is accumulated once per (cell, LEVEL) iteration, i.e. L times, interleaved
+    // with the level-0 flux2 term on the first pass (level -1 reads 0)
+    double w0 = wv.x;
     for (int kk = 0; kk < L; ++kk) {
       for (int i = 0; i < n; ++i) {
-        const int e = V.edgesOnCell[x * ME + i];
+        const int e = V.edgesOnCell[x * V.MEP + i];
         const double sgn = V.edgesOnCell_sign[x * ME + i];
-        const double flux = (cf1 * AT(ru, e, 0) + cf2 * AT(ru, e, 1) + cf3 * AT(ru, e, 2));
-        wv += sgn * (zb[i * V.cellSlot + ix] + copysign(1.0, flux) * zb3[i * V.cellSlot + ix]) * flux;
+        const double z = zb[i * V.cellSlot + ix], z3 = zb3[i * V.cellSlot + ix];
+        const double flux = (cf1 * G1(ru, e, 0) + cf2 * G1(ru, e, 1) + cf3 * G1(ru, e, 2));
+        w0 += sgn * (z + copysign(1.0, flux) * z3) * flux;
         if (kk == 0) {
-          const double flux2 = fm * AT(ru, e, 0) * (fp * 0.0);
-          wv += sgn * (zb[i * V.cellSlot + ix] + copysign(1.0, flux2) * zb3[i * V.cellSlot + ix]) * flux2;
+          const double flux2 = fm.x * G1(ru, e, 0) * (fp.x * 0.0);
+          w0 += sgn * (z + copysign(1.0, flux2) * z3) * flux2;
         }
       }
     }
-    wv /= (cf1 * rz[ix] + cf2 * rz[ix + 1] + cf3 * rz[ix + 2]);
+    wv.x = w0 / (cf1 * rz2.x + cf2 * rz2.y + cf3 * rz[ix + 2]);
+    wv.y = wv.y / (fm.y * rz2.y + fp.y * rz2.x);
   } else {
-    for (int i = 0; i < n; ++i) {
-      const int e = V.edgesOnCell[x * ME + i];
-      const double flux2 = fm * AT(ru, e, k) * (fp * AT(ru, e, k - 1));                                // a product, as written (:1855)
-      wv += V.edgesOnCell_sign[x * ME + i] * (zb[i * V.cellSlot + ix] + copysign(1.0, flux2) * zb3[i * V.cellSlot + ix]) * flux2;
-    }
-    wv /= (fm * rz[ix] + fp * rz[ix - 1]);
+    const D2 rzm = below(rz, ix, k0, rz2);
+    wv = wv / (fm * rz2 + fp * rzm);
   }
-  FLD(w)[ix] = wv;
+  st2m(FLD(w), ix, wv, m0, m1);
 }
 
 // ============================================================================================
 // atm_rk_dynamics_substep_finish  :1951-2007
 __global__ void k_finish_cell(const View V, int lt_split, int first, int last, double inv_split) {
-  COLUMN_THREAD(V.nCells)
-  if (!inx || k >= L) return;
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
   if (lt_split) {
-    FLD(rw_save)[ix] = FLD(rw)[ix]; FLD(rtheta_p_save)[ix] = FLD(rtheta_p)[ix]; FLD(rho_p_save)[ix] = FLD(rho_p)[ix];
-    FLD(w)[ix] = FLD(w_2)[ix]; FLD(theta_m)[ix] = FLD(theta_m_2)[ix]; FLD(rho_zz)[ix] = FLD(rho_zz_2)[ix];
+    st2m(FLD(rw_save), ix, ld2(FLD(rw), ix), m0, m1); st2m(FLD(rtheta_p_save), ix, ld2(FLD(rtheta_p), ix), m0, m1);
+    st2m(FLD(rho_p_save), ix, ld2(FLD(rho_p), ix), m0, m1);
+    st2m(FLD(w), ix, ld2(FLD(w_2), ix), m0, m1); st2m(FLD(theta_m), ix, ld2(FLD(theta_m_2), ix), m0, m1);
+    st2m(FLD(rho_zz), ix, ld2(FLD(rho_zz_2), ix), m0, m1);
   }
-  double ws = first ? FLD(wwAvg)[ix] : FLD(wwAvg)[ix] + FLD(wwAvg_split)[ix];
-  FLD(wwAvg_split)[ix] = ws;
-  if (last) { FLD(wwAvg)[ix] = ws * inv_split; FLD(rho_zz)[ix] = FLD(rho_zz_old_split)[ix]; }
+  const D2 ws = first ? ld2(FLD(wwAvg), ix) : ld2(FLD(wwAvg), ix) + ld2(FLD(wwAvg_split), ix);
+  st2m(FLD(wwAvg_split), ix, ws, m0, m1);
+  if (last) { st2m(FLD(wwAvg), ix, ws * inv_split, m0, m1); st2m(FLD(rho_zz), ix, ld2(FLD(rho_zz_old_split), ix), m0, m1); }
 }
 __global__ void k_finish_edge(const View V, int lt_split, int first, int last, double inv_split) {
-  COLUMN_THREAD(V.nEdges)
-  if (!inx || k >= L) return;
-  if (lt_split) { FLD(ru_save)[ix] = FLD(ru)[ix]; FLD(u)[ix] = FLD(u_2)[ix]; }
-  double rs = first ? FLD(ruAvg)[ix] : FLD(ruAvg)[ix] + FLD(ruAvg_split)[ix];
-  FLD(ruAvg_split)[ix] = rs;
-  if (last) FLD(ruAvg)[ix] = rs * inv_split;
+  PAIR_THREAD(V.nEdges)
+  if (!m0) return;
+  if (lt_split) { st2m(FLD(ru_save), ix, ld2(FLD(ru), ix), m0, m1); st2m(FLD(u), ix, ld2(FLD(u_2), ix), m0, m1); }
+  const D2 rs = first ? ld2(FLD(ruAvg), ix) : ld2(FLD(ruAvg), ix) + ld2(FLD(ruAvg_split), ix);
+  st2m(FLD(ruAvg_split), ix, rs, m0, m1);
+  if (last) st2m(FLD(ruAvg), ix, rs * inv_split, m0, m1);
 }
 
 // ============================================================================================

@@ -173,7 +173,8 @@ template <class T, class S> std::vector<T> build_vals(const S* src, int n, int w
 
 // ---- launch helpers --------------------------------------------------------------------------------
 struct Cfg { dim3 grid, block; };
-Cfg cfg_for(const mpasb200_t* h, int n) { return Cfg{dim3((unsigned)((n + h->CPB - 1) / h->CPB)), dim3((unsigned)h->LP, (unsigned)h->CPB)}; }
+// one thread per level PAIR: block = (LP/2, CPB) with CPB whole columns
+Cfg cfg_for(const mpasb200_t* h, int n) { return Cfg{dim3((unsigned)((n + h->CPB - 1) / h->CPB)), dim3((unsigned)(h->LP / 2), (unsigned)h->CPB)}; }
 
 cudaEvent_t pool_event(mpasb200_t* h) {
   if (h->ev_used == h->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
@@ -210,7 +211,7 @@ void drain_kernel_times(mpasb200_t* h) {
     }                                                                                       \
   } while (0)
 
-size_t tile_bytes(const mpasb200_t* h, int tiles) { return (size_t)tiles * h->CPB * (h->LP + 1) * sizeof(double); }
+size_t tile_bytes(const mpasb200_t* h, int tiles) { return (size_t)tiles * h->CPB * (h->LP + 2) * sizeof(double); }
 
 int post_launch(mpasb200_t* h) {
   cudaError_t e = cudaGetLastError();
@@ -295,7 +296,12 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
     else LAUNCH(k_acoustic<false>, h->nCells, tile_bytes(h, 4), h->V, dts, epssm, resm);
     return post_launch(h);
   }
-  LAUNCH(k_acoustic_flux, h->nCells, 0, h->V, dts, small_step);
+  if (h->nCells > 0) {
+    const int rows = std::max(1, 128 / h->LP);      // two-kernel exact mode: one thread per level
+    KTimer kt_(h, "k_acoustic_flux");
+    k_acoustic_flux<<<(h->nCells + rows - 1) / rows, dim3(h->LP, rows), 0, h->stream>>>(h->V, dts, small_step);
+    h->launches++;
+  }
   if (h->nCells > 0) {
     const int tb = 64;
     KTimer kt_(h, "k_acoustic_column");
@@ -446,8 +452,8 @@ int mpasb200_create(const MpasDims* dims, const MpasConfig* cfg, mpasb200_t** ou
   if ((e = cudaSetDevice(h->device)) != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); delete h; return MPASB200_ECUDA; }
   h->nCells = dims->nCells; h->nEdges = dims->nEdges; h->nVertices = dims->nVertices;
   h->L = dims->nVertLevels; h->L1 = h->L + 1; h->LP = (h->L1 + 3) / 4 * 4;
-  { int g = h->LP, b = 32; while (b) { int t = g % b; g = b; b = t; } h->CPB = 32 / g; if (h->CPB * h->LP < 128) h->CPB *= 2; }
-  if (h->LP * h->CPB > 1024) { g_create_error = "nVertLevels too large for one block per column group"; delete h; return MPASB200_EINVAL; }
+  { const int T = h->LP / 2; int g = T, b = 32; while (b) { int t = g % b; g = b; b = t; } h->CPB = 32 / g; while (h->CPB * T < 128) h->CPB *= 2; }
+  if (h->LP / 2 * h->CPB > 1024) { g_create_error = "nVertLevels too large for one block per column group"; delete h; return MPASB200_EINVAL; }
   cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   h->stream = h->own_stream;
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
@@ -552,7 +558,68 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
 #define UP_INT(member, src, n, w, rowNew) if ((rc = dev_upload<int>(h, &V.member, build_vals<int, int32_t>(src, n, w, rowNew)))) return rc
 #define UP_DBL(member, src, n, w, rowNew) if ((rc = dev_upload<double>(h, &V.member, build_vals<double, double>(src, n, w, rowNew)))) return rc
   UP_INT(nEdgesOnCell, m->nEdgesOnCell, nC, 1, cNew);
-  UP_IDS(edgesOnCell, m->edgesOnCell, nC, ME, cNew, nE, eNew);
+  const int MEP = (ME + 3) / 4 * 4;
+  V.MEP = MEP;
+  {
+    // edgesOnCell with a 16-byte-aligned row pitch, plus per-(cell, slot) copies of what a cell kernel needs
+    // from its slot-i edge (cellsOnEdge, dvEdge, invDcEdge, meshScalingDel2/4, advection list): exact copies,
+    // so the arithmetic is unchanged; they remove the second level of dependent index loads.
+    const std::vector<int> eocC = build_ids(m->edgesOnCell, nC, ME, cNew, nE, eNew, pol);       // [new cell][ME] -> new edge
+    const std::vector<int> coe = build_ids(m->cellsOnEdge, nE, 2, eNew, nC, cNew, pol);          // [new edge][2] -> new cell
+    const std::vector<double> dvE = build_vals<double, double>(m->dvEdge, nE, 1, eNew), idcE = build_vals<double, double>(m->invDcEdge, nE, 1, eNew);
+    const std::vector<double> ms2E = build_vals<double, double>(m->meshScalingDel2, nE, 1, eNew), ms4E = build_vals<double, double>(m->meshScalingDel4, nE, 1, eNew);
+    const std::vector<int> nAdvE = build_vals<int, int32_t>(m->nAdvCellsForEdge, nE, 1, eNew);
+    const std::vector<int> advE = build_ids(m->advCellsForEdge, nE, NA, eNew, nC, cNew, pol);
+    const std::vector<double> acE = build_vals<double, double>(m->adv_coefs, nE, NA, eNew), a3E = build_vals<double, double>(m->adv_coefs_3rd, nE, NA, eNew);
+    int nap = 2;
+    for (int e = 0; e < nE; ++e) nap = std::max(nap, nAdvE[e]);
+    nap = (nap + 1) / 2 * 2;
+    V.NAP = nap;
+    std::vector<int> eoc((size_t)(nC + 1) * MEP, nE), c1((size_t)(nC + 1) * MEP, nC), c2((size_t)(nC + 1) * MEP, nC);
+    std::vector<double> dvS((size_t)(nC + 1) * ME, 0.0), idcS((size_t)(nC + 1) * ME, 0.0), ms2S((size_t)(nC + 1) * ME, 0.0), ms4S((size_t)(nC + 1) * ME, 0.0);
+    std::vector<int> nAdvS((size_t)(nC + 1) * ME, 0), advS((size_t)(nC + 1) * ME * nap, nC);
+    std::vector<double> acS((size_t)(nC + 1) * ME * nap, 0.0), a3S((size_t)(nC + 1) * ME * nap, 0.0);
+    for (int c = 0; c <= nC; ++c)
+      for (int i = 0; i < ME; ++i) {
+        const int e = eocC[(size_t)c * ME + i];
+        eoc[(size_t)c * MEP + i] = e;
+        c1[(size_t)c * MEP + i] = coe[(size_t)e * 2]; c2[(size_t)c * MEP + i] = coe[(size_t)e * 2 + 1];
+        dvS[(size_t)c * ME + i] = dvE[e]; idcS[(size_t)c * ME + i] = idcE[e]; ms2S[(size_t)c * ME + i] = ms2E[e]; ms4S[(size_t)c * ME + i] = ms4E[e];
+        nAdvS[(size_t)c * ME + i] = nAdvE[e];
+        for (int j = 0; j < nAdvE[e] && j < nap; ++j) {
+          const size_t d = ((size_t)c * ME + i) * nap + j;
+          advS[d] = advE[(size_t)e * NA + j]; acS[d] = acE[(size_t)e * NA + j]; a3S[d] = a3E[(size_t)e * NA + j];
+        }
+      }
+    if ((rc = dev_upload<int>(h, &V.edgesOnCell, eoc))) return rc;
+    if ((rc = dev_upload<int>(h, &V.c1OnCell, c1))) return rc;
+    if ((rc = dev_upload<int>(h, &V.c2OnCell, c2))) return rc;
+    if ((rc = dev_upload<double>(h, &V.dvOnCell, dvS))) return rc;
+    if ((rc = dev_upload<double>(h, &V.invDcOnCell, idcS))) return rc;
+    if ((rc = dev_upload<double>(h, &V.ms2OnCell, ms2S))) return rc;
+    if ((rc = dev_upload<double>(h, &V.ms4OnCell, ms4S))) return rc;
+    if ((rc = dev_upload<int>(h, &V.nAdvOnCell, nAdvS))) return rc;
+    if ((rc = dev_upload<int>(h, &V.advCellOnCell, advS))) return rc;
+    if ((rc = dev_upload<double>(h, &V.advCoefOnCell, acS))) return rc;
+    if ((rc = dev_upload<double>(h, &V.adv3OnCell, a3S))) return rc;
+    // per-edge {cell1, cell2, vertex1, vertex2} in one 16-byte word, and the divergence-damping skip flag
+    const std::vector<int> voe = build_ids(m->verticesOnEdge, nE, 2, eNew, nV, vNew, pol);
+    const std::vector<unsigned char> shr = build_vals<unsigned char, uint8_t>(m->isShared, nC, 1, cNew);
+    std::vector<int4> ecv((size_t)nE + 1);
+    std::vector<unsigned char> skip((size_t)nE + 1, 0);
+    for (int e = 0; e <= nE; ++e) {
+      ecv[e] = make_int4(coe[(size_t)e * 2], coe[(size_t)e * 2 + 1], voe[(size_t)e * 2], voe[(size_t)e * 2 + 1]);
+      skip[e] = (shr[coe[(size_t)e * 2]] && shr[coe[(size_t)e * 2 + 1]]) ? 1 : 0;
+    }
+    if ((rc = dev_upload<int4>(h, &V.ecv, ecv))) return rc;
+    if ((rc = dev_upload<unsigned char>(h, &V.divdampSkip, skip))) return rc;
+    // dcEdge of each vertex's three edges
+    const std::vector<int> eov = build_ids(m->edgesOnVertex, nV, VD, vNew, nE, eNew, pol);
+    const std::vector<double> dcE = build_vals<double, double>(m->dcEdge, nE, 1, eNew);
+    std::vector<double> dcV((size_t)(nV + 1) * VD, 0.0);
+    for (size_t i = 0; i < dcV.size(); ++i) dcV[i] = dcE[eov[i]];
+    if ((rc = dev_upload<double>(h, &V.dcOnVertex, dcV))) return rc;
+  }
   UP_IDS(verticesOnCell, m->verticesOnCell, nC, ME, cNew, nV, vNew);
   UP_INT(kiteForCell, m->kiteForCell, nC, ME, cNew);
   UP_DBL(edgesOnCellSign, m->edgesOnCellSign, nC, ME, cNew);

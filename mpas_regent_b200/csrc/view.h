@@ -2,9 +2,13 @@
 //
 // Layout in HBM (DESIGN.md "Data layout"):
 //   3-D field            : double[(N+1)][LP]        levels contiguous, LP = roundup(nVertLevels+1, 4)
-//                          (every column starts on a 32-byte sector), entity N is the zero pad entity
+//                          (every column starts on a 32-byte sector, level pairs are 16-byte aligned
+//                          -> 128-bit loads), entity N is the zero pad entity
 //   array-typed 3-D field: double[slots][(N+1)][LP] (slot-major: each slot is its own 3-D field)
 //   static per-entity    : T[(N+1)][width]          resolved 0-based ids, pad row N points at pads
+//   per-(cell, slot)     : copies of the per-edge statics a cell needs for its edgesOnCell slots
+//                          (dvEdge, invDcEdge, cellsOnEdge, meshScaling, advection lists), so a
+//                          cell kernel reaches its neighbour columns after ONE level of index loads
 // Entities are stored in space-filling-curve order; the permutation lives on the host side of the
 // library and in perm arrays used only by upload/download/pack/unpack.
 #pragma once
@@ -16,25 +20,35 @@ struct View {
   // dimensions
   int nCells, nEdges, nVertices, L, LP;
   int maxEdges, maxEdges2, vertexDegree, nAdv;
+  int MEP;           // edgesOnCell row pitch (ints), multiple of 4
+  int NAP;           // advection list pitch (entries per (cell, slot)), even
   size_t cellSlot;   // (nCells+1)*LP: distance between slots of a cell array-typed field
   // 3-D fields + vertical fields, by field id
   double* f[MPASB200_F_COUNT];
   // cell statics
-  const int* nEdgesOnCell; const int* edgesOnCell; const int* verticesOnCell; const int* kiteForCell;
+  const int* nEdgesOnCell; const int* edgesOnCell /* [c][MEP] */; const int* verticesOnCell; const int* kiteForCell;
+  const int* c1OnCell; const int* c2OnCell;            // [c][MEP]: cellsOnEdge[e][0/1] of the cell's slot-i edge
   const double* edgesOnCellSign; const double* edgesOnCell_sign; const double* invAreaCell; const double* cosLatCell;
+  const double* dvOnCell; const double* invDcOnCell; const double* ms2OnCell; const double* ms4OnCell;   // [c][maxEdges]
   const double* defc_a; const double* defc_b; const int* bdyMaskCell; const double* specZoneMaskCell;
   const unsigned char* isShared; const unsigned char* inCpr;
+  const int* nAdvOnCell;       // [c][maxEdges]
+  const int* advCellOnCell;    // [c][maxEdges][NAP]
+  const double* advCoefOnCell; const double* adv3OnCell;   // [c][maxEdges][NAP]
   // edge statics
+  const int4* ecv;             // {cell1, cell2, vertex1, vertex2}
   const int* cellsOnEdge; const int* verticesOnEdge; const int* nEdgesOnEdge; const int* edgesOnEdge_ECP; const int* edgesOnEdge;
   const double* weightsOnEdge; const double* dcEdge; const double* dvEdge; const double* invDcEdge; const double* invDvEdge;
   const double* cosAngleEdge; const double* sinAngleEdge; const double* cosLatEdge;
   const int* nAdvCellsForEdge; const int* advCellsForEdge; const double* adv_coefs; const double* adv_coefs_3rd;
   const double* meshScalingDel2; const double* meshScalingDel4; const double* specZoneMaskEdge;
+  const unsigned char* divdampSkip;   // isShared[cell1] && isShared[cell2]   (dynamics_tasks.rg:1750)
   // vertex statics
   const int* edgesOnVertex; const double* edgesOnVertexSign; const double* edgesOnVertex_sign; const double* kiteAreasOnVertex;
+  const double* dcOnVertex;    // [v][3]: dcEdge of the vertex's edges
   const double* fVertex; const double* invAreaTriangle;
   // scratch (library-private, not region fields)
-  double* scr_rs; double* scr_ts;     // horizontal flux parts of rs/ts in the acoustic step  [(nCells+1)][LP]
+  double* scr_rs; double* scr_ts;     // horizontal flux parts of rs/ts in the two-kernel acoustic step  [(nCells+1)][LP]
 };
 
 // scalar constants a task needs (filled on the host from MpasConfig + task arguments)
@@ -42,7 +56,7 @@ struct DynTendParams {
   int rk_step; int mixing; int mix_full; int rayleigh_u; int visc4_on; int cam_on; int vmix_u_on; int vmix_t_on;
   double kdiff_scale;      // (c_s*len_disp)^2
   double kdiff_cap;        // 0.01*len_disp^2 * (1/dt)
-  double cam_base;         // 2.0833*len_disp*cam_coef
+  double cam_base;         // unused (kept for layout stability)
   double h_mom_eddy_visc4, h_theta_eddy_visc4, v_mom_eddy_visc2, v_theta_eddy_visc2;
   double prandtl_inv, r_earth, inv_r_earth, omega2 /* 2*omega */, gravity, del4u_div_factor;
   double rayleigh_coef_inverse; int rayleigh_levels;
