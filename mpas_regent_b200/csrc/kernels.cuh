@@ -759,31 +759,30 @@ __global__ void k_smlstep(const View V, int nRelaxZone) {
 // at every point, Q25); the back-substitution is absent (Q28); cr.theta_m stands in for tend_rt and
 // cr.w for tend_rw (Q27).  Differs from the literal left-to-right evaluation only by the regrouping
 // of terms inside one level (a few ulp; checked against the oracle at 1e-12).
-struct AcLevel {   // per-level quantities of the affine form
-  double P, Q;
-};
-DI AcLevel ac_level(int k, double dts, double resm, double rw_old_k, double w_k, double ts, double rs, double rt_old, double rho_old,
+// Per-level pieces of the affine form.  Everything is local to the level except (rp0m, rt0m), the
+// constant parts of level k-1's new rho_pp / rtheta_pp.
+struct AcTerms { double A0, A1, A2, al, r1, r2, r3, Q; };
+DI AcTerms ac_terms(double dts, double resm, double rw_old_k, double w_k, double ts, double rs, double rt_old, double rho_old,
                     double zz_k, double zz_m, double cofwt_k, double cofwt_m, double rz_k, double rz_m, double cofwz_k, double cofwr_k,
-                    double fm, double fp, double dsk, double rws_k, double rw_k, double rp0m, double rt0m, double rp1m, double rt1m,
-                    double a_k, double al_k) {
-  AcLevel o;
-  if (k == 0) { o.P = rw_old_k; o.Q = 0.0; return o; }
-  const double r3 = rws_k - rw_k;
-  const double r1 = r3 - dts * dsk * (fm * zz_k + fp * zz_m) * (fm * rz_k + fp * rz_m) * w_k;       // :1682-1684
-  const double r2 = 1.0 + dts * dsk;                                                                // :1685
+                    double fm, double fp, double dsk, double rws_k, double rw_k, double rp1m, double rt1m, double a_k, double al_k) {
+  AcTerms o;
+  o.r3 = rws_k - rw_k;
+  o.r1 = o.r3 - dts * dsk * (fm * zz_k + fp * zz_m) * (fm * rz_k + fp * rz_m) * w_k;                 // :1682-1684
+  o.r2 = 1.0 + dts * dsk;                                                                           // :1685
   // terms of :1662-1667 that do not involve level k-1's new values
-  const double A0 = rw_old_k + (dts * w_k - cofwz_k * ((zz_k * ts - zz_m * 0.0) + resm * (zz_k * rt_old))
-                                - cofwr_k * ((rs + 0.0) + resm * rho_old) + cofwt_k * (ts + resm * rt_old));
-  const double A1 = resm * (cofwz_k * zz_m + cofwt_m);        // coefficient of rtheta_pp_new(k-1)
-  const double A2 = resm * cofwr_k;                           // coefficient of -rho_pp_new(k-1)
-  const double B0 = A0 + A1 * rt0m - A2 * rp0m;
-  const double B1 = A1 * rt1m - A2 * rp1m - a_k;                                                    // :1670
-  o.P = (B0 * al_k + r1) / r2 - r3;                                                                 // :1671, :1682-1686
-  o.Q = B1 * al_k / r2;
+  o.A0 = rw_old_k + (dts * w_k - cofwz_k * ((zz_k * ts - zz_m * 0.0) + resm * (zz_k * rt_old))
+                     - cofwr_k * ((rs + 0.0) + resm * rho_old) + cofwt_k * (ts + resm * rt_old));
+  o.A1 = resm * (cofwz_k * zz_m + cofwt_m);        // coefficient of rtheta_pp_new(k-1)
+  o.A2 = resm * cofwr_k;                           // coefficient of -rho_pp_new(k-1)
+  o.al = al_k;                                                                                      // :1671
+  o.Q = (o.A1 * rt1m - o.A2 * rp1m - a_k) * al_k / o.r2;                                            // :1670
   return o;
 }
+DI double ac_P(const AcTerms& t, double rp0m, double rt0m) {
+  return ((t.A0 + t.A1 * rt0m - t.A2 * rp0m) * t.al + t.r1) / t.r2 - t.r3;                          // :1682-1686
+}
 template <bool S0>
-__global__ void k_acoustic(const View V, double dts, double epssm, double resm) {
+__global__ void __launch_bounds__(256, 3) k_acoustic(const View V, double dts, double epssm, double resm) {
   extern __shared__ double sm[];
   PAIR_THREAD(V.nCells)
   const int TS = LP + 2;
@@ -796,18 +795,22 @@ __global__ void k_acoustic(const View V, double dts, double epssm, double resm) 
     if (k0 == L) { FLD(wwAvg)[ix] = 0; FLD(rw_p)[ix] = 0; }
     if (k1 == L) { FLD(wwAvg)[ix + 1] = 0; FLD(rw_p)[ix + 1] = 0; }
   }
-  D2 rs = bc(0), ts = bc(0), rw_old = bc(0), rw_oldp = bc(0), rho_old = bc(0), rt_old = bc(0), ww_old = bc(0);
-  D2 coftz = bc(0), coftz_p = bc(0), cofrz = bc(0), rdzw = bc(0), w2 = bc(0), tr = bc(0), tm2 = bc(0);
+  D2 rs = bc(0), ts = bc(0), rw_old = bc(0);
+  double rw_oldp_y = 0.0;
+  AcTerms t0;                      // level k0's terms wait for level k0-1 (another thread) behind the barrier
+  t0.A0 = t0.A1 = t0.A2 = t0.al = t0.r1 = t0.r3 = t0.Q = 0.0; t0.r2 = 1.0;
   if (m0) {
     const double* tm = FLD(theta_m);
-    cofrz = ld2(FLD(cofrz), k0); rdzw = ld2(FLD(rdzw), k0);
+    const D2 cofrz = ld2(FLD(cofrz), k0), rdzw = ld2(FLD(rdzw), k0);
+    D2 rho_old = bc(0), rt_old = bc(0), rw_oldp = bc(0);
     if (!S0) {
       rw_old = ld2(FLD(rw_p), ix); rw_oldp = above(FLD(rw_p), ix, k0, L, rw_old);
-      rho_old = ld2(FLD(rho_pp), ix); rt_old = ld2(FLD(rtheta_pp), ix); ww_old = ld2(FLD(wwAvg), ix);
+      rho_old = ld2(FLD(rho_pp), ix); rt_old = ld2(FLD(rtheta_pp), ix);
     }
+    rw_oldp_y = rw_oldp.y;
     st2m(FLD(rtheta_pp_old), ix, S0 ? bc(0.0) : rt_old, m0, m1);                                      // :1615-1623
-    w2 = ld2(FLD(w), ix); tr = ld2(FLD(tend_rho), ix); tm2 = ld2(tm, ix);
     if (!spec) {
+      const D2 w2 = ld2(FLD(w), ix), tr = ld2(FLD(tend_rho), ix), tm2 = ld2(tm, ix);
       const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
       const double* ru_p = FLD(ru_p);
       const double inva = V.invAreaCell[x];
@@ -819,46 +822,48 @@ __global__ void k_acoustic(const View V, double dts, double epssm, double resm) 
         rs -= flux;
         ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
       }
-      coftz = ld2(FLD(coftz), ix); coftz_p = above(FLD(coftz), ix, k0, L, coftz);
+      const D2 coftz = ld2(FLD(coftz), ix), coftz_p = above(FLD(coftz), ix, k0, L, coftz);
       rs = rho_old + dts * tr + rs - cofrz * resm * (rw_oldp - rw_old);                               // :1657
       ts = rt_old + dts * tm2 + ts - resm * rdzw * (coftz_p * rw_oldp - coftz * rw_old);              // :1658
-      // new rho_pp / rtheta_pp of THIS level as affine functions of x(k):  rp0 + cofrz*x,  rt0 + rdzw*coftz*x
+      // new rho_pp / rtheta_pp of a level as affine functions of x(k):  rp0 + cofrz*x,  rt0 + rdzw*coftz*x
       const D2 rp0 = rs - cofrz * rw_oldp, rt0 = ts - rdzw * (coftz_p * rw_oldp);
-      s_rp0[k0] = rp0.x; s_rt0[k0] = rt0.x;
-      if (m1) { s_rp0[k1] = rp0.y; s_rt0[k1] = rt0.y; }
+      const D2 zz = ld2(FLD(zz), ix), zzm = below(FLD(zz), ix, k0, zz);
+      const D2 cwt = ld2(FLD(cofwt), ix), cwtm = below(FLD(cofwt), ix, k0, cwt);
+      const D2 rz = ld2(FLD(rho_zz), ix), rzm = below(FLD(rho_zz), ix, k0, rz);
+      const D2 cwz = ld2(FLD(cofwz), ix), cwr = ld2(FLD(cofwr), ix);
+      const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0);
+      const D2 ds = ld2(FLD(dss), ix), rws = ld2(FLD(rw_save), ix), rwv = ld2(FLD(rw), ix);
+      const D2 at = ld2(FLD(a_tri), ix), al = ld2(FLD(alpha_tri), ix);
+      if (k0 > 0) {
+        const double cofrz_m = FLD(cofrz)[k0 - 1], rdzw_m = FLD(rdzw)[k0 - 1], coftz_m = FLD(coftz)[ix - 1];
+        t0 = ac_terms(dts, resm, rw_old.x, w2.x, ts.x, rs.x, rt_old.x, rho_old.x, zz.x, zzm.x, cwt.x, cwtm.x, rz.x, rzm.x, cwz.x, cwr.x,
+                      fm.x, fp.x, ds.x, rws.x, rwv.x, cofrz_m, rdzw_m * coftz_m, at.x, al.x);
+        s_Q[k0] = t0.Q;
+      } else { s_P[0] = rw_old.x; s_Q[0] = 0.0; }
+      if (m1) {                     // level k1's partner is this thread's own level k0
+        const AcTerms t1 = ac_terms(dts, resm, rw_old.y, w2.y, ts.y, rs.y, rt_old.y, rho_old.y, zz.y, zzm.y, cwt.y, cwtm.y, rz.y, rzm.y,
+                                    cwz.y, cwr.y, fm.y, fp.y, ds.y, rws.y, rwv.y, cofrz.x, rdzw.x * coftz.x, at.y, al.y);
+        s_P[k1] = ac_P(t1, rp0.x, rt0.x); s_Q[k1] = t1.Q;
+        s_rp0[k1] = rp0.y; s_rt0[k1] = rt0.y;
+      }
     }
   }
   __syncthreads();
-  if (m0 && !spec) {
-    const D2 zz = ld2(FLD(zz), ix), zzm = below(FLD(zz), ix, k0, zz);
-    const D2 cwt = ld2(FLD(cofwt), ix), cwtm = below(FLD(cofwt), ix, k0, cwt);
-    const D2 rz = ld2(FLD(rho_zz), ix), rzm = below(FLD(rho_zz), ix, k0, rz);
-    const D2 cwz = ld2(FLD(cofwz), ix), cwr = ld2(FLD(cofwr), ix);
-    const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0);
-    const D2 ds = ld2(FLD(dss), ix), rws = ld2(FLD(rw_save), ix), rwv = ld2(FLD(rw), ix);
-    const D2 at = ld2(FLD(a_tri), ix), al = ld2(FLD(alpha_tri), ix);
-    // level k-1 partners: (rp0, rt0) from smem; rp1 = cofrz(k-1), rt1 = rdzw(k-1)*coftz(k-1)
-    const double cofrz_m = k0 > 0 ? FLD(cofrz)[k0 - 1] : 0.0, rdzw_m = k0 > 0 ? FLD(rdzw)[k0 - 1] : 0.0;
-    const double coftz_m = k0 > 0 ? FLD(coftz)[ix - 1] : 0.0;
-    const AcLevel l0 = ac_level(k0, dts, resm, rw_old.x, w2.x, ts.x, rs.x, rt_old.x, rho_old.x, zz.x, zzm.x, cwt.x, cwtm.x, rz.x, rzm.x,
-                                cwz.x, cwr.x, fm.x, fp.x, ds.x, rws.x, rwv.x, k0 > 0 ? s_rp0[k0 - 1] : 0.0, k0 > 0 ? s_rt0[k0 - 1] : 0.0,
-                                cofrz_m, rdzw_m * coftz_m, at.x, al.x);
-    s_P[k0] = l0.P; s_Q[k0] = l0.Q;
-    if (m1) {
-      const AcLevel l1 = ac_level(k1, dts, resm, rw_old.y, w2.y, ts.y, rs.y, rt_old.y, rho_old.y, zz.y, zzm.y, cwt.y, cwtm.y, rz.y, rzm.y,
-                                  cwz.y, cwr.y, fm.y, fp.y, ds.y, rws.y, rwv.y, s_rp0[k0], s_rt0[k0], cofrz.x, rdzw.x * coftz.x, at.y, al.y);
-      s_P[k1] = l1.P; s_Q[k1] = l1.Q;
-    }
-  }
+  if (m0 && !spec && k0 > 0) s_P[k0] = ac_P(t0, s_rp0[k0 - 1], s_rt0[k0 - 1]);
   __syncthreads();
-  if (inx && !spec && k0 == 0) {            // the sweep: one multiply-add per level, levels ascending (M4)
+  if (inx && !spec && k0 == 0) {            // the sweep: one fused multiply-add per level, levels ascending (M4)
     double xv = s_P[0];
-    for (int kk = 1; kk < L; ++kk) { xv = s_P[kk] + s_Q[kk] * xv; s_P[kk] = xv; }
+#pragma unroll 4
+    for (int kk = 1; kk < L; ++kk) { xv = __fma_rn(s_Q[kk], xv, s_P[kk]); s_P[kk] = xv; }
   }
   __syncthreads();
   if (!m0) return;
-  D2 rw_new, rho_new, rt_new, ww_new = ww_old;
+  const D2 ww_old = S0 ? bc(0.0) : ld2(FLD(wwAvg), ix);
+  D2 rw_new, rho_new, rt_new, ww_new;
   if (!spec) {
+    const D2 cofrz = ld2(FLD(cofrz), k0), rdzw = ld2(FLD(rdzw), k0);
+    const D2 coftz = ld2(FLD(coftz), ix), coftz_p = above(FLD(coftz), ix, k0, L, coftz);
+    const D2 rw_oldp = mk(rw_old.y, rw_oldp_y);
     rw_new = mk(s_P[k0], m1 ? s_P[k1] : 0.0);
     const D2 wa = ww_old + 0.5 * (1.0 - epssm) * rw_old;                                              // :1661
     const D2 wb = wa + 0.5 * (1.0 + epssm) * rw_new;                                                  // :1689
@@ -866,9 +871,10 @@ __global__ void k_acoustic(const View V, double dts, double epssm, double resm) 
     rho_new = rs - cofrz * (rw_oldp - rw_new);                                                        // :1694
     rt_new = ts - rdzw * (coftz_p * rw_oldp - coftz * rw_new);                                        // :1695-1696
   } else {                                                                                            // :1698-1703
-    rho_new = rho_old + dts * tr;
-    rt_new = rt_old + dts * tm2;
-    rw_new = rw_old + dts * w2;
+    const D2 rho_old = S0 ? bc(0.0) : ld2(FLD(rho_pp), ix), rt_old = S0 ? bc(0.0) : ld2(FLD(rtheta_pp), ix);
+    rho_new = rho_old + dts * ld2(FLD(tend_rho), ix);
+    rt_new = rt_old + dts * ld2(FLD(theta_m), ix);
+    rw_new = rw_old + dts * ld2(FLD(w), ix);
     ww_new = ww_old + 0.5 * (1.0 + epssm) * rw_new;
   }
   st2m(FLD(rho_pp), ix, rho_new, m0, m1); st2m(FLD(rtheta_pp), ix, rt_new, m0, m1);
@@ -1123,4 +1129,106 @@ __global__ void k_unpack(const PackArgs A, const int* __restrict__ idx, int n, i
   const int k = threadIdx.x; const int i = blockIdx.x * blockDim.y + threadIdx.y; const int fi = blockIdx.y;
   if (i >= n || k >= L1) return;
   A.f[fi][(size_t)idx[i] * LP + k] = buf[((size_t)fi * n + i) * L1 + k];
+}
+
+// ============================================================================================
+// EXPERIMENTAL variants of k_divdamp used to measure which latency-hiding structure pays on B200
+// (profiles/r1_divdamp_variants.md).  Selected through mpasb200_debug_divdamp only.
+DI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// V1: skip flag and ecv fetched together, own-column load issued before the dependent gathers
+__global__ void k_divdamp_v1(const View V, double coef_divdamp) {
+  PAIR_THREAD(V.nEdges)
+  if (!m0) return;
+  const unsigned char skip = V.divdampSkip[x];
+  const int4 cv = V.ecv[x];
+  const D2 r = ld2(FLD(ru_p), ix);
+  const double sz = 1.0 - V.specZoneMaskEdge[x];
+  if (skip) return;
+  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
+  const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
+  st2m(FLD(ru_p), ix, r + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), m0, m1);
+}
+// V2: V1 + every block prefetches the index words of the block that will run ~one wave later into L2
+__global__ void k_divdamp_v2(const View V, double coef_divdamp, int ahead) {
+  PAIR_THREAD(V.nEdges)
+  if (threadIdx.x == 0) {
+    const long xa = (long)x + (long)ahead * blockDim.y;
+    if (xa < V.nEdges) { prefetch_l2(&V.ecv[xa]); prefetch_l2(&V.divdampSkip[xa]); prefetch_l2(&V.specZoneMaskEdge[xa]); }
+  }
+  if (!m0) return;
+  const unsigned char skip = V.divdampSkip[x];
+  const int4 cv = V.ecv[x];
+  const D2 r = ld2(FLD(ru_p), ix);
+  const double sz = 1.0 - V.specZoneMaskEdge[x];
+  if (skip) return;
+  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
+  const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
+  st2m(FLD(ru_p), ix, r + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), m0, m1);
+}
+// V3: two edges per thread (x and x + half), all 14 gathers in flight together
+__global__ void k_divdamp_v3(const View V, double coef_divdamp) {
+  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;
+  const int LP = V.LP, L = V.L;
+  const int half = (V.nEdges + 1) / 2;
+  const int xa = blockIdx.x * blockDim.y + threadIdx.y, xb = xa + half;
+  const bool ina = xa < half && k0 < L, inb = xb < V.nEdges && xa < half && k0 < L;
+  if (!ina) return;
+  const bool m1 = k1 < L;
+  const size_t ia = (size_t)xa * LP + k0, ib = (size_t)(inb ? xb : xa) * LP + k0;
+  const unsigned char sa = V.divdampSkip[xa], sb = inb ? V.divdampSkip[xb] : 1;
+  const int4 ca = V.ecv[xa], cb = V.ecv[inb ? xb : xa];
+  const D2 ra = ld2(FLD(ru_p), ia), rb = ld2(FLD(ru_p), ib);
+  const double za = 1.0 - V.specZoneMaskEdge[xa], zb = 1.0 - V.specZoneMaskEdge[inb ? xb : xa];
+  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
+  const D2 a1 = G2(rpp, ca.x), b1 = G2(rppo, ca.x), a2 = G2(rpp, ca.y), b2 = G2(rppo, ca.y), t1 = G2(tm, ca.x), t2 = G2(tm, ca.y);
+  const D2 c1 = G2(rpp, cb.x), d1 = G2(rppo, cb.x), c2 = G2(rpp, cb.y), d2 = G2(rppo, cb.y), u1 = G2(tm, cb.x), u2 = G2(tm, cb.y);
+  if (!sa) st2m(FLD(ru_p), ia, ra + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * za / (t1 + t2), true, m1);
+  if (!sb) st2m(FLD(ru_p), ib, rb + coef_divdamp * ((-(c2 - d2)) - (-(c1 - d1))) * zb / (u1 + u2), true, m1);
+}
+// V4: persistent blocks looping over edge tiles, the next tile's index words are loaded before the
+// current tile's gathers are consumed
+__global__ void k_divdamp_v4(const View V, double coef_divdamp) {
+  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;
+  const int LP = V.LP, L = V.L;
+  if (k0 >= L) return;
+  const bool m1 = k1 < L;
+  const int stride = gridDim.x * blockDim.y;
+  int x = blockIdx.x * blockDim.y + threadIdx.y;
+  if (x >= V.nEdges) return;
+  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
+  int4 cv = V.ecv[x]; unsigned char skip = V.divdampSkip[x]; double sz = 1.0 - V.specZoneMaskEdge[x];
+  D2 r = ld2(FLD(ru_p), (size_t)x * LP + k0);
+  while (true) {
+    const int xn = x + stride;
+    const bool more = xn < V.nEdges;
+    const int xs = more ? xn : x;
+    const int4 cvn = V.ecv[xs]; const unsigned char skn = V.divdampSkip[xs]; const double szn = 1.0 - V.specZoneMaskEdge[xs];
+    const D2 rn = ld2(FLD(ru_p), (size_t)xs * LP + k0);
+    if (!skip) {
+      const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
+      st2m(FLD(ru_p), (size_t)x * LP + k0, r + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), true, m1);
+    }
+    if (!more) break;
+    x = xn; cv = cvn; skip = skn; sz = szn; r = rn;
+  }
+}
+// V5: four levels per thread (two 128-bit words), half the threads per column
+__global__ void k_divdamp_v5(const View V, double coef_divdamp) {
+  const int k0 = 4 * (int)threadIdx.x;
+  const int LP = V.LP, L = V.L;
+  const int x = blockIdx.x * blockDim.y + threadIdx.y;
+  if (x >= V.nEdges || k0 >= L) return;
+  const size_t ix = (size_t)x * LP + k0;
+  const unsigned char skip = V.divdampSkip[x];
+  const int4 cv = V.ecv[x];
+  const D2 r0 = ld2(FLD(ru_p), ix), r1 = ld2(FLD(ru_p), ix + 2);
+  const double sz = 1.0 - V.specZoneMaskEdge[x];
+  if (skip) return;
+  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
+  const size_t i1 = (size_t)cv.x * LP + k0, i2 = (size_t)cv.y * LP + k0;
+  const D2 a1 = ld2(rpp, i1), b1 = ld2(rppo, i1), a2 = ld2(rpp, i2), b2 = ld2(rppo, i2), t1 = ld2(tm, i1), t2 = ld2(tm, i2);
+  const D2 A1 = ld2(rpp, i1 + 2), B1 = ld2(rppo, i1 + 2), A2 = ld2(rpp, i2 + 2), B2 = ld2(rppo, i2 + 2), T1 = ld2(tm, i1 + 2), T2 = ld2(tm, i2 + 2);
+  st2m(FLD(ru_p), ix, r0 + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), true, k0 + 1 < L);
+  st2m(FLD(ru_p), ix + 2, r1 + coef_divdamp * ((-(A2 - B2)) - (-(A1 - B1))) * sz / (T1 + T2), k0 + 2 < L, k0 + 3 < L);
 }

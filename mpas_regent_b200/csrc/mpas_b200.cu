@@ -884,6 +884,26 @@ int mpasb200_field_by_name(const char* name) {
   for (int i = 0; i < MPASB200_F_COUNT; ++i) if (!std::strcmp(name, kFields[i].name)) return i;
   return -1;
 }
+// Experimental launch variants of the divergence-damping kernel (not part of the public header): used by
+// profiles/ scripts to measure latency-hiding structures.  variant 0 = production kernel.
+int mpasb200_debug_divdamp(mpasb200_t* h, int variant, double dts, int arg) {
+  REQUIRE_MESH();
+  Entry en(h, -1);
+  const double coef = 2.0 * h->c.config_smdiv * h->c.config_len_disp * (1.0 / dts);
+  const int nE = h->nEdges, T = h->LP / 2, C = h->CPB;
+  switch (variant) {
+    case 0: LAUNCH(k_divdamp, nE, 0, h->V, coef); break;
+    case 1: LAUNCH(k_divdamp_v1, nE, 0, h->V, coef); break;
+    case 2: LAUNCH(k_divdamp_v2, nE, 0, h->V, coef, arg); break;
+    case 3: { KTimer kt(h, "k_divdamp_v3"); const int half = (nE + 1) / 2;
+              k_divdamp_v3<<<(half + C - 1) / C, dim3(T, C), 0, h->stream>>>(h->V, coef); h->launches++; } break;
+    case 4: { KTimer kt(h, "k_divdamp_v4"); k_divdamp_v4<<<arg, dim3(T, C), 0, h->stream>>>(h->V, coef); h->launches++; } break;
+    case 5: { KTimer kt(h, "k_divdamp_v5"); const int T4 = h->LP / 4, C4 = 256 / T4;
+              k_divdamp_v5<<<(nE + C4 - 1) / C4, dim3(T4, C4), 0, h->stream>>>(h->V, coef); h->launches++; } break;
+    default: return fail(h, MPASB200_EINVAL, "unknown variant");
+  }
+  return post_launch(h);
+}
 int mpasb200_enable_kernel_timing(mpasb200_t* h, int on) {
   if (!h) return MPASB200_EINVAL;
   std::unique_lock<std::mutex> lk(h->mu);

@@ -1,0 +1,262 @@
+"""One process per GPU: owned/ghost partitions of the mesh and the halo exchanges of the RK3 step.
+
+The reference computes the owned / ghost partitions (mesh_loading.rg:399-483) but never runs more
+than one of them (main.rg:54-55; CURIS_2021_DependentPartitioning_BearE.md:50-58).  Here every rank
+holds [owned | ghost ring 1 | ghost ring 2] cells plus all their edges and vertices, runs every task
+on all of them (ghost entities are recomputed redundantly) and repairs the ghost values that the
+stencils invalidate with packed neighbour exchanges.  With 2 rings the literal dataflow needs three
+kinds of exchange per RK stage:
+
+    after atm_compute_dyn_tend            cells    w                       (read at cellsOnEdge by the next stage's tend_u)
+    after every atm_advance_acoustic_step cells    rtheta_pp, rtheta_pp_old (read at cellsOnEdge by divergence damping)
+    after atm_compute_solve_diagnostics   cells    ke, divergence ; edges pv_edge, v ; vertices vorticity
+
+Everything else on the path is pointwise or column-local and keeps ghost values valid.  Owned results
+are bit-identical to the single-partition run: each entity sums over its own slots in the same order
+whatever rank computes it (tests/test_parallel.py, CPU: world_size-2 gloo; GPU: tests/test_parity_gpu.py).
+
+The wire is torch.distributed (NCCL send/recv over NVLink on the GPU box, gloo in the CPU tests);
+pack / unpack run in libmpas_b200 (k_pack / k_unpack) on the stream that carries the step.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi, partition
+from ._abi import CELL, EDGE, FIELD_ENTITY, FIELD_SLOTS, VERTEX
+from .dynamics import TaskAPI
+
+ENT = {"cell": CELL, "edge": EDGE, "vertex": VERTEX}
+
+#: task name (hook key) -> {entity: [fields]} exchanged right after it
+EXCHANGES: Dict[str, Dict[str, List[str]]] = {
+    "compute_dyn_tend": {"cell": ["w"]},
+    "advance_acoustic_step": {"cell": ["rtheta_pp", "rtheta_pp_old"]},
+    "compute_solve_diagnostics": {"cell": ["ke", "divergence"], "edge": ["pv_edge", "v"], "vertex": ["vorticity"]},
+}
+
+
+def split_state(fields: Dict[str, np.ndarray], lm: partition.LocalMesh) -> Dict[str, np.ndarray]:
+    """restrict global 3-D fields to a rank's local entities (rows in local order)."""
+    rows = {CELL: lm.cells, EDGE: lm.edges, VERTEX: lm.vertices}
+    out = {}
+    for k, a in fields.items():
+        if k not in FIELD_ENTITY:
+            continue
+        out[k] = np.ascontiguousarray(a[rows[FIELD_ENTITY[k]]])
+    return out
+
+
+class Exchanger:
+    """moves ghost columns of a set of fields; subclasses provide the wire."""
+
+    def exchange(self, spec: Dict[str, List[str]]):
+        raise NotImplementedError
+
+
+class InProcessExchanger:
+    """All ranks live in one process (tests, and the single-GPU emulation of an N-rank run): ghost columns are
+    copied owner -> holder through download_field / upload_field."""
+
+    def __init__(self, backends: Sequence[TaskAPI], locals_: Sequence[partition.LocalMesh]):
+        self.b, self.l = list(backends), list(locals_)
+
+    def exchange(self, spec: Dict[str, List[str]]):
+        for ent, names in spec.items():
+            for name in names:
+                arrs = [b.download_field(name) for b in self.b]
+                for h, lm in enumerate(self.l):
+                    for o, ridx in lm.recv[ent].items():
+                        arrs[h][ridx] = arrs[o][self.l[o].send[ent][h]]
+                for b, a in zip(self.b, arrs):
+                    b.upload_field(name, a)
+
+
+class HostDistExchanger(Exchanger):
+    """torch.distributed with host tensors (gloo): the CPU test of the N > 1 plumbing.  Works with any TaskAPI
+    backend through download_field / upload_field."""
+
+    def __init__(self, backend: TaskAPI, lm: partition.LocalMesh):
+        import torch.distributed as dist
+        self.dist, self.b, self.lm = dist, backend, lm
+
+    def exchange(self, spec: Dict[str, List[str]]):
+        import torch
+        dist = self.dist
+        for ent, names in spec.items():
+            arrs = {n: self.b.download_field(n) for n in names}
+            ops, recvs = [], []
+            for peer in sorted(set(self.lm.send[ent]) | set(self.lm.recv[ent])):
+                if peer in self.lm.send[ent]:
+                    sidx = self.lm.send[ent][peer]
+                    buf = torch.from_numpy(np.ascontiguousarray(np.stack([arrs[n][sidx] for n in names])))
+                    ops.append(dist.P2POp(dist.isend, buf, peer))
+                if peer in self.lm.recv[ent]:
+                    ridx = self.lm.recv[ent][peer]
+                    rbuf = torch.empty((len(names), len(ridx), arrs[names[0]].shape[1]), dtype=torch.float64)
+                    ops.append(dist.P2POp(dist.irecv, rbuf, peer))
+                    recvs.append((ridx, rbuf))
+            if ops:
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()
+            for ridx, rbuf in recvs:
+                a = rbuf.numpy()
+                for i, n in enumerate(names):
+                    arrs[n][ridx] = a[i]
+            for n in names:
+                self.b.upload_field(n, arrs[n])
+
+
+class NcclExchanger(Exchanger):
+    """GPU path: k_pack -> NCCL send/recv (NVLink) -> k_unpack, all ordered on the step's stream."""
+
+    def __init__(self, dyn, lm: partition.LocalMesh, stream):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.dyn, self.lm, self.stream = torch, dist, dyn, lm, stream
+        L1 = dyn.dims.nVertLevels + 1
+        self.L1 = L1
+        self.lists = {}
+        maxf = max(len(f) for spec in EXCHANGES.values() for f in spec.values())
+        self.sbuf, self.rbuf = {}, {}
+        for ent in ("cell", "edge", "vertex"):
+            for peer, idx in lm.send[ent].items():
+                self.lists[("s", ent, peer)] = dyn.register_list(ENT[ent], idx)
+                self.sbuf[(ent, peer)] = torch.empty(maxf * len(idx) * L1, dtype=torch.float64, device="cuda")
+            for peer, idx in lm.recv[ent].items():
+                self.lists[("r", ent, peer)] = dyn.register_list(ENT[ent], idx)
+                self.rbuf[(ent, peer)] = torch.empty(maxf * len(idx) * L1, dtype=torch.float64, device="cuda")
+        self.bytes_per_step = 0
+
+    def exchange(self, spec: Dict[str, List[str]]):
+        torch, dist, lm = self.torch, self.dist, self.lm
+        with torch.cuda.stream(self.stream):
+            ops, post = [], []
+            for ent, names in spec.items():
+                nf = len(names)
+                for peer in sorted(set(lm.send[ent]) | set(lm.recv[ent])):
+                    if peer in lm.send[ent]:
+                        n = len(lm.send[ent][peer])
+                        buf = self.sbuf[(ent, peer)][: nf * n * self.L1]
+                        self.dyn.pack(self.lists[("s", ent, peer)], names, buf.data_ptr())
+                        ops.append(dist.P2POp(dist.isend, buf, peer))
+                    if peer in lm.recv[ent]:
+                        n = len(lm.recv[ent][peer])
+                        rb = self.rbuf[(ent, peer)][: nf * n * self.L1]
+                        ops.append(dist.P2POp(dist.irecv, rb, peer))
+                        post.append((self.lists[("r", ent, peer)], names, rb))
+            if ops:
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()          # stream-ordered for NCCL: makes the current stream wait, not the host
+            for lid, names, rb in post:
+                self.dyn.unpack(lid, names, rb.data_ptr())
+
+
+class DistributedDynamics:
+    """atm_srk3 on one rank of an N-rank run: the reference's task sequence (rk_timestep.rg:378-481) with the
+    exchanges of EXCHANGES after the tasks that need them."""
+
+    def __init__(self, dyn: TaskAPI, exchanger):
+        self.dyn, self.ex = dyn, exchanger
+        self.t_init = 0.0
+
+    def _hook(self, name: str):
+        spec = EXCHANGES.get(name)
+        if spec:
+            self.ex.exchange(spec)
+
+    def init_diagnostics(self):
+        """atm_core_init's atm_compute_solve_diagnostics(..., -1) (atm_core.rg:31)."""
+        self.dyn.atm_compute_solve_diagnostics(False, -1)
+        self._hook("compute_solve_diagnostics")
+
+    def step(self, dt: float):
+        self.dyn.atm_srk3_by_tasks(dt, hook=self._hook)
+
+    # ---- bench helper: rank 0 builds + partitions the global problem, every rank loads its shard -------------
+    @classmethod
+    def for_bench(cls, n_cells: int, L: int, cfg, stream, rank: int, world: int):
+        import torch.distributed as dist
+        from . import dynamics
+        t0 = time.time()
+        shm = os.environ.get("MPAS_B200_SHARDS", "/dev/shm/mpas_b200_shards")
+        tag = os.path.join(shm, f"x1.{n_cells}_L{L}_w{world}")
+        if rank == 0:
+            import bench
+            mesh, st, _ = bench.build_inputs(n_cells, L)
+            shards = make_shards(st, world)
+            os.makedirs(tag, exist_ok=True)
+            for r, sh in enumerate(shards):
+                save_shard(os.path.join(tag, f"rank{r}"), sh)
+            del shards, st
+        dist.barrier()
+        sh = load_shard(os.path.join(tag, f"rank{rank}"))
+        lm, static, fields, vert = sh["lm"], sh["static"], sh["f"], sh["vert"]
+        dims = _abi.make_dims(len(lm.cells), len(lm.edges), len(lm.vertices), L)
+        dyn = dynamics.Dynamics(dims, cfg)
+        dyn.set_stream(stream.cuda_stream)
+        dyn.upload_mesh(static)
+        dyn.upload_state(fields, vert)
+        del fields
+        run = cls(dyn, NcclExchanger(dyn, lm, stream))
+        run.lm = lm
+        run.init_diagnostics()
+        run.t_init = time.time() - t0
+        return run
+
+
+# ---- shards --------------------------------------------------------------------------------------------------
+def make_shards(st, world: int, colours: Optional[np.ndarray] = None):
+    """partition a global HostState (CORRECTED policy) into per-rank {lm, static, f, vert}."""
+    mesh = st.mesh
+    n_global = (mesh.nCells, mesh.nEdges, mesh.nVertices)
+    col = colours if colours is not None else (mesh.partition if mesh.partition is not None and mesh.partition.max() + 1 == world
+                                               else partition.sfc_colouring(mesh, world))
+    part = partition.partition_regions(mesh, col, world, _abi.INDEX_CORRECTED)
+    locs, statics = [], []
+    for r in range(world):
+        lm, loc = partition.build_local(st.static, n_global, col, part, r, mesh.v["cellsOnVertex"])
+        locs.append(lm); statics.append(loc)
+    partition.build_halo_lists(locs)
+    return [dict(lm=lm, static=loc, f=split_state(st.f, lm), vert=dict(st.vert)) for lm, loc in zip(locs, statics)]
+
+
+def save_shard(path: str, sh):
+    os.makedirs(path, exist_ok=True)
+    lm = sh["lm"]
+    meta = dict(rank=lm.rank, n_owned=np.asarray(lm.n_owned), cells=lm.cells, edges=lm.edges, vertices=lm.vertices,
+                interior=lm.interior_cells)
+    for ent in ("cell", "edge", "vertex"):
+        meta[f"owner_{ent}"] = lm.owner[ent]
+        for peer, idx in lm.send[ent].items():
+            meta[f"send_{ent}_{peer}"] = idx
+        for peer, idx in lm.recv[ent].items():
+            meta[f"recv_{ent}_{peer}"] = idx
+    np.savez(os.path.join(path, "lm.npz"), **meta)
+    for sub in ("static", "f", "vert"):
+        os.makedirs(os.path.join(path, sub), exist_ok=True)
+        for k, a in sh[sub].items():
+            np.save(os.path.join(path, sub, k + ".npy"), a)
+
+
+def load_shard(path: str):
+    z = np.load(os.path.join(path, "lm.npz"))
+    lm = partition.LocalMesh(rank=int(z["rank"]), n_owned=tuple(int(v) for v in z["n_owned"]), cells=z["cells"], edges=z["edges"],
+                             vertices=z["vertices"], owner={e: z[f"owner_{e}"] for e in ("cell", "edge", "vertex")})
+    lm.interior_cells = z["interior"]
+    for ent in ("cell", "edge", "vertex"):
+        lm.send[ent], lm.recv[ent] = {}, {}
+    for k in z.files:
+        for kind in ("send", "recv"):
+            if k.startswith(kind + "_"):
+                _, ent, peer = k.split("_")
+                getattr(lm, kind)[ent][int(peer)] = z[k]
+    out = dict(lm=lm)
+    for sub in ("static", "f", "vert"):
+        d = os.path.join(path, sub)
+        out[sub] = {f[:-4]: np.load(os.path.join(d, f)) for f in sorted(os.listdir(d)) if f.endswith(".npy")}
+    return out

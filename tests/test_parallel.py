@@ -1,0 +1,186 @@
+"""Partitioning + halo exchange (host logic), on the CPU: the CPU oracle stands in for the GPU kernels so the
+N-rank plumbing (partition sets, local meshes, send/recv lists, exchange schedule) is checked without a GPU.
+N-rank results on owned entities must be BIT-IDENTICAL to the single-partition run."""
+import os
+
+import numpy as np
+import pytest
+
+from mpas_regent_b200 import _abi, dynamics, init_jw, parallel, partition
+from mpas_regent_b200 import mesh as M
+from mpas_regent_b200._abi import CELL, EDGE, FIELD_ENTITY, VERTEX, VERTICAL
+
+L = 6
+DT = 600.0
+
+
+def test_partition_regions_reproduces_survey_numbers(grid2562):
+    """SURVEY.md 8c cross-checks on the bundled mesh + 16-way METIS colouring, colours 0/1/2/15 and totals."""
+    want = {
+        M.LITERAL: dict(ghost_1=[267, 282, 266, 334], ghost_2=[475, 488, 438, 559], shared_1=[102, 88, 114, 108],
+                        private_1=[59, 67, 47, 56], shared_2=[143, 119, 155, 143], private_2=[18, 36, 6, 21],
+                        totals=dict(ghost_1=4405, ghost_2=7374, shared_1=1586)),
+        M.CORRECTED: dict(ghost_1=[54, 46, 49, 53], ghost_2=[114, 97, 103, 111], shared_1=[48, 41, 44, 48],
+                          private_1=[113, 114, 117, 116], shared_2=[88, 77, 83, 89], private_2=[73, 78, 78, 75],
+                          totals=dict(ghost_1=790, ghost_2=1662, shared_1=706)),
+    }
+    for pol, w in want.items():
+        part = partition.partition_regions(grid2562, grid2562.partition, 16, pol)
+        for k, vals in w.items():
+            if k == "totals":
+                for kk, tot in vals.items():
+                    assert sum(len(a) for a in getattr(part, kk)) == tot, (pol, kk)
+            else:
+                assert [len(getattr(part, k)[c]) for c in (0, 1, 2, 15)] == vals, (pol, k)
+        for c in range(16):     # the algebra of mesh_loading.rg:448-471
+            p = set(part.p[c])
+            assert not (set(part.ghost_1[c]) & p) and not (set(part.ghost_2[c]) & p)
+            assert set(part.shared_1[c]) | set(part.private_1[c]) == p
+            assert set(part.private_2[c]) <= set(part.private_1[c])
+            if pol == M.CORRECTED:
+                assert set(part.ghost_1[c]) <= set(part.ghost_2[c])
+
+
+def test_sfc_colouring_is_balanced_and_compact(grid2562):
+    col = partition.sfc_colouring(grid2562, 8)
+    sizes = np.bincount(col, minlength=8)
+    assert sizes.max() - sizes.min() <= 1
+    part = partition.partition_regions(grid2562, col, 8, M.CORRECTED)
+    assert max(len(g) for g in part.ghost_1) < 120        # compact chunks: ring ~ O(sqrt(n))
+
+
+def _shards(mesh, world):
+    st = init_jw.make_state(mesh, L, _abi.INDEX_CORRECTED)
+    return st, parallel.make_shards(st, world)
+
+
+def test_halo_lists_are_symmetric(grid642):
+    st, shards = _shards(grid642, 4)
+    locs = [s["lm"] for s in shards]
+    for ent, attr in (("cell", "cells"), ("edge", "edges"), ("vertex", "vertices")):
+        owned_total = 0
+        for h, lm in enumerate(locs):
+            n_own = lm.n_owned[("cell", "edge", "vertex").index(ent)]
+            owned_total += n_own
+            assert np.all(lm.owner[ent][:n_own] == h) and np.all(lm.owner[ent][n_own:] != h)
+            for o, ridx in lm.recv[ent].items():
+                sidx = locs[o].send[ent][h]
+                assert np.array_equal(getattr(lm, attr)[ridx], getattr(locs[o], attr)[sidx])     # same global entities, same order
+                assert np.all(ridx >= n_own) and np.all(sidx < locs[o].n_owned[("cell", "edge", "vertex").index(ent)])
+            covered = np.concatenate([v for v in lm.recv[ent].values()]) if lm.recv[ent] else np.zeros(0, int)
+            assert len(covered) == len(getattr(lm, attr)) - n_own                               # every ghost has exactly one source
+        assert owned_total == {"cell": grid642.nCells, "edge": grid642.nEdges, "vertex": grid642.nVertices}[ent]
+
+
+def _single(mesh, st, steps):
+    from oracle.oracle import Oracle
+    o = Oracle(dynamics.dims_of(mesh, L), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX))
+    o.upload_mesh(st.static); o.upload_state(st.f, st.vert)
+    o.atm_compute_solve_diagnostics(False, -1)
+    for _ in range(steps):
+        o.atm_srk3(DT)
+    return o
+
+
+def _rank_backend(sh):
+    from oracle.oracle import Oracle
+    lm = sh["lm"]
+    o = Oracle(_abi.make_dims(len(lm.cells), len(lm.edges), len(lm.vertices), L), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX))
+    o.upload_mesh(sh["static"]); o.upload_state(sh["f"], sh["vert"])
+    return o
+
+
+def _assert_owned_equal(single, backend, lm, names=None):
+    rows = {CELL: lm.cells, EDGE: lm.edges, VERTEX: lm.vertices}
+    nown = {CELL: lm.n_owned[0], EDGE: lm.n_owned[1], VERTEX: lm.n_owned[2]}
+    for name, ent, _ in _abi.FIELDS:
+        if names and name not in names:
+            continue
+        a = backend.download_field(name)
+        ref = single.download_field(name)
+        if ent == VERTICAL:
+            assert np.array_equal(a, ref, equal_nan=True), name
+        else:
+            n = nown[ent]
+            assert np.array_equal(a[:n], ref[rows[ent][:n]], equal_nan=True), (name, lm.rank)
+
+
+def _task_schedule(cfg):
+    """the (task, args) list of one atm_srk3, recorded from the shared host replay (rk_timestep.rg:378-481)."""
+    seq = []
+
+    class Rec(dynamics.TaskAPI):
+        def __init__(self):
+            self.cfg, self.dims = cfg, None
+
+        def _call(self, name, *args):
+            seq.append((name, args))
+
+    Rec().atm_srk3_by_tasks(DT)
+    return seq
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_n_ranks_equal_single_partition_bitwise(grid642, world):
+    st, shards = _shards(grid642, world)
+    single = _single(grid642, st, 2)
+    backs = [_rank_backend(s) for s in shards]
+    ex = parallel.InProcessExchanger(backs, [s["lm"] for s in shards])
+    # lock-step: every rank runs the same task, then ONE exchange serves all of them
+    for b in backs:
+        b.atm_compute_solve_diagnostics(False, -1)
+    ex.exchange(parallel.EXCHANGES["compute_solve_diagnostics"])
+    seq = _task_schedule(backs[0].cfg)
+    for _ in range(2):
+        for name, args in seq:
+            for b in backs:
+                b._call(name, *args)
+            spec = parallel.EXCHANGES.get(name)
+            if spec:
+                ex.exchange(spec)
+    for b, s in zip(backs, shards):
+        _assert_owned_equal(single, b, s["lm"])
+
+
+def _gloo_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mpas_regent_b200 import icosa
+        mesh = icosa.make_icosahedral_mesh(642)
+        st, shards = _shards(mesh, world)
+        sh = shards[rank]
+        b = _rank_backend(sh)
+        run = parallel.DistributedDynamics(b, parallel.HostDistExchanger(b, sh["lm"]))
+        run.init_diagnostics()
+        for _ in range(2):
+            run.step(DT)
+        single = _single(mesh, st, 2)
+        _assert_owned_equal(single, b, sh["lm"])
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world_size_2(tmp_path):
+    """the torch.distributed path (batch_isend_irecv), world_size 2, gloo on 127.0.0.1."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_shard_roundtrip(grid642, tmp_path):
+    st, shards = _shards(grid642, 2)
+    parallel.save_shard(str(tmp_path / "r0"), shards[0])
+    sh = parallel.load_shard(str(tmp_path / "r0"))
+    lm0, lm1 = shards[0]["lm"], sh["lm"]
+    assert np.array_equal(lm0.cells, lm1.cells) and lm0.n_owned == lm1.n_owned
+    for ent in ("cell", "edge", "vertex"):
+        assert lm0.send[ent].keys() == lm1.send[ent].keys()
+        for p in lm0.recv[ent]:
+            assert np.array_equal(lm0.recv[ent][p], lm1.recv[ent][p])
+    for k in shards[0]["f"]:
+        assert np.array_equal(shards[0]["f"][k], sh["f"][k])

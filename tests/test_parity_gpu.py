@@ -203,3 +203,58 @@ def test_acoustic_modes(grid2562, exact):
         for n in ("rw_p", "rho_pp", "rtheta_pp", "wwAvg", "rtheta_pp_old", "ru_p"):
             assert np.array_equal(g.download_field(n), ora.download_field(n)), n
     g.close(); ora.close()
+
+
+def test_emulated_ranks_on_one_gpu_equal_single_partition(grid642):
+    """4 ranks emulated as 4 handles on one GPU (pack/unpack + the exchange schedule of parallel.EXCHANGES):
+    owned entities are bit-identical to the single-partition GPU run."""
+    import torch
+    from mpas_regent_b200 import dynamics, init_jw, parallel
+    from tests.test_parallel import _task_schedule, _assert_owned_equal
+    Lh = 6
+    st = init_jw.make_state(grid642, Lh, _abi.INDEX_CORRECTED)
+    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX)
+    single = dynamics.Dynamics(dynamics.dims_of(grid642, Lh), cfg)
+    single.upload_mesh(st.static); single.upload_state(st.f, st.vert)
+    single.atm_compute_solve_diagnostics(False, -1)
+    shards = parallel.make_shards(st, 4)
+    backs = []
+    for sh in shards:
+        lm = sh["lm"]
+        b = dynamics.Dynamics(_abi.make_dims(len(lm.cells), len(lm.edges), len(lm.vertices), Lh), cfg)
+        b.upload_mesh(sh["static"]); b.upload_state(sh["f"], sh["vert"])
+        backs.append(b)
+    # device-side exchange through k_pack / k_unpack and torch buffers (what NcclExchanger does, minus the wire)
+    lists = {}
+    for h, sh in enumerate(shards):
+        for ent in ("cell", "edge", "vertex"):
+            for peer, idx in sh["lm"].send[ent].items():
+                lists[("s", h, ent, peer)] = backs[h].register_list(parallel.ENT[ent], idx)
+            for peer, idx in sh["lm"].recv[ent].items():
+                lists[("r", h, ent, peer)] = backs[h].register_list(parallel.ENT[ent], idx)
+
+    def exchange(spec):
+        for b in backs:
+            b.sync()
+        for ent, names in spec.items():
+            for h, sh in enumerate(shards):
+                for o, ridx in sh["lm"].recv[ent].items():
+                    buf = torch.empty(len(names) * len(ridx) * (Lh + 1), dtype=torch.float64, device="cuda")
+                    backs[o].pack(lists[("s", o, ent, h)], names, buf.data_ptr()); backs[o].sync()
+                    backs[h].unpack(lists[("r", h, ent, o)], names, buf.data_ptr()); backs[h].sync()
+
+    for b in backs:
+        b.atm_compute_solve_diagnostics(False, -1)
+    exchange(parallel.EXCHANGES["compute_solve_diagnostics"])
+    seq = _task_schedule(cfg)
+    for _ in range(2):
+        single.atm_srk3(600.0)
+        for name, args in seq:
+            for b in backs:
+                b._call(name, *args)
+            if name in parallel.EXCHANGES:
+                exchange(parallel.EXCHANGES[name])
+    for b, sh in zip(backs, shards):
+        _assert_owned_equal(single, b, sh["lm"])
+        b.close()
+    single.close()
