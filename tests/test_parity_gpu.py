@@ -258,3 +258,20 @@ def test_emulated_ranks_on_one_gpu_equal_single_partition(grid642):
         _assert_owned_equal(single, b, sh["lm"])
         b.close()
     single.close()
+
+
+def test_nccl_ranks_equal_single_gpu():
+    """real multi-process run over NCCL when the box has >= 2 GPUs (gpurun --gpus N)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", os.path.join(root, "tests", "run_multigpu_check.py")],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0 and "MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
