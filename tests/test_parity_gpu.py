@@ -275,3 +275,21 @@ def test_nccl_ranks_equal_single_gpu():
                           "--master-port", "29533", os.path.join(root, "tests", "run_multigpu_check.py")],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0 and "MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_hundred_step_drift(grid2562):
+    """100 RK3 steps of the JW-style state (BASELINE.json config 2, at the bundled mesh's size): the deviation from the
+    oracle must stay within the stated growth bound 1e-12 * (1 + step) per field."""
+    st, ora, g = build_pair(grid2562, 10, _abi.INDEX_CORRECTED, m5=True, rkarg=_abi.RKARG_STAGE_INDEX)
+    ora.set_threads(ora.max_threads())
+    for b in (ora, g):
+        b.atm_compute_solve_diagnostics(False, -1)
+    done = 0
+    for upto in (1, 10, 100):
+        for b in (ora, g):
+            for _ in range(upto - done):
+                b.atm_srk3(DT)
+        done = upto
+        worst = compare(g, ora, tol=1e-12 * (1 + upto), what=f"after {upto} steps")
+        assert worst[0] <= 1e-12 * (1 + upto)
+    g.close(); ora.close()
