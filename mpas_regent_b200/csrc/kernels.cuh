@@ -52,6 +52,39 @@ DI void st2m(double* p, size_t i, D2 v, bool m0, bool m1) {
   else { if (m0) p[i] = v.x; if (m1) p[i + 1] = v.y; }
 }
 
+DI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Blocks are short-lived (8 columns each), so the index loads at the top of a block are an exposed DRAM round
+// trip.  Every block therefore prefetches into L2 the static index rows of the block that will run about one
+// wave later (profiles/r1_divdamp_variants.md: +11 % on a light gather kernel for three instructions).
+#define PF_AHEAD 1400    /* ~ resident blocks on 148 SMs */
+DI void prefetch_cell_rows(const View& V, long xa, int lane) {
+  if (xa >= V.nCells) return;
+  const int ME = V.maxEdges;
+  switch (lane) {
+    case 0: prefetch_l2(V.edgesOnCell + xa * V.MEP); prefetch_l2(V.nEdgesOnCell + xa); break;
+    case 1: prefetch_l2(V.c1OnCell + xa * V.MEP); break;
+    case 2: prefetch_l2(V.c2OnCell + xa * V.MEP); break;
+    case 3: prefetch_l2(V.edgesOnCell_sign + xa * ME); break;
+    case 4: prefetch_l2(V.edgesOnCellSign + xa * ME); break;
+    case 5: prefetch_l2(V.dvOnCell + xa * ME); break;
+    case 6: prefetch_l2(V.invDcOnCell + xa * ME); prefetch_l2(V.invAreaCell + xa); break;
+    case 7: prefetch_l2(V.ms2OnCell + xa * ME); prefetch_l2(V.ms4OnCell + xa * ME); break;
+    default: break;
+  }
+}
+DI void prefetch_edge_rows(const View& V, long xa, int lane, const int* eoe) {
+  if (xa >= V.nEdges) return;
+  switch (lane) {
+    case 0: prefetch_l2(V.ecv + xa); break;
+    case 1: prefetch_l2(V.invDcEdge + xa); prefetch_l2(V.invDvEdge + xa); break;
+    case 2: if (eoe) { prefetch_l2(eoe + xa * V.maxEdges2); prefetch_l2(eoe + xa * V.maxEdges2 + 16); } break;
+    case 3: if (eoe) { prefetch_l2(V.weightsOnEdge + xa * V.maxEdges2); prefetch_l2(V.weightsOnEdge + xa * V.maxEdges2 + 16); } break;
+    default: break;
+  }
+}
+#define PF_CELLS() prefetch_cell_rows(V, (long)x + (long)PF_AHEAD * blockDim.y, threadIdx.x)
+#define PF_EDGES(eoe) prefetch_edge_rows(V, (long)x + (long)PF_AHEAD * blockDim.y, threadIdx.x, (eoe))
+
 #define FLD(name) (V.f[MPASB200_F_##name])
 #define PAIR_THREAD(n)                                          \
   const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;             \
@@ -543,6 +576,26 @@ __global__ void k_dt_cellB(const View V, const DynTendParams P) {
   st2m(FLD(tend_w_euler), ix, twe, m0, m1);
 }
 
+// horizontal theta flux through each edge, evaluated ONCE per edge  (:1333-1340).  The reference evaluates
+// flux_arr for edge e inside the loop of each of e's two cells; the value depends only on (e, level), so it is
+// computed here per edge into library scratch and the cell pass sums it in slot order -- same bits, half the
+// 2-ring gathers, and the gather lives in a kernel with a single level of index loads.
+__global__ void k_dt_theta_flux(const View V) {
+  PAIR_THREAD(V.nEdges)
+  if (!m0) return;
+  const int NA = V.nAdv;
+  const double* tm = FLD(theta_m);
+  const int na = V.nAdvCellsForEdge[x];
+  const D2 sg = sgn1(ld2(FLD(ru), ix));
+  D2 fa = bc(0.0);
+#pragma unroll 5
+  for (int j = 0; j < na; ++j) {
+    const D2 sw = V.adv_coefs[x * NA + j] + sg * V.adv_coefs_3rd[x * NA + j];
+    fa += sw * G2(tm, V.advCellsForEdge[x * NA + j]);
+  }
+  st2m(V.scr_flux, ix, fa, m0, m1);
+}
+
 DI double wdwz_at(int k, int L, double rw_k, double rw_m, const double* s) {      // :1277-1287, s = w of the column in smem
   double r = 0.0;
   if (k == 1 || k == L - 1) r = 0.25 * (rw_k + rw_m) * (s[k] + s[k - 1]);
@@ -642,18 +695,11 @@ __global__ void k_dt_cellC(const View V, const DynTendParams P) {
   if (m0) {
     const double* ru = FLD(ru);
     D2 fa_last = bc(0.0);
+#pragma unroll 2
     for (int i = 0; i < n; ++i) {                                                                     // :1328-1344
       const int e = V.edgesOnCell[x * V.MEP + i];
       const D2 ru_e = G2(ru, e);
-      const int na = V.nAdvOnCell[x * ME + i];
-      const size_t ab = ((size_t)x * ME + i) * V.NAP;
-      const D2 sg = sgn1(ru_e);
-      D2 fa = bc(0.0);
-#pragma unroll 4
-      for (int j = 0; j < na; ++j) {
-        const D2 sw = V.advCoefOnCell[ab + j] + sg * V.adv3OnCell[ab + j];
-        fa += sw * G2(tm, V.advCellOnCell[ab + j]);
-      }
+      const D2 fa = G2(V.scr_flux, e);              // flux_arr of this edge (k_dt_theta_flux)
       tt -= V.edgesOnCell_sign[x * ME + i] * ru_e * fa;
       fa_last = fa;
     }
@@ -969,17 +1015,35 @@ __global__ void k_acoustic_column(const View V, double dts, int small_step, doub
 
 // ============================================================================================
 // atm_divergence_damping_3d  :1726-1763
+// Persistent blocks loop over edge tiles; the next tile's index word, skip flag and own column are loaded
+// before the current tile's gathers are consumed, so the index round trip is off the critical path
+// (profiles/r1_divdamp_variants.md, variant v4: 3.37 -> 4.37 TB/s).
 __global__ void k_divdamp(const View V, double coef_divdamp) {
-  PAIR_THREAD(V.nEdges)
-  if (!m0) return;
-  if (V.divdampSkip[x]) return;
-  const int4 cv = V.ecv[x];
+  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;
+  const int LP = V.LP, L = V.L;
+  if (k0 >= L) return;
+  const bool m1 = k1 < L;
+  const int stride = gridDim.x * blockDim.y;
+  int x = blockIdx.x * blockDim.y + threadIdx.y;
+  if (x >= V.nEdges) return;
   const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
-  const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
-  const D2 r = ld2(FLD(ru_p), ix);
-  const D2 divCell1 = -(a1 - b1);
-  const D2 divCell2 = -(a2 - b2);
-  st2m(FLD(ru_p), ix, r + coef_divdamp * (divCell2 - divCell1) * (1.0 - V.specZoneMaskEdge[x]) / (t1 + t2), m0, m1);
+  int4 cv = V.ecv[x]; unsigned char skip = V.divdampSkip[x]; double sz = 1.0 - V.specZoneMaskEdge[x];
+  D2 r = ld2(FLD(ru_p), (size_t)x * LP + k0);
+  while (true) {
+    const int xn = x + stride;
+    const bool more = xn < V.nEdges;
+    const int xs = more ? xn : x;
+    const int4 cvn = V.ecv[xs]; const unsigned char skn = V.divdampSkip[xs]; const double szn = 1.0 - V.specZoneMaskEdge[xs];
+    const D2 rn = ld2(FLD(ru_p), (size_t)xs * LP + k0);
+    if (!skip) {
+      const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
+      const D2 divCell1 = -(a1 - b1);
+      const D2 divCell2 = -(a2 - b2);
+      st2m(FLD(ru_p), (size_t)x * LP + k0, r + coef_divdamp * (divCell2 - divCell1) * sz / (t1 + t2), true, m1);
+    }
+    if (!more) break;
+    x = xn; cv = cvn; skip = skn; sz = szn; r = rn;
+  }
 }
 
 // ============================================================================================
@@ -1134,8 +1198,6 @@ __global__ void k_unpack(const PackArgs A, const int* __restrict__ idx, int n, i
 // ============================================================================================
 // EXPERIMENTAL variants of k_divdamp used to measure which latency-hiding structure pays on B200
 // (profiles/r1_divdamp_variants.md).  Selected through mpasb200_debug_divdamp only.
-DI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // V1: skip flag and ecv fetched together, own-column load issued before the dependent gathers
 __global__ void k_divdamp_v1(const View V, double coef_divdamp) {
   PAIR_THREAD(V.nEdges)
@@ -1231,4 +1293,75 @@ __global__ void k_divdamp_v5(const View V, double coef_divdamp) {
   const D2 A1 = ld2(rpp, i1 + 2), B1 = ld2(rppo, i1 + 2), A2 = ld2(rpp, i2 + 2), B2 = ld2(rppo, i2 + 2), T1 = ld2(tm, i1 + 2), T2 = ld2(tm, i2 + 2);
   st2m(FLD(ru_p), ix, r0 + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), true, k0 + 1 < L);
   st2m(FLD(ru_p), ix + 2, r1 + coef_divdamp * ((-(A2 - B2)) - (-(A1 - B1))) * sz / (T1 + T2), k0 + 2 < L, k0 + 3 < L);
+}
+// V6: one-wave-ahead L2 prefetch of DATA as well as index words.  Exact: the index word of the tile `ahead`
+// blocks later (itself prefetched 2*ahead earlier) is loaded and the gather lines it points to are prefetched.
+DI void prefetch_col(const double* p, size_t col, int LP, int k0) { prefetch_l2(p + col * LP + k0); }
+__global__ void k_divdamp_v6(const View V, double coef_divdamp, int ahead) {
+  PAIR_THREAD(V.nEdges)
+  const bool pf_lane = (threadIdx.x & 7) == 0;          // one lane per 128-byte line of a column
+  const long xa = (long)x + (long)ahead * blockDim.y, xb = (long)x + 2L * ahead * blockDim.y;
+  unsigned char skip = 1; int4 cv = make_int4(0, 0, 0, 0); D2 r = bc(0); double sz = 0;
+  if (m0) {
+    skip = V.divdampSkip[x]; cv = V.ecv[x]; r = ld2(FLD(ru_p), ix); sz = 1.0 - V.specZoneMaskEdge[x];
+  }
+  if (pf_lane && k0 < V.L) {
+    if (xb < V.nEdges && threadIdx.x == 0) { prefetch_l2(&V.ecv[xb]); prefetch_l2(&V.divdampSkip[xb]); prefetch_l2(&V.specZoneMaskEdge[xb]); }
+    if (xa < V.nEdges) {
+      const int4 ca = V.ecv[xa];
+      prefetch_col(FLD(ru_p), xa, LP, k0);
+      prefetch_col(FLD(rtheta_pp), ca.x, LP, k0); prefetch_col(FLD(rtheta_pp_old), ca.x, LP, k0); prefetch_col(FLD(theta_m), ca.x, LP, k0);
+      prefetch_col(FLD(rtheta_pp), ca.y, LP, k0); prefetch_col(FLD(rtheta_pp_old), ca.y, LP, k0); prefetch_col(FLD(theta_m), ca.y, LP, k0);
+    }
+  }
+  if (!m0 || skip) return;
+  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
+  const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
+  st2m(FLD(ru_p), ix, r + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), m0, m1);
+}
+// V7: V4 (persistent, next tile's index words in registers) with four levels per thread
+__global__ void k_divdamp_v7(const View V, double coef_divdamp) {
+  const int k0 = 4 * (int)threadIdx.x;
+  const int LP = V.LP, L = V.L;
+  if (k0 >= L) return;
+  const int stride = gridDim.x * blockDim.y;
+  int x = blockIdx.x * blockDim.y + threadIdx.y;
+  if (x >= V.nEdges) return;
+  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
+  int4 cv = V.ecv[x]; unsigned char skip = V.divdampSkip[x]; double sz = 1.0 - V.specZoneMaskEdge[x];
+  D2 r0 = ld2(FLD(ru_p), (size_t)x * LP + k0), r1 = ld2(FLD(ru_p), (size_t)x * LP + k0 + 2);
+  while (true) {
+    const int xn = x + stride;
+    const bool more = xn < V.nEdges;
+    const int xs = more ? xn : x;
+    const int4 cvn = V.ecv[xs]; const unsigned char skn = V.divdampSkip[xs]; const double szn = 1.0 - V.specZoneMaskEdge[xs];
+    const D2 rn0 = ld2(FLD(ru_p), (size_t)xs * LP + k0), rn1 = ld2(FLD(ru_p), (size_t)xs * LP + k0 + 2);
+    if (!skip) {
+      const size_t i1 = (size_t)cv.x * LP + k0, i2 = (size_t)cv.y * LP + k0, ix = (size_t)x * LP + k0;
+      const D2 a1 = ld2(rpp, i1), b1 = ld2(rppo, i1), a2 = ld2(rpp, i2), b2 = ld2(rppo, i2), t1 = ld2(tm, i1), t2 = ld2(tm, i2);
+      const D2 A1 = ld2(rpp, i1 + 2), B1 = ld2(rppo, i1 + 2), A2 = ld2(rpp, i2 + 2), B2 = ld2(rppo, i2 + 2), T1 = ld2(tm, i1 + 2), T2 = ld2(tm, i2 + 2);
+      st2m(FLD(ru_p), ix, r0 + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), true, k0 + 1 < L);
+      st2m(FLD(ru_p), ix + 2, r1 + coef_divdamp * ((-(A2 - B2)) - (-(A1 - B1))) * sz / (T1 + T2), k0 + 2 < L, k0 + 3 < L);
+    }
+    if (!more) break;
+    x = xn; cv = cvn; skip = skn; sz = szn; r0 = rn0; r1 = rn1;
+  }
+}
+// V8: persistent tile loop WITHOUT next-tile prefetch (isolates the effect of block scheduling overhead)
+__global__ void k_divdamp_v8(const View V, double coef_divdamp) {
+  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;
+  const int LP = V.LP, L = V.L;
+  if (k0 >= L) return;
+  const bool m1 = k1 < L;
+  const int stride = gridDim.x * blockDim.y;
+  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
+  for (int x = blockIdx.x * blockDim.y + threadIdx.y; x < V.nEdges; x += stride) {
+    if (V.divdampSkip[x]) continue;
+    const int4 cv = V.ecv[x];
+    const size_t ix = (size_t)x * LP + k0;
+    const D2 r = ld2(FLD(ru_p), ix);
+    const double sz = 1.0 - V.specZoneMaskEdge[x];
+    const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
+    st2m(FLD(ru_p), ix, r + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), true, m1);
+  }
 }

@@ -44,6 +44,7 @@ struct mpasb200 {
   MpasDims d; MpasConfig c;
   int device = 0;
   int nCells, nEdges, nVertices, L, LP, L1, CPB;
+  int num_sms = 148;
   View V;                               // device pointers
   std::vector<void*> allocs;            // everything cudaMalloc'ed
   int64_t bytes = 0;
@@ -279,10 +280,12 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
     LAUNCH(k_dt_edge<true>, h->nEdges, sm2, h->V, P);
     LAUNCH(k_dt_cellA, h->nCells, 0, h->V, P);
     LAUNCH(k_dt_cellB, h->nCells, 0, h->V, P);
+    LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
     LAUNCH(k_dt_cellC<true>, h->nCells, sm2, h->V, P);
   } else {
     LAUNCH(k_dt_cell0<false>, h->nCells, 0, h->V, P, C.config_len_disp, cam_coef);
     LAUNCH(k_dt_edge<false>, h->nEdges, sm2, h->V, P);
+    LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
     LAUNCH(k_dt_cellC<false>, h->nCells, sm2, h->V, P);
   }
   return post_launch(h);
@@ -313,7 +316,12 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
 int t_divdamp(mpasb200_t* h, double dts) {
   const double rdts = 1.0 / dts;
   const double coef_divdamp = 2.0 * h->c.config_smdiv * h->c.config_len_disp * rdts;
-  LAUNCH(k_divdamp, h->nEdges, 0, h->V, coef_divdamp);
+  if (h->nEdges > 0) {        // persistent: 9 resident blocks per SM loop over the edge tiles
+    const int tiles = (h->nEdges + h->CPB - 1) / h->CPB;
+    KTimer kt_(h, "k_divdamp");
+    k_divdamp<<<std::min(tiles, h->num_sms * 9), dim3(h->LP / 2, h->CPB), 0, h->stream>>>(h->V, coef_divdamp);
+    h->launches++;
+  }
   return post_launch(h);
 }
 int t_recover(mpasb200_t* h, int ns, int rk_step, double dt) {
@@ -454,6 +462,7 @@ int mpasb200_create(const MpasDims* dims, const MpasConfig* cfg, mpasb200_t** ou
   h->L = dims->nVertLevels; h->L1 = h->L + 1; h->LP = (h->L1 + 3) / 4 * 4;
   { const int T = h->LP / 2; int g = T, b = 32; while (b) { int t = g % b; g = b; b = t; } h->CPB = 32 / g; while (h->CPB * T < 128) h->CPB *= 2; }
   if (h->LP / 2 * h->CPB > 1024) { g_create_error = "nVertLevels too large for one block per column group"; delete h; return MPASB200_EINVAL; }
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
   cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   h->stream = h->own_stream;
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
@@ -473,10 +482,11 @@ int mpasb200_create(const MpasDims* dims, const MpasConfig* cfg, mpasb200_t** ou
   }
   const size_t scr = ((size_t)(h->nCells + 1) * h->LP + 15) / 16 * 16;
   double* arena = nullptr;
-  int rc = dev_alloc(h, &arena, total + 2 * scr);
+  const size_t scr_e = ((size_t)(h->nEdges + 1) * h->LP + 15) / 16 * 16;
+  int rc = dev_alloc(h, &arena, total + 2 * scr + scr_e);
   if (rc) { g_create_error = h->err; mpasb200_destroy(h); return rc; }
   for (int id = 0; id < MPASB200_F_COUNT; ++id) V.f[id] = arena + off[id];
-  V.scr_rs = arena + total; V.scr_ts = arena + total + scr;
+  V.scr_rs = arena + total; V.scr_ts = arena + total + scr; V.scr_flux = arena + total + 2 * scr;
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) { g_create_error = "arena memset failed"; mpasb200_destroy(h); return MPASB200_ECUDA; }
   *out = h;
   return 0;
@@ -892,7 +902,7 @@ int mpasb200_debug_divdamp(mpasb200_t* h, int variant, double dts, int arg) {
   const double coef = 2.0 * h->c.config_smdiv * h->c.config_len_disp * (1.0 / dts);
   const int nE = h->nEdges, T = h->LP / 2, C = h->CPB;
   switch (variant) {
-    case 0: LAUNCH(k_divdamp, nE, 0, h->V, coef); break;
+    case 0: { KTimer kt(h, "k_divdamp"); k_divdamp<<<h->num_sms * 9, dim3(T, C), 0, h->stream>>>(h->V, coef); h->launches++; } break;
     case 1: LAUNCH(k_divdamp_v1, nE, 0, h->V, coef); break;
     case 2: LAUNCH(k_divdamp_v2, nE, 0, h->V, coef, arg); break;
     case 3: { KTimer kt(h, "k_divdamp_v3"); const int half = (nE + 1) / 2;
@@ -900,6 +910,10 @@ int mpasb200_debug_divdamp(mpasb200_t* h, int variant, double dts, int arg) {
     case 4: { KTimer kt(h, "k_divdamp_v4"); k_divdamp_v4<<<arg, dim3(T, C), 0, h->stream>>>(h->V, coef); h->launches++; } break;
     case 5: { KTimer kt(h, "k_divdamp_v5"); const int T4 = h->LP / 4, C4 = 256 / T4;
               k_divdamp_v5<<<(nE + C4 - 1) / C4, dim3(T4, C4), 0, h->stream>>>(h->V, coef); h->launches++; } break;
+    case 6: LAUNCH(k_divdamp_v6, nE, 0, h->V, coef, arg); break;
+    case 7: { KTimer kt(h, "k_divdamp_v7"); const int T4 = h->LP / 4, C4 = 256 / T4;
+              k_divdamp_v7<<<arg, dim3(T4, C4), 0, h->stream>>>(h->V, coef); h->launches++; } break;
+    case 8: { KTimer kt(h, "k_divdamp_v8"); k_divdamp_v8<<<arg, dim3(T, C), 0, h->stream>>>(h->V, coef); h->launches++; } break;
     default: return fail(h, MPASB200_EINVAL, "unknown variant");
   }
   return post_launch(h);

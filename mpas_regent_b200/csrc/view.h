@@ -48,6 +48,7 @@ struct View {
   const double* dcOnVertex;    // [v][3]: dcEdge of the vertex's edges
   const double* fVertex; const double* invAreaTriangle;
   // scratch (library-private, not region fields)
+  double* scr_flux;                   // horizontal theta flux per edge (k_dt_theta_flux)  [(nEdges+1)][LP]
   double* scr_rs; double* scr_ts;     // horizontal flux parts of rs/ts in the two-kernel acoustic step  [(nCells+1)][LP]
 };
 

@@ -43,14 +43,15 @@ K: Dict[str, Tuple[List[str], List[str]]] = {
                         ["wduz", "q", "tend_u", "tend_u_euler"]),
     "k_dt_edge<false>": (["u", "rw", "pv_edge", "rho_edge", "ke", "h_divergence", "w", "tend_ru_physics", "tend_u_euler"],
                          ["wduz", "q", "tend_u"]),
+    "k_dt_theta_flux": (["ru", "theta_m"], ["scr_e"]),
     "k_dt_cellA": (["ru", "rho_zz", "uReconstructZonal", "uReconstructMeridional", "theta_m", "kdiff", "rho_edge"],
                    ["w", "ru_edge_w", "delsq_theta", "tend_theta_euler"]),
     "k_dt_cellB": (["w", "kdiff", "rho_edge"], ["delsq_w", "tend_w_euler"]),
-    "k_dt_cellC<true>": (["w", "tend_w_euler", "delsq_w", "rw", "pressure_p", "dpdz", "cqw", "ru", "theta_m", "theta_m_save",
+    "k_dt_cellC<true>": (["w", "tend_w_euler", "delsq_w", "rw", "pressure_p", "dpdz", "cqw", "ru", "scr_e", "theta_m", "theta_m_save",
                           "rw_save", "rho_zz", "rt_diabatic_tend", "tend_theta_euler", "delsq_theta", "tend_rtheta_physics"],
                          ["wdwz", "tend_w_euler", "w", "flux_arr", "wdtz", "tend_rtheta_adv", "rthdynten", "tend_theta_euler",
                           "tend_theta"]),
-    "k_dt_cellC<false>": (["ru", "rho_zz", "uReconstructZonal", "uReconstructMeridional", "rw", "tend_w_euler", "theta_m",
+    "k_dt_cellC<false>": (["ru", "scr_e", "rho_zz", "uReconstructZonal", "uReconstructMeridional", "rw", "tend_w_euler", "theta_m",
                            "ru_save", "theta_m_save", "rw_save", "rt_diabatic_tend", "tend_theta_euler", "tend_rtheta_physics"],
                           ["ru_edge_w", "wdwz", "w", "flux_arr", "wdtz", "tend_rtheta_adv", "rthdynten", "tend_theta"]),
     "k_smlstep": (["u_tend", "zb_cell", "zb3_cell", "zz", "w"], ["w"]),
@@ -80,6 +81,8 @@ K: Dict[str, Tuple[List[str], List[str]]] = {
 def _u(name: str) -> float:
     if name == "scr":
         return 1.0
+    if name == "scr_e":
+        return 3.0
     s = FIELD_SLOTS[name]
     return MULT[FIELD_ENTITY[name]] * (USED_SLOTS if s > 1 else 1)
 
@@ -87,7 +90,7 @@ def _u(name: str) -> float:
 def units(kernel: str, scratch: bool = True) -> float:
     """8-byte units per cell-level moved by one launch of ``kernel`` (reads + writes)."""
     r, w = K[kernel]
-    return sum(_u(n) for n in r + w if scratch or n != "scr")
+    return sum(_u(n) for n in r + w if scratch or not n.startswith("scr"))
 
 
 # One RK3 step, canonical sequence (stage 0 takes the rk_step == 0 branches), rk_timestep.rg:404-481.
@@ -98,9 +101,9 @@ def step_launches(canonical: bool = True) -> List[str]:
             seq.append("k_vert_imp")
         if stage == 0 and canonical:
             seq += ["k_dt_cell0<true>", "k_dt_edge_delsq", "k_dt_vertex_delsq", "k_dt_cell_delsq", "k_dt_edge<true>",
-                    "k_dt_cellA", "k_dt_cellB", "k_dt_cellC<true>"]
+                    "k_dt_cellA", "k_dt_cellB", "k_dt_theta_flux", "k_dt_cellC<true>"]
         else:
-            seq += ["k_dt_cell0<false>", "k_dt_edge<false>", "k_dt_cellC<false>"]
+            seq += ["k_dt_cell0<false>", "k_dt_edge<false>", "k_dt_theta_flux", "k_dt_cellC<false>"]
         seq.append("k_smlstep")
         for ss in range((1 if stage < 2 else 2) + 1):
             seq += ["k_acoustic<true>" if ss == 0 else "k_acoustic<false>", "k_divdamp"]
@@ -128,8 +131,8 @@ TASK_KERNELS = {
     "compute_moist_coefficients": ["k_moist"],
     "compute_vert_imp_coefs": ["k_vert_imp"],
     "compute_dyn_tend:rk0": ["k_dt_cell0<true>", "k_dt_edge_delsq", "k_dt_vertex_delsq", "k_dt_cell_delsq", "k_dt_edge<true>",
-                             "k_dt_cellA", "k_dt_cellB", "k_dt_cellC<true>"],
-    "compute_dyn_tend:rk>0": ["k_dt_cell0<false>", "k_dt_edge<false>", "k_dt_cellC<false>"],
+                             "k_dt_cellA", "k_dt_cellB", "k_dt_theta_flux", "k_dt_cellC<true>"],
+    "compute_dyn_tend:rk>0": ["k_dt_cell0<false>", "k_dt_edge<false>", "k_dt_theta_flux", "k_dt_cellC<false>"],
     "set_smlstep_pert_variables": ["k_smlstep"],
     "advance_acoustic_step:s0": ["k_acoustic<true>"],
     "advance_acoustic_step": ["k_acoustic<false>"],

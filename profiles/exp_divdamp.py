@@ -25,7 +25,7 @@ for _ in range(2):
     g.atm_srk3(dt)
 g.sync()
 g.enable_kernel_timing(True); g.reset_kernel_timing()
-for _ in range(3):
+for _ in range(1):
     g.atm_srk3(dt)
 kt = g.kernel_times()
 print("== per-kernel table, one RK3 step (ms per launch, GB/s algorithmic) ==")
@@ -33,8 +33,8 @@ tot = 0.0
 for k, (ms, n) in sorted(kt.items(), key=lambda kv: -kv[1][0]):
     u = traffic.units(k, scratch=False) if k in traffic.K else float("nan")
     gbs = u * 8 * nC * L / (ms / n * 1e-3) / 1e9
-    tot += ms / 3
-    print(f"{k:22s} {ms / n:8.3f} ms x {n // 3:2d}/step = {ms / 3:7.3f} ms/step   {u:5.0f} units  {gbs:7.0f} GB/s")
+    tot += ms / 1
+    print(f"{k:22s} {ms / n:8.3f} ms x {n // 1:2d}/step = {ms / 1:7.3f} ms/step   {u:5.0f} units  {gbs:7.0f} GB/s")
 print(f"total {tot:.2f} ms/step")
 lib = g._lib
 lib.mpasb200_debug_divdamp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
@@ -43,7 +43,12 @@ bytes_dd = 9 * 8 * nC * L
 print("== divdamp variants ==")
 for var, arg, label in [(0, 0, "production"), (1, 0, "v1 flag+ecv together"), (2, 1332, "v2 +L2 prefetch 1332 ahead"),
                         (2, 2664, "v2 +L2 prefetch 2664 ahead"), (3, 0, "v3 two edges/thread"), (4, 148 * 9, "v4 persistent 1332 blocks"),
-                        (4, 148 * 18, "v4 persistent 2664 blocks"), (4, 148 * 36, "v4 persistent 5328 blocks"), (5, 0, "v5 four levels/thread")]:
+                        (4, 148 * 18, "v4 persistent 2664 blocks"), (4, 148 * 36, "v4 persistent 5328 blocks"), (5, 0, "v5 four levels/thread"),
+                        (6, 333, "v6 L2 data prefetch 333 ahead"), (6, 666, "v6 L2 data prefetch 666 ahead"), (6, 1332, "v6 L2 data prefetch 1332 ahead"),
+                        (6, 2664, "v6 L2 data prefetch 2664 ahead"), (7, 148 * 8, "v7 persistent + 4 levels, 1184 blocks"),
+                        (7, 148 * 16, "v7 persistent + 4 levels, 2368 blocks"),
+                        (8, 148 * 9, "v8 persistent, no prefetch, 1332 blocks"), (8, 148 * 18, "v8 persistent, no prefetch, 2664 blocks"),
+                        (8, 148 * 72, "v8 persistent, no prefetch, 10656 blocks")]:
     g.reset_kernel_timing()
     for _ in range(12):
         rc = lib.mpasb200_debug_divdamp(g._h, var, 100.0, arg)
