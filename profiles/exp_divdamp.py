@@ -16,7 +16,8 @@ from mpas_regent_b200 import _abi, dynamics, traffic  # noqa: E402
 nC = int(sys.argv[1]) if len(sys.argv) > 1 else 655362
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 55
 mesh, st, t_init = bench.build_inputs(nC, L)
-g = dynamics.Dynamics(dynamics.dims_of(mesh, L), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX))
+LIB = os.environ.get("MPASB200_LIB")          # optional: an alternative build of the library (launch-bound experiments)
+g = dynamics.Dynamics(dynamics.dims_of(mesh, L), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX), lib_path=LIB)
 g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
 del st
 dt = bench.dt_for(nC)
@@ -40,6 +41,8 @@ lib = g._lib
 lib.mpasb200_debug_divdamp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
 lib.mpasb200_debug_divdamp.restype = C.c_int
 bytes_dd = 9 * 8 * nC * L
+if os.environ.get("SKIP_VARIANTS"):
+    sys.exit(0)
 print("== divdamp variants ==")
 for var, arg, label in [(0, 0, "production"), (1, 0, "v1 flag+ecv together"), (2, 1332, "v2 +L2 prefetch 1332 ahead"),
                         (2, 2664, "v2 +L2 prefetch 2664 ahead"), (3, 0, "v3 two edges/thread"), (4, 148 * 9, "v4 persistent 1332 blocks"),
