@@ -121,6 +121,14 @@ def build_inputs(n_cells: int, L: int):
     return st.mesh, st, time.time() - t0
 
 
+def host_threads() -> int:
+    """host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the oracle takes an explicit count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(sample_cells: int, L: int, steps: int, warmup: int, threads: int):
     """The oracle (a port: the Regent reference cannot run here) on a bounded sample of the workload."""
     from mpas_regent_b200 import _abi, dynamics, icosa, init_jw
@@ -146,8 +154,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.oracle import Oracle
-    threads = Oracle.max_threads()
+    threads = host_threads()
     val, sec = cpu_baseline(args.cpu_sample_cells, args.levels, max(1, args.steps), max(0, args.warmup), threads)
     sample = (f"oracle port (literal C++ restatement, OpenMP over the outer entity loop), x1.{args.cpu_sample_cells} "
               f"icosahedral mesh x {args.levels} levels, {args.steps} RK3 steps after {args.warmup} warm-up")
@@ -160,10 +167,28 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route everything that libraries print on stdout (e.g. "NCCL version ...") to stderr, so that stdout carries
+    exactly ONE line: the JSON result."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -295,8 +320,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle.oracle import Oracle
-        thr = Oracle.max_threads()
+        thr = host_threads()
         v1, s1 = cpu_baseline(args.cpu_sample_cells, L, 1, 0, 1)
         vN, sN = cpu_baseline(args.cpu_sample_cells, L, 2, 1, thr)
         cpu = {"value": vN, "unit": UNIT, "cores": thr, "kind": "port",
@@ -322,7 +346,7 @@ def main():
             "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in top},
             "e2e": e2e, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
