@@ -292,8 +292,12 @@ def main():
             u = traffic.units(key, scratch=False)
             bytes_per_launch = u * 8.0 * n_local * L
             achieved = bytes_per_launch / (kms / kn * 1e-3) / 1e9
+            traffic_bytes = None        # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+            tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if world == 1 and nC == 655362 and L == 55 and os.path.exists(tj):
+                traffic_bytes = json.load(open(tj))["bytes_per_launch"].get(name)
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "traffic": traffic_bytes, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                     "avg_launch_ms": kms / kn, "launches_timed": kn, "share_of_step": kms / ms}
     step_bytes = traffic.SURVEY_STEP_UNITS_CANONICAL * 8.0 * nC * L
     step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9

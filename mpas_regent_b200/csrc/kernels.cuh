@@ -154,7 +154,7 @@ __global__ void k_moist(const View V) {
 // atm_compute_vert_imp_coefs  :513-592
 // One block owns whole columns: everything read from the previous call (gamma_tri[k-1]) is read
 // before the barrier, everything this call produces for neighbours (coftz, cofwt) goes through smem.
-__global__ void __launch_bounds__(256, LB_MISC) k_vert_imp(const View V, double dtseps, double c2, double rcv, double gravity) {
+__global__ void k_vert_imp(const View V, double dtseps, double c2, double rcv, double gravity) {
   extern __shared__ double sm[];
   PAIR_THREAD(V.nCells)
   const int TS = LP + 2;
@@ -296,7 +296,7 @@ __global__ void k_diag_ke_holl(const View V) {     // hollingsworth part 2 :403-
 // atm_compute_dyn_tend_work  :814-1480
 // cell pre-pass: kdiff (:858-917), h_divergence (:924-938), tend_rho + dpdz (:942-951)
 template <bool RK0>
-__global__ void __launch_bounds__(256, LB_MISC) k_dt_cell0(const View V, const DynTendParams P, double len_disp, double cam_coef) {
+__global__ void k_dt_cell0(const View V, const DynTendParams P, double len_disp, double cam_coef) {
   PAIR_THREAD(V.nCells)
   if (!m0) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
@@ -403,7 +403,7 @@ DI double vmix_u_at(double rho_e, double visc, double up, double uc, double um, 
 
 // u tendency  :958-1163
 template <bool RK0>
-__global__ void __launch_bounds__(256, LB_EDGE) k_dt_edge(const View V, const DynTendParams P) {
+__global__ void k_dt_edge(const View V, const DynTendParams P) {
   extern __shared__ double sm[];
   PAIR_THREAD(V.nEdges)
   const int TS = LP + 2;
@@ -541,7 +541,7 @@ DI D2 w_adv_curv(const View& V, const DynTendParams& P, int x, int k0, size_t ix
 }
 
 // rk_step == 0, cell pass A: w after advection+curvature (:1170-1218) and the first del^2 of theta (:1365-1382)
-__global__ void __launch_bounds__(256, LB_MISC) k_dt_cellA(const View V, const DynTendParams P) {
+__global__ void k_dt_cellA(const View V, const DynTendParams P) {
   PAIR_THREAD(V.nCells)
   if (!m0) return;
   st2m(FLD(w), ix, w_adv_curv(V, P, x, k0, ix, LP, m0, m1), m0, m1);
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(256, LB_MISC) k_dt_cellA(const View V, const D
   st2m(FLD(tend_theta_euler), ix, tte, m0, m1);
 }
 // rk_step == 0, cell pass B: first del^2 of w  :1231-1254  (needs pass A's w on neighbour cells)
-__global__ void __launch_bounds__(256, LB_MISC) k_dt_cellB(const View V, const DynTendParams P) {
+__global__ void k_dt_cellB(const View V, const DynTendParams P) {
   PAIR_THREAD(V.nCells)
   if (!m0) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
@@ -783,7 +783,7 @@ __global__ void __launch_bounds__(256, LB_CELLC) k_dt_cellC(const View V, const 
 
 // ============================================================================================
 // atm_set_smlstep_pert_variables_work  :1503-1528  (levels 0..L-1 of the cells of cpr; level -1 reads 0)
-__global__ void __launch_bounds__(256, LB_MISC) k_smlstep(const View V, int nRelaxZone) {
+__global__ void k_smlstep(const View V, int nRelaxZone) {
   PAIR_THREAD(V.nCells)
   if (!m0) return;
   if (!V.inCpr[x] || V.bdyMaskCell[x] > nRelaxZone) return;
