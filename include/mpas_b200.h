@@ -103,6 +103,8 @@ typedef struct {
   int32_t use_graph;                  /* 1: mpasb200_srk3 replays a captured CUDA graph */
   int32_t acoustic_exact;             /* 1: evaluate the acoustic column sweep strictly left-to-right (two kernels, one
                                          thread per column); 0 (default): fused kernel, affine sweep (a few ulp apart) */
+  int32_t acoustic_tma;               /* acoustic step form: 0 = one fused kernel, plain loads; 1 = one fused kernel, own-column strips staged
+                                         with cp.async.bulk (TMA); 2 (default) = lean gather kernel + TMA streaming/sweep kernel */
 } MpasConfig;
 
 /* ---- level-0 ("static") region data -------------------------------------------- *

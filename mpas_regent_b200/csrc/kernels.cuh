@@ -941,6 +941,182 @@ __global__ void __launch_bounds__(256, S0 ? LB_AC + 1 : LB_AC) k_acoustic(const 
   st2m(FLD(rw_p), ix, rw_new, wr0, m1); st2m(FLD(wwAvg), ix, ww_new, wr0, m1);
 }
 
+// Split form of the acoustic step, phase 1 (lean, register-light): the edgesOnCell gathers only  (:1644-1652).
+// rs_h / ts_h go to library scratch and are streamed by phase 2 as two more strips.
+__global__ void k_acoustic_gather(const View V, double dts) {
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
+  if (V.specZoneMaskCell[x] != 0.0) return;
+  const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
+  const double* ru_p = FLD(ru_p); const double* tm = FLD(theta_m);
+  const double inva = V.invAreaCell[x];
+  D2 rs = bc(0), ts = bc(0);
+#pragma unroll 2
+  for (int i = 0; i < n; ++i) {
+    const int e = V.edgesOnCell[x * V.MEP + i];
+    const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+    const D2 flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G2(ru_p, e) * inva;
+    rs -= flux;
+    ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
+  }
+  st2m(V.scr_rs, ix, rs, m0, m1); st2m(V.scr_ts, ix, ts, m0, m1);
+}
+
+// ---- TMA (bulk async copy) helpers: global -> shared strips whose bytes in flight cost no registers -----------------
+DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DI void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+DI void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+DI void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+DI void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (int spin = 0; spin < (1 << 28); ++spin) {
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();      // a lost transaction must fail loudly, never hang the GPU
+}
+
+// TMA form of the fused acoustic kernel (MpasConfig.acoustic_tma = 1).  A block owns C whole columns; for a tile
+// of C consecutive columns every own-column input field is ONE contiguous strip of C*LP doubles, fetched with one
+// cp.async.bulk per field into shared memory (14 or 18 strips per block, issued up front by 18 threads; completion on
+// an mbarrier).  While the strips are in flight the threads do the index loads and the edgesOnCell gathers.  All
+// column arithmetic then reads shared memory.  Same arithmetic as k_acoustic.
+enum { AF_tend_rho, AF_theta_m, AF_w, AF_coftz, AF_cofwz, AF_cofwr, AF_cofwt, AF_a_tri, AF_alpha_tri, AF_zz, AF_rw_save, AF_rw,
+       AF_dss, AF_rho_zz, AF_rs, AF_ts, AF_rho_pp, AF_rtheta_pp, AF_rw_p, AF_wwAvg, AF_COUNT };
+struct AcPtrs { const double* p[AF_COUNT]; };
+template <bool S0, int ABL = 0>     // ABL: ablation switches for profiling only (1 = no gathers, 2 = no sweep, 4 = no stores)
+__global__ void __launch_bounds__(128, 5) k_acoustic_tma(const View V, const AcPtrs F, double dts, double epssm, double resm) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  PAIR_THREAD(V.nCells)
+  const int C = blockDim.y, TS = LP + 2, NF = S0 ? (int)AF_rho_pp : (int)AF_COUNT;
+  const int CL = C * LP;
+  double* in = reinterpret_cast<double*>(smraw);                 // [NF][C*LP]
+  double* s_rp0 = in + (size_t)NF * CL + (size_t)threadIdx.y * TS;
+  double* s_rt0 = s_rp0 + (size_t)C * TS;
+  double* s_P = s_rt0 + (size_t)C * TS;
+  double* s_Q = s_P + (size_t)C * TS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(in + (size_t)NF * CL + (size_t)4 * C * TS);
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  const size_t tile0 = (size_t)blockIdx.x * C * LP;
+  if (tid == 0) mbar_expect_tx(bar, (uint32_t)(NF * CL * sizeof(double)));
+  for (int f = tid; f < NF; f += blockDim.x * blockDim.y)         // one strip per thread (blocks can be smaller than NF)
+    bulk_g2s(in + (size_t)f * CL, F.p[f] + tile0, (uint32_t)(CL * sizeof(double)), bar);
+  const size_t cl = (size_t)threadIdx.y * LP + k0;                 // this thread's level pair inside a strip
+#define SIN(f) (in + (size_t)(f) * CL)
+  const bool spec = inx ? (V.specZoneMaskCell[x] != 0.0) : false;
+  if (S0 && inx) {                                                                                    // :1625-1630, level L
+    if (k0 == L) { FLD(wwAvg)[ix] = 0; FLD(rw_p)[ix] = 0; }
+    if (k1 == L) { FLD(wwAvg)[ix + 1] = 0; FLD(rw_p)[ix + 1] = 0; }
+  }
+  D2 rs = bc(0), ts = bc(0);
+  if (m0 && !spec && !(ABL & 8)) {                                 // gathers overlap with the bulk copies
+    const double* tm = FLD(theta_m);
+    const int ME = V.maxEdges, n = (ABL & 1) ? 0 : V.nEdgesOnCell[x];
+    const double* ru_p = FLD(ru_p);
+    const double inva = V.invAreaCell[x];
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {                                                                     // :1644-1652
+      const int e = V.edgesOnCell[x * V.MEP + i];
+      const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+      const D2 flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G2(ru_p, e) * inva;
+      rs -= flux;
+      ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
+    }
+  }
+  mbar_wait(bar, 0);
+  D2 rw_old = bc(0), rw_oldp = bc(0), rho_old = bc(0), rt_old = bc(0);
+  D2 cofrz = bc(0), rdzw = bc(0), coftz = bc(0), coftz_p = bc(0);
+  AcTerms t0;
+  t0.A0 = t0.A1 = t0.A2 = t0.al = t0.r1 = t0.r3 = t0.Q = 0.0; t0.r2 = 1.0;
+  double P0 = 0.0, Q0 = 0.0, P1 = 0.0, Q1 = 1.0;
+  if (m0) {
+    cofrz = ld2(FLD(cofrz), k0); rdzw = ld2(FLD(rdzw), k0);
+    if (!S0) {
+      rw_old = ld2(SIN(AF_rw_p), cl); rw_oldp = above(SIN(AF_rw_p), cl, k0, L, rw_old);
+      rho_old = ld2(SIN(AF_rho_pp), cl); rt_old = ld2(SIN(AF_rtheta_pp), cl);
+    }
+    st2m(FLD(rtheta_pp_old), ix, S0 ? bc(0.0) : rt_old, m0, m1);                                      // :1615-1623
+    if (!spec) {
+      const D2 w2 = ld2(SIN(AF_w), cl), tr = ld2(SIN(AF_tend_rho), cl), tm2 = ld2(SIN(AF_theta_m), cl);
+      coftz = ld2(SIN(AF_coftz), cl); coftz_p = above(SIN(AF_coftz), cl, k0, L, coftz);
+      if (ABL & 8) { rs = ld2(SIN(AF_rs), cl); ts = ld2(SIN(AF_ts), cl); }      // phase 1 of the split form (k_acoustic_gather)
+      rs = rho_old + dts * tr + rs - cofrz * resm * (rw_oldp - rw_old);                               // :1657
+      ts = rt_old + dts * tm2 + ts - resm * rdzw * (coftz_p * rw_oldp - coftz * rw_old);              // :1658
+      const D2 rp0 = rs - cofrz * rw_oldp, rt0 = ts - rdzw * (coftz_p * rw_oldp);
+      const D2 zz = ld2(SIN(AF_zz), cl), zzm = below(SIN(AF_zz), cl, k0, zz);
+      const D2 cwt = ld2(SIN(AF_cofwt), cl), cwtm = below(SIN(AF_cofwt), cl, k0, cwt);
+      const D2 rz = ld2(SIN(AF_rho_zz), cl), rzm = below(SIN(AF_rho_zz), cl, k0, rz);
+      const D2 cwz = ld2(SIN(AF_cofwz), cl), cwr = ld2(SIN(AF_cofwr), cl);
+      const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0);
+      const D2 ds = ld2(SIN(AF_dss), cl), rws = ld2(SIN(AF_rw_save), cl), rwv = ld2(SIN(AF_rw), cl);
+      const D2 at = ld2(SIN(AF_a_tri), cl), al = ld2(SIN(AF_alpha_tri), cl);
+      if (k0 > 0) {
+        const double cofrz_m = FLD(cofrz)[k0 - 1], rdzw_m = FLD(rdzw)[k0 - 1], coftz_m = SIN(AF_coftz)[cl - 1];
+        t0 = ac_terms(dts, resm, rw_old.x, w2.x, ts.x, rs.x, rt_old.x, rho_old.x, zz.x, zzm.x, cwt.x, cwtm.x, rz.x, rzm.x, cwz.x, cwr.x,
+                      fm.x, fp.x, ds.x, rws.x, rwv.x, cofrz_m, rdzw_m * coftz_m, at.x, al.x);
+        Q0 = t0.Q;
+      } else { P0 = rw_old.x; Q0 = 0.0; }
+      if (m1) {
+        const AcTerms t1 = ac_terms(dts, resm, rw_old.y, w2.y, ts.y, rs.y, rt_old.y, rho_old.y, zz.y, zzm.y, cwt.y, cwtm.y, rz.y, rzm.y,
+                                    cwz.y, cwr.y, fm.y, fp.y, ds.y, rws.y, rwv.y, cofrz.x, rdzw.x * coftz.x, at.y, al.y);
+        P1 = ac_P(t1, rp0.x, rt0.x); Q1 = t1.Q;
+        s_rp0[k1] = rp0.y; s_rt0[k1] = rt0.y;
+      }
+    }
+  }
+  __syncthreads();
+  // Two-level sweep: every thread folds its two levels into one affine map, ONE thread per column runs the
+  // recurrence over the 28 pair maps (half the serial length), every thread then finishes its own two levels.
+  const int pr = threadIdx.x;
+  if (m0 && !spec) {
+    if (k0 > 0) P0 = ac_P(t0, s_rp0[k0 - 1], s_rt0[k0 - 1]);
+    s_P[pr] = __fma_rn(Q1, P0, P1); s_Q[pr] = Q1 * Q0;          // level k1 is the identity map (P1 = 0, Q1 = 1) when it is inactive
+  }
+  __syncthreads();
+  if (inx && !spec && k0 == 0 && !(ABL & 2)) {
+    const int np = (L + 1) / 2;
+    double xe = s_P[0];
+#pragma unroll 4
+    for (int p = 1; p < np; ++p) { xe = __fma_rn(s_Q[p], xe, s_P[p]); s_P[p] = xe; }
+  }
+  __syncthreads();
+  if (!m0) return;
+  const D2 ww_old = S0 ? bc(0.0) : ld2(SIN(AF_wwAvg), cl);
+  D2 rw_new, rho_new, rt_new, ww_new;
+  if (!spec) {
+    const double xprev = pr > 0 ? s_P[pr - 1] : 0.0;           // rw_p_new of the level below this pair
+    const double x0 = __fma_rn(Q0, xprev, P0);
+    rw_new = mk(x0, m1 ? __fma_rn(Q1, x0, P1) : 0.0);
+    const D2 wa = ww_old + 0.5 * (1.0 - epssm) * rw_old;                                              // :1661
+    const D2 wb = wa + 0.5 * (1.0 + epssm) * rw_new;                                                  // :1689
+    ww_new = mk(k0 > 0 ? wb.x : ww_old.x, wb.y);
+    rho_new = rs - cofrz * (rw_oldp - rw_new);                                                        // :1694
+    rt_new = ts - rdzw * (coftz_p * rw_oldp - coftz * rw_new);                                        // :1695-1696
+  } else {                                                                                            // :1698-1703
+    rho_new = rho_old + dts * ld2(SIN(AF_tend_rho), cl);
+    rt_new = rt_old + dts * ld2(SIN(AF_theta_m), cl);
+    rw_new = rw_old + dts * ld2(SIN(AF_w), cl);
+    ww_new = ww_old + 0.5 * (1.0 + epssm) * rw_new;
+  }
+  if ((ABL & 4) && rho_new.x != 1.2345e300) return;       // profiling only: keep the math, drop the stores
+  st2m(FLD(rho_pp), ix, rho_new, m0, m1); st2m(FLD(rtheta_pp), ix, rt_new, m0, m1);
+  const bool wr0 = S0 || spec || k0 > 0;
+  st2m(FLD(rw_p), ix, rw_new, wr0, m1); st2m(FLD(wwAvg), ix, ww_new, wr0, m1);
+#undef SIN
+}
+
 // Two-kernel, strictly left-to-right form (MpasConfig.acoustic_exact = 1).  One thread per level in
 // phase 1, one thread per column in phase 2.
 __global__ void k_acoustic_flux(const View V, double dts, int small_step) {

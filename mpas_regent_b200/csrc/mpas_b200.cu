@@ -294,6 +294,33 @@ int t_smlstep(mpasb200_t* h) { LAUNCH(k_smlstep, h->nCells, 0, h->V, h->c.nRelax
 int t_acoustic(mpasb200_t* h, double dts, int small_step) {
   const double epssm = h->c.config_epssm;
   const double resm = (1.0 - epssm) / (1.0 + epssm);
+  const bool tma_fits = ((size_t)AF_COUNT * h->LP + (size_t)4 * (h->LP + 2)) * sizeof(double) + 16 <= 48 * 1024 && h->LP / 2 <= 128;
+  if (!h->c.acoustic_exact && h->c.acoustic_tma && h->nCells > 0 && tma_fits) {
+    const View& V = h->V;
+    AcPtrs F;
+#define AF(n) F.p[AF_##n] = V.f[MPASB200_F_##n]
+    AF(tend_rho); AF(theta_m); AF(w); AF(coftz); AF(cofwz); AF(cofwr); AF(cofwt); AF(a_tri); AF(alpha_tri); AF(zz); AF(rw_save); AF(rw);
+    AF(dss); AF(rho_zz); AF(rho_pp); AF(rtheta_pp); AF(rw_p); AF(wwAvg);
+#undef AF
+    F.p[AF_rs] = V.scr_rs; F.p[AF_ts] = V.scr_ts;
+    const int split = h->c.acoustic_tma == 2;
+    if (split) LAUNCH(k_acoustic_gather, h->nCells, 0, h->V, dts);
+    const int T = h->LP / 2, NF = small_step == 0 ? (int)AF_rho_pp : (int)AF_COUNT;
+    int C = 4;                               // columns per block: as many as fit the default 48 KB of dynamic shared memory
+    auto smem_for = [&](int c) { return ((size_t)NF * c * h->LP + (size_t)4 * c * (h->LP + 2)) * sizeof(double) + 16; };
+    while (C > 1 && (smem_for(C) > 48 * 1024 || C * T > 128)) C /= 2;
+    const size_t smem = smem_for(C);
+    dim3 block(T, C), grid((h->nCells + C - 1) / C);
+    {
+      KTimer kt_(h, small_step == 0 ? "k_acoustic_tma<true>" : "k_acoustic_tma<false>");
+      if (small_step == 0) { if (split) k_acoustic_tma<true, 8><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm);
+                             else k_acoustic_tma<true, 0><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm); }
+      else { if (split) k_acoustic_tma<false, 8><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm);
+             else k_acoustic_tma<false, 0><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm); }
+    }
+    h->launches++;
+    return post_launch(h);
+  }
   if (!h->c.acoustic_exact) {
     if (small_step == 0) LAUNCH(k_acoustic<true>, h->nCells, tile_bytes(h, 4), h->V, dts, epssm, resm);
     else LAUNCH(k_acoustic<false>, h->nCells, tile_bytes(h, 4), h->V, dts, epssm, resm);
@@ -439,7 +466,7 @@ void mpasb200_default_config(MpasConfig* c) {
   c->config_horiz_mixing = MPASB200_MIX_2D_SMAGORINSKY;
   c->nRelaxZone = 5; c->number_of_sub_steps = 2; c->config_dynamics_split_steps = 1;
   c->index_policy = MPASB200_INDEX_CORRECTED; c->rkarg_policy = MPASB200_RKARG_SUBSTEP_TRUNC;
-  c->sfc_renumber = 1; c->device = -1; c->use_graph = 0; c->acoustic_exact = 0;
+  c->sfc_renumber = 1; c->device = -1; c->use_graph = 0; c->acoustic_exact = 0; c->acoustic_tma = 2;
 }
 
 const char* mpasb200_last_error(const mpasb200_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -483,7 +510,7 @@ int mpasb200_create(const MpasDims* dims, const MpasConfig* cfg, mpasb200_t** ou
   const size_t scr = ((size_t)(h->nCells + 1) * h->LP + 15) / 16 * 16;
   double* arena = nullptr;
   const size_t scr_e = ((size_t)(h->nEdges + 1) * h->LP + 15) / 16 * 16;
-  int rc = dev_alloc(h, &arena, total + 2 * scr + scr_e);
+  int rc = dev_alloc(h, &arena, total + 2 * scr + scr_e + (size_t)16 * h->LP);   // + slack: bulk strips of a last, partial tile
   if (rc) { g_create_error = h->err; mpasb200_destroy(h); return rc; }
   for (int id = 0; id < MPASB200_F_COUNT; ++id) V.f[id] = arena + off[id];
   V.scr_rs = arena + total; V.scr_ts = arena + total + scr; V.scr_flux = arena + total + 2 * scr;
@@ -916,6 +943,34 @@ int mpasb200_debug_divdamp(mpasb200_t* h, int variant, double dts, int arg) {
     case 8: { KTimer kt(h, "k_divdamp_v8"); k_divdamp_v8<<<arg, dim3(T, C), 0, h->stream>>>(h->V, coef); h->launches++; } break;
     default: return fail(h, MPASB200_EINVAL, "unknown variant");
   }
+  return post_launch(h);
+}
+// Ablation launches of the TMA acoustic kernel (profiling only; results are NOT the task's results).
+int mpasb200_debug_acoustic(mpasb200_t* h, int abl, double dts) {
+  REQUIRE_MESH();
+  Entry en(h, -1);
+  const View& V = h->V;
+  AcPtrs F;
+#define AF(n) F.p[AF_##n] = V.f[MPASB200_F_##n]
+  AF(tend_rho); AF(theta_m); AF(w); AF(coftz); AF(cofwz); AF(cofwr); AF(cofwt); AF(a_tri); AF(alpha_tri); AF(zz); AF(rw_save); AF(rw);
+  AF(dss); AF(rho_zz); AF(rho_pp); AF(rtheta_pp); AF(rw_p); AF(wwAvg);
+#undef AF
+  F.p[AF_rs] = V.scr_rs; F.p[AF_ts] = V.scr_ts;
+  const double epssm = h->c.config_epssm, resm = (1.0 - epssm) / (1.0 + epssm);
+  const int C = 4, T = h->LP / 2, NF = (int)AF_COUNT;
+  const size_t smem = ((size_t)NF * C * h->LP + (size_t)4 * C * (h->LP + 2)) * sizeof(double) + 16;
+  dim3 block(T, C), grid((h->nCells + C - 1) / C);
+  KTimer kt_(h, "k_acoustic_tma_abl");
+  switch (abl) {
+    case 0: k_acoustic_tma<false, 0><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm); break;
+    case 1: k_acoustic_tma<false, 1><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm); break;
+    case 2: k_acoustic_tma<false, 2><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm); break;
+    case 3: k_acoustic_tma<false, 3><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm); break;
+    case 4: k_acoustic_tma<false, 4><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm); break;
+    case 7: k_acoustic_tma<false, 7><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm); break;
+    default: return fail(h, MPASB200_EINVAL, "unknown ablation");
+  }
+  h->launches++;
   return post_launch(h);
 }
 int mpasb200_enable_kernel_timing(mpasb200_t* h, int on) {

@@ -63,11 +63,17 @@ K: Dict[str, Tuple[List[str], List[str]]] = {
     "k_acoustic_column": (["tend_rho", "theta_m", "w", "coftz", "cofwz", "cofwr", "cofwt", "a_tri", "alpha_tri", "zz",
                            "rw_save", "rw", "dss", "rho_zz", "scr", "scr", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"],
                           ["rho_pp", "rtheta_pp", "rw_p", "wwAvg"]),
+    "k_acoustic_tma<true>": (["scr", "scr", "theta_m", "tend_rho", "w", "coftz", "cofwz", "cofwr", "cofwt", "a_tri", "alpha_tri", "zz",
+                              "rw_save", "rw", "dss", "rho_zz"], ["rtheta_pp_old", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"]),
+    "k_acoustic_tma<false>": (["scr", "scr", "theta_m", "tend_rho", "w", "coftz", "cofwz", "cofwr", "cofwt", "a_tri", "alpha_tri", "zz",
+                               "rw_save", "rw", "dss", "rho_zz", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"],
+                              ["rtheta_pp_old", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"]),
     "k_acoustic<true>": (["ru_p", "theta_m", "tend_rho", "w", "coftz", "cofwz", "cofwr", "cofwt", "a_tri", "alpha_tri", "zz",
                           "rw_save", "rw", "dss", "rho_zz"], ["rtheta_pp_old", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"]),
     "k_acoustic<false>": (["ru_p", "theta_m", "tend_rho", "w", "coftz", "cofwz", "cofwr", "cofwt", "a_tri", "alpha_tri", "zz",
                            "rw_save", "rw", "dss", "rho_zz", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"],
                           ["rtheta_pp_old", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"]),
+    "k_acoustic_gather": (["ru_p", "theta_m"], ["scr", "scr"]),
     "k_divdamp": (["rtheta_pp", "rtheta_pp_old", "theta_m", "ru_p"], ["ru_p"]),
     "k_rec_cell1": (["rho_p_save", "rho_pp", "rho_base", "wwAvg", "rw_save", "rw_p", "zz", "rtheta_base", "rtheta_p_save",
                      "rtheta_pp"], ["rho_p", "rho_zz", "wwAvg", "rw", "w", "rtheta_p", "theta_m"]),
@@ -106,7 +112,7 @@ def step_launches(canonical: bool = True) -> List[str]:
             seq += ["k_dt_cell0<false>", "k_dt_edge<false>", "k_dt_theta_flux", "k_dt_cellC<false>"]
         seq.append("k_smlstep")
         for ss in range((1 if stage < 2 else 2) + 1):
-            seq += ["k_acoustic<true>" if ss == 0 else "k_acoustic<false>", "k_divdamp"]
+            seq += ["k_acoustic_gather", "k_acoustic_tma<true>" if ss == 0 else "k_acoustic_tma<false>", "k_divdamp"]
         seq += ["k_diag_vertex", "k_diag_cell", "k_diag_edge<true>" if stage == 2 else "k_diag_edge<false>"]
     seq += ["k_finish_cell", "k_finish_edge"]
     return seq
@@ -134,8 +140,10 @@ TASK_KERNELS = {
                              "k_dt_cellA", "k_dt_cellB", "k_dt_theta_flux", "k_dt_cellC<true>"],
     "compute_dyn_tend:rk>0": ["k_dt_cell0<false>", "k_dt_edge<false>", "k_dt_theta_flux", "k_dt_cellC<false>"],
     "set_smlstep_pert_variables": ["k_smlstep"],
-    "advance_acoustic_step:s0": ["k_acoustic<true>"],
-    "advance_acoustic_step": ["k_acoustic<false>"],
+    "advance_acoustic_step:s0": ["k_acoustic_gather", "k_acoustic_tma<true>"],
+    "advance_acoustic_step": ["k_acoustic_gather", "k_acoustic_tma<false>"],
+    "advance_acoustic_step:s0:fused": ["k_acoustic<true>"],
+    "advance_acoustic_step:fused": ["k_acoustic<false>"],
     "advance_acoustic_step:s0:exact": ["k_acoustic_flux:s0", "k_acoustic_column:s0"],
     "advance_acoustic_step:exact": ["k_acoustic_flux", "k_acoustic_column"],
     "divergence_damping_3d": ["k_divdamp"],

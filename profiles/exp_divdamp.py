@@ -17,7 +17,7 @@ nC = int(sys.argv[1]) if len(sys.argv) > 1 else 655362
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 55
 mesh, st, t_init = bench.build_inputs(nC, L)
 LIB = os.environ.get("MPASB200_LIB")          # optional: an alternative build of the library (launch-bound experiments)
-g = dynamics.Dynamics(dynamics.dims_of(mesh, L), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX), lib_path=LIB)
+g = dynamics.Dynamics(dynamics.dims_of(mesh, L), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, acoustic_tma=int(os.environ.get("ACOUSTIC_TMA", "0"))), lib_path=LIB)
 g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
 del st
 dt = bench.dt_for(nC)
@@ -41,6 +41,17 @@ lib = g._lib
 lib.mpasb200_debug_divdamp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
 lib.mpasb200_debug_divdamp.restype = C.c_int
 bytes_dd = 9 * 8 * nC * L
+lib = g._lib
+if os.environ.get("ABLATE"):
+    lib.mpasb200_debug_acoustic.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    lib.mpasb200_debug_acoustic.restype = C.c_int
+    print("== acoustic (TMA) ablations: 1 = no gathers, 2 = no sweep, 4 = no stores ==")
+    for abl in (0, 1, 2, 3, 4, 7):
+        g.reset_kernel_timing()
+        for _ in range(6):
+            assert lib.mpasb200_debug_acoustic(g._h, abl, 20.0) == 0
+        (name, (ms, n)), = g.kernel_times().items()
+        print(f"ablation {abl}: {ms / n:7.3f} ms")
 if os.environ.get("SKIP_VARIANTS"):
     sys.exit(0)
 print("== divdamp variants ==")

@@ -188,18 +188,18 @@ def test_error_paths(grid642):
     g.close()
 
 
-@pytest.mark.parametrize("exact", [0, 1], ids=["fused_affine", "two_kernel_exact"])
+@pytest.mark.parametrize("exact", [0, 1, 2, 3], ids=["fused_affine", "two_kernel_exact", "fused_affine_tma", "split_gather_tma"])
 def test_acoustic_modes(grid2562, exact):
     """both evaluations of the acoustic column sweep agree with the oracle (1e-12); the strictly
     left-to-right one (acoustic_exact=1) is additionally bit-identical on the fields the sweep produces."""
-    st, ora, g = build_pair(grid2562, L_SMALL, _abi.INDEX_CORRECTED, m5=True, acoustic_exact=exact)
+    st, ora, g = build_pair(grid2562, L_SMALL, _abi.INDEX_CORRECTED, m5=True, acoustic_exact=int(exact == 1), acoustic_tma=(exact - 1 if exact >= 2 else 0))
     _warm(ora, g)
     for b in (ora, g):
         for ss, dts in ((0, 360.0), (1, 360.0), (2, 360.0)):
             b.atm_advance_acoustic_step(dts, ss)
             b.atm_divergence_damping_3d(dts)
     compare(g, ora, what=f"acoustic exact={exact}")
-    if exact:
+    if exact == 1:
         for n in ("rw_p", "rho_pp", "rtheta_pp", "wwAvg", "rtheta_pp_old", "ru_p"):
             assert np.array_equal(g.download_field(n), ora.download_field(n)), n
     g.close(); ora.close()
