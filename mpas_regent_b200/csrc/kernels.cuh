@@ -401,14 +401,68 @@ DI double vmix_u_at(double rho_e, double visc, double up, double uc, double um, 
   return rho_e * visc * ((up - uc) / (zp - z0) - (uc - um) / (z0 - zm)) / (0.5 * (zp - zm));
 }
 
-// u tendency  :958-1163
-template <bool RK0>
+// tend_u_euler at rk_step == 0: pressure gradient (:964-970), 2nd-order Smagorinsky mixing (:1044-1047), the second del^2
+// of the 4th-order filter (:1072-1090) and the optional vertical mixing (:1094-1146).  A lean gather kernel of its own:
+// k_dt_edge then is the same kernel for every stage and just reads tend_u_euler.
+__global__ void k_dt_edge_euler(const View V, const DynTendParams P) {
+  extern __shared__ double sm[];
+  PAIR_THREAD(V.nEdges)
+  const int TS = LP + 2;
+  double* s_um = sm + (size_t)threadIdx.y * TS;      // u_mix (vertical mixing of the perturbation from the initial state)
+  const double* u = FLD(u);
+  const bool vmix_pert = P.vmix_u_on && !P.mix_full;
+  int4 cv = make_int4(0, 0, 0, 0);
+  D2 rho_e = bc(0.0), tue = bc(0.0);
+  if (m0) {
+    cv = V.ecv[x];
+    rho_e = ld2(FLD(rho_edge), ix);
+    const double invDc = V.invDcEdge[x];
+    const double* pp = FLD(pressure_p); const double* zz = FLD(zz); const double* dpdz = FLD(dpdz);
+    tue = -ld2(FLD(cqu), ix) * ((G2(pp, cv.y) - G2(pp, cv.x)) * invDc / (0.5 * (G2(zz, cv.y) + G2(zz, cv.x)))
+                                - 0.5 * ld2(FLD(zxu), ix) * (G2(dpdz, cv.x) + G2(dpdz, cv.y)));      // :967-969
+    const double* kd = FLD(kdiff);
+    const D2 u_diffusion = u_diffusion2(V, x, cv, k0, LP);
+    const D2 kdiffu = 0.5 * (G2(kd, cv.x) + G2(kd, cv.y));
+    tue += rho_e * kdiffu * u_diffusion * V.meshScalingDel2[x];                                     // :1046-1047
+    if (P.visc4_on) {                                                                               // :1072-1090
+      const double* dd = FLD(delsq_divergence); const double* dvo = FLD(delsq_vorticity);
+      const double u_mix_scale = V.meshScalingDel4[x] * P.h_mom_eddy_visc4;
+      const double r_dc4 = u_mix_scale * P.del4u_div_factor * invDc;
+      const double r_dv4 = u_mix_scale * dmin(V.invDvEdge[x], 4 * invDc);
+      const D2 ud4 = rho_e * ((G2(dd, cv.y) - G2(dd, cv.x)) * r_dc4 - (G2(dvo, cv.w) - G2(dvo, cv.z)) * r_dv4);
+      tue -= ud4;
+    }
+    if (vmix_pert) {                                                                                // :1120-1123
+      const D2 umix = ld2(u, ix) - ld2(FLD(u_init), k0) * V.cosAngleEdge[x] - ld2(FLD(v_init), k0) * V.sinAngleEdge[x];
+      s_um[k0] = umix.x; if (m1) s_um[k1] = umix.y;
+      st2m(FLD(u_mix), ix, umix, m0, m1);
+    }
+  }
+  if (vmix_pert) __syncthreads();          // uniform: P is a kernel argument
+  if (!m0) return;
+  if (P.vmix_u_on) {                                                                                // :1094-1146
+    const double* zg = FLD(zgrid);
+    for (int c = 0; c < 2; ++c) {
+      const int k = k0 + c;
+      if (!(k > 0 && k < L - 1)) continue;
+      const double z1 = 0.5 * (G1(zg, cv.x, k - 1) + G1(zg, cv.y, k - 1)), z2 = 0.5 * (G1(zg, cv.x, k) + G1(zg, cv.y, k));
+      const double z3 = 0.5 * (G1(zg, cv.x, k + 1) + G1(zg, cv.y, k + 1)), z4 = 0.5 * (G1(zg, cv.x, k + 2) + G1(zg, cv.y, k + 2));
+      double up, uc, um;
+      if (P.mix_full) { up = G1(u, x, k + 1); uc = G1(u, x, k); um = G1(u, x, k - 1); }
+      else { up = s_um[k + 1]; uc = s_um[k]; um = s_um[k - 1]; }
+      const double add = vmix_u_at(c ? rho_e.y : rho_e.x, P.v_mom_eddy_visc2, up, uc, um, z1, z2, z3, z4);
+      if (c) tue.y += add; else tue.x += add;
+    }
+  }
+  st2m(FLD(tend_u_euler), ix, tue, m0, m1);
+}
+
+// u tendency  :958-1163 (tend_u_euler comes from k_dt_edge_euler at rk_step 0, from the previous stages otherwise)
 __global__ void k_dt_edge(const View V, const DynTendParams P) {
   extern __shared__ double sm[];
   PAIR_THREAD(V.nEdges)
   const int TS = LP + 2;
   double* s_wduz = sm + (size_t)threadIdx.y * TS;
-  double* s_um = sm + (size_t)(blockDim.y + threadIdx.y) * TS;      // u_mix (vertical mixing of the perturbation)
   const double* u = FLD(u);
   int4 cv = make_int4(0, 0, 0, 0);
   D2 u2 = bc(0.0), wduz = bc(0.0);
@@ -424,11 +478,6 @@ __global__ void k_dt_edge(const View V, const DynTendParams P) {
     if (m1) wduz.y = wduz_at(k1, L, rwavg.y, fzm.y, fzp.y, um.y, u2.x, u2.y, up);
     s_wduz[k0] = wduz.x; if (m1) s_wduz[k1] = wduz.y;
     st2m(FLD(wduz), ix, wduz, m0, m1);
-    if (RK0 && P.vmix_u_on && !P.mix_full) {                                                        // :1120-1123
-      const D2 umix = u2 - ld2(FLD(u_init), k0) * V.cosAngleEdge[x] - ld2(FLD(v_init), k0) * V.sinAngleEdge[x];
-      s_um[k0] = umix.x; if (m1) s_um[k1] = umix.y;
-      st2m(FLD(u_mix), ix, umix, m0, m1);
-    }
   }
   if (inx && k0 == L) s_wduz[L] = FLD(wduz)[ix];          // level L: never written, read as stored
   if (inx && k1 == L) s_wduz[L] = FLD(wduz)[ix + 1];
@@ -463,41 +512,7 @@ __global__ void k_dt_edge(const View V, const DynTendParams P) {
     tend_u -= (P.omega2 * V.cosAngleEdge[x] * V.cosLatEdge[x] * rho_e * 0.25 * wsum)
               - (u2 * 0.25 * wsum * rho_e * P.inv_r_earth);                                        // :1011-1017
   }
-  D2 tue;
-  if (RK0) {
-    const double* pp = FLD(pressure_p); const double* zz = FLD(zz); const double* dpdz = FLD(dpdz);
-    tue = -ld2(FLD(cqu), ix) * ((G2(pp, cv.y) - G2(pp, cv.x)) * invDc / (0.5 * (G2(zz, cv.y) + G2(zz, cv.x)))
-                                - 0.5 * ld2(FLD(zxu), ix) * (G2(dpdz, cv.x) + G2(dpdz, cv.y)));      // :967-969
-    const double* kd = FLD(kdiff);
-    const D2 u_diffusion = u_diffusion2(V, x, cv, k0, LP);
-    const D2 kdiffu = 0.5 * (G2(kd, cv.x) + G2(kd, cv.y));
-    tue += rho_e * kdiffu * u_diffusion * V.meshScalingDel2[x];                                     // :1046-1047
-    if (P.visc4_on) {                                                                               // :1072-1090
-      const double* dd = FLD(delsq_divergence); const double* dvo = FLD(delsq_vorticity);
-      const double u_mix_scale = V.meshScalingDel4[x] * P.h_mom_eddy_visc4;
-      const double r_dc4 = u_mix_scale * P.del4u_div_factor * invDc;
-      const double r_dv4 = u_mix_scale * dmin(V.invDvEdge[x], 4 * invDc);
-      const D2 ud4 = rho_e * ((G2(dd, cv.y) - G2(dd, cv.x)) * r_dc4 - (G2(dvo, cv.w) - G2(dvo, cv.z)) * r_dv4);
-      tue -= ud4;
-    }
-    if (P.vmix_u_on) {                                                                              // :1094-1146
-      const double* zg = FLD(zgrid);
-      for (int c = 0; c < 2; ++c) {
-        const int k = k0 + c;
-        if (!(k > 0 && k < L - 1)) continue;
-        const double z1 = 0.5 * (G1(zg, cv.x, k - 1) + G1(zg, cv.y, k - 1)), z2 = 0.5 * (G1(zg, cv.x, k) + G1(zg, cv.y, k));
-        const double z3 = 0.5 * (G1(zg, cv.x, k + 1) + G1(zg, cv.y, k + 1)), z4 = 0.5 * (G1(zg, cv.x, k + 2) + G1(zg, cv.y, k + 2));
-        double up, uc, um;
-        if (P.mix_full) { up = G1(u, x, k + 1); uc = G1(u, x, k); um = G1(u, x, k - 1); }
-        else { up = s_um[k + 1]; uc = s_um[k]; um = s_um[k - 1]; }
-        const double add = vmix_u_at(c ? rho_e.y : rho_e.x, P.v_mom_eddy_visc2, up, uc, um, z1, z2, z3, z4);
-        if (c) tue.y += add; else tue.x += add;
-      }
-    }
-    st2m(FLD(tend_u_euler), ix, tue, m0, m1);
-  } else {
-    tue = ld2(FLD(tend_u_euler), ix);
-  }
+  const D2 tue = ld2(FLD(tend_u_euler), ix);
   if (P.rayleigh_u) {                                                                               // :1152-1159
     const int lim = L - P.rayleigh_levels + 1;
     if (k0 > lim) tend_u.x -= rho_e.x * u2.x * ((double)((double)k0 - (L - P.rayleigh_levels)) * P.rayleigh_coef_inverse);

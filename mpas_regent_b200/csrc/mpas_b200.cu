@@ -277,14 +277,15 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
       LAUNCH(k_dt_vertex_delsq, h->nVertices, 0, h->V);
       LAUNCH(k_dt_cell_delsq, h->nCells, 0, h->V);
     }
-    LAUNCH(k_dt_edge<true>, h->nEdges, sm2, h->V, P);
+    LAUNCH(k_dt_edge_euler, h->nEdges, tile_bytes(h, 1), h->V, P);
+    LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
     LAUNCH(k_dt_cellA, h->nCells, 0, h->V, P);
     LAUNCH(k_dt_cellB, h->nCells, 0, h->V, P);
     LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
     LAUNCH(k_dt_cellC<true>, h->nCells, sm2, h->V, P);
   } else {
     LAUNCH(k_dt_cell0<false>, h->nCells, 0, h->V, P, C.config_len_disp, cam_coef);
-    LAUNCH(k_dt_edge<false>, h->nEdges, sm2, h->V, P);
+    LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
     LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
     LAUNCH(k_dt_cellC<false>, h->nCells, sm2, h->V, P);
   }

@@ -38,11 +38,10 @@ K: Dict[str, Tuple[List[str], List[str]]] = {
     "k_dt_edge_delsq": (["divergence", "vorticity"], ["delsq_u"]),
     "k_dt_vertex_delsq": (["delsq_u"], ["delsq_vorticity"]),
     "k_dt_cell_delsq": (["delsq_u"], ["delsq_divergence"]),
-    "k_dt_edge<true>": (["u", "rw", "pv_edge", "rho_edge", "ke", "h_divergence", "w", "tend_ru_physics", "cqu", "pressure_p",
-                         "zz", "dpdz", "zxu", "divergence", "vorticity", "kdiff", "delsq_divergence", "delsq_vorticity"],
-                        ["wduz", "q", "tend_u", "tend_u_euler"]),
-    "k_dt_edge<false>": (["u", "rw", "pv_edge", "rho_edge", "ke", "h_divergence", "w", "tend_ru_physics", "tend_u_euler"],
-                         ["wduz", "q", "tend_u"]),
+    "k_dt_edge_euler": (["rho_edge", "cqu", "pressure_p", "zz", "dpdz", "zxu", "divergence", "vorticity", "kdiff", "delsq_divergence",
+                         "delsq_vorticity"], ["tend_u_euler"]),
+    "k_dt_edge": (["u", "rw", "pv_edge", "rho_edge", "ke", "h_divergence", "w", "tend_ru_physics", "tend_u_euler"],
+                  ["wduz", "q", "tend_u"]),
     "k_dt_theta_flux": (["ru", "theta_m"], ["scr_e"]),
     "k_dt_cellA": (["ru", "rho_zz", "uReconstructZonal", "uReconstructMeridional", "theta_m", "kdiff", "rho_edge"],
                    ["w", "ru_edge_w", "delsq_theta", "tend_theta_euler"]),
@@ -106,10 +105,10 @@ def step_launches(canonical: bool = True) -> List[str]:
         if stage == 1:
             seq.append("k_vert_imp")
         if stage == 0 and canonical:
-            seq += ["k_dt_cell0<true>", "k_dt_edge_delsq", "k_dt_vertex_delsq", "k_dt_cell_delsq", "k_dt_edge<true>",
+            seq += ["k_dt_cell0<true>", "k_dt_edge_delsq", "k_dt_vertex_delsq", "k_dt_cell_delsq", "k_dt_edge_euler", "k_dt_edge",
                     "k_dt_cellA", "k_dt_cellB", "k_dt_theta_flux", "k_dt_cellC<true>"]
         else:
-            seq += ["k_dt_cell0<false>", "k_dt_edge<false>", "k_dt_theta_flux", "k_dt_cellC<false>"]
+            seq += ["k_dt_cell0<false>", "k_dt_edge", "k_dt_theta_flux", "k_dt_cellC<false>"]
         seq.append("k_smlstep")
         for ss in range((1 if stage < 2 else 2) + 1):
             seq += ["k_acoustic_gather", "k_acoustic_tma<true>" if ss == 0 else "k_acoustic_tma<false>", "k_divdamp"]
@@ -136,9 +135,9 @@ TASK_KERNELS = {
     "rk_integration_setup": ["k_setup_cell", "k_setup_edge"],
     "compute_moist_coefficients": ["k_moist"],
     "compute_vert_imp_coefs": ["k_vert_imp"],
-    "compute_dyn_tend:rk0": ["k_dt_cell0<true>", "k_dt_edge_delsq", "k_dt_vertex_delsq", "k_dt_cell_delsq", "k_dt_edge<true>",
+    "compute_dyn_tend:rk0": ["k_dt_cell0<true>", "k_dt_edge_delsq", "k_dt_vertex_delsq", "k_dt_cell_delsq", "k_dt_edge_euler", "k_dt_edge",
                              "k_dt_cellA", "k_dt_cellB", "k_dt_theta_flux", "k_dt_cellC<true>"],
-    "compute_dyn_tend:rk>0": ["k_dt_cell0<false>", "k_dt_edge<false>", "k_dt_theta_flux", "k_dt_cellC<false>"],
+    "compute_dyn_tend:rk>0": ["k_dt_cell0<false>", "k_dt_edge", "k_dt_theta_flux", "k_dt_cellC<false>"],
     "set_smlstep_pert_variables": ["k_smlstep"],
     "advance_acoustic_step:s0": ["k_acoustic_gather", "k_acoustic_tma<true>"],
     "advance_acoustic_step": ["k_acoustic_gather", "k_acoustic_tma<false>"],

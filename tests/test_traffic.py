@@ -25,7 +25,7 @@ def test_task_units_not_below_survey():
 def test_step_units():
     assert T.step_units(True, scratch=False) >= T.SURVEY_STEP_UNITS_CANONICAL
     assert T.step_units(False, scratch=False) >= T.SURVEY_STEP_UNITS_LITERAL
-    assert len(T.step_launches(True)) == 57 and len(T.step_launches(False)) == 52
+    assert len(T.step_launches(True)) == 58 and len(T.step_launches(False)) == 52
 
 
 def test_every_kernel_in_the_library_is_declared():
