@@ -71,6 +71,22 @@ typedef enum { MPASB200_MIX_2D_SMAGORINSKY = 0, MPASB200_MIX_2D_FIXED = 1, MPASB
  * STAGE_INDEX   : the RK stage index 0,1,2 (what MPAS does).                          */
 typedef enum { MPASB200_RKARG_SUBSTEP_TRUNC = 0, MPASB200_RKARG_STAGE_INDEX = 1 } mpasb200_rkarg_policy_t;
 
+/* Which text of the acoustic loop runs.
+ * LITERAL   : the reference as it executes: the ru_p / ruAvg edge update is commented out
+ *             (dynamics_tasks.rg:1585-1613), so is the tridiagonal back-substitution (:1674-1677), and
+ *             atm_srk3 never calls atm_recover_large_step_variables (rk_timestep.rg:459-460).
+ * CORRECTED : those three pieces enabled with the semantics of the MPAS-A routines they were transcribed from
+ *             (atm_advance_acoustic_step_work, atm_recover_large_step_variables_work of MPAS v7): the edge update
+ *             as written in the commented lines; the cell part evaluated column by column (rs/ts kept for the
+ *             whole column, forward elimination, then back-substitution with gamma_tri, then Rayleigh damping,
+ *             then rho_pp / rtheta_pp); recover called after the acoustic loop of every RK stage with
+ *             (number_sub_steps[rk_step], rk_step, dt), with three of its expressions restored
+ *             (ru = ru_save + ru_p, :1840; flux = fzm*ru(k) + fzp*ru(k-1), :1856; exner = (zz*(rgas/p0)*
+ *             (rtheta_p+rtheta_base))^rcv, :1819).  Everything else, including the reference's field bindings
+ *             (cr.w for tend_rw, cr.theta_m for tend_rt, er.tend_ru), stays literal.  Parity for this mode is against
+ *             the oracle's restatement of exactly this text; the reference cannot run it.                     */
+typedef enum { MPASB200_PHYSICS_LITERAL = 0, MPASB200_PHYSICS_CORRECTED = 1 } mpasb200_physics_mode_t;
+
 /* ---- dimensions (constants.rg:18-26) ------------------------------------------- */
 typedef struct {
   int32_t nCells, nEdges, nVertices;  /* entities in the regions handed to the tasks  */
@@ -105,6 +121,7 @@ typedef struct {
                                          thread per column); 0 (default): fused kernel, affine sweep (a few ulp apart) */
   int32_t acoustic_tma;               /* acoustic step form: 0 = one fused kernel, plain loads; 1 = one fused kernel, own-column strips staged
                                          with cp.async.bulk (TMA); 2 (default) = lean gather kernel + TMA streaming/sweep kernel */
+  int32_t physics_mode;               /* mpasb200_physics_mode_t; default LITERAL */
 } MpasConfig;
 
 /* ---- level-0 ("static") region data -------------------------------------------- *
@@ -201,8 +218,9 @@ int  mpasb200_timestep(mpasb200_t *h, double dt);
 
 /* ---- halo exchange building blocks (one process per GPU; the wire is the host's job) ------ *
  * Lists are LOCAL entity indices in the caller's (un-renumbered) numbering.  pack gathers
- * `nfields` fields x `n` columns x (nVertLevels+1) levels into the contiguous device
- * buffer `d_buf` laid out [field][i][level]; unpack scatters the same layout back.
+ * `n` columns x `nfields` fields x (nVertLevels+1) levels into the contiguous device
+ * buffer `d_buf` laid out [i][field][level] (one contiguous row per listed entity, so a list that
+ * concatenates several peers yields one contiguous slice per peer); unpack scatters the same layout back.
  * A list is registered once and referred to by the returned id.                         */
 int  mpasb200_register_list(mpasb200_t *h, int entity, const int32_t *idx, int32_t n, int32_t *list_id);
 int  mpasb200_pack(mpasb200_t *h, int list_id, const int32_t *fields, int32_t nfields, void *d_buf);

@@ -21,6 +21,7 @@ _ENT = {"CELL": CELL, "EDGE": EDGE, "VERTEX": VERTEX}
 INDEX_LITERAL, INDEX_CORRECTED = 0, 1
 MIX_2D_SMAGORINSKY, MIX_2D_FIXED, MIX_OTHER = 0, 1, 2
 RKARG_SUBSTEP_TRUNC, RKARG_STAGE_INDEX = 0, 1
+PHYSICS_LITERAL, PHYSICS_CORRECTED = 0, 1
 
 E_OK, E_INVAL, E_CUDA, E_NODEVICE, E_STATE, E_NOMEM = 0, -1, -2, -3, -4, -5
 
@@ -61,7 +62,7 @@ _CFG_D = ("gravity", "rgas", "cp", "cv", "omega", "sphere_radius", "prandtl", "c
           "config_h_theta_eddy_visc4", "config_rayleigh_damp_u_timescale_days", "config_mpas_cam_coef")
 _CFG_I = ("config_number_rayleigh_damp_u_levels", "config_horiz_mixing", "config_mix_full", "config_rayleigh_damp_u",
           "nRelaxZone", "number_of_sub_steps", "config_dynamics_split_steps", "index_policy", "rkarg_policy",
-          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma")
+          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma", "physics_mode")
 
 
 class MpasConfig(C.Structure):
@@ -121,6 +122,7 @@ def default_config(**over) -> MpasConfig:
     c.nRelaxZone, c.number_of_sub_steps, c.config_dynamics_split_steps = 5, 2, 1
     c.index_policy, c.rkarg_policy = INDEX_CORRECTED, RKARG_SUBSTEP_TRUNC
     c.sfc_renumber, c.device, c.use_graph, c.acoustic_exact, c.acoustic_tma = 1, -1, 0, 0, 2
+    c.physics_mode = PHYSICS_LITERAL
     for k, v in over.items():
         if not hasattr(c, k):
             raise AttributeError(k)

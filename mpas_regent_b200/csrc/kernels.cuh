@@ -977,6 +977,125 @@ __global__ void k_acoustic_gather(const View V, double dts) {
   st2m(V.scr_rs, ix, rs, m0, m1); st2m(V.scr_ts, ix, ts, m0, m1);
 }
 
+// ---- MPASB200_PHYSICS_CORRECTED (mpas_b200.h): the acoustic step with its three disabled pieces enabled ------------
+// Edge update :1581-1613, exactly the commented lines; every edge (the nCellsSolve test stays out).
+template <bool S0>
+__global__ void k_acoustic_u(const View V, double dts, double c2, double gravity) {
+  PAIR_THREAD(V.nEdges)
+  if (!m0) return;
+  const D2 tru = ld2(FLD(tend_ru), ix);
+  if (S0) {                                                                                           // :1601-1613
+    const D2 r = dts * tru;
+    st2m(FLD(ru_p), ix, r, m0, m1); st2m(FLD(ruAvg), ix, r, m0, m1);
+    return;
+  }
+  const int4 cv = V.ecv[x];
+  const double* rpp = FLD(rtheta_pp); const double* zz = FLD(zz); const double* ex = FLD(exner); const double* rho = FLD(rho_pp);
+  D2 pgrad = ((G2(rpp, cv.y) - G2(rpp, cv.x)) * V.invDcEdge[x]) / (0.5 * (G2(zz, cv.y) + G2(zz, cv.x)));      // :1591
+  pgrad = pgrad * (ld2(FLD(cqu), ix) * 0.5 * c2 * (G2(ex, cv.x) + G2(ex, cv.y)));                          // :1592
+  pgrad = pgrad + 0.5 * ld2(FLD(zxu), ix) * gravity * (G2(rho, cv.x) + G2(rho, cv.y));                     // :1593
+  const D2 r = ld2(FLD(ru_p), ix) + dts * (tru - (1.0 - V.specZoneMaskEdge[x]) * pgrad);                   // :1594
+  st2m(FLD(ru_p), ix, r, m0, m1);
+  st2m(FLD(ruAvg), ix, ld2(FLD(ruAvg), ix) + r, m0, m1);                                                   // :1597
+}
+
+// Cell part :1615-1704, column by column as in MPAS: rs/ts for the whole column, right-hand side, forward elimination
+// (:1670-1671), back-substitution (:1674-1677), Rayleigh damping (:1681-1690), rho_pp / rtheta_pp (:1694-1696).
+// The horizontal flux sums come from k_acoustic_gather (scratch).  One thread per level pair; the two sweeps are run
+// strictly in order by one thread per column out of shared memory, so the result is bit-identical to the oracle.
+template <bool S0>
+__global__ void __launch_bounds__(256) k_acoustic_col(const View V, double dts, double epssm, double resm) {
+  extern __shared__ double sm[];
+  PAIR_THREAD(V.nCells)
+  const int TS = LP + 2, CB = blockDim.y, ty = threadIdx.y;
+  double* s_rs = sm + (size_t)(0 * CB + ty) * TS;
+  double* s_ts = sm + (size_t)(1 * CB + ty) * TS;
+  double* s_x = sm + (size_t)(2 * CB + ty) * TS;
+  double* s_a = sm + (size_t)(3 * CB + ty) * TS;
+  double* s_al = sm + (size_t)(4 * CB + ty) * TS;
+  double* s_g = sm + (size_t)(5 * CB + ty) * TS;
+  const bool spec = inx ? (V.specZoneMaskCell[x] != 0.0) : false;
+  const bool act = m0 && !spec;
+  if (S0 && inx) {                                                                                    // :1625-1630, level L
+    if (k0 == L) { FLD(wwAvg)[ix] = 0; FLD(rw_p)[ix] = 0; }
+    if (k1 == L) { FLD(wwAvg)[ix + 1] = 0; FLD(rw_p)[ix + 1] = 0; }
+  }
+  D2 rs = bc(0), ts = bc(0), rw_old = bc(0), rw_oldp = bc(0), rho_old = bc(0), rt_old = bc(0);
+  D2 zz = bc(0), zzm = bc(0), w2 = bc(0);
+  if (m0) {
+    if (!S0) {
+      rw_old = ld2(FLD(rw_p), ix); rw_oldp = above(FLD(rw_p), ix, k0, L, rw_old);
+      rho_old = ld2(FLD(rho_pp), ix); rt_old = ld2(FLD(rtheta_pp), ix);
+    }
+    st2m(FLD(rtheta_pp_old), ix, S0 ? bc(0.0) : rt_old, m0, m1);                                      // :1615-1623
+  }
+  if (act) {
+    const D2 cofrz = ld2(FLD(cofrz), k0), rdzw = ld2(FLD(rdzw), k0);
+    const D2 coftz = ld2(FLD(coftz), ix), coftz_p = above(FLD(coftz), ix, k0, L, coftz);
+    rs = rho_old + dts * ld2(FLD(tend_rho), ix) + ld2(V.scr_rs, ix) - cofrz * resm * (rw_oldp - rw_old);                // :1657
+    ts = rt_old + dts * ld2(FLD(theta_m), ix) + ld2(V.scr_ts, ix) - resm * rdzw * (coftz_p * rw_oldp - coftz * rw_old);   // :1658
+    s_rs[k0] = rs.x; s_ts[k0] = ts.x;
+    if (m1) { s_rs[k1] = rs.y; s_ts[k1] = ts.y; }
+  }
+  __syncthreads();
+  if (act) {
+    zz = ld2(FLD(zz), ix); zzm = below(FLD(zz), ix, k0, zz); w2 = ld2(FLD(w), ix);
+    const D2 rsm = mk(k0 > 0 ? s_rs[k0 - 1] : 0.0, rs.x), tsm = mk(k0 > 0 ? s_ts[k0 - 1] : 0.0, ts.x);
+    const D2 rtm = S0 ? bc(0.0) : below(FLD(rtheta_pp), ix, k0, rt_old), rhm = S0 ? bc(0.0) : below(FLD(rho_pp), ix, k0, rho_old);
+    const D2 cwt = ld2(FLD(cofwt), ix), cwtm = below(FLD(cofwt), ix, k0, cwt);
+    const D2 cwz = ld2(FLD(cofwz), ix), cwr = ld2(FLD(cofwr), ix);
+    const D2 xr = rw_old + (dts * w2 - cwz * ((zz * ts - zzm * tsm) + resm * (zz * rt_old - zzm * rtm))             // :1662-1667
+                            - cwr * ((rs + rsm) + resm * (rho_old + rhm))
+                            + cwt * (ts + resm * rt_old)
+                            + cwtm * (tsm + resm * rtm));
+    const D2 at = ld2(FLD(a_tri), ix), al = ld2(FLD(alpha_tri), ix), gt = ld2(FLD(gamma_tri), ix);
+    s_x[k0] = k0 > 0 ? xr.x : rw_old.x; s_a[k0] = at.x; s_al[k0] = al.x; s_g[k0] = gt.x;
+    if (m1) { s_x[k1] = xr.y; s_a[k1] = at.y; s_al[k1] = al.y; s_g[k1] = gt.y; }
+  }
+  __syncthreads();
+  if (act && k0 == 0) {
+    double xv = s_x[0];
+    for (int kk = 1; kk < L; ++kk) { xv = (s_x[kk] - s_a[kk] * xv) * s_al[kk]; s_x[kk] = xv; }       // :1670-1671
+    xv = S0 ? 0.0 : FLD(rw_p)[(size_t)x * LP + L];
+    s_x[L] = xv;
+    for (int kk = L - 1; kk >= 0; --kk) { xv = s_x[kk] - s_g[kk] * xv; s_x[kk] = xv; }               // :1674-1677
+  }
+  __syncthreads();
+  D2 xn = bc(0), ww_new = bc(0);
+  if (act) {
+    xn = mk(s_x[k0], m1 ? s_x[k1] : 0.0);
+    const D2 ww_old = S0 ? bc(0.0) : ld2(FLD(wwAvg), ix);
+    const D2 rz = ld2(FLD(rho_zz), ix), rzm = below(FLD(rho_zz), ix, k0, rz);
+    const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0);
+    const D2 ds = ld2(FLD(dss), ix), d3 = ld2(FLD(rw_save), ix) - ld2(FLD(rw), ix);
+    D2 xd = xn + (d3 - dts * ds * (fm * zz + fp * zzm) * (fm * rz + fp * rzm) * w2);                  // :1682-1684
+    xd = xd / (1.0 + dts * ds);                                                                       // :1685
+    xd = xd - d3;                                                                                     // :1686
+    const D2 wb = (ww_old + 0.5 * (1.0 - epssm) * rw_old) + 0.5 * (1.0 + epssm) * xd;                 // :1661, :1689
+    if (k0 > 0) { xn.x = xd.x; ww_new.x = wb.x; } else ww_new.x = ww_old.x;
+    xn.y = xd.y; ww_new.y = wb.y;
+    s_a[k0] = xn.x;                                                     // s_a is free now: the final rw_p of the column
+    if (m1) s_a[k1] = xn.y;
+    if (k0 == 0) s_a[L] = s_x[L];
+  }
+  __syncthreads();
+  if (!m0) return;
+  if (act) {
+    const D2 cofrz = ld2(FLD(cofrz), k0), rdzw = ld2(FLD(rdzw), k0);
+    const D2 coftz = ld2(FLD(coftz), ix), coftz_p = above(FLD(coftz), ix, k0, L, coftz);
+    const D2 xp = mk(s_a[k1], k1 + 1 <= L ? s_a[k1 + 1] : 0.0);
+    st2m(FLD(rho_pp), ix, rs - cofrz * (xp - xn), m0, m1);                                            // :1694
+    st2m(FLD(rtheta_pp), ix, ts - rdzw * (coftz_p * xp - coftz * xn), m0, m1);                        // :1695-1696
+    st2m(FLD(rw_p), ix, xn, m0, m1); st2m(FLD(wwAvg), ix, ww_new, m0, m1);
+  } else {                                                                                            // :1698-1703
+    const D2 ww_old = S0 ? bc(0.0) : ld2(FLD(wwAvg), ix);
+    const D2 rw_new = rw_old + dts * ld2(FLD(w), ix);
+    st2m(FLD(rho_pp), ix, rho_old + dts * ld2(FLD(tend_rho), ix), m0, m1);
+    st2m(FLD(rtheta_pp), ix, rt_old + dts * ld2(FLD(theta_m), ix), m0, m1);
+    st2m(FLD(rw_p), ix, rw_new, m0, m1); st2m(FLD(wwAvg), ix, ww_new = ww_old + 0.5 * (1.0 + epssm) * rw_new, m0, m1);
+  }
+}
+
 // ---- TMA (bulk async copy) helpers: global -> shared strips whose bytes in flight cost no registers -----------------
 DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 DI void mbar_init(uint64_t* bar, int count) {
@@ -1386,17 +1505,18 @@ __global__ void k_field_to_stage(const double* __restrict__ field, double* __res
   const int s = (int)(t % slots); const size_t r = t / slots; const int k = (int)(r % L1); const int i = (int)(r / L1);
   staging[t] = field[s * slotStride + (size_t)map[i] * LP + k];
 }
-// halo buffers: [field][i][L1]; idx holds internal indices
+// halo buffers: [i][field][L1] (one contiguous row per listed entity, so the rows of one peer are one contiguous
+// slice of a list that concatenates all peers); idx holds internal indices
 struct PackArgs { double* f[32]; int nf; };
 __global__ void k_pack(const PackArgs A, const int* __restrict__ idx, int n, int L1, int LP, double* __restrict__ buf) {
   const int k = threadIdx.x; const int i = blockIdx.x * blockDim.y + threadIdx.y; const int fi = blockIdx.y;
   if (i >= n || k >= L1) return;
-  buf[((size_t)fi * n + i) * L1 + k] = A.f[fi][(size_t)idx[i] * LP + k];
+  buf[((size_t)i * A.nf + fi) * L1 + k] = A.f[fi][(size_t)idx[i] * LP + k];
 }
 __global__ void k_unpack(const PackArgs A, const int* __restrict__ idx, int n, int L1, int LP, const double* __restrict__ buf) {
   const int k = threadIdx.x; const int i = blockIdx.x * blockDim.y + threadIdx.y; const int fi = blockIdx.y;
   if (i >= n || k >= L1) return;
-  A.f[fi][(size_t)idx[i] * LP + k] = buf[((size_t)fi * n + i) * L1 + k];
+  A.f[fi][(size_t)idx[i] * LP + k] = buf[((size_t)i * A.nf + fi) * L1 + k];
 }
 
 // ============================================================================================

@@ -194,6 +194,8 @@ class TaskAPI:
             for small_step in range(number_sub_steps[rk_step] + 1):
                 self.atm_advance_acoustic_step(rk_sub_timestep[rk_step], small_step); h("advance_acoustic_step")
                 self.atm_divergence_damping_3d(rk_sub_timestep[rk_step]); h("divergence_damping_3d")
+            if c.physics_mode == _abi.PHYSICS_CORRECTED:      # rk_timestep.rg:459-460, commented out in the reference
+                self.atm_recover_large_step_variables(number_sub_steps[rk_step], rk_step, dt); h("recover_large_step_variables")
             self.atm_compute_solve_diagnostics(False, rk_step); h("compute_solve_diagnostics")
         self.atm_rk_dynamics_substep_finish(1, dynamics_split); h("rk_dynamics_substep_finish")
 
@@ -211,6 +213,7 @@ class Dynamics(TaskAPI):
             msg = self._lib.mpasb200_last_error(None)
             raise MpasB200Error(f"mpasb200_create failed ({rc}): {msg.decode() if msg else ''}")
         self._keep = []
+        self._ids_cache = {}
 
     # ---- plumbing ------------------------------------------------------------------------------
     def _check(self, rc: int, what: str):
@@ -272,12 +275,19 @@ class Dynamics(TaskAPI):
         self._check(self._lib.mpasb200_register_list(self._h, entity, idx.ctypes.data, idx.shape[0], C.byref(lid)), "register_list")
         return int(lid.value)
 
+    def _field_ids(self, fields: Sequence[str]) -> np.ndarray:
+        key = tuple(fields)
+        ids = self._ids_cache.get(key)
+        if ids is None:
+            ids = self._ids_cache[key] = np.asarray([FIELD_ID[f] for f in fields], dtype=np.int32)
+        return ids
+
     def pack(self, list_id: int, fields: Sequence[str], d_buf_ptr: int):
-        ids = np.asarray([FIELD_ID[f] for f in fields], dtype=np.int32)
+        ids = self._field_ids(fields)
         self._check(self._lib.mpasb200_pack(self._h, list_id, ids.ctypes.data, len(ids), C.c_void_p(d_buf_ptr)), "pack")
 
     def unpack(self, list_id: int, fields: Sequence[str], d_buf_ptr: int):
-        ids = np.asarray([FIELD_ID[f] for f in fields], dtype=np.int32)
+        ids = self._field_ids(fields)
         self._check(self._lib.mpasb200_unpack(self._h, list_id, ids.ctypes.data, len(ids), C.c_void_p(d_buf_ptr)), "unpack")
 
     # ---- introspection ------------------------------------------------------------------------------------

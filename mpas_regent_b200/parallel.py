@@ -112,48 +112,62 @@ class HostDistExchanger(Exchanger):
 
 
 class NcclExchanger(Exchanger):
-    """GPU path: k_pack -> NCCL send/recv (NVLink) -> k_unpack, all ordered on the step's stream."""
+    """GPU path: k_pack -> NCCL send/recv (NVLink) -> k_unpack, all ordered on the step's stream.
+
+    Per entity type ONE send list and ONE recv list (all peers concatenated) are registered, so an exchange is one
+    pack launch, one grouped NCCL send/recv and one unpack launch per entity type; the rows of a peer are a
+    contiguous slice of the [i][field][level] buffer.  Buffers and the P2P descriptors are built once per
+    exchange kind."""
 
     def __init__(self, dyn, lm: partition.LocalMesh, stream):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.dyn, self.lm, self.stream = torch, dist, dyn, lm, stream
-        L1 = dyn.dims.nVertLevels + 1
-        self.L1 = L1
-        self.lists = {}
-        maxf = max(len(f) for spec in EXCHANGES.values() for f in spec.values())
-        self.sbuf, self.rbuf = {}, {}
+        self.L1 = dyn.dims.nVertLevels + 1
+        self.ent = {}
         for ent in ("cell", "edge", "vertex"):
-            for peer, idx in lm.send[ent].items():
-                self.lists[("s", ent, peer)] = dyn.register_list(ENT[ent], idx)
-                self.sbuf[(ent, peer)] = torch.empty(maxf * len(idx) * L1, dtype=torch.float64, device="cuda")
-            for peer, idx in lm.recv[ent].items():
-                self.lists[("r", ent, peer)] = dyn.register_list(ENT[ent], idx)
-                self.rbuf[(ent, peer)] = torch.empty(maxf * len(idx) * L1, dtype=torch.float64, device="cuda")
-        self.bytes_per_step = 0
+            peers_s, peers_r = sorted(lm.send[ent]), sorted(lm.recv[ent])
+            s_idx = np.concatenate([lm.send[ent][p] for p in peers_s]) if peers_s else np.zeros(0, np.int32)
+            r_idx = np.concatenate([lm.recv[ent][p] for p in peers_r]) if peers_r else np.zeros(0, np.int32)
+            s_off = np.cumsum([0] + [len(lm.send[ent][p]) for p in peers_s])
+            r_off = np.cumsum([0] + [len(lm.recv[ent][p]) for p in peers_r])
+            self.ent[ent] = dict(peers_s=peers_s, peers_r=peers_r, s_off=s_off, r_off=r_off, ns=len(s_idx), nr=len(r_idx),
+                                 ls=dyn.register_list(ENT[ent], s_idx) if len(s_idx) else -1,
+                                 lr=dyn.register_list(ENT[ent], r_idx) if len(r_idx) else -1)
+        self.plans = {}
+
+    def _plan(self, spec):
+        key = tuple((e, tuple(n)) for e, n in sorted(spec.items()))
+        if key in self.plans:
+            return self.plans[key]
+        torch, dist = self.torch, self.dist
+        items, ops = [], []
+        for ent, names in spec.items():
+            E, nf = self.ent[ent], len(names)
+            row = nf * self.L1
+            sbuf = torch.empty(max(E["ns"] * row, 1), dtype=torch.float64, device="cuda")
+            rbuf = torch.empty(max(E["nr"] * row, 1), dtype=torch.float64, device="cuda")
+            for i, p in enumerate(E["peers_s"]):
+                ops.append(dist.P2POp(dist.isend, sbuf[E["s_off"][i] * row:E["s_off"][i + 1] * row], p))
+            for i, p in enumerate(E["peers_r"]):
+                ops.append(dist.P2POp(dist.irecv, rbuf[E["r_off"][i] * row:E["r_off"][i + 1] * row], p))
+            items.append((E, list(names), sbuf, rbuf))
+        self.plans[key] = (items, ops)
+        return self.plans[key]
 
     def exchange(self, spec: Dict[str, List[str]]):
-        torch, dist, lm = self.torch, self.dist, self.lm
+        torch, dist = self.torch, self.dist
+        items, ops = self._plan(spec)
         with torch.cuda.stream(self.stream):
-            ops, post = [], []
-            for ent, names in spec.items():
-                nf = len(names)
-                for peer in sorted(set(lm.send[ent]) | set(lm.recv[ent])):
-                    if peer in lm.send[ent]:
-                        n = len(lm.send[ent][peer])
-                        buf = self.sbuf[(ent, peer)][: nf * n * self.L1]
-                        self.dyn.pack(self.lists[("s", ent, peer)], names, buf.data_ptr())
-                        ops.append(dist.P2POp(dist.isend, buf, peer))
-                    if peer in lm.recv[ent]:
-                        n = len(lm.recv[ent][peer])
-                        rb = self.rbuf[(ent, peer)][: nf * n * self.L1]
-                        ops.append(dist.P2POp(dist.irecv, rb, peer))
-                        post.append((self.lists[("r", ent, peer)], names, rb))
+            for E, names, sbuf, _ in items:
+                if E["ls"] >= 0:
+                    self.dyn.pack(E["ls"], names, sbuf.data_ptr())
             if ops:
                 for r in dist.batch_isend_irecv(ops):
                     r.wait()          # stream-ordered for NCCL: makes the current stream wait, not the host
-            for lid, names, rb in post:
-                self.dyn.unpack(lid, names, rb.data_ptr())
+            for E, names, _, rbuf in items:
+                if E["lr"] >= 0:
+                    self.dyn.unpack(E["lr"], names, rbuf.data_ptr())
 
 
 class DistributedDynamics:

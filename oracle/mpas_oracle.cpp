@@ -760,8 +760,101 @@ int oracle_set_smlstep_pert_variables(oracle_t* o) {
   return 0;
 }
 
+// MPASB200_PHYSICS_CORRECTED form of atm_advance_acoustic_step_work (mpas_b200.h).  The three
+// pieces the reference has commented out are enabled with the semantics of MPAS v7's routine of the same name:
+//   * edge loop  :1585-1613  exactly the commented lines (ru_p, ruAvg), every edge (the nCellsSolve test stays out);
+//   * cell loop  :1632-1704  column by column: rs/ts live for the whole column (the reference zeroes them at every
+//     point only because its loop variable is a point, Q25); forward elimination :1670-1671 for all levels, then the
+//     back-substitution :1674-1677 `rw_p(k) -= gamma_tri(k) * rw_p(k+1)` for k = nVertLevels-1 .. 0 (Fortran
+//     k = nVertLevels,1,-1), then Rayleigh damping :1681-1690, then rho_pp / rtheta_pp :1694-1696.
+// Field bindings stay the reference's (cr.w for tend_rw, cr.theta_m for tend_rt, er.tend_ru).
+static int acoustic_step_corrected(oracle_t* o, double dts, int small_step) {
+  const int L = o->L, nC = o->nCells, nE = o->nEdges, ME = o->maxEdges;
+  const double epssm = o->c.config_epssm, rgas = o->c.rgas, gravity = o->c.gravity;
+  const double rcv = rgas / (o->c.cp - rgas); const double c2 = o->c.cp * rcv;
+  const double resm = (1.0 - epssm) / (1.0 + epssm);
+  VF(cofrz); VF(fzm); VF(fzp); VF(rdzw);
+  CF(a_tri); CF(alpha_tri); CF(gamma_tri); CF(coftz); CF(cofwr); CF(cofwt); CF(cofwz); CF(dss); CF(rho_pp); CF(rho_zz); CF(rtheta_pp);
+  CF(rw); CF(rw_save); CF(tend_rho); CF(theta_m); CF(w); CF(zz); CF(rtheta_pp_old); CF(rw_p); CF(wwAvg); CF(ru_p);
+  CF(exner); CF(cqu); CF(zxu); CF(tend_ru); CF(ruAvg);
+  if (small_step != 0) {                                                    // :1581-1599
+    OMP_FOR
+    for (int e = 0; e < nE; ++e) {
+      int cell1 = o->cellsOnEdge[e * 2 + 0], cell2 = o->cellsOnEdge[e * 2 + 1];
+      for (int k = 0; k < L; ++k) {
+        double pgrad = ((rtheta_pp(cell2, k) - rtheta_pp(cell1, k)) * o->invDcEdge[e]) / (0.5 * (zz(cell2, k) + zz(cell1, k)));   // :1591
+        pgrad *= cqu(e, k) * 0.5 * c2 * (exner(cell1, k) + exner(cell2, k));                                                  // :1592
+        pgrad += 0.5 * zxu(e, k) * gravity * (rho_pp(cell1, k) + rho_pp(cell2, k));                                           // :1593
+        ru_p(e, k) += dts * (tend_ru(e, k) - (1.0 - o->specZoneMaskEdge[e]) * pgrad);                                          // :1594
+        ruAvg(e, k) += ru_p(e, k);                                                                                             // :1597
+      }
+    }
+  } else {                                                                  // :1601-1613
+    OMP_FOR
+    for (int e = 0; e < nE; ++e) for (int k = 0; k < L; ++k) { ru_p(e, k) = dts * tend_ru(e, k); ruAvg(e, k) = ru_p(e, k); }
+  }
+  OMP_FOR
+  for (int c = 0; c < nC; ++c) {
+    std::vector<double> rs(L), ts(L);
+    for (int k = 0; k < L; ++k) rtheta_pp_old(c, k) = (small_step == 0) ? 0.0 : rtheta_pp(c, k);       // :1615-1623
+    if (small_step == 0) {                                                  // :1625-1636
+      for (int k = 0; k <= L; ++k) { wwAvg(c, k) = 0; rw_p(c, k) = 0; }
+      for (int k = 0; k < L; ++k) { rho_pp(c, k) = 0; rtheta_pp(c, k) = 0; }
+    }
+    if (o->specZoneMaskCell[c] == 0.0) {                                    // :1638
+      for (int k = 0; k < L; ++k) { ts[k] = 0; rs[k] = 0; }
+      for (int i = 0; i < o->nEdgesOnCell[c]; ++i) {                        // :1644-1652
+        int e = o->edgesOnCell[c * ME + i];
+        int cell1 = o->cellsOnEdge[e * 2 + 0], cell2 = o->cellsOnEdge[e * 2 + 1];
+        for (int k = 0; k < L; ++k) {
+          double flux = o->edgesOnCellSign[c * ME + i] * dts * o->dvEdge[e] * ru_p(e, k) * o->invAreaCell[c];
+          rs[k] -= flux;
+          ts[k] -= flux * 0.5 * (theta_m(cell2, k) + theta_m(cell1, k));
+        }
+      }
+      for (int k = 0; k < L; ++k) {                                         // :1657-1658
+        rs[k] = rho_pp(c, k) + dts * tend_rho(c, k) + rs[k] - cofrz[k] * resm * (rw_p(c, k + 1) - rw_p(c, k));
+        ts[k] = rtheta_pp(c, k) + dts * theta_m(c, k) + ts[k] - resm * rdzw[k] * (coftz(c, k + 1) * rw_p(c, k + 1) - coftz(c, k) * rw_p(c, k));
+      }
+      for (int k = 1; k < L; ++k) {                                         // :1660-1667
+        wwAvg(c, k) += 0.5 * (1.0 - epssm) * rw_p(c, k);
+        rw_p(c, k) += dts * w(c, k) - cofwz(c, k)
+                      * ((zz(c, k) * ts[k] - zz(c, k - 1) * ts[k - 1]) + resm * (zz(c, k) * rtheta_pp(c, k) - zz(c, k - 1) * rtheta_pp(c, k - 1)))
+                      - cofwr(c, k) * ((rs[k] + rs[k - 1]) + resm * (rho_pp(c, k) + rho_pp(c, k - 1)))
+                      + cofwt(c, k) * (ts[k] + resm * rtheta_pp(c, k))
+                      + cofwt(c, k - 1) * (ts[k - 1] + resm * rtheta_pp(c, k - 1));
+      }
+      for (int k = 1; k < L; ++k) {                                         // :1670-1671
+        rw_p(c, k) -= a_tri(c, k) * rw_p(c, k - 1);
+        rw_p(c, k) *= alpha_tri(c, k);
+      }
+      for (int k = L - 1; k >= 0; --k) rw_p(c, k) -= gamma_tri(c, k) * rw_p(c, k + 1);                 // :1674-1677
+      for (int k = 1; k < L; ++k) {                                         // :1681-1690
+        rw_p(c, k) += (rw_save(c, k) - rw(c, k)) - dts * dss(c, k)
+                      * (fzm[k] * zz(c, k) + fzp[k] * zz(c, k - 1)) * (fzm[k] * rho_zz(c, k) + fzp[k] * rho_zz(c, k - 1)) * w(c, k);
+        rw_p(c, k) /= (1.0 + dts * dss(c, k));
+        rw_p(c, k) -= (rw_save(c, k) - rw(c, k));
+        wwAvg(c, k) += 0.5 * (1.0 + epssm) * rw_p(c, k);
+      }
+      for (int k = 0; k < L; ++k) {                                         // :1694-1696
+        rho_pp(c, k) = rs[k] - cofrz[k] * (rw_p(c, k + 1) - rw_p(c, k));
+        rtheta_pp(c, k) = ts[k] - rdzw[k] * (coftz(c, k + 1) * rw_p(c, k + 1) - coftz(c, k) * rw_p(c, k));
+      }
+    } else {                                                                // :1698-1703
+      for (int k = 0; k < L; ++k) {
+        rho_pp(c, k) = rho_pp(c, k) + dts * tend_rho(c, k);
+        rtheta_pp(c, k) = rtheta_pp(c, k) + dts * theta_m(c, k);
+        rw_p(c, k) = rw_p(c, k) + dts * w(c, k);
+        wwAvg(c, k) = wwAvg(c, k) + 0.5 * (1.0 + epssm) * rw_p(c, k);
+      }
+    }
+  }
+  return 0;
+}
+
 // atm_advance_acoustic_step_work -- dynamics_tasks.rg:1546-1705
 int oracle_advance_acoustic_step(oracle_t* o, double dts, int small_step) {
+  if (o->c.physics_mode == MPASB200_PHYSICS_CORRECTED) return acoustic_step_corrected(o, dts, small_step);
   const int L = o->L, nC = o->nCells, ME = o->maxEdges;
   const double epssm = o->c.config_epssm, rgas = o->c.rgas;
   const double rcv = rgas / (o->c.cp - rgas); const double c2 = o->c.cp * rcv; (void)c2;
@@ -857,6 +950,7 @@ int oracle_recover_large_step_variables(oracle_t* o, int ns, int rk_step, double
   CF(rw_p); CF(rw_save); CF(zz); CF(ru_p); CF(ru_save); CF(pressure_p); CF(theta_m); CF(u); CF(exner); CF(rho_p); CF(rho_zz);
   CF(rtheta_p); CF(rw); CF(w); CF(wwAvg); CF(ruAvg); CF(ru);
   F3A zb_cell = o->fa(MPASB200_F_zb_cell), zb3_cell = o->fa(MPASB200_F_zb3_cell);
+  const bool fix = o->c.physics_mode == MPASB200_PHYSICS_CORRECTED;         // three expressions restored, see mpas_b200.h
   for (int k = 0; k < L; ++k) rho_zz(nC, k) = 1.0;                          // :1792-1794 the "garbage cell" = the pad cell
   double invNs = 1 / (double)(ns);
   OMP_FOR
@@ -872,7 +966,8 @@ int oracle_recover_large_step_variables(oracle_t* o, int ns, int rk_step, double
     if (rk_step == 2) {
       rtheta_p(c, k) = rtheta_p_save(c, k) + rtheta_pp(c, k) - dt * rho_zz(c, k) * rt_diabatic_tend(c, k);
       theta_m(c, k) = (rtheta_p(c, k) + rtheta_base(c, k)) / rho_zz(c, k);
-      exner(c, k) = zz(c, k) * (rgas / p0) * pow((rtheta_p(c, k) + rtheta_base(c, k)), rcv);
+      exner(c, k) = fix ? pow(zz(c, k) * (rgas / p0) * (rtheta_p(c, k) + rtheta_base(c, k)), rcv)
+                        : zz(c, k) * (rgas / p0) * pow((rtheta_p(c, k) + rtheta_base(c, k)), rcv);      // :1819
       pressure_p(c, k) = zz(c, k) * rgas * (exner(c, k) * rtheta_p(c, k) + rtheta_base(c, k) * (exner(c, k) - exner_base(c, k)));
     } else {
       rtheta_p(c, k) = rtheta_p_save(c, k) + rtheta_pp(c, k);
@@ -884,7 +979,7 @@ int oracle_recover_large_step_variables(oracle_t* o, int ns, int rk_step, double
     int cell1 = o->cellsOnEdge[e * 2 + 0], cell2 = o->cellsOnEdge[e * 2 + 1];
     ruAvg(e, k) *= invNs;
     ruAvg(e, k) += ru_save(e, k);
-    ru(e, k) = ru_save(e, k) * ru_p(e, k);
+    ru(e, k) = fix ? ru_save(e, k) + ru_p(e, k) : ru_save(e, k) * ru_p(e, k);                          // :1840
     u(e, k) = 2 * ru(e, k) / (rho_zz(cell1, k) + rho_zz(cell2, k));
   }
   OMP_FOR
@@ -894,7 +989,7 @@ int oracle_recover_large_step_variables(oracle_t* o, int ns, int rk_step, double
         int e = o->edgesOnCell[c * ME + i];
         double flux = (cf1[0] * ru(e, 0) + cf2[0] * ru(e, 1) + cf3[0] * ru(e, 2));
         w(c, 0) += o->edgesOnCell_sign[c * ME + i] * (zb_cell(c, 0, i) + copysign(1.0, flux) * zb3_cell(c, 0, i)) * flux;
-        double flux2 = fzm[k] * ru(e, k) * (fzp[k] * ru(e, k - 1));
+        double flux2 = fix ? fzm[k] * ru(e, k) + fzp[k] * ru(e, k - 1) : fzm[k] * ru(e, k) * (fzp[k] * ru(e, k - 1));   // :1856
         w(c, k) += o->edgesOnCell_sign[c * ME + i] * (zb_cell(c, k, i) + copysign(1.0, flux2) * zb3_cell(c, k, i)) * flux2;
       }
     }
@@ -967,7 +1062,8 @@ int oracle_srk3(oracle_t* o, double dt) {
       oracle_advance_acoustic_step(o, rk_sub_timestep[rk_step], small_step);
       oracle_divergence_damping_3d(o, rk_sub_timestep[rk_step]);
     }
-    // :459-460 atm_recover_large_step_variables is commented out (Q5)
+    // :459-460 atm_recover_large_step_variables is commented out (Q5); CORRECTED calls it with the commented arguments
+    if (C.physics_mode == MPASB200_PHYSICS_CORRECTED) oracle_recover_large_step_variables(o, number_sub_steps[rk_step], rk_step, dt);
     oracle_compute_solve_diagnostics(o, 0, rk_step);                        // :467
   }
   oracle_rk_dynamics_substep_finish(o, 1, dynamics_split);                  // :481

@@ -224,7 +224,7 @@ def test_emulated_ranks_on_one_gpu_equal_single_partition(grid642):
         b = dynamics.Dynamics(_abi.make_dims(len(lm.cells), len(lm.edges), len(lm.vertices), Lh), cfg)
         b.upload_mesh(sh["static"]); b.upload_state(sh["f"], sh["vert"])
         backs.append(b)
-    # device-side exchange through k_pack / k_unpack and torch buffers (what NcclExchanger does, minus the wire)
+    # device-side exchange through k_pack / k_unpack and torch buffers (the building blocks NcclExchanger uses, minus the wire)
     lists = {}
     for h, sh in enumerate(shards):
         for ent in ("cell", "edge", "vertex"):
