@@ -200,6 +200,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--graph", type=int, default=0)
+    ap.add_argument("--physics", choices=("literal", "corrected"), default="literal",
+                    help="literal = the reference as it executes (headline); corrected = acoustic u update + back-substitution + "
+                         "recover wired in (SURVEY.md 8f rank 1, MPASB200_PHYSICS_CORRECTED)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -219,7 +222,9 @@ def main():
 
     L, nC = args.levels, args.mesh
     dt = dt_for(nC)
-    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, device=local_rank, use_graph=args.graph)
+    corrected = args.physics == "corrected"
+    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, device=local_rank, use_graph=args.graph,
+                              physics_mode=_abi.PHYSICS_CORRECTED if corrected else _abi.PHYSICS_LITERAL)
     stream = torch.cuda.Stream()
 
     if world == 1:
@@ -299,7 +304,8 @@ def main():
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic_bytes, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                     "avg_launch_ms": kms / kn, "launches_timed": kn, "share_of_step": kms / ms}
-    step_bytes = traffic.SURVEY_STEP_UNITS_CANONICAL * 8.0 * nC * L
+    step_units = traffic.step_units(True, scratch=False, corrected_physics=True) if corrected else traffic.SURVEY_STEP_UNITS_CANONICAL
+    step_bytes = step_units * 8.0 * nC * L
     step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
 
     # ---- end to end through the C ABI with host buffers ----
@@ -339,7 +345,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"x1.{nC} synthetic icosahedral Voronoi mesh, {L} levels, JW-style analytic state, dt={dt:.2f}s, "
-                                   f"one atm_srk3 per step (canonical stage-index sequence: stage 0 takes the rk_step==0 branches)",
+                                   f"one atm_srk3 per step (canonical stage-index sequence: stage 0 takes the rk_step==0 branches)"
+                                   + ("; CORRECTED physics mode (u update, back-substitution, recover wired in)" if corrected else ""),
                        "parallelism": parallelism, "l2": "working set (tens of GB) >> 126 MB L2; no flush needed",
                        "host_init_s": round(t_init, 1), "device_bytes": g.device_bytes, "cuda_graph": bool(args.graph)},
             "gpu_launches": launches,

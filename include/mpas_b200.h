@@ -80,9 +80,9 @@ typedef enum { MPASB200_RKARG_SUBSTEP_TRUNC = 0, MPASB200_RKARG_STAGE_INDEX = 1 
  *             as written in the commented lines; the cell part evaluated column by column (rs/ts kept for the
  *             whole column, forward elimination, then back-substitution with gamma_tri, then Rayleigh damping,
  *             then rho_pp / rtheta_pp); recover called after the acoustic loop of every RK stage with
- *             (number_sub_steps[rk_step], rk_step, dt), with three of its expressions restored
- *             (ru = ru_save + ru_p, :1840; flux = fzm*ru(k) + fzp*ru(k-1), :1856; exner = (zz*(rgas/p0)*
- *             (rtheta_p+rtheta_base))^rcv, :1819).  Everything else, including the reference's field bindings
+ *             (number_sub_steps[rk_step], rk_step, dt), with four of its expressions restored
+ *             (w(level 0) = 0 before the flux sums instead of rw/0, :1810; exner = (zz*(rgas/p0)*
+ *             (rtheta_p+rtheta_base))^rcv, :1819; ru = ru_save + ru_p, :1840; flux = fzm*ru(k) + fzp*ru(k-1), :1856).  Everything else, including the reference's field bindings
  *             (cr.w for tend_rw, cr.theta_m for tend_rt, er.tend_ru), stays literal.  Parity for this mode is against
  *             the oracle's restatement of exactly this text; the reference cannot run it.                     */
 typedef enum { MPASB200_PHYSICS_LITERAL = 0, MPASB200_PHYSICS_CORRECTED = 1 } mpasb200_physics_mode_t;

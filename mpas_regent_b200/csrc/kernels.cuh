@@ -1375,7 +1375,8 @@ __global__ void k_rec_pad(const View V) {           // :1792-1794: rho_zz = 1 on
   const int k = threadIdx.x;
   if (k < V.L) FLD(rho_zz)[(size_t)V.nCells * V.LP + k] = 1.0;
 }
-__global__ void k_rec_cell1(const View V, double invNs, int rk_step, double dt, double rgas, double rcv) {   // :1800-1826
+// `fix` (MPASB200_PHYSICS_CORRECTED) restores four expressions: w(level 0) :1810, exner :1819, ru :1840, flux2 :1856 (mpas_b200.h).
+__global__ void k_rec_cell1(const View V, double invNs, int rk_step, double dt, double rgas, double rcv, int fix) {   // :1800-1826
   PAIR_THREAD(V.nCells)
   if (!m0) return;
   const D2 rws = ld2(FLD(rw_save), ix);
@@ -1388,14 +1389,17 @@ __global__ void k_rec_cell1(const View V, double invNs, int rk_step, double dt, 
   const D2 rwv = rws + ld2(FLD(rw_p), ix);
   st2m(FLD(rw), ix, rwv, m0, m1);
   const D2 zz = ld2(FLD(zz), ix);
-  st2m(FLD(w), ix, rwv / (ld2(FLD(fzm), k0) * zz + ld2(FLD(fzp), k0) * below(FLD(zz), ix, k0, zz)), m0, m1);   // :1810
+  D2 wd = rwv / (ld2(FLD(fzm), k0) * zz + ld2(FLD(fzp), k0) * below(FLD(zz), ix, k0, zz));                  // :1810
+  if (fix && k0 == 0) wd.x = 0.0;                                                                      // MPAS: w(1) = 0, k = 2..nVertLevels
+  st2m(FLD(w), ix, wd, m0, m1);
   const D2 rtb = ld2(FLD(rtheta_base), ix);
   if (rk_step == 2) {
     const D2 rtp = ld2(FLD(rtheta_p_save), ix) + ld2(FLD(rtheta_pp), ix) - dt * rho_zz * ld2(FLD(rt_diabatic_tend), ix);
     st2m(FLD(rtheta_p), ix, rtp, m0, m1);
     st2m(FLD(theta_m), ix, (rtp + rtb) / rho_zz, m0, m1);
     const D2 s = rtp + rtb;
-    const D2 ex = zz * (rgas / 100000) * mk(pow(s.x, rcv), pow(s.y, rcv));                              // :1819
+    const D2 sz = zz * (rgas / 100000) * s;
+    const D2 ex = fix ? mk(pow(sz.x, rcv), pow(sz.y, rcv)) : zz * (rgas / 100000) * mk(pow(s.x, rcv), pow(s.y, rcv));   // :1819
     st2m(FLD(exner), ix, ex, m0, m1);
     st2m(FLD(pressure_p), ix, zz * rgas * (ex * rtp + rtb * (ex - ld2(FLD(exner_base), ix))), m0, m1);   // :1821
   } else {
@@ -1404,7 +1408,7 @@ __global__ void k_rec_cell1(const View V, double invNs, int rk_step, double dt, 
     st2m(FLD(theta_m), ix, (rtp + rtb) / rho_zz, m0, m1);
   }
 }
-__global__ void k_rec_edge(const View V, double invNs) {                                               // :1835-1842
+__global__ void k_rec_edge(const View V, double invNs, int fix) {                                      // :1835-1842
   PAIR_THREAD(V.nEdges)
   if (!m0) return;
   const int4 cv = V.ecv[x];
@@ -1413,11 +1417,12 @@ __global__ void k_rec_edge(const View V, double invNs) {                        
   D2 ra = ld2(FLD(ruAvg), ix);
   ra *= invNs; ra += rus;
   st2m(FLD(ruAvg), ix, ra, m0, m1);
-  const D2 ruv = rus * ld2(FLD(ru_p), ix);                                                            // a product, as written (:1840)
+  const D2 rup = ld2(FLD(ru_p), ix);
+  const D2 ruv = fix ? rus + rup : rus * rup;                                                         // a product, as written (:1840)
   st2m(FLD(ru), ix, ruv, m0, m1);
   st2m(FLD(u), ix, 2 * ruv / (G2(rz, cv.x) + G2(rz, cv.y)), m0, m1);
 }
-__global__ void k_rec_cell2(const View V, int nRelaxZone) {                                            // :1844-1871
+__global__ void k_rec_cell2(const View V, int nRelaxZone, int fix) {                                   // :1844-1871
   PAIR_THREAD(V.nCells)
   if (!m0) return;
   if (V.bdyMaskCell[x] > nRelaxZone) return;
@@ -1431,27 +1436,36 @@ __global__ void k_rec_cell2(const View V, int nRelaxZone) {                     
   for (int i = 0; i < n; ++i) {
     const int e = V.edgesOnCell[x * V.MEP + i];
     const D2 ru2 = G2(ru, e);
-    const D2 flux2 = fm * ru2 * (fp * below(ru, (size_t)e * LP + k0, k0, ru2));
+    const D2 rum = below(ru, (size_t)e * LP + k0, k0, ru2);
+    const D2 flux2 = fix ? fm * ru2 + fp * rum : fm * ru2 * (fp * rum);
     const D2 add = V.edgesOnCell_sign[x * ME + i] * (ld2(zb, i * V.cellSlot + ix) + sgn1(flux2) * ld2(zb3, i * V.cellSlot + ix)) * flux2;
     if (k0 > 0) wv.x += add.x;
     wv.y += add.y;
   }
   if (k0 == 0) {
     // level 0: the surface term is accumulated once per (cell, LEVEL) iteration, i.e. L times, interleaved
-    // with the level-0 flux2 term on the first pass (level -1 reads 0)
-    double w0 = wv.x;
-    for (int kk = 0; kk < L; ++kk) {
-      for (int i = 0; i < n; ++i) {
+    // with the level-0 flux2 term on the first pass (level -1 reads 0).  The terms do not depend on the pass, so they
+    // are formed once; the L*n additions keep the reference's order.
+    double t1[16], t2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      t1[i] = 0.0; t2[i] = 0.0;
+      if (i < n) {
         const int e = V.edgesOnCell[x * V.MEP + i];
         const double sgn = V.edgesOnCell_sign[x * ME + i];
         const double z = zb[i * V.cellSlot + ix], z3 = zb3[i * V.cellSlot + ix];
         const double flux = (cf1 * G1(ru, e, 0) + cf2 * G1(ru, e, 1) + cf3 * G1(ru, e, 2));
-        w0 += sgn * (z + copysign(1.0, flux) * z3) * flux;
-        if (kk == 0) {
-          const double flux2 = fm.x * G1(ru, e, 0) * (fp.x * 0.0);
-          w0 += sgn * (z + copysign(1.0, flux2) * z3) * flux2;
-        }
+        t1[i] = sgn * (z + copysign(1.0, flux) * z3) * flux;
+        const double flux2 = fix ? fm.x * G1(ru, e, 0) + fp.x * 0.0 : fm.x * G1(ru, e, 0) * (fp.x * 0.0);
+        t2[i] = sgn * (z + copysign(1.0, flux2) * z3) * flux2;
       }
+    }
+    double w0 = wv.x;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) if (i < n) { w0 += t1[i]; w0 += t2[i]; }
+    for (int kk = 1; kk < L; ++kk) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (i < n) w0 += t1[i];
     }
     wv.x = w0 / (cf1 * rz2.x + cf2 * rz2.y + cf3 * rz[ix + 2]);
     wv.y = wv.y / (fm.y * rz2.y + fp.y * rz2.x);

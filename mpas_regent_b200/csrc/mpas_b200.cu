@@ -295,6 +295,15 @@ int t_smlstep(mpasb200_t* h) { LAUNCH(k_smlstep, h->nCells, 0, h->V, h->c.nRelax
 int t_acoustic(mpasb200_t* h, double dts, int small_step) {
   const double epssm = h->c.config_epssm;
   const double resm = (1.0 - epssm) / (1.0 + epssm);
+  if (h->c.physics_mode == MPASB200_PHYSICS_CORRECTED) {        // edge update, flux gather, column solve with back-substitution
+    const double rcv = h->c.rgas / (h->c.cp - h->c.rgas), c2 = h->c.cp * rcv;
+    if (small_step == 0) LAUNCH(k_acoustic_u<true>, h->nEdges, 0, h->V, dts, c2, h->c.gravity);
+    else LAUNCH(k_acoustic_u<false>, h->nEdges, 0, h->V, dts, c2, h->c.gravity);
+    LAUNCH(k_acoustic_gather, h->nCells, 0, h->V, dts);
+    if (small_step == 0) LAUNCH(k_acoustic_col<true>, h->nCells, tile_bytes(h, 6), h->V, dts, epssm, resm);
+    else LAUNCH(k_acoustic_col<false>, h->nCells, tile_bytes(h, 6), h->V, dts, epssm, resm);
+    return post_launch(h);
+  }
   const bool tma_fits = ((size_t)AF_COUNT * h->LP + (size_t)4 * (h->LP + 2)) * sizeof(double) + 16 <= 48 * 1024 && h->LP / 2 <= 128;
   if (!h->c.acoustic_exact && h->c.acoustic_tma && h->nCells > 0 && tma_fits) {
     const View& V = h->V;
@@ -357,9 +366,10 @@ int t_recover(mpasb200_t* h, int ns, int rk_step, double dt) {
   const double invNs = 1 / (double)(ns);
   const double rcv = C.rgas / (C.cp - C.rgas);
   k_rec_pad<<<1, h->LP, 0, h->stream>>>(h->V); h->launches++;
-  LAUNCH(k_rec_cell1, h->nCells, 0, h->V, invNs, rk_step, dt, C.rgas, rcv);
-  LAUNCH(k_rec_edge, h->nEdges, 0, h->V, invNs);
-  LAUNCH(k_rec_cell2, h->nCells, 0, h->V, C.nRelaxZone);
+  const int fix = C.physics_mode == MPASB200_PHYSICS_CORRECTED;
+  LAUNCH(k_rec_cell1, h->nCells, 0, h->V, invNs, rk_step, dt, C.rgas, rcv, fix);
+  LAUNCH(k_rec_edge, h->nEdges, 0, h->V, invNs, fix);
+  LAUNCH(k_rec_cell2, h->nCells, 0, h->V, C.nRelaxZone, fix);
   return post_launch(h);
 }
 int t_finish(mpasb200_t* h, int substep, int split) {
@@ -404,7 +414,8 @@ int t_srk3(mpasb200_t* h, double dt) {
       T(MPASB200_T_ACOUSTIC, t_acoustic(h, rk_sub_timestep[rk_step], small_step));
       T(MPASB200_T_DIVDAMP, t_divdamp(h, rk_sub_timestep[rk_step]));
     }
-    // :459-460 atm_recover_large_step_variables is commented out in the reference (Q5)
+    // :459-460 atm_recover_large_step_variables is commented out in the reference (Q5); CORRECTED calls it as commented
+    if (C.physics_mode == MPASB200_PHYSICS_CORRECTED) T(MPASB200_T_RECOVER, t_recover(h, number_sub_steps[rk_step], rk_step, dt));
     T(MPASB200_T_DIAG, t_diag(h, 0, rk_step));                             // :467
   }
   T(MPASB200_T_FINISH, t_finish(h, 1, dynamics_split));                    // :481
@@ -468,6 +479,7 @@ void mpasb200_default_config(MpasConfig* c) {
   c->nRelaxZone = 5; c->number_of_sub_steps = 2; c->config_dynamics_split_steps = 1;
   c->index_policy = MPASB200_INDEX_CORRECTED; c->rkarg_policy = MPASB200_RKARG_SUBSTEP_TRUNC;
   c->sfc_renumber = 1; c->device = -1; c->use_graph = 0; c->acoustic_exact = 0; c->acoustic_tma = 2;
+  c->physics_mode = MPASB200_PHYSICS_LITERAL;
 }
 
 const char* mpasb200_last_error(const mpasb200_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }

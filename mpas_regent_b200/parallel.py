@@ -40,6 +40,21 @@ EXCHANGES: Dict[str, Dict[str, List[str]]] = {
 }
 
 
+#: MPASB200_PHYSICS_CORRECTED: the acoustic edge update reads rho_pp across cells and atm_recover_large_step_variables runs,
+#: so everything the acoustic step leaves invalid on the outer ghost ring is repaired, and so is what recover derives
+#: from ru_p on the outermost edges (u, ru, ruAvg) and gathers from them (w).
+EXCHANGES_CORRECTED: Dict[str, Dict[str, List[str]]] = {
+    "compute_dyn_tend": {"cell": ["w"]},
+    "advance_acoustic_step": {"cell": ["rtheta_pp", "rtheta_pp_old", "rho_pp", "rw_p", "wwAvg"]},
+    "recover_large_step_variables": {"cell": ["w"], "edge": ["u", "ru", "ruAvg"]},
+    "compute_solve_diagnostics": {"cell": ["ke", "divergence"], "edge": ["pv_edge", "v"], "vertex": ["vorticity"]},
+}
+
+
+def exchanges_for(cfg) -> Dict[str, Dict[str, List[str]]]:
+    return EXCHANGES_CORRECTED if cfg.physics_mode == _abi.PHYSICS_CORRECTED else EXCHANGES
+
+
 def split_state(fields: Dict[str, np.ndarray], lm: partition.LocalMesh) -> Dict[str, np.ndarray]:
     """restrict global 3-D fields to a rank's local entities (rows in local order)."""
     rows = {CELL: lm.cells, EDGE: lm.edges, VERTEX: lm.vertices}
@@ -176,10 +191,11 @@ class DistributedDynamics:
 
     def __init__(self, dyn: TaskAPI, exchanger):
         self.dyn, self.ex = dyn, exchanger
+        self.exchanges = exchanges_for(dyn.cfg)
         self.t_init = 0.0
 
     def _hook(self, name: str):
-        spec = EXCHANGES.get(name)
+        spec = self.exchanges.get(name)
         if spec:
             self.ex.exchange(spec)
 

@@ -73,6 +73,14 @@ K: Dict[str, Tuple[List[str], List[str]]] = {
                            "rw_save", "rw", "dss", "rho_zz", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"],
                           ["rtheta_pp_old", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"]),
     "k_acoustic_gather": (["ru_p", "theta_m"], ["scr", "scr"]),
+    # MPASB200_PHYSICS_CORRECTED
+    "k_acoustic_u<true>": (["tend_ru"], ["ru_p", "ruAvg"]),
+    "k_acoustic_u<false>": (["tend_ru", "rtheta_pp", "zz", "exner", "rho_pp", "cqu", "zxu", "ru_p", "ruAvg"], ["ru_p", "ruAvg"]),
+    "k_acoustic_col<true>": (["scr", "scr", "theta_m", "tend_rho", "w", "coftz", "cofwz", "cofwr", "cofwt", "a_tri", "alpha_tri", "gamma_tri",
+                              "zz", "rw_save", "rw", "dss", "rho_zz"], ["rtheta_pp_old", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"]),
+    "k_acoustic_col<false>": (["scr", "scr", "theta_m", "tend_rho", "w", "coftz", "cofwz", "cofwr", "cofwt", "a_tri", "alpha_tri", "gamma_tri",
+                               "zz", "rw_save", "rw", "dss", "rho_zz", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"],
+                              ["rtheta_pp_old", "rho_pp", "rtheta_pp", "rw_p", "wwAvg"]),
     "k_divdamp": (["rtheta_pp", "rtheta_pp_old", "theta_m", "ru_p"], ["ru_p"]),
     "k_rec_cell1": (["rho_p_save", "rho_pp", "rho_base", "wwAvg", "rw_save", "rw_p", "zz", "rtheta_base", "rtheta_p_save",
                      "rtheta_pp"], ["rho_p", "rho_zz", "wwAvg", "rw", "w", "rtheta_p", "theta_m"]),
@@ -99,7 +107,7 @@ def units(kernel: str, scratch: bool = True) -> float:
 
 
 # One RK3 step, canonical sequence (stage 0 takes the rk_step == 0 branches), rk_timestep.rg:404-481.
-def step_launches(canonical: bool = True) -> List[str]:
+def step_launches(canonical: bool = True, corrected_physics: bool = False) -> List[str]:
     seq = ["k_setup_cell", "k_setup_edge", "k_moist", "k_vert_imp"]
     for stage in range(3):
         if stage == 1:
@@ -111,14 +119,20 @@ def step_launches(canonical: bool = True) -> List[str]:
             seq += ["k_dt_cell0<false>", "k_dt_edge", "k_dt_theta_flux", "k_dt_cellC<false>"]
         seq.append("k_smlstep")
         for ss in range((1 if stage < 2 else 2) + 1):
-            seq += ["k_acoustic_gather", "k_acoustic_tma<true>" if ss == 0 else "k_acoustic_tma<false>", "k_divdamp"]
+            t = "<true>" if ss == 0 else "<false>"
+            if corrected_physics:
+                seq += ["k_acoustic_u" + t, "k_acoustic_gather", "k_acoustic_col" + t, "k_divdamp"]
+            else:
+                seq += ["k_acoustic_gather", "k_acoustic_tma" + t, "k_divdamp"]
+        if corrected_physics:
+            seq += ["k_rec_pad", "k_rec_cell1", "k_rec_edge", "k_rec_cell2"]
         seq += ["k_diag_vertex", "k_diag_cell", "k_diag_edge<true>" if stage == 2 else "k_diag_edge<false>"]
     seq += ["k_finish_cell", "k_finish_edge"]
     return seq
 
 
-def step_units(canonical: bool = True, scratch: bool = True) -> float:
-    return sum(units(k, scratch) for k in step_launches(canonical))
+def step_units(canonical: bool = True, scratch: bool = True, corrected_physics: bool = False) -> float:
+    return sum(units(k, scratch) for k in step_launches(canonical, corrected_physics) if k != "k_rec_pad")
 
 
 # the contract figures (units of 8 B per cell-level) -- per task call and per step.
@@ -145,6 +159,9 @@ TASK_KERNELS = {
     "advance_acoustic_step:fused": ["k_acoustic<false>"],
     "advance_acoustic_step:s0:exact": ["k_acoustic_flux:s0", "k_acoustic_column:s0"],
     "advance_acoustic_step:exact": ["k_acoustic_flux", "k_acoustic_column"],
+    "advance_acoustic_step:s0:corrected_physics": ["k_acoustic_u<true>", "k_acoustic_gather", "k_acoustic_col<true>"],
+    "advance_acoustic_step:corrected_physics": ["k_acoustic_u<false>", "k_acoustic_gather", "k_acoustic_col<false>"],
+    "recover_large_step_variables": ["k_rec_cell1", "k_rec_edge", "k_rec_cell2"],
     "divergence_damping_3d": ["k_divdamp"],
     "compute_solve_diagnostics": ["k_diag_vertex", "k_diag_cell", "k_diag_edge<false>"],
     "compute_solve_diagnostics:v": ["k_diag_vertex", "k_diag_cell", "k_diag_edge<true>"],

@@ -950,7 +950,7 @@ int oracle_recover_large_step_variables(oracle_t* o, int ns, int rk_step, double
   CF(rw_p); CF(rw_save); CF(zz); CF(ru_p); CF(ru_save); CF(pressure_p); CF(theta_m); CF(u); CF(exner); CF(rho_p); CF(rho_zz);
   CF(rtheta_p); CF(rw); CF(w); CF(wwAvg); CF(ruAvg); CF(ru);
   F3A zb_cell = o->fa(MPASB200_F_zb_cell), zb3_cell = o->fa(MPASB200_F_zb3_cell);
-  const bool fix = o->c.physics_mode == MPASB200_PHYSICS_CORRECTED;         // three expressions restored, see mpas_b200.h
+  const bool fix = o->c.physics_mode == MPASB200_PHYSICS_CORRECTED;         // four expressions restored, see mpas_b200.h
   for (int k = 0; k < L; ++k) rho_zz(nC, k) = 1.0;                          // :1792-1794 the "garbage cell" = the pad cell
   double invNs = 1 / (double)(ns);
   OMP_FOR
@@ -961,7 +961,7 @@ int oracle_recover_large_step_variables(oracle_t* o, int ns, int rk_step, double
     wwAvg(c, k) *= invNs;
     wwAvg(c, k) += rw_save(c, k);
     rw(c, k) = rw_save(c, k) + rw_p(c, k);
-    w(c, k) = rw(c, k) / (fzm[k] * zz(c, k) + fzp[k] * zz(c, k - 1));
+    w(c, k) = (fix && k == 0) ? 0.0 : rw(c, k) / (fzm[k] * zz(c, k) + fzp[k] * zz(c, k - 1));   // :1810; MPAS: w(1) = 0, k = 2..nVertLevels
     if (k == L) w(c, k) = 0.0;                                              // never fires
     if (rk_step == 2) {
       rtheta_p(c, k) = rtheta_p_save(c, k) + rtheta_pp(c, k) - dt * rho_zz(c, k) * rt_diabatic_tend(c, k);

@@ -18,10 +18,12 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    L, dt, steps = 12, 400.0, 3
+    corrected = len(sys.argv) > 1 and sys.argv[1] == "corrected"
+    L, dt, steps = 12, 400.0, (1 if corrected else 3)     # corrected physics: the first step is the finite one
     mesh = icosa.make_icosahedral_mesh(2562)
     st = init_jw.make_state(mesh, L, _abi.INDEX_CORRECTED)
-    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, device=local)
+    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, device=local,
+                              physics_mode=_abi.PHYSICS_CORRECTED if corrected else _abi.PHYSICS_LITERAL)
     stream = torch.cuda.Stream()
     sh = parallel.make_shards(st, world)[rank]
     lm = sh["lm"]
@@ -41,7 +43,7 @@ def main():
     _assert_owned_equal(single, d, lm)
     dist.barrier()
     if rank == 0:
-        print(f"MULTIGPU_OK world={world} owned_cells={lm.n_owned[0]} ghosts={len(lm.cells) - lm.n_owned[0]}")
+        print(f"MULTIGPU_OK physics={'corrected' if corrected else 'literal'} world={world} owned_cells={lm.n_owned[0]} ghosts={len(lm.cells) - lm.n_owned[0]}")
     dist.destroy_process_group()
 
 

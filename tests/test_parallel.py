@@ -72,9 +72,9 @@ def test_halo_lists_are_symmetric(grid642):
         assert owned_total == {"cell": grid642.nCells, "edge": grid642.nEdges, "vertex": grid642.nVertices}[ent]
 
 
-def _single(mesh, st, steps):
+def _single(mesh, st, steps, physics=_abi.PHYSICS_LITERAL):
     from oracle.oracle import Oracle
-    o = Oracle(dynamics.dims_of(mesh, L), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX))
+    o = Oracle(dynamics.dims_of(mesh, L), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, physics_mode=physics))
     o.upload_mesh(st.static); o.upload_state(st.f, st.vert)
     o.atm_compute_solve_diagnostics(False, -1)
     for _ in range(steps):
@@ -82,10 +82,11 @@ def _single(mesh, st, steps):
     return o
 
 
-def _rank_backend(sh):
+def _rank_backend(sh, physics=_abi.PHYSICS_LITERAL):
     from oracle.oracle import Oracle
     lm = sh["lm"]
-    o = Oracle(_abi.make_dims(len(lm.cells), len(lm.edges), len(lm.vertices), L), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX))
+    o = Oracle(_abi.make_dims(len(lm.cells), len(lm.edges), len(lm.vertices), L),
+               _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, physics_mode=physics))
     o.upload_mesh(sh["static"]); o.upload_state(sh["f"], sh["vert"])
     return o
 
@@ -120,22 +121,25 @@ def _task_schedule(cfg):
     return seq
 
 
+@pytest.mark.parametrize("physics", [_abi.PHYSICS_LITERAL, _abi.PHYSICS_CORRECTED], ids=["literal", "corrected_physics"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_n_ranks_equal_single_partition_bitwise(grid642, world):
+def test_n_ranks_equal_single_partition_bitwise(grid642, world, physics):
     st, shards = _shards(grid642, world)
-    single = _single(grid642, st, 2)
-    backs = [_rank_backend(s) for s in shards]
+    single = _single(grid642, st, 2, physics)
+    backs = [_rank_backend(s, physics) for s in shards]
     ex = parallel.InProcessExchanger(backs, [s["lm"] for s in shards])
+    exchanges = parallel.exchanges_for(backs[0].cfg)
     # lock-step: every rank runs the same task, then ONE exchange serves all of them
     for b in backs:
         b.atm_compute_solve_diagnostics(False, -1)
-    ex.exchange(parallel.EXCHANGES["compute_solve_diagnostics"])
+    ex.exchange(exchanges["compute_solve_diagnostics"])
     seq = _task_schedule(backs[0].cfg)
+    assert ("recover_large_step_variables" in [n for n, _ in seq]) == (physics == _abi.PHYSICS_CORRECTED)
     for _ in range(2):
         for name, args in seq:
             for b in backs:
                 b._call(name, *args)
-            spec = parallel.EXCHANGES.get(name)
+            spec = exchanges.get(name)
             if spec:
                 ex.exchange(spec)
     for b, s in zip(backs, shards):

@@ -205,15 +205,17 @@ def test_acoustic_modes(grid2562, exact):
     g.close(); ora.close()
 
 
-def test_emulated_ranks_on_one_gpu_equal_single_partition(grid642):
-    """4 ranks emulated as 4 handles on one GPU (pack/unpack + the exchange schedule of parallel.EXCHANGES):
+@pytest.mark.parametrize("physics", [_abi.PHYSICS_LITERAL, _abi.PHYSICS_CORRECTED], ids=["literal", "corrected_physics"])
+def test_emulated_ranks_on_one_gpu_equal_single_partition(grid642, physics):
+    """4 ranks emulated as 4 handles on one GPU (pack/unpack + the exchange schedule of parallel.exchanges_for):
     owned entities are bit-identical to the single-partition GPU run."""
     import torch
     from mpas_regent_b200 import dynamics, init_jw, parallel
     from tests.test_parallel import _task_schedule, _assert_owned_equal
     Lh = 6
     st = init_jw.make_state(grid642, Lh, _abi.INDEX_CORRECTED)
-    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX)
+    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, physics_mode=physics)
+    exchanges = parallel.exchanges_for(cfg)
     single = dynamics.Dynamics(dynamics.dims_of(grid642, Lh), cfg)
     single.upload_mesh(st.static); single.upload_state(st.f, st.vert)
     single.atm_compute_solve_diagnostics(False, -1)
@@ -245,15 +247,15 @@ def test_emulated_ranks_on_one_gpu_equal_single_partition(grid642):
 
     for b in backs:
         b.atm_compute_solve_diagnostics(False, -1)
-    exchange(parallel.EXCHANGES["compute_solve_diagnostics"])
+    exchange(exchanges["compute_solve_diagnostics"])
     seq = _task_schedule(cfg)
     for _ in range(2):
         single.atm_srk3(600.0)
         for name, args in seq:
             for b in backs:
                 b._call(name, *args)
-            if name in parallel.EXCHANGES:
-                exchange(parallel.EXCHANGES[name])
+            if name in exchanges:
+                exchange(exchanges[name])
     for b, sh in zip(backs, shards):
         _assert_owned_equal(single, b, sh["lm"])
         b.close()
@@ -271,10 +273,11 @@ def test_nccl_ranks_equal_single_gpu():
         pytest.skip("needs >= 2 GPUs")
     n = 2 if n < 4 else 4
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-                          "--master-port", "29533", os.path.join(root, "tests", "run_multigpu_check.py")],
-                         capture_output=True, text=True, timeout=600, cwd=root)
-    assert out.returncode == 0 and "MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+    for physics, port in (("literal", "29533"), ("corrected", "29535")):
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                              "--master-port", port, os.path.join(root, "tests", "run_multigpu_check.py"), physics],
+                             capture_output=True, text=True, timeout=600, cwd=root)
+        assert out.returncode == 0 and "MULTIGPU_OK" in out.stdout, physics + out.stdout[-2000:] + out.stderr[-3000:]
 
 
 def test_hundred_step_drift(grid2562):
@@ -293,3 +296,78 @@ def test_hundred_step_drift(grid2562):
         worst = compare(g, ora, tol=1e-12 * (1 + upto), what=f"after {upto} steps")
         assert worst[0] <= 1e-12 * (1 + upto)
     g.close(); ora.close()
+
+
+# ---- MPASB200_PHYSICS_CORRECTED: u update + back-substitution + recover wired -----------------
+CORRECTED_TASKS = [
+    ("acoustic_step0", lambda b: b.atm_advance_acoustic_step(240.0, 0)),
+    ("acoustic_step1", lambda b: b.atm_advance_acoustic_step(360.0, 1)),
+    ("acoustic_loop", lambda b: [(b.atm_advance_acoustic_step(360.0, s), b.atm_divergence_damping_3d(360.0)) for s in range(3)]),
+    ("recover_rk0", lambda b: b.atm_recover_large_step_variables(1, 0, DT)),
+    ("recover_rk2", lambda b: b.atm_recover_large_step_variables(2, 2, DT)),
+    ("acoustic_loop_then_recover", lambda b: ([(b.atm_advance_acoustic_step(360.0, s), b.atm_divergence_damping_3d(360.0)) for s in range(3)],
+                                              b.atm_recover_large_step_variables(2, 2, DT))),
+]
+ACOUSTIC_OUT = ("ru_p", "ruAvg", "rw_p", "wwAvg", "rho_pp", "rtheta_pp", "rtheta_pp_old")
+
+
+@pytest.fixture(scope="module", params=[_abi.INDEX_CORRECTED, _abi.INDEX_LITERAL], ids=["corrected", "literal"])
+def warmed_physics(request, grid2562):
+    """state after one LITERAL step (finite everywhere), then both backends switched to CORRECTED physics."""
+    st, ora0, _ = build_pair(grid2562, L_SMALL, request.param, m5=True, gpu=False)
+    ora0.atm_compute_solve_diagnostics(False, -1)
+    ora0.atm_srk3(DT)
+    snap = {n: ora0.download_field(n) for (n, _, _) in _abi.FIELDS}
+    ora0.close()
+    st, ora, g = build_pair(grid2562, L_SMALL, request.param, m5=True, physics_mode=_abi.PHYSICS_CORRECTED)
+    yield ora, g, snap
+    g.close(); ora.close()
+
+
+@pytest.mark.parametrize("name,fn", CORRECTED_TASKS, ids=[t[0] for t in CORRECTED_TASKS])
+def test_corrected_physics_task_parity(warmed_physics, name, fn):
+    ora, g, snap = warmed_physics
+    for n, a in snap.items():
+        ora.upload_field(n, a); g.upload_field(n, a)
+    fn(ora); fn(g)
+    compare(g, ora, what="corrected physics " + name)
+    if name.startswith("acoustic") and "recover" not in name:
+        # the column solve runs strictly in the oracle's order (no FMA contraction): bit-identical
+        for n in ACOUSTIC_OUT:
+            assert np.array_equal(g.download_field(n), ora.download_field(n), equal_nan=True), n
+        assert np.isfinite(ora.download_field("rw_p")).all() and np.abs(ora.download_field("ru_p")).max() > 0
+
+
+@pytest.mark.parametrize("policy", [_abi.INDEX_CORRECTED, _abi.INDEX_LITERAL], ids=["corrected", "literal"])
+def test_corrected_physics_full_step_parity(grid2562, policy):
+    """atm_srk3 with the acoustic loop completed and recover called after it (rk_timestep.rg:459-460).  The first step
+    stays finite; the reference's remaining quirks (cr.w / cr.theta_m used as tendencies, Q17/Q27) then drive the state
+    to Inf/NaN, so the second step checks identical NaN/Inf masks."""
+    st, ora, g = build_pair(grid2562, L_SMALL, policy, m5=True, physics_mode=_abi.PHYSICS_CORRECTED)
+    u0 = ora.download_field("u")
+    for b in (ora, g):
+        b.atm_compute_solve_diagnostics(False, -1)
+        b.atm_srk3(DT)
+    assert np.isfinite(ora.download_field("u")).all() and not np.array_equal(u0, ora.download_field("u"))
+    compare(g, ora, what="corrected physics, 1 step")
+    for b in (ora, g):
+        b.atm_srk3(DT)
+    compare(g, ora, what="corrected physics, 2 steps")
+    g.close(); ora.close()
+
+
+def test_corrected_physics_by_tasks_equals_driver_and_graph(grid642):
+    from mpas_regent_b200 import dynamics, init_jw
+    st = init_jw.make_state(grid642, 10, _abi.INDEX_CORRECTED)
+    outs = []
+    for mode in ("tasks", "driver", "graph"):
+        cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, use_graph=int(mode == "graph"), physics_mode=_abi.PHYSICS_CORRECTED)
+        g = dynamics.Dynamics(dynamics.dims_of(grid642, 10), cfg)
+        g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
+        g.atm_compute_solve_diagnostics(False, -1)
+        g.atm_srk3_by_tasks(600.0) if mode == "tasks" else g.atm_srk3(600.0)
+        outs.append(g.download_all())
+        g.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
+        assert np.array_equal(outs[0][n], outs[2][n], equal_nan=True), n

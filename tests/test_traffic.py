@@ -26,6 +26,9 @@ def test_step_units():
     assert T.step_units(True, scratch=False) >= T.SURVEY_STEP_UNITS_CANONICAL
     assert T.step_units(False, scratch=False) >= T.SURVEY_STEP_UNITS_LITERAL
     assert len(T.step_launches(True)) == 58 and len(T.step_launches(False)) == 52
+    # corrected physics: + 7 edge updates + 3 x 4 recover launches; more bytes than the literal step, never fewer
+    assert len(T.step_launches(True, corrected_physics=True)) == 58 + 7 + 12
+    assert T.step_units(True, scratch=False, corrected_physics=True) > T.step_units(True, scratch=False)
 
 
 def test_every_kernel_in_the_library_is_declared():
