@@ -187,6 +187,14 @@ int  mpasb200_upload_field(mpasb200_t *h, int field, const void *base, int64_t s
 int  mpasb200_download_field(mpasb200_t *h, int field, void *base, int64_t stride_x, int64_t stride_k);
 int  mpasb200_zero_field(mpasb200_t *h, int field);
 int  mpasb200_sync(mpasb200_t *h);
+/* Pipelined variants for contiguous, page-locked host arrays ([n][nVertLevels+1][slots]): the H2D / D2H copies run on the
+ * library's own copy streams (both PCIe directions and the compute stream overlap), ordered against the tasks by events:
+ * an upload is visible to every task enqueued after it, a download sees every task enqueued before it.  The host array
+ * may be reused (upload) or read (download) after mpasb200_transfer_wait().  Each field gets its own device staging
+ * buffer per direction on first use (counted in mpasb200_device_bytes).                                            */
+int  mpasb200_upload_field_async(mpasb200_t *h, int field, const void *base);
+int  mpasb200_download_field_async(mpasb200_t *h, int field, void *base);
+int  mpasb200_transfer_wait(mpasb200_t *h);
 
 /* ---- one entry per hot-path task: scalars only -------------------------------------- */
 /* atm_rk_integration_setup            dynamics_tasks.rg:747-778   */

@@ -1051,14 +1051,22 @@ __global__ void __launch_bounds__(256) k_acoustic_col(const View V, double dts, 
     const D2 at = ld2(FLD(a_tri), ix), al = ld2(FLD(alpha_tri), ix), gt = ld2(FLD(gamma_tri), ix);
     s_x[k0] = k0 > 0 ? xr.x : rw_old.x; s_a[k0] = at.x; s_al[k0] = al.x; s_g[k0] = gt.x;
     if (m1) { s_x[k1] = xr.y; s_a[k1] = at.y; s_al[k1] = al.y; s_g[k1] = gt.y; }
+    if (k0 == 0) s_x[L] = S0 ? 0.0 : FLD(rw_p)[(size_t)x * LP + L];
   }
+  if (threadIdx.x == 0) s_al[L + 1] = act ? 1.0 : 0.0;
   __syncthreads();
-  if (act && k0 == 0) {
-    double xv = s_x[0];
-    for (int kk = 1; kk < L; ++kk) { xv = (s_x[kk] - s_a[kk] * xv) * s_al[kk]; s_x[kk] = xv; }       // :1670-1671
-    xv = S0 ? 0.0 : FLD(rw_p)[(size_t)x * LP + L];
-    s_x[L] = xv;
-    for (int kk = L - 1; kk >= 0; --kk) { xv = s_x[kk] - s_g[kk] * xv; s_x[kk] = xv; }               // :1674-1677
+  {   // the two sweeps, strictly in order: one lane per column, all in the block's first warp
+    const int lin = ty * blockDim.x + threadIdx.x;
+    if (lin < CB && sm[(size_t)(4 * CB + lin) * TS + L + 1] != 0.0) {
+      double* cx = sm + (size_t)(2 * CB + lin) * TS; const double* ca = sm + (size_t)(3 * CB + lin) * TS;
+      const double* cal = sm + (size_t)(4 * CB + lin) * TS; const double* cg = sm + (size_t)(5 * CB + lin) * TS;
+      double xv = cx[0];
+#pragma unroll 4
+      for (int kk = 1; kk < L; ++kk) { xv = (cx[kk] - ca[kk] * xv) * cal[kk]; cx[kk] = xv; }         // :1670-1671
+      xv = cx[L];
+#pragma unroll 4
+      for (int kk = L - 1; kk >= 0; --kk) { xv = cx[kk] - cg[kk] * xv; cx[kk] = xv; }                 // :1674-1677
+    }
   }
   __syncthreads();
   D2 xn = bc(0), ww_new = bc(0);
@@ -1422,52 +1430,79 @@ __global__ void k_rec_edge(const View V, double invNs, int fix) {               
   st2m(FLD(ru), ix, ruv, m0, m1);
   st2m(FLD(u), ix, 2 * ruv / (G2(rz, cv.x) + G2(rz, cv.y)), m0, m1);
 }
-__global__ void k_rec_cell2(const View V, int nRelaxZone, int fix) {                                   // :1844-1871
-  PAIR_THREAD(V.nCells)
-  if (!m0) return;
-  if (V.bdyMaskCell[x] > nRelaxZone) return;
-  const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
-  const double* ru = FLD(ru); const double* zb = FLD(zb_cell); const double* zb3 = FLD(zb3_cell); const double* rz = FLD(rho_zz);
-  const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0);
-  const double cf1 = FLD(cf1)[0], cf2 = FLD(cf2)[0], cf3 = FLD(cf3)[0];
-  D2 wv = ld2(FLD(w), ix);
-  const D2 rz2 = ld2(rz, ix);
-  // levels k0 (if > 0) and k1: w += sign*(zb + sign(flux2)*zb3)*flux2, flux2 a PRODUCT as written (:1855)
-  for (int i = 0; i < n; ++i) {
-    const int e = V.edgesOnCell[x * V.MEP + i];
-    const D2 ru2 = G2(ru, e);
-    const D2 rum = below(ru, (size_t)e * LP + k0, k0, ru2);
-    const D2 flux2 = fix ? fm * ru2 + fp * rum : fm * ru2 * (fp * rum);
-    const D2 add = V.edgesOnCell_sign[x * ME + i] * (ld2(zb, i * V.cellSlot + ix) + sgn1(flux2) * ld2(zb3, i * V.cellSlot + ix)) * flux2;
-    if (k0 > 0) wv.x += add.x;
-    wv.y += add.y;
-  }
-  if (k0 == 0) {
-    // level 0: the surface term is accumulated once per (cell, LEVEL) iteration, i.e. L times, interleaved
-    // with the level-0 flux2 term on the first pass (level -1 reads 0).  The terms do not depend on the pass, so they
-    // are formed once; the L*n additions keep the reference's order.
-    double t1[16], t2[16];
+template <int N>
+DI double rec_chain(const double* c, double w0, int L) {      // passes 1..L-1 of the level-0 accumulation, terms in registers
+  double t[N];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      t1[i] = 0.0; t2[i] = 0.0;
-      if (i < n) {
-        const int e = V.edgesOnCell[x * V.MEP + i];
-        const double sgn = V.edgesOnCell_sign[x * ME + i];
-        const double z = zb[i * V.cellSlot + ix], z3 = zb3[i * V.cellSlot + ix];
-        const double flux = (cf1 * G1(ru, e, 0) + cf2 * G1(ru, e, 1) + cf3 * G1(ru, e, 2));
-        t1[i] = sgn * (z + copysign(1.0, flux) * z3) * flux;
-        const double flux2 = fix ? fm.x * G1(ru, e, 0) + fp.x * 0.0 : fm.x * G1(ru, e, 0) * (fp.x * 0.0);
-        t2[i] = sgn * (z + copysign(1.0, flux2) * z3) * flux2;
+  for (int i = 0; i < N; ++i) t[i] = c[i];
+  for (int kk = 1; kk < L; ++kk) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) w0 += t[i];
+  }
+  return w0;
+}
+__global__ void k_rec_cell2(const View V, int nRelaxZone, int fix) {                                   // :1844-1871
+  extern __shared__ double sm[];
+  PAIR_THREAD(V.nCells)
+  // per column: t1[16], t2[16], w0, n  (the level-0 chain below runs with one lane per column in the block's first warp)
+  double* s_col = sm + (size_t)threadIdx.y * 34;
+  const bool act = m0 && V.bdyMaskCell[x] <= nRelaxZone;
+  const int ME = V.maxEdges, n = act ? V.nEdgesOnCell[x] : 0;
+  const double* ru = FLD(ru); const double* zb = FLD(zb_cell); const double* zb3 = FLD(zb3_cell); const double* rz = FLD(rho_zz);
+  const double cf1 = FLD(cf1)[0], cf2 = FLD(cf2)[0], cf3 = FLD(cf3)[0];
+  D2 wv = bc(0.0), rz2 = bc(0.0), fm = bc(0.0), fp = bc(0.0);
+  if (threadIdx.x == 0) s_col[33] = 0.0;
+  if (act) {
+    fm = ld2(FLD(fzm), k0); fp = ld2(FLD(fzp), k0);
+    wv = ld2(FLD(w), ix);
+    rz2 = ld2(rz, ix);
+    // levels k0 (if > 0) and k1: w += sign*(zb + sign(flux2)*zb3)*flux2, flux2 a PRODUCT as written (:1855)
+    for (int i = 0; i < n; ++i) {
+      const int e = V.edgesOnCell[x * V.MEP + i];
+      const D2 ru2 = G2(ru, e);
+      const D2 rum = below(ru, (size_t)e * LP + k0, k0, ru2);
+      const D2 flux2 = fix ? fm * ru2 + fp * rum : fm * ru2 * (fp * rum);
+      const double sgn = V.edgesOnCell_sign[x * ME + i];
+      const D2 z = ld2(zb, i * V.cellSlot + ix), z3 = ld2(zb3, i * V.cellSlot + ix);
+      const D2 add = sgn * (z + sgn1(flux2) * z3) * flux2;
+      if (k0 > 0) wv.x += add.x;
+      wv.y += add.y;
+      if (k0 == 0) {
+        // level 0: the surface term is accumulated once per (cell, LEVEL) iteration, i.e. L times, interleaved with the
+        // level-0 flux2 term on the first pass (level -1 reads 0).  The terms do not depend on the pass: form them once.
+        const double flux = (cf1 * ru2.x + cf2 * ru2.y + cf3 * G1(ru, e, 2));
+        s_col[i] = sgn * (z.x + copysign(1.0, flux) * z3.x) * flux;
+        const double f20 = fix ? fm.x * ru2.x + fp.x * 0.0 : fm.x * ru2.x * (fp.x * 0.0);
+        s_col[16 + i] = sgn * (z.x + copysign(1.0, f20) * z3.x) * f20;
       }
     }
-    double w0 = wv.x;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) if (i < n) { w0 += t1[i]; w0 += t2[i]; }
-    for (int kk = 1; kk < L; ++kk) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) if (i < n) w0 += t1[i];
+    if (k0 == 0) { s_col[32] = wv.x; s_col[33] = (double)n; }
+  }
+  __syncthreads();
+  {   // the L*n additions in the reference's order: one lane per column, all in the block's first warp(s)
+    const int lin = threadIdx.y * blockDim.x + threadIdx.x;
+    if (lin < (int)blockDim.y) {
+      double* c = sm + (size_t)lin * 34;
+      const int nn = (int)c[33];
+      if (nn > 0) {
+        double w0 = c[32];
+        for (int i = 0; i < nn; ++i) { w0 += c[i]; w0 += c[16 + i]; }
+        switch (nn) {                  // the common cell degrees keep their terms in registers
+          case 5: w0 = rec_chain<5>(c, w0, L); break;
+          case 6: w0 = rec_chain<6>(c, w0, L); break;
+          case 7: w0 = rec_chain<7>(c, w0, L); break;
+          default:
+            for (int kk = 1; kk < L; ++kk)
+              for (int i = 0; i < nn; ++i) w0 += c[i];
+        }
+        c[32] = w0;
+      }
     }
-    wv.x = w0 / (cf1 * rz2.x + cf2 * rz2.y + cf3 * rz[ix + 2]);
+  }
+  __syncthreads();
+  if (!act) return;
+  if (k0 == 0) {
+    wv.x = s_col[32] / (cf1 * rz2.x + cf2 * rz2.y + cf3 * rz[ix + 2]);
     wv.y = wv.y / (fm.y * rz2.y + fp.y * rz2.x);
   } else {
     const D2 rzm = below(rz, ix, k0, rz2);

@@ -59,6 +59,11 @@ struct mpasb200 {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // pipelined transfers: one staging buffer per field and direction, copies on their own streams
+  cudaStream_t up_stream = nullptr, dn_stream = nullptr;
+  struct Pipe { double* up = nullptr; double* dn = nullptr; cudaEvent_t up_copied = nullptr, up_scattered = nullptr, dn_gathered = nullptr,
+                dn_copied = nullptr; bool up_used = false, dn_used = false; };
+  std::vector<Pipe> pipe;
   double task_ms[MPASB200_T_COUNT] = {0}; int64_t task_calls[MPASB200_T_COUNT] = {0};
   int64_t launches = 0;
   bool capturing = false;
@@ -369,7 +374,7 @@ int t_recover(mpasb200_t* h, int ns, int rk_step, double dt) {
   const int fix = C.physics_mode == MPASB200_PHYSICS_CORRECTED;
   LAUNCH(k_rec_cell1, h->nCells, 0, h->V, invNs, rk_step, dt, C.rgas, rcv, fix);
   LAUNCH(k_rec_edge, h->nEdges, 0, h->V, invNs, fix);
-  LAUNCH(k_rec_cell2, h->nCells, 0, h->V, C.nRelaxZone, fix);
+  LAUNCH(k_rec_cell2, h->nCells, (size_t)h->CPB * 34 * sizeof(double), h->V, C.nRelaxZone, fix);
   return post_launch(h);
 }
 int t_finish(mpasb200_t* h, int substep, int split) {
@@ -542,6 +547,13 @@ int mpasb200_destroy(mpasb200_t* h) {
   for (auto& l : h->lists) if (l.d_idx) cudaFree(l.d_idx);
   if (h->d_stage) cudaFree(h->d_stage);
   if (h->h_stage) cudaFreeHost(h->h_stage);
+  for (auto& pp : h->pipe) {
+    if (pp.up) cudaFree(pp.up);
+    if (pp.dn) cudaFree(pp.dn);
+    for (cudaEvent_t e : {pp.up_copied, pp.up_scattered, pp.dn_gathered, pp.dn_copied}) if (e) cudaEventDestroy(e);
+  }
+  if (h->up_stream) cudaStreamDestroy(h->up_stream);
+  if (h->dn_stream) cudaStreamDestroy(h->dn_stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -801,6 +813,75 @@ int mpasb200_upload_field(mpasb200_t* h, int field, const void* base, int64_t st
 }
 int mpasb200_download_field(mpasb200_t* h, int field, void* base, int64_t stride_x, int64_t stride_k) {
   return field_xfer(h, field, base, stride_x, stride_k, false);
+}
+// Pipelined transfers.  Contiguous page-locked host arrays only.  Upload: H2D copy on the upload stream into the field's
+// own staging buffer, renumbering scatter on the compute stream (ordered before every later task).  Download: gather on the
+// compute stream (ordered after every earlier task), D2H copy on the download stream.  The two copy directions and the
+// compute stream overlap; a staging buffer is reused only after the event that frees it.
+static int field_xfer_async(mpasb200_t* h, int field, void* base, bool up) {
+  if (!h || !base) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  if (field < 0 || field >= MPASB200_F_COUNT) return fail(h, MPASB200_EINVAL, "field id out of range");
+  const FieldInfo& fi = kFields[field];
+  if (fi.entity == MPASB200_VERTICAL) return fail(h, MPASB200_EINVAL, "vertical fields have no asynchronous transfer");
+  if (!h->mesh_ok) return fail(h, MPASB200_ESTATE, "upload_mesh must precede field transfers (it fixes the renumbering)");
+  if (h->capturing) return fail(h, MPASB200_ESTATE, "transfer during graph capture");
+  const int n = entity_count(h, fi.entity);
+  if (n == 0) return 0;
+  const int L1 = h->L1, S = fi.slots;
+  const size_t elems = (size_t)n * L1 * S, bytes = elems * sizeof(double);
+  if (!h->up_stream) {
+    CK(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->dn_stream, cudaStreamNonBlocking));
+    h->pipe.resize(MPASB200_F_COUNT);
+  }
+  mpasb200_t::Pipe& pp = h->pipe[field];
+  if (!pp.up_copied) {
+    for (cudaEvent_t* e : {&pp.up_copied, &pp.up_scattered, &pp.dn_gathered, &pp.dn_copied}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  double*& stage = up ? pp.up : pp.dn;
+  if (!stage) {
+    cudaError_t e = cudaMalloc((void**)&stage, bytes);
+    if (e != cudaSuccess) { h->err = std::string("cudaMalloc(pipeline staging): ") + cudaGetErrorString(e); stage = nullptr; return MPASB200_ENOMEM; }
+    h->bytes += bytes;
+  }
+  const size_t slotStride = (size_t)(n + 1) * h->LP;
+  const int* map = h->d_newOf[fi.entity];
+  const unsigned blocks = (unsigned)((elems + 255) / 256);
+  if (up) {
+    if (pp.up_used) CK(cudaStreamWaitEvent(h->up_stream, pp.up_scattered, 0));        // staging free again
+    CK(cudaMemcpyAsync(pp.up, base, bytes, cudaMemcpyHostToDevice, h->up_stream));
+    CK(cudaEventRecord(pp.up_copied, h->up_stream));
+    CK(cudaStreamWaitEvent(h->stream, pp.up_copied, 0));
+    k_stage_to_field<<<blocks, 256, 0, h->stream>>>(h->V.f[field], pp.up, map, n, L1, h->LP, S, slotStride);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(pp.up_scattered, h->stream));
+    pp.up_used = true;
+  } else {
+    if (pp.dn_used) CK(cudaStreamWaitEvent(h->stream, pp.dn_copied, 0));              // staging free again
+    k_field_to_stage<<<blocks, 256, 0, h->stream>>>(h->V.f[field], pp.dn, map, n, L1, h->LP, S, slotStride);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(pp.dn_gathered, h->stream));
+    CK(cudaStreamWaitEvent(h->dn_stream, pp.dn_gathered, 0));
+    CK(cudaMemcpyAsync(base, pp.dn, bytes, cudaMemcpyDeviceToHost, h->dn_stream));
+    CK(cudaEventRecord(pp.dn_copied, h->dn_stream));
+    pp.dn_used = true;
+  }
+  return 0;
+}
+int mpasb200_upload_field_async(mpasb200_t* h, int field, const void* base) { return field_xfer_async(h, field, const_cast<void*>(base), true); }
+int mpasb200_download_field_async(mpasb200_t* h, int field, void* base) { return field_xfer_async(h, field, base, false); }
+int mpasb200_transfer_wait(mpasb200_t* h) {
+  if (!h) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  if (h->up_stream) { CK(cudaStreamSynchronize(h->up_stream)); }
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->dn_stream) { CK(cudaStreamSynchronize(h->dn_stream)); }
+  return 0;
 }
 int mpasb200_zero_field(mpasb200_t* h, int field) {
   if (!h || field < 0 || field >= MPASB200_F_COUNT) return MPASB200_EINVAL;

@@ -75,6 +75,9 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         lib.mpasb200_upload_field.argtypes = [H, I, C.c_void_p, C.c_int64, C.c_int64]
         lib.mpasb200_download_field.argtypes = [H, I, C.c_void_p, C.c_int64, C.c_int64]
         lib.mpasb200_zero_field.argtypes = [H, I]
+        lib.mpasb200_upload_field_async.argtypes = [H, I, C.c_void_p]
+        lib.mpasb200_download_field_async.argtypes = [H, I, C.c_void_p]
+        lib.mpasb200_transfer_wait.argtypes = [H]
         lib.mpasb200_sync.argtypes = [H]
         lib.mpasb200_register_list.argtypes = [H, I, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         lib.mpasb200_pack.argtypes = [H, I, C.c_void_p, C.c_int32, C.c_void_p]
@@ -91,6 +94,8 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         lib.mpasb200_reset_kernel_timing.argtypes = [H]
         lib.mpasb200_kernel_time.argtypes = [H, I, C.POINTER(C.c_char_p), C.POINTER(D), C.POINTER(C.c_int64)]
         for n in ("enable_kernel_timing", "reset_kernel_timing", "kernel_time"):
+            getattr(lib, "mpasb200_" + n).restype = I
+        for n in ("upload_field_async", "download_field_async", "transfer_wait"):
             getattr(lib, "mpasb200_" + n).restype = I
         for n in ("upload_field", "download_field", "zero_field", "sync", "register_list", "pack", "unpack", "set_stream",
                   "field_info", "enable_timing", "task_time", "reset_timing"):
@@ -258,6 +263,19 @@ class Dynamics(TaskAPI):
         L1 = self.dims.nVertLevels + 1
         self._check(self._lib.mpasb200_download_field(self._h, FIELD_ID[name], a.ctypes.data, 8 * L1 * s, 8 * s), "download_field")
         return a
+
+    def upload_field_async(self, name: str, a: np.ndarray):
+        """pipelined upload of a page-locked, C-contiguous array (mpas_b200.h); reuse ``a`` only after transfer_wait()."""
+        assert a.shape == self.field_shape(name) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        self._check(self._lib.mpasb200_upload_field_async(self._h, FIELD_ID[name], a.ctypes.data), "upload_field_async")
+
+    def download_field_async(self, name: str, out: np.ndarray):
+        """pipelined download into a page-locked, C-contiguous array; read ``out`` only after transfer_wait()."""
+        assert out.shape == self.field_shape(name) and out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
+        self._check(self._lib.mpasb200_download_field_async(self._h, FIELD_ID[name], out.ctypes.data), "download_field_async")
+
+    def transfer_wait(self):
+        self._check(self._lib.mpasb200_transfer_wait(self._h), "transfer_wait")
 
     def zero_field(self, name: str):
         self._check(self._lib.mpasb200_zero_field(self._h, FIELD_ID[name]), "zero_field")

@@ -371,3 +371,47 @@ def test_corrected_physics_by_tasks_equals_driver_and_graph(grid642):
     for n in outs[0]:
         assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
         assert np.array_equal(outs[0][n], outs[2][n], equal_nan=True), n
+
+
+def test_pipelined_transfers_match_blocking(grid642):
+    """mpasb200_upload_field_async / download_field_async / transfer_wait (copy streams + events) give the same bytes as
+    the blocking transfers, batch after batch, with the host buffers reused between batches."""
+    import torch
+    from mpas_regent_b200 import dynamics, init_jw
+    Lh = 9
+    st = init_jw.make_state(grid642, Lh, _abi.INDEX_CORRECTED)
+    names = ("u", "w", "theta_m", "rho_zz", "zb_cell")           # cell, edge and an array-typed field
+    outs = ("u", "ru_p", "rtheta_pp", "pv_edge", "vorticity", "zb_cell")
+    rng = np.random.default_rng(5)
+    batches = [{n: st.f[n] * (1.0 + 1e-3 * rng.standard_normal(st.f[n].shape)) for n in names} for _ in range(3)]
+    res = {}
+    for mode in ("blocking", "pipelined"):
+        g = dynamics.Dynamics(dynamics.dims_of(grid642, Lh), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX))
+        g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
+        g.atm_compute_solve_diagnostics(False, -1)
+        got = []
+        if mode == "blocking":
+            for b in batches:
+                for n in names:
+                    g.upload_field(n, b[n])
+                g.atm_srk3(500.0)
+                got.append({n: g.download_field(n) for n in outs})
+        else:
+            hin = {n: torch.empty(g.field_shape(n), dtype=torch.float64).pin_memory() for n in names}
+            hout = [{n: torch.empty(g.field_shape(n), dtype=torch.float64).pin_memory() for n in outs} for _ in batches]
+            for i, b in enumerate(batches):
+                g.transfer_wait() if i else None                 # the input buffers are reused: wait for their copies
+                for n in names:
+                    hin[n].numpy()[...] = b[n]
+                    g.upload_field_async(n, hin[n].numpy())
+                g.atm_srk3(500.0)
+                for n in outs:
+                    g.download_field_async(n, hout[i][n].numpy())
+            g.transfer_wait()
+            got = [{n: hout[i][n].numpy().copy() for n in outs} for i in range(len(batches))]
+        res[mode] = got
+        g.close()
+    for a, b in zip(res["blocking"], res["pipelined"]):
+        for n in outs:
+            assert np.array_equal(a[n], b[n], equal_nan=True), n
+    assert not np.array_equal(res["blocking"][0]["u"], res["blocking"][1]["u"])
