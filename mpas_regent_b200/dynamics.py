@@ -180,13 +180,13 @@ class TaskAPI:
 
     def atm_srk3_by_tasks(self, dt: float, hook=None):
         """atm_srk3 replayed task by task from the host, exactly in the reference's order
-        (rk_timestep.rg:378-481).  ``hook(name)`` is called after every task (halo exchange point)."""
+        (rk_timestep.rg:378-481).  ``hook(name, *args)`` is called after every task (halo exchange point)."""
         c = self.cfg
         number_of_sub_steps = c.number_of_sub_steps
         dynamics_split = c.config_dynamics_split_steps
         rk_sub_timestep = [dt / 3, dt / number_of_sub_steps, dt / number_of_sub_steps]
         number_sub_steps = [max(1, number_of_sub_steps // 2), max(1, number_of_sub_steps // 2), number_of_sub_steps]
-        h = hook or (lambda name: None)
+        h = hook or (lambda name, *args: None)
         self.atm_rk_integration_setup(); h("rk_integration_setup")
         self.atm_compute_moist_coefficients(); h("compute_moist_coefficients")
         self.atm_compute_vert_imp_coefs(rk_sub_timestep[0]); h("compute_vert_imp_coefs")
@@ -197,7 +197,7 @@ class TaskAPI:
             self.atm_compute_dyn_tend(rk_arg, dt); h("compute_dyn_tend")
             self.atm_set_smlstep_pert_variables(); h("set_smlstep_pert_variables")
             for small_step in range(number_sub_steps[rk_step] + 1):
-                self.atm_advance_acoustic_step(rk_sub_timestep[rk_step], small_step); h("advance_acoustic_step")
+                self.atm_advance_acoustic_step(rk_sub_timestep[rk_step], small_step); h("advance_acoustic_step", rk_sub_timestep[rk_step], small_step)
                 self.atm_divergence_damping_3d(rk_sub_timestep[rk_step]); h("divergence_damping_3d")
             if c.physics_mode == _abi.PHYSICS_CORRECTED:      # rk_timestep.rg:459-460, commented out in the reference
                 self.atm_recover_large_step_variables(number_sub_steps[rk_step], rk_step, dt); h("recover_large_step_variables")

@@ -7,7 +7,7 @@ on all of them (ghost entities are recomputed redundantly) and repairs the ghost
 stencils invalidate with packed neighbour exchanges.  With 2 rings the literal dataflow needs three
 kinds of exchange per RK stage:
 
-    after atm_compute_dyn_tend            cells    w                       (read at cellsOnEdge by the next stage's tend_u)
+    after the first acoustic step         cells    w                       (atm_compute_dyn_tend's w tendency; read at cellsOnEdge by the next stage's tend_u)
     after every atm_advance_acoustic_step cells    rtheta_pp, rtheta_pp_old (read at cellsOnEdge by divergence damping)
     after atm_compute_solve_diagnostics   cells    ke, divergence ; edges pv_edge, v ; vertices vorticity
 
@@ -32,23 +32,30 @@ from .dynamics import TaskAPI
 
 ENT = {"cell": CELL, "edge": EDGE, "vertex": VERTEX}
 
-#: task name (hook key) -> {entity: [fields]} exchanged right after it
+#: task name (hook key) -> {entity: [fields]} exchanged right after it.  atm_compute_dyn_tend leaves `w` (the w tendency,
+#: Q17) invalid on the outer ghost ring; nothing reads it across cells before the next stage's tend_u, and
+#: atm_set_smlstep_pert_variables rewrites it column by column, so it rides on the exchange after the FIRST acoustic
+#: step of the stage (10 exchanges per step instead of 13).
 EXCHANGES: Dict[str, Dict[str, List[str]]] = {
-    "compute_dyn_tend": {"cell": ["w"]},
+    "advance_acoustic_step:first": {"cell": ["w", "rtheta_pp", "rtheta_pp_old"]},
     "advance_acoustic_step": {"cell": ["rtheta_pp", "rtheta_pp_old"]},
     "compute_solve_diagnostics": {"cell": ["ke", "divergence"], "edge": ["pv_edge", "v"], "vertex": ["vorticity"]},
 }
-
 
 #: MPASB200_PHYSICS_CORRECTED: the acoustic edge update reads rho_pp across cells and atm_recover_large_step_variables runs,
 #: so everything the acoustic step leaves invalid on the outer ghost ring is repaired, and so is what recover derives
 #: from ru_p on the outermost edges (u, ru, ruAvg) and gathers from them (w).
 EXCHANGES_CORRECTED: Dict[str, Dict[str, List[str]]] = {
-    "compute_dyn_tend": {"cell": ["w"]},
+    "advance_acoustic_step:first": {"cell": ["w", "rtheta_pp", "rtheta_pp_old", "rho_pp", "rw_p", "wwAvg"]},
     "advance_acoustic_step": {"cell": ["rtheta_pp", "rtheta_pp_old", "rho_pp", "rw_p", "wwAvg"]},
     "recover_large_step_variables": {"cell": ["w"], "edge": ["u", "ru", "ruAvg"]},
     "compute_solve_diagnostics": {"cell": ["ke", "divergence"], "edge": ["pv_edge", "v"], "vertex": ["vorticity"]},
 }
+
+
+def exchange_key(name: str, args=()) -> str:
+    """hook key of a task call: the first acoustic step of a stage (small_step == 0) has its own."""
+    return "advance_acoustic_step:first" if name == "advance_acoustic_step" and len(args) >= 2 and int(args[1]) == 0 else name
 
 
 def exchanges_for(cfg) -> Dict[str, Dict[str, List[str]]]:
@@ -194,8 +201,8 @@ class DistributedDynamics:
         self.exchanges = exchanges_for(dyn.cfg)
         self.t_init = 0.0
 
-    def _hook(self, name: str):
-        spec = self.exchanges.get(name)
+    def _hook(self, name: str, *args):
+        spec = self.exchanges.get(exchange_key(name, args))
         if spec:
             self.ex.exchange(spec)
 

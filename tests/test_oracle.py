@@ -95,7 +95,7 @@ def test_srk3_call_sequence_counts(pair):
     """2 / 2 / 3 acoustic iterations per stage (rk_timestep.rg:450, output.txt)."""
     st, ora = pair
     calls = []
-    ora.atm_srk3_by_tasks(600.0, hook=calls.append)
+    ora.atm_srk3_by_tasks(600.0, hook=lambda name, *a: calls.append(name))
     assert calls.count("advance_acoustic_step") == 7 and calls.count("divergence_damping_3d") == 7
     assert calls.count("compute_dyn_tend") == 3 and calls.count("compute_vert_imp_coefs") == 2
     assert calls.count("compute_solve_diagnostics") == 3 and calls[-1] == "rk_dynamics_substep_finish"

@@ -139,7 +139,7 @@ def test_n_ranks_equal_single_partition_bitwise(grid642, world, physics):
         for name, args in seq:
             for b in backs:
                 b._call(name, *args)
-            spec = exchanges.get(name)
+            spec = exchanges.get(parallel.exchange_key(name, args))
             if spec:
                 ex.exchange(spec)
     for b, s in zip(backs, shards):

@@ -254,8 +254,8 @@ def test_emulated_ranks_on_one_gpu_equal_single_partition(grid642, physics):
         for name, args in seq:
             for b in backs:
                 b._call(name, *args)
-            if name in exchanges:
-                exchange(exchanges[name])
+            if parallel.exchange_key(name, args) in exchanges:
+                exchange(exchanges[parallel.exchange_key(name, args)])
     for b, sh in zip(backs, shards):
         _assert_owned_equal(single, b, sh["lm"])
         b.close()
