@@ -415,3 +415,16 @@ def test_pipelined_transfers_match_blocking(grid642):
         for n in outs:
             assert np.array_equal(a[n], b[n], equal_nan=True), n
     assert not np.array_equal(res["blocking"][0]["u"], res["blocking"][1]["u"])
+
+
+@pytest.mark.parametrize("levels", [4, 30, 58, 100], ids=lambda v: f"L{v}")
+def test_level_counts_that_change_the_block_shape(grid642, levels):
+    """block = (LP/2, columns per block) is derived from nVertLevels; cover shapes where LP/2 does not divide a warp
+    (L=58: 30 pair-threads per column), a very short column (L=4) and a tall column (L=100)."""
+    for physics in (_abi.PHYSICS_LITERAL, _abi.PHYSICS_CORRECTED):
+        st, ora, g = build_pair(grid642, levels, _abi.INDEX_CORRECTED, m5=True, physics_mode=physics)
+        for b in (ora, g):
+            b.atm_compute_solve_diagnostics(False, -1)
+            b.atm_srk3(300.0)
+        compare(g, ora, what=f"L={levels} physics={physics}")
+        g.close(); ora.close()
