@@ -168,6 +168,11 @@ typedef struct {
   const double  *invAreaTriangle;   /* [nVertices]          never written upstream   */
   /* coordinates used only to build the space-filling-curve order (may be null: no renumbering) */
   const double  *xCell, *yCell, *zCell;
+  /* launch classes 0..3 (may be null: one class).  Inside the library entities are numbered class by class (then
+   * along the curve), so a class is one contiguous range for mpasb200_set_range.  The multi-GPU driver uses
+   * cells: 0 = owned, not sent to any rank; 1 = owned, sent; 2 = ghost.  edges: 0 = both cells owned; 1 = the rest. */
+  const uint8_t *cellClass;         /* [nCells] */
+  const uint8_t *edgeClass;         /* [nEdges] */
 } MpasMeshPtrs;
 
 /* ---- lifecycle ------------------------------------------------------------------ */
@@ -233,8 +238,13 @@ int  mpasb200_timestep(mpasb200_t *h, double dt);
 int  mpasb200_register_list(mpasb200_t *h, int entity, const int32_t *idx, int32_t n, int32_t *list_id);
 int  mpasb200_pack(mpasb200_t *h, int list_id, const int32_t *fields, int32_t nfields, void *d_buf);
 int  mpasb200_unpack(mpasb200_t *h, int list_id, const int32_t *fields, int32_t nfields, const void *d_buf);
-/* Restrict compute to a sub-range of entities (interior / boundary split for overlap):
- * tasks then run on [begin,end) of each entity type in the library's internal order.  */
+/* Restrict compute to a sub-range of entities (interior / boundary split, so a halo exchange can overlap interior
+ * compute): mpasb200_advance_acoustic_step runs on cells [begin,end) and mpasb200_divergence_damping_3d on edges
+ * [begin,end) of the library's internal order (with physics_mode CORRECTED the acoustic edge update follows the edge range);
+ * mpasb200_class_range gives the range of a launch class of MpasMeshPtrs.  begin < 0 restores the whole entity.  All
+ * other tasks always run on everything.                                                                              */
+int  mpasb200_class_range(mpasb200_t *h, int entity, int cls, int32_t *begin, int32_t *end);
+int  mpasb200_set_range(mpasb200_t *h, int entity, int32_t begin, int32_t end);
 int  mpasb200_set_stream(mpasb200_t *h, void *cuda_stream);  /* null = the handle's own stream */
 
 /* ---- introspection --------------------------------------------------------------------- */

@@ -92,6 +92,7 @@ MESH_MEMBERS = (
     ("edgesOnVertex_sign", np.float64, VERTEX, "vertexDegree"), ("kiteAreasOnVertex", np.float64, VERTEX, "vertexDegree"),
     ("fVertex", np.float64, VERTEX, 1), ("invAreaTriangle", np.float64, VERTEX, 1),
     ("xCell", np.float64, CELL, 1), ("yCell", np.float64, CELL, 1), ("zCell", np.float64, CELL, 1),
+    ("cellClass", np.uint8, CELL, 1), ("edgeClass", np.uint8, EDGE, 1),
 )
 
 

@@ -107,6 +107,15 @@ DI void prefetch_edge_rows(const View& V, long xa, int lane, const int* eoe) {
   const size_t ix = (size_t)(inx ? x : 0) * LP + k0;            \
   const bool m0 = inx && k0 < L, m1 = inx && k1 < L;            \
   (void)ix; (void)m1; (void)k1;
+// the same for the kernels that honour mpasb200_set_range: internal indices [V.xoff, V.xend), xend <= n set by the host
+#define PAIR_THREAD_R()                                         \
+  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;             \
+  const int x = V.xoff + blockIdx.x * blockDim.y + threadIdx.y; \
+  const bool inx = x < V.xend;                                  \
+  const int LP = V.LP; const int L = V.L;                       \
+  const size_t ix = (size_t)(inx ? x : 0) * LP + k0;            \
+  const bool m0 = inx && k0 < L, m1 = inx && k1 < L;            \
+  (void)ix; (void)m1; (void)k1;
 #define G2(p, e) ld2((p), (size_t)(e) * LP + k0)                 /* the level pair of neighbour column e */
 #define G1(p, e, k_) ((p)[(size_t)(e) * LP + (k_)])
 // values one level below / above the pair: (f[k0-1], f[k0]) and (f[k1], f[k1+1])
@@ -858,7 +867,7 @@ DI double ac_P(const AcTerms& t, double rp0m, double rt0m) {
 template <bool S0>
 __global__ void __launch_bounds__(256, S0 ? LB_AC + 1 : LB_AC) k_acoustic(const View V, double dts, double epssm, double resm) {
   extern __shared__ double sm[];
-  PAIR_THREAD(V.nCells)
+  PAIR_THREAD_R()
   const int TS = LP + 2;
   double* s_rp0 = sm + (size_t)threadIdx.y * TS;
   double* s_rt0 = sm + (size_t)(blockDim.y + threadIdx.y) * TS;
@@ -959,7 +968,7 @@ __global__ void __launch_bounds__(256, S0 ? LB_AC + 1 : LB_AC) k_acoustic(const 
 // Split form of the acoustic step, phase 1 (lean, register-light): the edgesOnCell gathers only  (:1644-1652).
 // rs_h / ts_h go to library scratch and are streamed by phase 2 as two more strips.
 __global__ void k_acoustic_gather(const View V, double dts) {
-  PAIR_THREAD(V.nCells)
+  PAIR_THREAD_R()
   if (!m0) return;
   if (V.specZoneMaskCell[x] != 0.0) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
@@ -981,7 +990,7 @@ __global__ void k_acoustic_gather(const View V, double dts) {
 // Edge update :1581-1613, exactly the commented lines; every edge (the nCellsSolve test stays out).
 template <bool S0>
 __global__ void k_acoustic_u(const View V, double dts, double c2, double gravity) {
-  PAIR_THREAD(V.nEdges)
+  PAIR_THREAD_R()
   if (!m0) return;
   const D2 tru = ld2(FLD(tend_ru), ix);
   if (S0) {                                                                                           // :1601-1613
@@ -1006,7 +1015,7 @@ __global__ void k_acoustic_u(const View V, double dts, double c2, double gravity
 template <bool S0>
 __global__ void __launch_bounds__(256) k_acoustic_col(const View V, double dts, double epssm, double resm) {
   extern __shared__ double sm[];
-  PAIR_THREAD(V.nCells)
+  PAIR_THREAD_R()
   const int TS = LP + 2, CB = blockDim.y, ty = threadIdx.y;
   double* s_rs = sm + (size_t)(0 * CB + ty) * TS;
   double* s_ts = sm + (size_t)(1 * CB + ty) * TS;
@@ -1139,7 +1148,7 @@ struct AcPtrs { const double* p[AF_COUNT]; };
 template <bool S0, int ABL = 0>     // ABL: ablation switches for profiling only (1 = no gathers, 2 = no sweep, 4 = no stores)
 __global__ void __launch_bounds__(128, 5) k_acoustic_tma(const View V, const AcPtrs F, double dts, double epssm, double resm) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  PAIR_THREAD(V.nCells)
+  PAIR_THREAD_R()
   const int C = blockDim.y, TS = LP + 2, NF = S0 ? (int)AF_rho_pp : (int)AF_COUNT;
   const int CL = C * LP;
   double* in = reinterpret_cast<double*>(smraw);                 // [NF][C*LP]
@@ -1151,7 +1160,7 @@ __global__ void __launch_bounds__(128, 5) k_acoustic_tma(const View V, const AcP
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   if (tid == 0) mbar_init(bar, 1);
   __syncthreads();
-  const size_t tile0 = (size_t)blockIdx.x * C * LP;
+  const size_t tile0 = ((size_t)V.xoff + (size_t)blockIdx.x * C) * LP;
   if (tid == 0) mbar_expect_tx(bar, (uint32_t)(NF * CL * sizeof(double)));
   for (int f = tid; f < NF; f += blockDim.x * blockDim.y)         // one strip per thread (blocks can be smaller than NF)
     bulk_g2s(in + (size_t)f * CL, F.p[f] + tile0, (uint32_t)(CL * sizeof(double)), bar);
@@ -1355,14 +1364,15 @@ __global__ void k_divdamp(const View V, double coef_divdamp) {
   if (k0 >= L) return;
   const bool m1 = k1 < L;
   const int stride = gridDim.x * blockDim.y;
-  int x = blockIdx.x * blockDim.y + threadIdx.y;
-  if (x >= V.nEdges) return;
+  const int nE = V.xend;
+  int x = V.xoff + blockIdx.x * blockDim.y + threadIdx.y;
+  if (x >= nE) return;
   const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
   int4 cv = V.ecv[x]; unsigned char skip = V.divdampSkip[x]; double sz = 1.0 - V.specZoneMaskEdge[x];
   D2 r = ld2(FLD(ru_p), (size_t)x * LP + k0);
   while (true) {
     const int xn = x + stride;
-    const bool more = xn < V.nEdges;
+    const bool more = xn < nE;
     const int xs = more ? xn : x;
     const int4 cvn = V.ecv[xs]; const unsigned char skn = V.divdampSkip[xs]; const double szn = 1.0 - V.specZoneMaskEdge[xs];
     const D2 rn = ld2(FLD(ru_p), (size_t)xs * LP + k0);

@@ -51,6 +51,9 @@ struct mpasb200 {
   bool mesh_ok = false;
   // renumbering: newOf[entity][old] = internal index (size n+1, pad -> pad)
   std::vector<int> newOf[3];
+  // launch classes (MpasMeshPtrs.cellClass / edgeClass): internal numbering is class-major, classBegin[ent][c] .. classBegin[ent][c+1]
+  int classBegin[3][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+  int rangeB[3] = {0, 0, 0}, rangeE[3] = {0, 0, 0}; bool rangeSet[3] = {false, false, false};     // mpasb200_set_range
   int* d_newOf[3] = {nullptr, nullptr, nullptr};
   // staging
   double* d_stage = nullptr; size_t stage_elems = 0;
@@ -296,22 +299,33 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
   }
   return post_launch(h);
 }
+// mpasb200_set_range: the acoustic step and the divergence damping run on [begin, end) of the cells / edges
+struct Range { int b, e, n; bool whole; };
+Range range_of(const mpasb200_t* h, int ent, int n) {
+  if (!h->rangeSet[ent]) return Range{0, n, n, true};
+  const int b = std::min(h->rangeB[ent], n), e = std::min(h->rangeE[ent], n);
+  return Range{b, e, std::max(0, e - b), b == 0 && e == n};
+}
+View ranged(const mpasb200_t* h, const Range& r) { View v = h->V; v.xoff = r.b; v.xend = r.e; return v; }
 int t_smlstep(mpasb200_t* h) { LAUNCH(k_smlstep, h->nCells, 0, h->V, h->c.nRelaxZone); return post_launch(h); }
 int t_acoustic(mpasb200_t* h, double dts, int small_step) {
   const double epssm = h->c.config_epssm;
   const double resm = (1.0 - epssm) / (1.0 + epssm);
+  const Range rc_ = range_of(h, MPASB200_CELL, h->nCells), re_ = range_of(h, MPASB200_EDGE, h->nEdges);
+  const View Vc = ranged(h, rc_), Ve = ranged(h, re_);
   if (h->c.physics_mode == MPASB200_PHYSICS_CORRECTED) {        // edge update, flux gather, column solve with back-substitution
     const double rcv = h->c.rgas / (h->c.cp - h->c.rgas), c2 = h->c.cp * rcv;
-    if (small_step == 0) LAUNCH(k_acoustic_u<true>, h->nEdges, 0, h->V, dts, c2, h->c.gravity);
-    else LAUNCH(k_acoustic_u<false>, h->nEdges, 0, h->V, dts, c2, h->c.gravity);
-    LAUNCH(k_acoustic_gather, h->nCells, 0, h->V, dts);
-    if (small_step == 0) LAUNCH(k_acoustic_col<true>, h->nCells, tile_bytes(h, 6), h->V, dts, epssm, resm);
-    else LAUNCH(k_acoustic_col<false>, h->nCells, tile_bytes(h, 6), h->V, dts, epssm, resm);
+    if (small_step == 0) LAUNCH(k_acoustic_u<true>, re_.n, 0, Ve, dts, c2, h->c.gravity);
+    else LAUNCH(k_acoustic_u<false>, re_.n, 0, Ve, dts, c2, h->c.gravity);
+    LAUNCH(k_acoustic_gather, rc_.n, 0, Vc, dts);
+    if (small_step == 0) LAUNCH(k_acoustic_col<true>, rc_.n, tile_bytes(h, 6), Vc, dts, epssm, resm);
+    else LAUNCH(k_acoustic_col<false>, rc_.n, tile_bytes(h, 6), Vc, dts, epssm, resm);
     return post_launch(h);
   }
   const bool tma_fits = ((size_t)AF_COUNT * h->LP + (size_t)4 * (h->LP + 2)) * sizeof(double) + 16 <= 48 * 1024 && h->LP / 2 <= 128;
   if (!h->c.acoustic_exact && h->c.acoustic_tma && h->nCells > 0 && tma_fits) {
-    const View& V = h->V;
+    if (rc_.n == 0) return 0;
+    const View& V = Vc;
     AcPtrs F;
 #define AF(n) F.p[AF_##n] = V.f[MPASB200_F_##n]
     AF(tend_rho); AF(theta_m); AF(w); AF(coftz); AF(cofwz); AF(cofwr); AF(cofwt); AF(a_tri); AF(alpha_tri); AF(zz); AF(rw_save); AF(rw);
@@ -319,13 +333,13 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
 #undef AF
     F.p[AF_rs] = V.scr_rs; F.p[AF_ts] = V.scr_ts;
     const int split = h->c.acoustic_tma == 2;
-    if (split) LAUNCH(k_acoustic_gather, h->nCells, 0, h->V, dts);
+    if (split) LAUNCH(k_acoustic_gather, rc_.n, 0, Vc, dts);
     const int T = h->LP / 2, NF = small_step == 0 ? (int)AF_rho_pp : (int)AF_COUNT;
     int C = 4;                               // columns per block: as many as fit the default 48 KB of dynamic shared memory
     auto smem_for = [&](int c) { return ((size_t)NF * c * h->LP + (size_t)4 * c * (h->LP + 2)) * sizeof(double) + 16; };
     while (C > 1 && (smem_for(C) > 48 * 1024 || C * T > 128)) C /= 2;
     const size_t smem = smem_for(C);
-    dim3 block(T, C), grid((h->nCells + C - 1) / C);
+    dim3 block(T, C), grid((rc_.n + C - 1) / C);
     {
       KTimer kt_(h, small_step == 0 ? "k_acoustic_tma<true>" : "k_acoustic_tma<false>");
       if (small_step == 0) { if (split) k_acoustic_tma<true, 8><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm);
@@ -337,10 +351,11 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
     return post_launch(h);
   }
   if (!h->c.acoustic_exact) {
-    if (small_step == 0) LAUNCH(k_acoustic<true>, h->nCells, tile_bytes(h, 4), h->V, dts, epssm, resm);
-    else LAUNCH(k_acoustic<false>, h->nCells, tile_bytes(h, 4), h->V, dts, epssm, resm);
+    if (small_step == 0) LAUNCH(k_acoustic<true>, rc_.n, tile_bytes(h, 4), Vc, dts, epssm, resm);
+    else LAUNCH(k_acoustic<false>, rc_.n, tile_bytes(h, 4), Vc, dts, epssm, resm);
     return post_launch(h);
   }
+  if (!rc_.whole) return fail(h, MPASB200_ESTATE, "acoustic_exact does not support mpasb200_set_range");
   if (h->nCells > 0) {
     const int rows = std::max(1, 128 / h->LP);      // two-kernel exact mode: one thread per level
     KTimer kt_(h, "k_acoustic_flux");
@@ -358,10 +373,11 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
 int t_divdamp(mpasb200_t* h, double dts) {
   const double rdts = 1.0 / dts;
   const double coef_divdamp = 2.0 * h->c.config_smdiv * h->c.config_len_disp * rdts;
-  if (h->nEdges > 0) {        // persistent: 9 resident blocks per SM loop over the edge tiles
-    const int tiles = (h->nEdges + h->CPB - 1) / h->CPB;
+  const Range re_ = range_of(h, MPASB200_EDGE, h->nEdges);
+  if (re_.n > 0) {            // persistent: 9 resident blocks per SM loop over the edge tiles
+    const int tiles = (re_.n + h->CPB - 1) / h->CPB;
     KTimer kt_(h, "k_divdamp");
-    k_divdamp<<<std::min(tiles, h->num_sms * 9), dim3(h->LP / 2, h->CPB), 0, h->stream>>>(h->V, coef_divdamp);
+    k_divdamp<<<std::min(tiles, h->num_sms * 9), dim3(h->LP / 2, h->CPB), 0, h->stream>>>(ranged(h, re_), coef_divdamp);
     h->launches++;
   }
   return post_launch(h);
@@ -515,6 +531,7 @@ int mpasb200_create(const MpasDims* dims, const MpasConfig* cfg, mpasb200_t** ou
   View& V = h->V;
   std::memset(&V, 0, sizeof(V));
   V.nCells = h->nCells; V.nEdges = h->nEdges; V.nVertices = h->nVertices; V.L = h->L; V.LP = h->LP;
+  V.xoff = 0; V.xend = 0;      // set per launch by ranged() for the kernels that use PAIR_THREAD_R
   V.maxEdges = dims->maxEdges; V.maxEdges2 = dims->maxEdges2; V.vertexDegree = dims->vertexDegree; V.nAdv = dims->nAdvCells;
   V.cellSlot = (size_t)(h->nCells + 1) * h->LP;
   // one arena for every field (zero-filled: memory-model rule M1)
@@ -584,23 +601,46 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
   std::vector<int>& cNew = h->newOf[MPASB200_CELL]; std::vector<int>& eNew = h->newOf[MPASB200_EDGE]; std::vector<int>& vNew = h->newOf[MPASB200_VERTEX];
   cNew.resize(nC + 1); eNew.resize(nE + 1); vNew.resize(nV + 1);
   std::iota(cNew.begin(), cNew.end(), 0); std::iota(eNew.begin(), eNew.end(), 0); std::iota(vNew.begin(), vNew.end(), 0);
-  if (h->c.sfc_renumber && m->xCell && m->yCell && m->zCell && nC > 0) {
-    std::vector<std::pair<uint64_t, int>> key(nC);
+  const bool sfc = h->c.sfc_renumber && m->xCell && m->yCell && m->zCell && nC > 0;
+  const int nEnt[3] = {nC, nE, nV};
+  for (int ent = 0; ent < 3; ++ent) { for (int c = 0; c < 5; ++c) h->classBegin[ent][c] = c ? nEnt[ent] : 0; h->rangeB[ent] = h->rangeE[ent] = 0; h->rangeSet[ent] = false; }
+  if (sfc || m->cellClass || m->edgeClass) {
+    // cells: class-major (if classes are given), then along the Hilbert curve (or in the caller's order)
+    typedef std::pair<std::pair<int, uint64_t>, int> Key;
+    std::vector<Key> key(nC);
     for (int c = 0; c < nC; ++c) {
-      const double x = m->xCell[c], y = m->yCell[c], z = m->zCell[c];
-      double r = std::sqrt(x * x + y * y + z * z); if (!(r > 0)) r = 1;
-      auto q = [&](double t) { double u = (t / r + 1.0) * 0.5; u = std::min(std::max(u, 0.0), 1.0); return (uint32_t)(u * 2097151.0); };
-      key[c] = {hilbert3(q(x), q(y), q(z)), c};
+      uint64_t hk = (uint64_t)c;
+      if (sfc) {
+        const double x = m->xCell[c], y = m->yCell[c], z = m->zCell[c];
+        double r = std::sqrt(x * x + y * y + z * z); if (!(r > 0)) r = 1;
+        auto q = [&](double t) { double u = (t / r + 1.0) * 0.5; u = std::min(std::max(u, 0.0), 1.0); return (uint32_t)(u * 2097151.0); };
+        hk = hilbert3(q(x), q(y), q(z));
+      }
+      const int cls = m->cellClass ? m->cellClass[c] : 0;
+      if (cls > 3) return fail(h, MPASB200_EINVAL, "cellClass must be 0..3");
+      key[c] = {{cls, hk}, c};
     }
     std::sort(key.begin(), key.end());
     for (int r = 0; r < nC; ++r) cNew[key[r].second] = r;
-    std::vector<std::pair<uint64_t, int>> ek(nE);
+    if (m->cellClass) for (int c = 1; c < 5; ++c) {
+      int cnt = 0; for (int i = 0; i < nC; ++i) cnt += (m->cellClass[i] < c);
+      h->classBegin[MPASB200_CELL][c] = cnt;
+    }
+    std::vector<Key> ek(nE);
     for (int e = 0; e < nE; ++e) {
       const uint64_t a = cNew[resolve(m->cellsOnEdge[e * 2], nC, pol)], b = cNew[resolve(m->cellsOnEdge[e * 2 + 1], nC, pol)];
-      ek[e] = {(std::min(a, b) << 32) | std::max(a, b), e};
+      const int cls = m->edgeClass ? m->edgeClass[e] : 0;
+      if (cls > 3) return fail(h, MPASB200_EINVAL, "edgeClass must be 0..3");
+      ek[e] = {{cls, sfc ? ((std::min(a, b) << 32) | std::max(a, b)) : (uint64_t)e}, e};
     }
     std::sort(ek.begin(), ek.end());
     for (int r = 0; r < nE; ++r) eNew[ek[r].second] = r;
+    if (m->edgeClass) for (int c = 1; c < 5; ++c) {
+      int cnt = 0; for (int i = 0; i < nE; ++i) cnt += (m->edgeClass[i] < c);
+      h->classBegin[MPASB200_EDGE][c] = cnt;
+    }
+  }
+  if (sfc) {
     std::vector<std::pair<uint64_t, int>> vk(nV);
     for (int v = 0; v < nV; ++v) {
       uint64_t best = ~0ULL;
@@ -900,6 +940,21 @@ int mpasb200_sync(mpasb200_t* h) {
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
+int mpasb200_class_range(mpasb200_t* h, int entity, int cls, int32_t* begin, int32_t* end) {
+  if (!h || entity < 0 || entity > 2 || cls < 0 || cls > 3 || !begin || !end) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  if (!h->mesh_ok) return fail(h, MPASB200_ESTATE, "upload_mesh has not been called");
+  *begin = h->classBegin[entity][cls]; *end = h->classBegin[entity][cls + 1];
+  return 0;
+}
+int mpasb200_set_range(mpasb200_t* h, int entity, int32_t begin, int32_t end) {
+  if (!h || entity < 0 || entity > 2) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  if (begin < 0 || end < 0) { h->rangeSet[entity] = false; return 0; }
+  if (end < begin) return fail(h, MPASB200_EINVAL, "set_range: end < begin");
+  h->rangeB[entity] = begin; h->rangeE[entity] = end; h->rangeSet[entity] = true;
+  return 0;
+}
 int mpasb200_set_stream(mpasb200_t* h, void* s) {
   if (!h) return MPASB200_EINVAL;
   std::unique_lock<std::mutex> lk(h->mu);
@@ -1024,7 +1079,7 @@ int mpasb200_debug_divdamp(mpasb200_t* h, int variant, double dts, int arg) {
   const double coef = 2.0 * h->c.config_smdiv * h->c.config_len_disp * (1.0 / dts);
   const int nE = h->nEdges, T = h->LP / 2, C = h->CPB;
   switch (variant) {
-    case 0: { KTimer kt(h, "k_divdamp"); k_divdamp<<<h->num_sms * 9, dim3(T, C), 0, h->stream>>>(h->V, coef); h->launches++; } break;
+    case 0: { KTimer kt(h, "k_divdamp"); k_divdamp<<<h->num_sms * 9, dim3(T, C), 0, h->stream>>>(ranged(h, range_of(h, MPASB200_EDGE, nE)), coef); h->launches++; } break;
     case 1: LAUNCH(k_divdamp_v1, nE, 0, h->V, coef); break;
     case 2: LAUNCH(k_divdamp_v2, nE, 0, h->V, coef, arg); break;
     case 3: { KTimer kt(h, "k_divdamp_v3"); const int half = (nE + 1) / 2;
@@ -1044,7 +1099,7 @@ int mpasb200_debug_divdamp(mpasb200_t* h, int variant, double dts, int arg) {
 int mpasb200_debug_acoustic(mpasb200_t* h, int abl, double dts) {
   REQUIRE_MESH();
   Entry en(h, -1);
-  const View& V = h->V;
+  const View V = ranged(h, range_of(h, MPASB200_CELL, h->nCells));
   AcPtrs F;
 #define AF(n) F.p[AF_##n] = V.f[MPASB200_F_##n]
   AF(tend_rho); AF(theta_m); AF(w); AF(coftz); AF(cofwz); AF(cofwr); AF(cofwt); AF(a_tri); AF(alpha_tri); AF(zz); AF(rw_save); AF(rw);

@@ -19,6 +19,7 @@
 struct View {
   // dimensions
   int nCells, nEdges, nVertices, L, LP;
+  int xoff, xend;    // a launch covers internal indices [xoff, min(n, xend)) of its entity type (mpasb200_set_range)
   int maxEdges, maxEdges2, vertexDegree, nAdv;
   int MEP;           // edgesOnCell row pitch (ints), multiple of 4
   int NAP;           // advection list pitch (entries per (cell, slot)), even

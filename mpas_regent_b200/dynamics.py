@@ -83,6 +83,9 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         lib.mpasb200_pack.argtypes = [H, I, C.c_void_p, C.c_int32, C.c_void_p]
         lib.mpasb200_unpack.argtypes = [H, I, C.c_void_p, C.c_int32, C.c_void_p]
         lib.mpasb200_set_stream.argtypes = [H, C.c_void_p]
+        lib.mpasb200_class_range.argtypes = [H, I, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.mpasb200_set_range.argtypes = [H, I, C.c_int32, C.c_int32]
+        lib.mpasb200_class_range.restype = lib.mpasb200_set_range.restype = I
         lib.mpasb200_launch_count.argtypes, lib.mpasb200_launch_count.restype = [H], C.c_int64
         lib.mpasb200_device_bytes.argtypes, lib.mpasb200_device_bytes.restype = [H], C.c_int64
         lib.mpasb200_field_info.argtypes = [I, C.POINTER(I), C.POINTER(I), C.POINTER(C.c_char_p)]
@@ -178,9 +181,11 @@ class TaskAPI:
     def atm_timestep(self, dt: float):
         self._call("timestep", float(dt))
 
-    def atm_srk3_by_tasks(self, dt: float, hook=None):
+    def atm_srk3_by_tasks(self, dt: float, hook=None, acoustic_pair=None):
         """atm_srk3 replayed task by task from the host, exactly in the reference's order
-        (rk_timestep.rg:378-481).  ``hook(name, *args)`` is called after every task (halo exchange point)."""
+        (rk_timestep.rg:378-481).  ``hook(name, *args)`` is called after every task (halo exchange point).
+        ``acoustic_pair(dts, small_step)``, if given, runs one iteration of the acoustic loop (:450-457) in place of
+        the two task calls and their hooks (the multi-GPU driver splits them to overlap the halo exchange)."""
         c = self.cfg
         number_of_sub_steps = c.number_of_sub_steps
         dynamics_split = c.config_dynamics_split_steps
@@ -197,6 +202,9 @@ class TaskAPI:
             self.atm_compute_dyn_tend(rk_arg, dt); h("compute_dyn_tend")
             self.atm_set_smlstep_pert_variables(); h("set_smlstep_pert_variables")
             for small_step in range(number_sub_steps[rk_step] + 1):
+                if acoustic_pair is not None:
+                    acoustic_pair(rk_sub_timestep[rk_step], small_step)
+                    continue
                 self.atm_advance_acoustic_step(rk_sub_timestep[rk_step], small_step); h("advance_acoustic_step", rk_sub_timestep[rk_step], small_step)
                 self.atm_divergence_damping_3d(rk_sub_timestep[rk_step]); h("divergence_damping_3d")
             if c.physics_mode == _abi.PHYSICS_CORRECTED:      # rk_timestep.rg:459-460, commented out in the reference
@@ -285,6 +293,16 @@ class Dynamics(TaskAPI):
 
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.mpasb200_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")
+
+    def class_range(self, entity: int, cls: int):
+        """[begin, end) of a launch class (MpasMeshPtrs.cellClass / edgeClass) in the library's internal order."""
+        b, e = C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.mpasb200_class_range(self._h, entity, cls, C.byref(b), C.byref(e)), "class_range")
+        return int(b.value), int(e.value)
+
+    def set_range(self, entity: int, begin: int = -1, end: int = -1):
+        """restrict atm_advance_acoustic_step (cells) / atm_divergence_damping_3d (edges) to [begin, end); no arguments = everything."""
+        self._check(self._lib.mpasb200_set_range(self._h, entity, begin, end), "set_range")
 
     # ---- halo building blocks ------------------------------------------------------------------------
     def register_list(self, entity: int, idx: np.ndarray) -> int:

@@ -62,6 +62,21 @@ def exchanges_for(cfg) -> Dict[str, Dict[str, List[str]]]:
     return EXCHANGES_CORRECTED if cfg.physics_mode == _abi.PHYSICS_CORRECTED else EXCHANGES
 
 
+def launch_classes(lm: partition.LocalMesh, static: Dict[str, np.ndarray]):
+    """(cellClass, edgeClass) of a local mesh for MpasMeshPtrs: cells 0 = owned and not sent, 1 = owned and sent to some
+    rank, 2 = ghost; edges 0 = both cells owned, 1 = the rest.  The acoustic step of class-1 cells can run first, its
+    results travel while class 0 is computed; class-0 edges can be damped before the ghosts arrive."""
+    n_own = lm.n_owned[0]
+    cc = np.zeros(len(lm.cells), np.uint8)
+    cc[n_own:] = 2
+    for idx in lm.send["cell"].values():
+        cc[idx] = 1
+    coe = np.asarray(static["cellsOnEdge"]).reshape(-1, 2).astype(np.int64) - 1          # local ids are 1-based, 0 = absent
+    owned = (coe >= 0) & (coe < n_own)
+    ec = np.where(owned.all(axis=1), 0, 1).astype(np.uint8)
+    return cc, ec
+
+
 def split_state(fields: Dict[str, np.ndarray], lm: partition.LocalMesh) -> Dict[str, np.ndarray]:
     """restrict global 3-D fields to a rank's local entities (rows in local order)."""
     rows = {CELL: lm.cells, EDGE: lm.edges, VERTEX: lm.vertices}
@@ -177,6 +192,36 @@ class NcclExchanger(Exchanger):
         self.plans[key] = (items, ops)
         return self.plans[key]
 
+    # ---- the same exchange on a communication stream, so that compute enqueued after start() overlaps it ----------
+    def start(self, spec: Dict[str, List[str]]):
+        """everything enqueued on the compute stream so far is visible to the pack; returns at once."""
+        torch, dist = self.torch, self.dist
+        if not hasattr(self, "comm"):
+            self.comm = torch.cuda.Stream()
+            self.ev_ready, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
+        items, ops = self._plan(spec)
+        self.ev_ready.record(self.stream)
+        self.comm.wait_event(self.ev_ready)
+        self.dyn.set_stream(self.comm.cuda_stream)
+        try:
+            with torch.cuda.stream(self.comm):
+                for E, names, sbuf, _ in items:
+                    if E["ls"] >= 0:
+                        self.dyn.pack(E["ls"], names, sbuf.data_ptr())
+                if ops:
+                    for r in dist.batch_isend_irecv(ops):
+                        r.wait()
+                for E, names, _, rbuf in items:
+                    if E["lr"] >= 0:
+                        self.dyn.unpack(E["lr"], names, rbuf.data_ptr())
+                self.ev_done.record(self.comm)
+        finally:
+            self.dyn.set_stream(self.stream.cuda_stream)
+
+    def finish(self):
+        """compute enqueued after this sees the unpacked ghosts."""
+        self.stream.wait_event(self.ev_done)
+
     def exchange(self, spec: Dict[str, List[str]]):
         torch, dist = self.torch, self.dist
         items, ops = self._plan(spec)
@@ -211,8 +256,31 @@ class DistributedDynamics:
         self.dyn.atm_compute_solve_diagnostics(False, -1)
         self._hook("compute_solve_diagnostics")
 
+    def enable_overlap(self):
+        """Overlap the acoustic-loop exchanges with interior compute (needs launch classes in the uploaded mesh and an
+        exchanger with start()/finish()): boundary-owned cells first, their columns travel while the interior is advanced
+        and the interior edges are damped; the edges next to ghosts follow after the unpack.  Ghost cells are never
+        advanced: everything the owned entities read from them arrives by exchange."""
+        d = self.dyn
+        self._cells = [d.class_range(CELL, c) for c in (0, 1)]
+        self._edges = [d.class_range(EDGE, c) for c in (0, 1)]
+        self.overlap = hasattr(self.ex, "start")
+        return self.overlap
+
+    def _acoustic_pair(self, dts: float, small_step: int):
+        d = self.dyn
+        spec = self.exchanges[exchange_key("advance_acoustic_step", (dts, small_step))]
+        d.set_range(CELL, *self._cells[1]); d.atm_advance_acoustic_step(dts, small_step)      # sent cells first
+        self.ex.start(spec)
+        d.set_range(CELL, *self._cells[0]); d.atm_advance_acoustic_step(dts, small_step)      # interior, overlaps the exchange
+        d.set_range(EDGE, *self._edges[0]); d.atm_divergence_damping_3d(dts)
+        self.ex.finish()
+        d.set_range(EDGE, *self._edges[1]); d.atm_divergence_damping_3d(dts)
+        d.set_range(CELL); d.set_range(EDGE)
+
     def step(self, dt: float):
-        self.dyn.atm_srk3_by_tasks(dt, hook=self._hook)
+        pair = self._acoustic_pair if getattr(self, "overlap", False) else None
+        self.dyn.atm_srk3_by_tasks(dt, hook=self._hook, acoustic_pair=pair)
 
     # ---- bench helper: rank 0 builds + partitions the global problem, every rank loads its shard -------------
     @classmethod
@@ -241,6 +309,8 @@ class DistributedDynamics:
         del fields
         run = cls(dyn, NcclExchanger(dyn, lm, stream))
         run.lm = lm
+        if cfg.physics_mode == _abi.PHYSICS_LITERAL and os.environ.get("MPAS_B200_OVERLAP", "1") != "0":
+            run.enable_overlap()
         run.init_diagnostics()
         run.t_init = time.time() - t0
         return run
@@ -259,6 +329,8 @@ def make_shards(st, world: int, colours: Optional[np.ndarray] = None):
         lm, loc = partition.build_local(st.static, n_global, col, part, r, mesh.v["cellsOnVertex"])
         locs.append(lm); statics.append(loc)
     partition.build_halo_lists(locs)
+    for lm, loc in zip(locs, statics):
+        loc["cellClass"], loc["edgeClass"] = launch_classes(lm, loc)
     return [dict(lm=lm, static=loc, f=split_state(st.f, lm), vert=dict(st.vert)) for lm, loc in zip(locs, statics)]
 
 

@@ -188,3 +188,25 @@ def test_shard_roundtrip(grid642, tmp_path):
             assert np.array_equal(lm0.recv[ent][p], lm1.recv[ent][p])
     for k in shards[0]["f"]:
         assert np.array_equal(shards[0]["f"][k], sh["f"][k])
+
+
+def test_launch_classes_for_overlap(grid642):
+    """cells: 0 = owned & never sent, 1 = owned & sent, 2 = ghost; edges: 0 = both cells owned.  A class-0 cell has only
+    owned neighbours, so advancing it needs nothing that an exchange in flight delivers."""
+    st, shards = _shards(grid642, 4)
+    for sh in shards:
+        lm, loc = sh["lm"], sh["static"]
+        cc, ec = loc["cellClass"], loc["edgeClass"]
+        n_own = lm.n_owned[0]
+        assert cc.dtype == np.uint8 and np.all(cc[n_own:] == 2) and np.all(cc[:n_own] < 2)
+        sent = np.unique(np.concatenate(list(lm.send["cell"].values())))
+        assert np.array_equal(np.nonzero(cc == 1)[0], sent)
+        coe = loc["cellsOnEdge"].reshape(-1, 2).astype(np.int64) - 1
+        both_owned = ((coe >= 0) & (coe < n_own)).all(axis=1)
+        assert np.array_equal(ec == 0, both_owned)
+        # every edge of a class-0 cell is a class-0 edge (its other cell is owned too)
+        eoc = loc["edgesOnCell"].astype(np.int64) - 1
+        for c in np.nonzero(cc == 0)[0][:200]:
+            es = eoc[c, :loc["nEdgesOnCell"][c]]
+            assert np.all(ec[es] == 0)
+        assert (cc == 0).sum() > 0 and (cc == 1).sum() > 0

@@ -205,8 +205,9 @@ def test_acoustic_modes(grid2562, exact):
     g.close(); ora.close()
 
 
-@pytest.mark.parametrize("physics", [_abi.PHYSICS_LITERAL, _abi.PHYSICS_CORRECTED], ids=["literal", "corrected_physics"])
-def test_emulated_ranks_on_one_gpu_equal_single_partition(grid642, physics):
+@pytest.mark.parametrize("physics,split", [(_abi.PHYSICS_LITERAL, False), (_abi.PHYSICS_CORRECTED, False), (_abi.PHYSICS_LITERAL, True)],
+                         ids=["literal", "corrected_physics", "literal_interior_boundary_split"])
+def test_emulated_ranks_on_one_gpu_equal_single_partition(grid642, physics, split):
     """4 ranks emulated as 4 handles on one GPU (pack/unpack + the exchange schedule of parallel.exchanges_for):
     owned entities are bit-identical to the single-partition GPU run."""
     import torch
@@ -249,13 +250,38 @@ def test_emulated_ranks_on_one_gpu_equal_single_partition(grid642, physics):
         b.atm_compute_solve_diagnostics(False, -1)
     exchange(exchanges["compute_solve_diagnostics"])
     seq = _task_schedule(cfg)
+    CELL, EDGE = parallel.CELL, parallel.EDGE
+    if split:      # the schedule of DistributedDynamics._acoustic_pair, with the blocking exchange in place of start()/finish()
+        for b, sh in zip(backs, shards):
+            lm = sh["lm"]
+            c0, c1, c2 = (b.class_range(CELL, c) for c in (0, 1, 2))
+            assert c0[0] == 0 and c0[1] == c1[0] and c1[1] == c2[0] == lm.n_owned[0] and c2[1] == len(lm.cells)
+            assert c1[1] - c1[0] == len(np.unique(np.concatenate(list(lm.send["cell"].values()))))
+            e0, e1 = b.class_range(EDGE, 0), b.class_range(EDGE, 1)
+            assert e0[0] == 0 and e0[1] == e1[0] and e1[1] == len(lm.edges)
     for _ in range(2):
         single.atm_srk3(600.0)
-        for name, args in seq:
+        i = 0
+        while i < len(seq):
+            name, args = seq[i]
+            if split and name == "advance_acoustic_step":
+                dts = args[0]
+                for b in backs:
+                    b.set_range(CELL, *b.class_range(CELL, 1)); b._call(name, *args)
+                exchange(exchanges[parallel.exchange_key(name, args)])
+                for b in backs:
+                    b.set_range(CELL, *b.class_range(CELL, 0)); b._call(name, *args)
+                    b.set_range(EDGE, *b.class_range(EDGE, 0)); b.atm_divergence_damping_3d(dts)
+                    b.set_range(EDGE, *b.class_range(EDGE, 1)); b.atm_divergence_damping_3d(dts)
+                    b.set_range(CELL); b.set_range(EDGE)
+                assert seq[i + 1][0] == "divergence_damping_3d"
+                i += 2
+                continue
             for b in backs:
                 b._call(name, *args)
             if parallel.exchange_key(name, args) in exchanges:
                 exchange(exchanges[parallel.exchange_key(name, args)])
+            i += 1
     for b, sh in zip(backs, shards):
         _assert_owned_equal(single, b, sh["lm"])
         b.close()
@@ -428,3 +454,54 @@ def test_level_counts_that_change_the_block_shape(grid642, levels):
             b.atm_srk3(300.0)
         compare(g, ora, what=f"L={levels} physics={physics}")
         g.close(); ora.close()
+
+
+@pytest.mark.parametrize("physics", [_abi.PHYSICS_LITERAL, _abi.PHYSICS_CORRECTED], ids=["literal", "corrected_physics"])
+def test_range_restricted_launches_equal_whole(grid642, physics):
+    """mpasb200_set_range: the acoustic step on cell ranges and the divergence damping on edge ranges, in any order of
+    disjoint ranges that covers everything, give the bytes of the unrestricted launches; launch classes only permute the
+    library's internal numbering."""
+    from mpas_regent_b200 import dynamics, init_jw
+    Lh = 9
+    st = init_jw.make_state(grid642, Lh, _abi.INDEX_CORRECTED)
+    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, physics_mode=physics)
+    nC, nE = grid642.nCells, grid642.nEdges
+    rng = np.random.default_rng(11)
+    outs = []
+    for mode in ("whole", "ranges", "classes"):
+        static = dict(st.static)
+        if mode == "classes":
+            static["cellClass"] = rng.integers(0, 3, nC).astype(np.uint8)
+            static["edgeClass"] = rng.integers(0, 2, nE).astype(np.uint8)
+        g = dynamics.Dynamics(dynamics.dims_of(grid642, Lh), cfg)
+        g.upload_mesh(static); g.upload_state(st.f, st.vert)
+        g.atm_compute_solve_diagnostics(False, -1)
+        g.atm_srk3(500.0)                               # populate everything
+        if mode == "whole":
+            cuts_c, cuts_e = [(0, nC)], [(0, nE)]
+        elif mode == "ranges":
+            cuts_c, cuts_e = [(nC // 3, nC), (0, 5), (5, nC // 3), (7, 7)], [(100, nE), (0, 100)]
+        else:
+            cuts_c = [g.class_range(parallel_CELL, c) for c in (2, 0, 1)]
+            cuts_e = [g.class_range(parallel_EDGE, c) for c in (1, 0)]
+            assert sum(e - b for b, e in cuts_c) == nC and sum(e - b for b, e in cuts_e) == nE
+            assert g.class_range(parallel_CELL, 1)[1] - g.class_range(parallel_CELL, 1)[0] == int((static["cellClass"] == 1).sum())
+        for ss in range(3):
+            if physics == _abi.PHYSICS_CORRECTED:      # the edge update precedes the cell part: edges first, one range at a time
+                for be in cuts_e:
+                    g.set_range(parallel_EDGE, *be); g.set_range(parallel_CELL, 0, 0); g.atm_advance_acoustic_step(360.0, ss)
+                g.set_range(parallel_EDGE, 0, 0)
+            for bc in cuts_c:
+                g.set_range(parallel_CELL, *bc); g.atm_advance_acoustic_step(360.0, ss)
+            g.set_range(parallel_CELL); g.set_range(parallel_EDGE)
+            for be in cuts_e:
+                g.set_range(parallel_EDGE, *be); g.atm_divergence_damping_3d(360.0)
+            g.set_range(parallel_EDGE)
+        outs.append(g.download_all())
+        g.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), ("ranges", n)
+        assert np.array_equal(outs[0][n], outs[2][n], equal_nan=True), ("classes", n)
+
+
+from mpas_regent_b200._abi import CELL as parallel_CELL, EDGE as parallel_EDGE  # noqa: E402
