@@ -209,7 +209,7 @@ class TaskAPI:
                 self.atm_divergence_damping_3d(rk_sub_timestep[rk_step]); h("divergence_damping_3d")
             if c.physics_mode == _abi.PHYSICS_CORRECTED:      # rk_timestep.rg:459-460, commented out in the reference
                 self.atm_recover_large_step_variables(number_sub_steps[rk_step], rk_step, dt); h("recover_large_step_variables")
-            self.atm_compute_solve_diagnostics(False, rk_step); h("compute_solve_diagnostics")
+            self.atm_compute_solve_diagnostics(False, rk_step); h("compute_solve_diagnostics", False, rk_step)
         self.atm_rk_dynamics_substep_finish(1, dynamics_split); h("rk_dynamics_substep_finish")
 
 

@@ -247,9 +247,25 @@ class DistributedDynamics:
         self.t_init = 0.0
 
     def _hook(self, name: str, *args):
+        if getattr(self, "overlap", False):
+            # the exchange after atm_compute_solve_diagnostics of stages 0 and 2 is needed by the next atm_compute_dyn_tend
+            # only: it travels under atm_compute_vert_imp_coefs (stage 1) or under substep_finish + the next step's
+            # setup / moist / vert_imp coefficients, none of which touches the exchanged fields
+            if name == "compute_vert_imp_coefs":
+                self.flush()
+            elif name == "compute_solve_diagnostics" and len(args) >= 2 and int(args[1]) in (0, 2):
+                self.ex.start(self.exchanges[name])
+                self._pending = True
+                return
         spec = self.exchanges.get(exchange_key(name, args))
         if spec:
             self.ex.exchange(spec)
+
+    def flush(self):
+        """complete an exchange that is still travelling (call before reading ghosts from outside a step)."""
+        if getattr(self, "_pending", False):
+            self.ex.finish()
+            self._pending = False
 
     def init_diagnostics(self):
         """atm_core_init's atm_compute_solve_diagnostics(..., -1) (atm_core.rg:31)."""

@@ -299,7 +299,7 @@ def test_nccl_ranks_equal_single_gpu():
         pytest.skip("needs >= 2 GPUs")
     n = 2 if n < 4 else 4
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for physics, port in (("literal", "29533"), ("corrected", "29535")):
+    for physics, port in (("literal", "29533"), ("overlap", "29537"), ("corrected", "29535")):
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                               "--master-port", port, os.path.join(root, "tests", "run_multigpu_check.py"), physics],
                              capture_output=True, text=True, timeout=600, cwd=root)
