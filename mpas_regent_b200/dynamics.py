@@ -227,6 +227,7 @@ class Dynamics(TaskAPI):
             raise MpasB200Error(f"mpasb200_create failed ({rc}): {msg.decode() if msg else ''}")
         self._keep = []
         self._ids_cache = {}
+        self._class_cache = {}
 
     # ---- plumbing ------------------------------------------------------------------------------
     def _check(self, rc: int, what: str):
@@ -252,6 +253,7 @@ class Dynamics(TaskAPI):
     def upload_mesh(self, static: Dict[str, np.ndarray]):
         m, keep = _abi.mesh_ptrs(static, self.dims)
         self._check(self._lib.mpasb200_upload_mesh(self._h, C.byref(m)), "upload_mesh")
+        self._class_cache = {}
         del keep
 
     def upload_field(self, name: str, a: np.ndarray):
@@ -299,6 +301,17 @@ class Dynamics(TaskAPI):
         b, e = C.c_int32(0), C.c_int32(0)
         self._check(self._lib.mpasb200_class_range(self._h, entity, cls, C.byref(b), C.byref(e)), "class_range")
         return int(b.value), int(e.value)
+
+    def restrict(self, entity: int, cls=None):
+        """run atm_advance_acoustic_step (cells) / atm_divergence_damping_3d (edges) on one launch class of
+        MpasMeshPtrs.cellClass / edgeClass only; None = everything."""
+        if cls is None:
+            self.set_range(entity)
+            return
+        r = self._class_cache.get((entity, cls))
+        if r is None:
+            r = self._class_cache[(entity, cls)] = self.class_range(entity, cls)
+        self.set_range(entity, r[0], r[1])
 
     def set_range(self, entity: int, begin: int = -1, end: int = -1):
         """restrict atm_advance_acoustic_step (cells) / atm_divergence_damping_3d (edges) to [begin, end); no arguments = everything."""

@@ -148,6 +148,14 @@ class HostDistExchanger(Exchanger):
                 self.b.upload_field(n, arrs[n])
 
 
+    # the overlapped schedule of DistributedDynamics on the CPU: same call sequence, the exchange simply blocks in start()
+    def start(self, spec: Dict[str, List[str]]):
+        self.exchange(spec)
+
+    def finish(self):
+        pass
+
+
 class NcclExchanger(Exchanger):
     """GPU path: k_pack -> NCCL send/recv (NVLink) -> k_unpack, all ordered on the step's stream.
 
@@ -277,22 +285,19 @@ class DistributedDynamics:
         exchanger with start()/finish()): boundary-owned cells first, their columns travel while the interior is advanced
         and the interior edges are damped; the edges next to ghosts follow after the unpack.  Ghost cells are never
         advanced: everything the owned entities read from them arrives by exchange."""
-        d = self.dyn
-        self._cells = [d.class_range(CELL, c) for c in (0, 1)]
-        self._edges = [d.class_range(EDGE, c) for c in (0, 1)]
-        self.overlap = hasattr(self.ex, "start")
+        self.overlap = hasattr(self.ex, "start") and hasattr(self.dyn, "restrict")
         return self.overlap
 
     def _acoustic_pair(self, dts: float, small_step: int):
         d = self.dyn
         spec = self.exchanges[exchange_key("advance_acoustic_step", (dts, small_step))]
-        d.set_range(CELL, *self._cells[1]); d.atm_advance_acoustic_step(dts, small_step)      # sent cells first
+        d.restrict(CELL, 1); d.atm_advance_acoustic_step(dts, small_step)      # sent cells first
         self.ex.start(spec)
-        d.set_range(CELL, *self._cells[0]); d.atm_advance_acoustic_step(dts, small_step)      # interior, overlaps the exchange
-        d.set_range(EDGE, *self._edges[0]); d.atm_divergence_damping_3d(dts)
+        d.restrict(CELL, 0); d.atm_advance_acoustic_step(dts, small_step)      # interior, overlaps the exchange
+        d.restrict(EDGE, 0); d.atm_divergence_damping_3d(dts)
         self.ex.finish()
-        d.set_range(EDGE, *self._edges[1]); d.atm_divergence_damping_3d(dts)
-        d.set_range(CELL); d.set_range(EDGE)
+        d.restrict(EDGE, 1); d.atm_divergence_damping_3d(dts)
+        d.restrict(CELL); d.restrict(EDGE)
 
     def step(self, dt: float):
         pair = self._acoustic_pair if getattr(self, "overlap", False) else None

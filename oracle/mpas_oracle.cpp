@@ -72,6 +72,10 @@ struct Oracle {
   std::vector<int> nEdgesOnCell, edgesOnCell, verticesOnCell, kiteForCell, bdyMaskCell;
   std::vector<double> edgesOnCellSign, edgesOnCell_sign, invAreaCell, latCell, defc_a, defc_b, specZoneMaskCell;
   std::vector<uint8_t> isShared, inCpr;
+  std::vector<uint8_t> cellClass, edgeClass;      // launch classes of MpasMeshPtrs (all 0 when absent)
+  int onlyClass[2] = {-1, -1};                   // oracle_set_class: restrict the acoustic step (cells) / divergence damping (edges)
+  bool cell_on(int c) const { return onlyClass[0] < 0 || cellClass[c] == onlyClass[0]; }
+  bool edge_on(int e) const { return onlyClass[1] < 0 || edgeClass[e] == onlyClass[1]; }
   std::vector<int> cellsOnEdge, verticesOnEdge, nEdgesOnEdge, edgesOnEdge_ECP, edgesOnEdge, nAdvCellsForEdge, advCellsForEdge;
   std::vector<double> weightsOnEdge, dcEdge, dvEdge, invDcEdge, invDvEdge, angleEdge, latEdge, adv_coefs, adv_coefs_3rd,
       meshScalingDel2, meshScalingDel4, specZoneMaskEdge;
@@ -137,6 +141,9 @@ int oracle_create(const MpasDims* dims, const MpasConfig* cfg, oracle_t** out) {
   return 0;
 }
 int oracle_destroy(oracle_t* o) { delete o; return 0; }
+// the counterpart of mpasb200_set_range(class_range(cls)): restrict the acoustic step to the cells, the divergence damping
+// (and the CORRECTED acoustic edge update) to the edges of one launch class; cls < 0 = everything
+int oracle_set_class(oracle_t* o, int entity, int cls) { if (entity < 0 || entity > 1) return -1; o->onlyClass[entity] = cls; return 0; }
 int oracle_set_threads(oracle_t* o, int n) { o->threads = n < 1 ? 1 : n; return 0; }
 int oracle_max_threads() {
 #ifdef _OPENMP
@@ -163,6 +170,8 @@ int oracle_upload_mesh(oracle_t* o, const MpasMeshPtrs* m) {
   fill_rows(o->bdyMaskCell, m->bdyMaskCell, nC, 1);
   fill_rows(o->specZoneMaskCell, m->specZoneMaskCell, nC, 1);
   fill_rows(o->isShared, m->isShared, nC, 1);
+  fill_rows(o->cellClass, m->cellClass, nC, 1);
+  fill_rows(o->edgeClass, m->edgeClass, nE, 1);
   o->inCpr.assign(nC + 1, 1); o->inCpr[nC] = 0;
   if (m->inCpr) std::memcpy(o->inCpr.data(), m->inCpr, nC);
   fill_ids(o->cellsOnEdge, m->cellsOnEdge, nE, 2, nC, pol);
@@ -780,6 +789,7 @@ static int acoustic_step_corrected(oracle_t* o, double dts, int small_step) {
   if (small_step != 0) {                                                    // :1581-1599
     OMP_FOR
     for (int e = 0; e < nE; ++e) {
+      if (!o->edge_on(e)) continue;
       int cell1 = o->cellsOnEdge[e * 2 + 0], cell2 = o->cellsOnEdge[e * 2 + 1];
       for (int k = 0; k < L; ++k) {
         double pgrad = ((rtheta_pp(cell2, k) - rtheta_pp(cell1, k)) * o->invDcEdge[e]) / (0.5 * (zz(cell2, k) + zz(cell1, k)));   // :1591
@@ -791,10 +801,11 @@ static int acoustic_step_corrected(oracle_t* o, double dts, int small_step) {
     }
   } else {                                                                  // :1601-1613
     OMP_FOR
-    for (int e = 0; e < nE; ++e) for (int k = 0; k < L; ++k) { ru_p(e, k) = dts * tend_ru(e, k); ruAvg(e, k) = ru_p(e, k); }
+    for (int e = 0; e < nE; ++e) if (o->edge_on(e)) for (int k = 0; k < L; ++k) { ru_p(e, k) = dts * tend_ru(e, k); ruAvg(e, k) = ru_p(e, k); }
   }
   OMP_FOR
   for (int c = 0; c < nC; ++c) {
+    if (!o->cell_on(c)) continue;
     std::vector<double> rs(L), ts(L);
     for (int k = 0; k < L; ++k) rtheta_pp_old(c, k) = (small_step == 0) ? 0.0 : rtheta_pp(c, k);       // :1615-1623
     if (small_step == 0) {                                                  // :1625-1636
@@ -865,15 +876,16 @@ int oracle_advance_acoustic_step(oracle_t* o, double dts, int small_step) {
   // the u / ru_p update is commented out in the reference (:1585-1613, Q24): both edge loops are empty.
   if (small_step == 0) {                                                    // :1615-1623
     OMP_FOR
-    for (int c = 0; c < nC; ++c) for (int k = 0; k < L; ++k) rtheta_pp_old(c, k) = 0;
+    for (int c = 0; c < nC; ++c) if (o->cell_on(c)) for (int k = 0; k < L; ++k) rtheta_pp_old(c, k) = 0;
   } else {
     OMP_FOR
-    for (int c = 0; c < nC; ++c) for (int k = 0; k < L; ++k) rtheta_pp_old(c, k) = rtheta_pp(c, k);
+    for (int c = 0; c < nC; ++c) if (o->cell_on(c)) for (int k = 0; k < L; ++k) rtheta_pp_old(c, k) = rtheta_pp(c, k);
   }
   OMP_FOR
-  for (int c = 0; c < nC; ++c) for (int k = 0; k <= L; ++k) if (small_step == 0) { wwAvg(c, k) = 0; rw_p(c, k) = 0; }   // :1625-1630
+  for (int c = 0; c < nC; ++c) if (o->cell_on(c)) for (int k = 0; k <= L; ++k) if (small_step == 0) { wwAvg(c, k) = 0; rw_p(c, k) = 0; }   // :1625-1630
   OMP_FOR
   for (int c = 0; c < nC; ++c) {
+    if (!o->cell_on(c)) continue;
     std::vector<double> rs(L), ts(L);                                       // task-level scratch, re-zeroed at every point (Q25)
     for (int k = 0; k < L; ++k) {                                           // :1632-1704, levels ascending (M4)
       if (small_step == 0) { rho_pp(c, k) = 0; rtheta_pp(c, k) = 0; }
@@ -928,6 +940,7 @@ int oracle_divergence_damping_3d(oracle_t* o, double dts) {
   double coef_divdamp = 2.0 * smdiv * o->c.config_len_disp * rdts;
   OMP_FOR
   for (int e = 0; e < nE; ++e) {
+    if (!o->edge_on(e)) continue;
     int cell1 = o->cellsOnEdge[e * 2 + 0], cell2 = o->cellsOnEdge[e * 2 + 1];
     if (!(o->isShared[cell1] && o->isShared[cell2])) {
       for (int k = 0; k < L; ++k) {

@@ -40,6 +40,7 @@ def load():
         lib.oracle_download_field.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.oracle_download_pad.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.oracle_set_threads.argtypes = [C.c_void_p, C.c_int]
+        lib.oracle_set_class.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.oracle_max_threads.restype = C.c_int
         _lib = lib
     return _lib
@@ -71,6 +72,10 @@ class Oracle(TaskAPI):
             self.close()
         except Exception:
             pass
+
+    def restrict(self, entity: int, cls=None):
+        """TaskAPI.restrict: the acoustic step / divergence damping run on one launch class only (None = everything)."""
+        self._lib.oracle_set_class(self._h, int(entity), -1 if cls is None else int(cls))
 
     def set_threads(self, n: int):
         self._lib.oracle_set_threads(self._h, n)

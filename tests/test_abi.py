@@ -72,3 +72,16 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "libmpas_oracle" not in txt, f
+
+
+def test_dynamics_restrict_maps_a_launch_class_to_its_range():
+    """Dynamics.restrict (what the overlapped multi-GPU schedule calls) = set_range(class_range(cls)), cached; None = everything."""
+    from mpas_regent_b200 import dynamics
+    d = object.__new__(dynamics.Dynamics)
+    d._class_cache = {}
+    calls, lookups = [], []
+    d.class_range = lambda ent, cls: (lookups.append((ent, cls)), (10 * cls, 10 * cls + 5))[1]
+    d.set_range = lambda ent, begin=-1, end=-1: calls.append((ent, begin, end))
+    d.restrict(_abi.CELL, 1); d.restrict(_abi.CELL, 1); d.restrict(_abi.EDGE, 0); d.restrict(_abi.CELL); d.restrict(_abi.EDGE, None)
+    assert calls == [(_abi.CELL, 10, 15), (_abi.CELL, 10, 15), (_abi.EDGE, 0, 5), (_abi.CELL, -1, -1), (_abi.EDGE, -1, -1)]
+    assert lookups == [(_abi.CELL, 1), (_abi.EDGE, 0)]

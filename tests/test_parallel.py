@@ -146,7 +146,50 @@ def test_n_ranks_equal_single_partition_bitwise(grid642, world, physics):
         _assert_owned_equal(single, b, s["lm"])
 
 
-def _gloo_worker(rank, world, port, tmp):
+def test_overlapped_schedule_in_process(grid642):
+    """the interior / boundary split of DistributedDynamics._acoustic_pair (sent cells, exchange, interior cells, interior
+    edges, edges next to ghosts; ghost cells never advanced) leaves owned entities bit-identical to the single partition."""
+    world = 4
+    st, shards = _shards(grid642, world)
+    single = _single(grid642, st, 2)
+    backs = [_rank_backend(s) for s in shards]
+    ex = parallel.InProcessExchanger(backs, [s["lm"] for s in shards])
+    exchanges = parallel.exchanges_for(backs[0].cfg)
+    for b in backs:
+        b.atm_compute_solve_diagnostics(False, -1)
+    ex.exchange(exchanges["compute_solve_diagnostics"])
+    seq = _task_schedule(backs[0].cfg)
+    for _ in range(2):
+        i = 0
+        while i < len(seq):
+            name, args = seq[i]
+            if name == "advance_acoustic_step":
+                assert seq[i + 1][0] == "divergence_damping_3d"
+                for b in backs:
+                    b.restrict(CELL, 1); b._call(name, *args)
+                ex.exchange(exchanges[parallel.exchange_key(name, args)])
+                for b in backs:
+                    b.restrict(CELL, 0); b._call(name, *args)
+                    b.restrict(EDGE, 0); b._call(*seq[i + 1][:1], *seq[i + 1][1])
+                    b.restrict(EDGE, 1); b._call(*seq[i + 1][:1], *seq[i + 1][1])
+                    b.restrict(CELL); b.restrict(EDGE)
+                i += 2
+                continue
+            for b in backs:
+                b._call(name, *args)
+            spec = exchanges.get(parallel.exchange_key(name, args))
+            if spec:
+                ex.exchange(spec)
+            i += 1
+    for b, s in zip(backs, shards):
+        _assert_owned_equal(single, b, s["lm"])
+    # ghost cells were never advanced: their rw_p is still what the upload left (zero), while owned cells moved
+    lm = shards[0]["lm"]
+    rw = backs[0].download_field("rw_p")
+    assert not rw[lm.n_owned[0]:].any() and rw[:lm.n_owned[0]].any()
+
+
+def _gloo_worker(rank, world, port, tmp, overlap=False):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -157,9 +200,12 @@ def _gloo_worker(rank, world, port, tmp):
         sh = shards[rank]
         b = _rank_backend(sh)
         run = parallel.DistributedDynamics(b, parallel.HostDistExchanger(b, sh["lm"]))
+        if overlap:
+            assert run.enable_overlap()
         run.init_diagnostics()
         for _ in range(2):
             run.step(DT)
+        run.flush()
         single = _single(mesh, st, 2)
         _assert_owned_equal(single, b, sh["lm"])
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
@@ -167,12 +213,14 @@ def _gloo_worker(rank, world, port, tmp):
         dist.destroy_process_group()
 
 
-def test_gloo_world_size_2(tmp_path):
-    """the torch.distributed path (batch_isend_irecv), world_size 2, gloo on 127.0.0.1."""
+@pytest.mark.parametrize("overlap", [False, True], ids=["plain", "overlapped_schedule"])
+def test_gloo_world_size_2(tmp_path, overlap):
+    """the torch.distributed path (batch_isend_irecv), world_size 2, gloo on 127.0.0.1; with ``overlap`` the schedule that
+    bench.py --gpus N runs (interior / boundary split, deferred diagnostics exchange), the exchange blocking in start()."""
     import socket
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path), overlap), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
 
 
