@@ -284,8 +284,10 @@ class DistributedDynamics:
         """Overlap the acoustic-loop exchanges with interior compute (needs launch classes in the uploaded mesh and an
         exchanger with start()/finish()): boundary-owned cells first, their columns travel while the interior is advanced
         and the interior edges are damped; the edges next to ghosts follow after the unpack.  Ghost cells are never
-        advanced: everything the owned entities read from them arrives by exchange."""
-        self.overlap = hasattr(self.ex, "start") and hasattr(self.dyn, "restrict")
+        advanced: everything the owned entities read from them arrives by exchange.  LITERAL physics only: with
+        physics_mode CORRECTED the acoustic edge update belongs to the same task call and must not run once per cell class."""
+        self.overlap = (hasattr(self.ex, "start") and hasattr(self.dyn, "restrict")
+                        and self.dyn.cfg.physics_mode == _abi.PHYSICS_LITERAL)
         return self.overlap
 
     def _acoustic_pair(self, dts: float, small_step: int):
