@@ -194,3 +194,100 @@ def test_recover_large_step_variables_literal(warmed, rk_step):             # dy
     ora.atm_recover_large_step_variables(ns, rk_step, dt)
     _check(ora, o)
     assert np.all(ora.download_pad("rho_zz")[:L] == 1.0)
+
+
+@pytest.mark.parametrize("twice", [False, True], ids=["once", "again_with_other_dts"])
+def test_compute_vert_imp_coefs(warmed, twice):                             # dynamics_tasks.rg:513-592
+    st, ora, f = warmed
+    _reset(ora, f)
+    cfg = ora.cfg
+    rgas = cfg.rgas; rcv = rgas / (cfg.cp - rgas); c2 = cfg.cp * rcv; g = cfg.gravity
+    cur = {k: f[k].copy() for k in ("cofrz", "cofwr", "cofwz", "coftz", "cofwt", "a_tri", "b_tri", "c_tri", "alpha_tri", "gamma_tri")}
+    fzm, fzp, rdzw, rdzu = f["fzm"], f["fzp"], f["rdzw"], f["rdzu"]
+    zz, ex, th = f["zz"], f["exner"], f["theta_m"]
+    for dts in ((200.0, 300.0) if twice else (200.0,)):
+        dtseps = .5 * dts * (1.0 + cfg.config_epssm)
+        cur["cofrz"][:L] = dtseps * rdzw[:L]
+        cofrz = cur["cofrz"]
+        cur["gamma_tri"][:, 0] = 0.0
+        k = np.arange(1, L)
+        m = k - 1
+        zf = fzm[k] * zz[:, k] + fzp[k] * zz[:, m]
+        cur["cofwr"][:, k] = .5 * dtseps * g * zf
+        cur["coftz"][:, :L] = 0.0
+        cur["cofwz"][:, k] = dtseps * c2 * zf * rdzu[k] * f["cqw"][:, k] * (fzm[k] * ex[:, k] + fzp[k] * ex[:, m])
+        cur["coftz"][:, k] = dtseps * (fzm[k] * th[:, k] + fzp[k] * th[:, m])
+        K = slice(0, L)
+        cur["cofwt"][:, K] = (.5 * dtseps * rcv * zz[:, K] * g * f["rho_base"][:, K] / (1.0 + f["qtot"][:, K]) * ex[:, K]
+                              / ((f["rtheta_base"][:, K] + f["rtheta_p"][:, K]) * f["exner_base"][:, K]))
+        cofwz, coftz, cofwr, cofwt = cur["cofwz"], cur["coftz"], cur["cofwr"], cur["cofwt"]
+        cur["a_tri"][:, k] = (-1.0 * cofwz[:, k] * coftz[:, m] * rdzw[m] * zz[:, m] + cofwr[:, k] * cofrz[m]
+                              - cofwt[:, m] * coftz[:, m] * rdzw[m])
+        cur["b_tri"][:, k] = (1.0 + cofwz[:, k] * (coftz[:, k] * rdzw[k] * zz[:, k] + coftz[:, k] * rdzw[m] * zz[:, m])
+                              - coftz[:, k] * (cofwt[:, k] * rdzw[k] - cofwt[:, k] * rdzw[m]) + cofwr[:, k] * ((cofrz[k] - cofrz[m])))
+        cur["c_tri"][:, k] = (-1.0 * cofwz[:, k] * coftz[:, k + 1] * rdzw[k] * zz[:, k] - cofwr[:, k] * cofrz[k]
+                              + cofwt[:, k] * coftz[:, k + 1] * rdzw[k])
+        # alpha uses gamma_tri of level k-1 as it is BEFORE this call's gamma loop (Q10): a separate, earlier loop
+        cur["alpha_tri"][:, k] = 1.0 / (cur["b_tri"][:, k] - cur["a_tri"][:, k] * cur["gamma_tri"][:, m])
+        cur["gamma_tri"][:, k] = cur["c_tri"][:, k] * cur["alpha_tri"][:, k]
+        ora.atm_compute_vert_imp_coefs(dts)
+    _check(ora, cur)
+
+
+@pytest.mark.parametrize("hollingsworth,rk_step", [(False, 0), (False, 2), (True, -1)])
+def test_compute_solve_diagnostics(warmed, hollingsworth, rk_step):         # dynamics_tasks.rg:328-454
+    st, ora, f = warmed
+    _reset(ora, f)
+    s = st.static
+    nC, nE, nV = s["nEdgesOnCell"].shape[0], s["cellsOnEdge"].shape[0], s["edgesOnVertex"].shape[0]
+    K = slice(0, L)
+    zero = lambda n: np.zeros((n, L))
+    get = lambda k, n: np.zeros(n) if s.get(k) is None else np.asarray(s[k], dtype=np.float64)
+    c1, c2 = _idx(s["cellsOnEdge"][:, 0], nC), _idx(s["cellsOnEdge"][:, 1], nC)
+    u = _pad(f["u"])[:, K]
+    h = _pad(f["h"])[:, K]
+    dc, dv = np.append(get("dcEdge", nE), 0.0), np.append(get("dvEdge", nE), 0.0)
+    o = {k: f[k].copy() for k in ("h_edge", "ke_edge", "vorticity", "divergence", "ke", "ke_vertex", "v", "pv_vertex", "pv_edge")}
+    o["h_edge"][:, K] = 0.5 * (h[c1] + h[c2])
+    o["ke_edge"][:, K] = (dc[:nE] * dv[:nE])[:, None] * u[:nE] ** 2
+    vort = zero(nV)
+    for i in range(s["edgesOnVertex"].shape[1]):
+        e = _idx(s["edgesOnVertex"][:, i], nE)
+        vort = vort + (get("edgesOnVertexSign", (nV, 3))[:, i] * dc[e])[:, None] * u[e]
+    o["vorticity"][:, K] = vort * get("invAreaTriangle", nV)[:, None]
+    div, ke = zero(nC), zero(nC)
+    kee = _pad(o["ke_edge"])[:, K]
+    for i in range(s["edgesOnCell"].shape[1]):
+        on = (i < s["nEdgesOnCell"])[:, None]
+        e = _idx(s["edgesOnCell"][:, i], nE)
+        div = np.where(on, div + ((s["edgesOnCellSign"][:, i] * dv[e])[:, None] + u[e]), div)         # "s + u", as written (:375)
+        ke = np.where(on, ke + 0.25 * kee[e], ke)
+    inva = get("invAreaCell", nC)[:, None]
+    o["divergence"][:, K] = div * inva
+    ke = ke * inva
+    if hollingsworth:
+        ev = [_idx(s["edgesOnVertex"][:, j], nE) for j in range(3)]
+        o["ke_vertex"][:, K] = (kee[ev[0]] + kee[ev[1]] + kee[ev[2]]) * (0.25 * get("invAreaTriangle", nV))[:, None]
+        ke_fact = 1.0 - 0.375
+        ke = ke * ke_fact
+        kev = _pad(o["ke_vertex"])[:, K]
+        kav = np.concatenate([np.asarray(s["kiteAreasOnVertex"], dtype=np.float64), np.zeros((1, 3))])
+        for i in range(s["edgesOnCell"].shape[1]):
+            on = (i < s["nEdgesOnCell"])[:, None]
+            vtx = _idx(s["verticesOnCell"][:, i], nV)
+            j = np.asarray(s["kiteForCell"])[:, i]
+            ke = np.where(on, ke + ((1.0 - ke_fact) * kav[vtx, j])[:, None] * kev[vtx] * inva, ke)
+    o["ke"][:, K] = ke
+    if not (rk_step != -1 and rk_step != 2):
+        v = zero(nE)
+        for i in range(1, s["edgesOnEdge_ECP"].shape[1]):                   # starts at 1, as written (:433)
+            on = (i < s["nEdgesOnEdge"])[:, None]
+            eoe = _idx(s["edgesOnEdge_ECP"][:, i], nE)
+            v = np.where(on, v + s["weightsOnEdge"][:, i][:, None] * u[eoe], v)
+        o["v"][:, K] = v
+    o["pv_vertex"][:, K] = get("fVertex", nV)[:, None] + o["vorticity"][:, K]
+    pvv = _pad(o["pv_vertex"])[:, K]
+    v1, v2 = _idx(s["verticesOnEdge"][:, 0], nV), _idx(s["verticesOnEdge"][:, 1], nV)
+    o["pv_edge"][:, K] = 0.5 * (pvv[v1] + pvv[v2])
+    ora.atm_compute_solve_diagnostics(hollingsworth, rk_step)
+    _check(ora, o)
