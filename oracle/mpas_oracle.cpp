@@ -11,7 +11,8 @@
 // task bodies, each function citing the lines it follows; (ii) the survey-derived
 // cross-checks on the bundled x1.2562 mesh (partition set sizes, pad-index counts) and the
 // only observable in output.txt ("Horizontal normal velocity at Edge 0 is 0.000000") are
-// reproduced in tests/test_oracle.py.
+// reproduced in tests/test_oracle.py; (iii) tests/test_oracle_restatements.py re-derives every non-trivial task from the
+// reference text as array-at-a-time numpy, independently of this file's loop form, and requires agreement to 1e-13.
 //
 // Memory model (the reference leaves it undefined):
 //   M1  every field byte is 0 until written.

@@ -291,3 +291,264 @@ def test_compute_solve_diagnostics(warmed, hollingsworth, rk_step):         # dy
     o["pv_edge"][:, K] = 0.5 * (pvv[v1] + pvv[v2])
     ora.atm_compute_solve_diagnostics(hollingsworth, rk_step)
     _check(ora, o)
+
+
+# ---- atm_compute_dyn_tend_work, dynamics_tasks.rg:814-1480 ------------------------------------------------------------
+def _flux4(q_im2, q_im1, q_i, q_ip1, ua):                                  # :781-783
+    return ua * (7. * (q_i + q_im1) - (q_ip1 + q_im2)) / 12.0
+
+
+def _flux3(q_im2, q_im1, q_i, q_ip1, ua, coef3):                           # :786-789
+    return _flux4(q_im2, q_im1, q_i, q_ip1, ua) + coef3 * np.abs(ua) * ((q_ip1 - q_im2) - 3. * (q_i - q_im1)) / 12.0
+
+
+def _np_dyn_tend(st, f, cfg, rk_step, dt, mixing, cam_coef, rayleigh):
+    """array-at-a-time restatement for config_v_mom_eddy_visc2 = config_v_theta_eddy_visc2 = 0 (constants.rg)."""
+    s = st.static
+    nC, nE, nV = s["nEdgesOnCell"].shape[0], s["cellsOnEdge"].shape[0], s["edgesOnVertex"].shape[0]
+    K = slice(0, L)
+    ME = s["edgesOnCell"].shape[1]
+    written = ("kdiff", "h_divergence", "tend_rho", "dpdz", "w", "ru_edge_w", "flux_arr", "delsq_w", "tend_w_euler", "wdwz",
+               "tend_theta", "delsq_theta", "tend_theta_euler", "wdtz", "tend_rtheta_adv", "rthdynten", "delsq_divergence",
+               "tend_u_euler", "wduz", "tend_u", "q", "delsq_u", "delsq_vorticity")
+    o = {k: f[k].copy() for k in written}
+    fzm, fzp, rdzw, rdzu = f["fzm"], f["fzp"], f["rdzw"], f["rdzu"]
+    c1, c2 = _idx(s["cellsOnEdge"][:, 0], nC), _idx(s["cellsOnEdge"][:, 1], nC)
+    v1, v2 = _idx(s["verticesOnEdge"][:, 0], nV), _idx(s["verticesOnEdge"][:, 1], nV)
+    eoc = [_idx(s["edgesOnCell"][:, i], nE) for i in range(ME)]
+    on = [(i < s["nEdgesOnCell"])[:, None] for i in range(ME)]
+    sgn = s["edgesOnCell_sign"]
+    dvE, invDcE = np.append(s["dvEdge"], 0.0), np.append(s["invDcEdge"], 0.0)
+    del2E, del4E = np.append(s["meshScalingDel2"], 0.0), np.append(s["meshScalingDel4"], 0.0)
+    c1E, c2E = np.append(c1, nC), np.append(c2, nC)
+    inva = s["invAreaCell"][:, None]
+    invDc, invDv = s["invDcEdge"][:, None], s["invDvEdge"][:, None]
+    ld = cfg.config_len_disp
+    prandtl_inv, invDt, r_earth = 1.0 / cfg.prandtl, 1.0 / dt, cfg.sphere_radius
+    inv_r_earth = 1.0 / r_earth
+    h_mom4, h_theta4 = cfg.config_h_mom_eddy_visc4, cfg.config_h_theta_eddy_visc4
+    u, v, ru = _pad(f["u"]), _pad(f["v"]), _pad(f["ru"])
+    rho_edge = _pad(f["rho_edge"])
+    if rk_step == 0:                                                                                   # :858-917
+        if mixing == _abi.MIX_2D_SMAGORINSKY:
+            dd, do = np.zeros((nC, L)), np.zeros((nC, L))
+            for i in range(ME):
+                a, b = s["defc_a"][:, i][:, None], s["defc_b"][:, i][:, None]
+                ue, ve = u[eoc[i]][:, K], v[eoc[i]][:, K]
+                dd = np.where(on[i], dd + (a * ue - b * ve), dd)
+                do = np.where(on[i], do + (b * ue + a * ve), do)
+            o["kdiff"][:, K] = np.minimum((cfg.config_smagorinsky_coef * ld) ** 2.0 * np.sqrt(dd ** 2.0 + do ** 2.0), (0.01 * ld ** 2.0) * invDt)
+            h_mom4 = cfg.config_visc4_2dsmag * ld ** 3.0
+            h_theta4 = h_mom4
+        elif mixing == _abi.MIX_2D_FIXED:
+            o["kdiff"][:, K] = 0.0
+        if cam_coef > 0.0:
+            for k in range(L - 2, L):
+                o["kdiff"][:, k] = np.maximum(o["kdiff"][:, k], 2.0 ** (k - (L - 2)) * 2.0833 * ld * cam_coef)
+    kdiff = _pad(o["kdiff"])
+    hd = np.zeros((nC, L))                                                                             # :924-938
+    for i in range(ME):
+        hd = np.where(on[i], hd + (sgn[:, i] * dvE[eoc[i]])[:, None] * ru[eoc[i]][:, K], hd)
+    hd = hd * inva
+    o["h_divergence"][:, K] = hd
+    if rk_step == 0:                                                                                   # :942-951
+        o["tend_rho"][:, K] = -hd - rdzw[K] * (f["rw"][:, 1:] - f["rw"][:, :-1] + f["tend_rho_physics"][:, K])
+        o["dpdz"][:, K] = -cfg.gravity * (f["rho_base"][:, K] * f["qtot"][:, K] + f["rho_p_save"][:, K] * (1.0 + f["qtot"][:, K]))
+    pp, zz, dpdz, rw, ke, hdp = _pad(f["pressure_p"]), _pad(f["zz"]), _pad(o["dpdz"]), _pad(f["rw"]), _pad(f["ke"]), _pad(o["h_divergence"])
+    ue = f["u"]
+    if rk_step == 0:                                                                                   # :964-970
+        o["tend_u_euler"][:, K] = -f["cqu"][:, K] * ((pp[c2][:, K] - pp[c1][:, K]) * invDc / (0.5 * (zz[c2][:, K] + zz[c1][:, K]))
+                                                     - 0.5 * f["zxu"][:, K] * (dpdz[c1][:, K] + dpdz[c2][:, K]))
+    wduz = o["wduz"]
+    wduz[:, K] = 0.0                                                                                   # :972-980
+    rwavg = 0.5 * (rw[c1] + rw[c2])
+    for k in range(L):
+        if k == 1 or k == L - 1:
+            wduz[:, k] = rwavg[:, k] * (fzm[k] * ue[:, k] + fzp[k] * ue[:, k - 1])
+        if 1 < k < L - 1:
+            wduz[:, k] = _flux3(ue[:, k - 2], ue[:, k - 1], ue[:, k], ue[:, k + 1], rwavg[:, k], 1.0)
+    tend_u = -rdzw[K] * (wduz[:, 1:] - wduz[:, :-1])                                                   # :987
+    q = np.zeros((nE, L))                                                                              # :991-1001, each term L times (Q14)
+    pv = _pad(f["pv_edge"])
+    for j in range(s["edgesOnEdge"].shape[1]):
+        onj = (j < s["nEdgesOnEdge"])[:, None]
+        eoe = _idx(s["edgesOnEdge"][:, j], nE)
+        term = s["weightsOnEdge"][:, j][:, None] * u[eoe][:, K] * (0.5 * (f["pv_edge"][:, K] + pv[eoe][:, K]))
+        for _ in range(L):
+            q = np.where(onj, q + term, q)
+    o["q"][:, K] = q
+    re_ = f["rho_edge"][:, K]
+    tend_u = tend_u + (re_ * (q - (ke[c2][:, K] - ke[c1][:, K]) * invDc) - ue[:, K] * 0.5 * (hdp[c1][:, K] + hdp[c2][:, K]))   # :1005-1007
+    w_in = _pad(f["w"])                                                     # cr.w as it is BEFORE the w section resets it
+    wsum = w_in[c1][:, :-1] + w_in[c1][:, 1:] + w_in[c2][:, :-1] + w_in[c2][:, 1:]
+    cosang, coslat = np.cos(s["angleEdge"])[:, None], np.cos(s["latEdge"])[:, None]
+    tend_u = tend_u - ((2.0 * cfg.omega * cosang * coslat * re_ * 0.25 * wsum) - (ue[:, K] * 0.25 * wsum * re_ * inv_r_earth))   # :1011-1017
+    if rk_step == 0:
+        div, vort = _pad(f["divergence"]), _pad(f["vorticity"])
+        r_dv = np.minimum(invDv, 4 * invDc)
+        u_diff = (div[c2][:, K] - div[c1][:, K]) * invDc - (vort[v2][:, K] - vort[v1][:, K]) * r_dv       # :1036-1047
+        o["delsq_u"][:, K] = 0.0 + u_diff
+        kdiffu = 0.5 * (kdiff[c1][:, K] + kdiff[c2][:, K])
+        o["tend_u_euler"][:, K] += re_ * kdiffu * u_diff * s["meshScalingDel2"][:, None]
+        if h_mom4 > 0.0:                                                                               # :1050-1090
+            dsu = _pad(o["delsq_u"])
+            dcE = np.append(s["dcEdge"], 0.0)
+            dv_ = np.zeros((nV, L))
+            for i in range(3):
+                e = _idx(s["edgesOnVertex"][:, i], nE)
+                dv_ = dv_ + (s["invAreaTriangle"] * dcE[e] * s["edgesOnVertex_sign"][:, i])[:, None] * dsu[e][:, K]
+            o["delsq_vorticity"][:, K] = dv_
+            dd_ = np.zeros((nC, L))
+            for i in range(ME):
+                dd_ = np.where(on[i], dd_ + (s["invAreaCell"] * dvE[eoc[i]] * sgn[:, i])[:, None] * dsu[eoc[i]][:, K], dd_)
+            o["delsq_divergence"][:, K] = dd_
+            ddp, dvp = _pad(o["delsq_divergence"]), _pad(o["delsq_vorticity"])
+            scale = s["meshScalingDel4"][:, None] * h_mom4
+            r_dc4 = scale * cfg.config_del4u_div_factor * invDc
+            r_dv4 = scale * np.minimum(invDv, 4 * invDc)
+            o["tend_u_euler"][:, K] -= re_ * ((ddp[c2][:, K] - ddp[c1][:, K]) * r_dc4 - (dvp[v2][:, K] - dvp[v1][:, K]) * r_dv4)
+    if rayleigh:                                                                                       # :1152-1159
+        nl = cfg.config_number_rayleigh_damp_u_levels
+        inv = 1.0 / (float(nl) * (cfg.config_rayleigh_damp_u_timescale_days * 86400.0))
+        for k in range(L):
+            if k > L - nl + 1:
+                tend_u[:, k] -= re_[:, k] * ue[:, k] * (float(k - (L - nl)) * inv)
+    o["tend_u"][:, K] = tend_u + (o["tend_u_euler"][:, K] + f["tend_ru_physics"][:, K])                 # :1162
+    # ---- w :1170-1320
+    w = o["w"]
+    w[:, K] = 0.0
+    n = s["nEdgesOnCell"]
+    has = n > 0
+    last = _idx(s["edgesOnCell"][np.arange(nC), np.maximum(n - 1, 0)], nE)          # Q18: only the last edge's values survive
+    rew = fzm[K] * ru[last][:, K] + fzp[K] * _below(ru[last])[:, K]
+    o["ru_edge_w"][:, 1:L] = np.where(has[:, None], rew[:, 1:], o["ru_edge_w"][:, 1:L])
+    fa = np.zeros((nC, L))
+    nadv = np.append(s["nAdvCellsForEdge"], 0)
+    advc = np.vstack([s["advCellsForEdge"], np.zeros((1, s["advCellsForEdge"].shape[1]), s["advCellsForEdge"].dtype)])
+    ac, a3 = np.vstack([s["adv_coefs"], np.zeros((1, 15))]), np.vstack([s["adv_coefs_3rd"], np.zeros((1, 15))])
+    wz = _pad(w)
+    for j in range(advc.shape[1]):
+        onj = (j < nadv[last])[:, None]
+        cellj = _idx(advc[last, j], nC)
+        sw = ac[last, j][:, None] + np.copysign(1.0, o["ru_edge_w"][:, K]) * a3[last, j][:, None]
+        fa[:, 1:] = np.where(onj, fa + sw * wz[cellj][:, K], fa)[:, 1:]
+    o["flux_arr"][:, K] = np.where(has[:, None], fa, o["flux_arr"][:, K])
+    for i in range(ME):                                                                                # :1198-1204
+        w[:, 1:L] = np.where(on[i], w[:, K] - sgn[:, i][:, None] * o["ru_edge_w"][:, K] * o["flux_arr"][:, K], w[:, K])[:, 1:]
+    rz, uz, um = f["rho_zz"], f["uReconstructZonal"], f["uReconstructMeridional"]
+    k, m = slice(1, L), slice(0, L - 1)
+    rzf = rz[:, k] * fzm[k] + rz[:, m] * fzp[k]
+    uzf, umf = fzm[k] * uz[:, k] + fzp[k] * uz[:, m], fzm[k] * um[:, k] + fzp[k] * um[:, m]
+    w[:, k] += rzf * (uzf ** 2.0 + umf ** 2.0) / r_earth + 2.0 * cfg.omega * np.cos(s["latCell"])[:, None] * uzf * rzf   # :1208-1218
+    if rk_step == 0:                                                                                   # :1222-1262
+        dw, twe = np.zeros((nC, L)), np.zeros((nC, L))
+        wp = _pad(w)
+        for i in range(ME):
+            e = eoc[i]
+            es = (0.5 * s["invAreaCell"] * sgn[:, i] * dvE[e] * invDcE[e])[:, None]
+            wtf = es * (rho_edge[e][:, K] + _below(rho_edge[e])[:, K]) * (wp[c2E[e]][:, K] - wp[c1E[e]][:, K])
+            dw[:, 1:] = np.where(on[i], dw + wtf, dw)[:, 1:]
+            wtf = wtf * (del2E[e][:, None] * 0.25 * (kdiff[c1E[e]][:, K] + kdiff[c2E[e]][:, K] + _below(kdiff[c1E[e]])[:, K] + _below(kdiff[c2E[e]])[:, K]))
+            twe[:, 1:] = np.where(on[i], twe + wtf, twe)[:, 1:]
+        o["delsq_w"][:, K] = dw
+        if h_mom4 > 0.0:
+            dwp = _pad(o["delsq_w"])
+            for i in range(ME):
+                e = eoc[i]
+                es = (del4E[e] * (h_mom4 * s["invAreaCell"]) * dvE[e] * sgn[:, i] * invDcE[e])[:, None]
+                twe[:, 1:] = np.where(on[i], twe - es * (dwp[c2E[e]][:, K] - dwp[c1E[e]][:, K]), twe)[:, 1:]
+        o["tend_w_euler"][:, K] = twe
+    wdwz = o["wdwz"]
+    wdwz[:, K] = 0.0                                                                                   # :1266-1276
+    rwc = f["rw"]
+    for kk in range(L):
+        if kk == 1 or kk == L - 1:
+            wdwz[:, kk] = 0.25 * (rwc[:, kk] + rwc[:, kk - 1]) * (w[:, kk] + w[:, kk - 1])
+        if 1 < kk < L - 1:
+            wdwz[:, kk] = _flux3(w[:, kk - 2], w[:, kk - 1], w[:, kk], w[:, kk + 1], 0.5 * (rwc[:, kk] + rwc[:, kk - 1]), 1.0)
+    w[:, k] = w[:, k] * (inva - rdzu[k] * (wdwz[:, 2:] - wdwz[:, 1:L]))                                # :1292 (Q19)
+    if rk_step == 0:                                                                                   # :1294-1299
+        ppc, dpc = f["pressure_p"], o["dpdz"]
+        o["tend_w_euler"][:, k] -= f["cqw"][:, k] * (rdzu[k] * (ppc[:, k] - ppc[:, m]) - (fzm[k] * dpc[:, k] + fzp[k] * dpc[:, m]))
+    w[:, k] += o["tend_w_euler"][:, k]                                                                  # :1316-1320
+    # ---- theta :1322-1480
+    tm, tms = _pad(f["theta_m"]), _pad(f["theta_m_save"])
+    tt = np.zeros((nC, L))
+    fa = o["flux_arr"][:, K].copy()
+    for i in range(ME):
+        e = eoc[i]
+        fi = np.zeros((nC, L))
+        for j in range(advc.shape[1]):
+            onj = (j < nadv[e])[:, None]
+            sw = ac[e, j][:, None] + np.copysign(1.0, ru[e][:, K]) * a3[e, j][:, None]
+            fi = np.where(onj, fi + sw * tm[_idx(advc[e, j], nC)][:, K], fi)
+        fa = np.where(on[i], fi, fa)
+        tt = np.where(on[i], tt - sgn[:, i][:, None] * ru[e][:, K] * fi, tt)
+    o["flux_arr"][:, K] = fa
+    if rk_step > 0:                                                                                    # :1340-1352
+        rus = _pad(f["ru_save"])
+        for i in range(ME):
+            e = eoc[i]
+            flux = (sgn[:, i] * dvE[e])[:, None] * (rus[e][:, K] - ru[e][:, K]) * 0.5 * (tms[c2E[e]][:, K] + tms[c1E[e]][:, K])
+            tt = np.where(on[i], tt - flux, tt)
+    if rk_step == 0:                                                                                   # :1354-1394
+        dth, tte = np.zeros((nC, L)), np.zeros((nC, L))
+        for i in range(ME):
+            e = eoc[i]
+            es = (s["invAreaCell"] * sgn[:, i] * dvE[e] * invDcE[e])[:, None]
+            pr_scale = (prandtl_inv * del2E[e])[:, None]
+            ttf = es * (tm[c2E[e]][:, K] - tm[c1E[e]][:, K]) * rho_edge[e][:, K]
+            dth = np.where(on[i], dth + ttf, dth)
+            ttf = ttf * (0.5 * (kdiff[c1E[e]][:, K] + kdiff[c2E[e]][:, K]) * pr_scale)
+            tte = np.where(on[i], tte + ttf, tte)
+        o["delsq_theta"][:, K] = dth
+        if h_theta4 > 0.0:
+            dtp = _pad(o["delsq_theta"])
+            for i in range(ME):
+                e = eoc[i]
+                es = (del4E[e] * (h_theta4 * prandtl_inv * s["invAreaCell"]) * dvE[e] * sgn[:, i] * invDcE[e])[:, None]
+                tte = np.where(on[i], tte - es * (dtp[c2E[e]][:, K] - dtp[c1E[e]][:, K]), tte)
+        o["tend_theta_euler"][:, K] = tte
+    wdtz = o["wdtz"]
+    wdtz[:, K] = 0.0                                                                                   # :1398-1412
+    tmc, tmsc, rws = f["theta_m"], f["theta_m_save"], f["rw_save"]
+    for kk in range(L):
+        if 0 < kk < L - 1:
+            wdtz[:, kk] = (rws[:, kk] - rwc[:, kk]) * (fzm[kk] * tmsc[:, kk] + fzp[kk] * tmsc[:, kk - 1])
+        if kk == 1:
+            wdtz[:, kk] += rwc[:, kk] * (fzm[kk] * tmc[:, kk] + fzp[kk] * tmc[:, kk - 1])
+        if kk == L - 1:
+            wdtz[:, kk] = rws[:, kk] * (fzm[kk] * tmsc[:, kk] + fzp[kk] * tmsc[:, kk - 1])
+    tt = tt * (inva - rdzw[K] * (wdtz[:, 1:] - wdtz[:, :-1]))                                           # :1415 (Q19)
+    o["tend_rtheta_adv"][:, K] = tt
+    o["rthdynten"][:, K] = tt / f["rho_zz"][:, K]
+    tt = tt + f["rho_zz"][:, K] * f["rt_diabatic_tend"][:, K]
+    o["tend_theta"][:, K] = tt + (o["tend_theta_euler"][:, K] + f["tend_rtheta_physics"][:, K])        # :1478
+    return o
+
+
+@pytest.mark.parametrize("rk_step,mixing,cam,rayleigh", [
+    (0, _abi.MIX_2D_SMAGORINSKY, 0.0, False), (1, _abi.MIX_2D_SMAGORINSKY, 0.0, False), (0, _abi.MIX_2D_FIXED, 0.2, False),
+    (0, _abi.MIX_OTHER, 0.0, True), (2, _abi.MIX_2D_SMAGORINSKY, 0.0, True)],
+    ids=["rk0_smagorinsky", "rk1", "rk0_fixed_cam", "rk0_other_rayleigh", "rk2_rayleigh"])
+def test_compute_dyn_tend(warmed, rk_step, mixing, cam, rayleigh):
+    st, ora, f0 = warmed
+    _reset(ora, f0)
+    # the warmed state already holds this task's own outputs (nothing on the literal path changes its inputs): perturb the
+    # inputs so that every output has to move
+    rng = np.random.default_rng(3)
+    f = dict(f0)
+    for n in ("u", "v", "ru", "rw", "w", "theta_m", "pv_edge", "ke", "pressure_p", "divergence", "vorticity", "rho_zz", "rho_p_save"):
+        f[n] = f0[n] * (1.0 + 0.05 * rng.standard_normal(f0[n].shape))
+        ora.upload_field(n, f[n])
+    want = _np_dyn_tend(st, f, ora.cfg, rk_step, 600.0, mixing, cam, rayleigh)
+    ora.atm_compute_dyn_tend(rk_step, 600.0, config_horiz_mixing=mixing, config_mpas_cam_coef=cam, config_rayleigh_damp_u=rayleigh)
+    _check(ora, want)
+    moved = [n for n in want if not np.array_equal(want[n], f[n], equal_nan=True)]
+    for n in ("tend_u", "tend_theta", "w", "q", "h_divergence", "wduz", "wdwz", "wdtz", "flux_arr", "rthdynten"):
+        assert n in moved and np.isfinite(want[n]).all() and np.abs(want[n]).max() > 0, n
+    if rk_step == 0:
+        for n in ("tend_u_euler", "tend_w_euler", "tend_theta_euler", "delsq_u", "delsq_w", "delsq_theta", "tend_rho", "dpdz"):
+            assert n in moved, n
+        if mixing != _abi.MIX_OTHER:
+            assert "kdiff" in moved
