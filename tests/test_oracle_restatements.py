@@ -143,9 +143,12 @@ def test_advance_acoustic_step_literal(warmed, small_step):                 # dy
     assert np.abs(o["rw_p"]).max() > 0
 
 
+@pytest.mark.parametrize("fix", [False, True], ids=["literal", "corrected_physics"])
 @pytest.mark.parametrize("rk_step", [0, 2])
-def test_recover_large_step_variables_literal(warmed, rk_step):             # dynamics_tasks.rg:1786-1871, as written
+def test_recover_large_step_variables(warmed, grid642, rk_step, fix):       # dynamics_tasks.rg:1786-1871, as written
     st, ora, f = warmed
+    if fix:        # MPASB200_PHYSICS_CORRECTED restores four expressions (include/mpas_b200.h)
+        st, ora, _ = build_pair(grid642, L, _abi.INDEX_CORRECTED, gpu=False, physics_mode=_abi.PHYSICS_CORRECTED)
     _reset(ora, f)
     s, cfg = st.static, ora.cfg
     nC, nE = s["nEdgesOnCell"].shape[0], s["cellsOnEdge"].shape[0]
@@ -161,10 +164,15 @@ def test_recover_large_step_variables_literal(warmed, rk_step):             # dy
     o["rw"][:, K] = f["rw_save"][:, K] + f["rw_p"][:, K]
     with np.errstate(all="ignore"):
         o["w"][:, K] = o["rw"][:, K] / (fzm * f["zz"][:, K] + fzp * _below(f["zz"])[:, K])
+        if fix:
+            o["w"][:, 0] = 0.0                                                    # MPAS: w(1) = 0, k = 2..nVertLevels (:1810)
         if rk_step == 2:
             o["rtheta_p"][:, K] = f["rtheta_p_save"][:, K] + f["rtheta_pp"][:, K] - dt * o["rho_zz"][:, K] * f["rt_diabatic_tend"][:, K]
             o["theta_m"][:, K] = (o["rtheta_p"][:, K] + f["rtheta_base"][:, K]) / o["rho_zz"][:, K]
-            o["exner"][:, K] = f["zz"][:, K] * (rgas / p0) * np.power(o["rtheta_p"][:, K] + f["rtheta_base"][:, K], rcv)
+            if fix:
+                o["exner"][:, K] = np.power(f["zz"][:, K] * (rgas / p0) * (o["rtheta_p"][:, K] + f["rtheta_base"][:, K]), rcv)   # :1819
+            else:
+                o["exner"][:, K] = f["zz"][:, K] * (rgas / p0) * np.power(o["rtheta_p"][:, K] + f["rtheta_base"][:, K], rcv)
             o["pressure_p"][:, K] = f["zz"][:, K] * rgas * (o["exner"][:, K] * o["rtheta_p"][:, K] + f["rtheta_base"][:, K] * (o["exner"][:, K] - f["exner_base"][:, K]))
         else:
             o["rtheta_p"][:, K] = f["rtheta_p_save"][:, K] + f["rtheta_pp"][:, K]
@@ -172,7 +180,7 @@ def test_recover_large_step_variables_literal(warmed, rk_step):             # dy
         c1, c2 = _idx(s["cellsOnEdge"][:, 0], nC), _idx(s["cellsOnEdge"][:, 1], nC)
         rz = _pad(o["rho_zz"]); rz[nC, :L] = 1.0                                   # the "garbage cell" (:1792-1794)
         o["ruAvg"][:, K] = f["ruAvg"][:, K] * invNs + f["ru_save"][:, K]
-        o["ru"][:, K] = f["ru_save"][:, K] * f["ru_p"][:, K]                      # a product, as written (:1840)
+        o["ru"][:, K] = f["ru_save"][:, K] + f["ru_p"][:, K] if fix else f["ru_save"][:, K] * f["ru_p"][:, K]   # a product, as written (:1840)
         o["u"][:, K] = 2 * o["ru"][:, K] / (rz[c1][:, K] + rz[c2][:, K])
         ru = _pad(o["ru"])
         cf1, cf2, cf3 = f["cf1"][0], f["cf2"][0], f["cf3"][0]
@@ -186,7 +194,7 @@ def test_recover_large_step_variables_literal(warmed, rk_step):             # dy
                 flux = cf1 * ru[e, 0] + cf2 * ru[e, 1] + cf3 * ru[e, 2]
                 w[:, 0] = np.where(on, w[:, 0] + sg * (f["zb_cell"][:, 0, i] + np.copysign(1.0, flux) * f["zb3_cell"][:, 0, i]) * flux, w[:, 0])
                 ru_m = ru[e, y - 1] if y > 0 else np.zeros(nC)
-                flux2 = fzm[y] * ru[e, y] * (fzp[y] * ru_m)
+                flux2 = fzm[y] * ru[e, y] + fzp[y] * ru_m if fix else fzm[y] * ru[e, y] * (fzp[y] * ru_m)          # :1856
                 w[:, y] = np.where(on, w[:, y] + sg * (f["zb_cell"][:, y, i] + np.copysign(1.0, flux2) * f["zb3_cell"][:, y, i]) * flux2, w[:, y])
         w[:, 0] = np.where(act, w[:, 0] / (cf1 * o["rho_zz"][:, 0] + cf2 * o["rho_zz"][:, 1] + cf3 * o["rho_zz"][:, 2]), w[:, 0])
         for y in range(1, L):
@@ -194,6 +202,9 @@ def test_recover_large_step_variables_literal(warmed, rk_step):             # dy
     ora.atm_recover_large_step_variables(ns, rk_step, dt)
     _check(ora, o)
     assert np.all(ora.download_pad("rho_zz")[:L] == 1.0)
+    if fix:
+        assert np.isfinite(o["w"]).all()
+        ora.close()
 
 
 @pytest.mark.parametrize("twice", [False, True], ids=["once", "again_with_other_dts"])
