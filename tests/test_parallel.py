@@ -258,3 +258,37 @@ def test_launch_classes_for_overlap(grid642):
             es = eoc[c, :loc["nEdgesOnCell"][c]]
             assert np.all(ec[es] == 0)
         assert (cc == 0).sum() > 0 and (cc == 1).sum() > 0
+
+
+@pytest.mark.parametrize("kind", ["random", "stripes", "one_rank_tiny"])
+def test_irregular_colourings_still_match_single_partition(grid642, kind):
+    """colourings a METIS file could contain: scattered cells (every cell next to another rank), latitude stripes, a rank
+    that owns three cells.  Owned entities stay bit-identical to the single partition, with and without the split schedule."""
+    rng = np.random.default_rng(1)
+    n = grid642.nCells
+    if kind == "random":
+        col = rng.integers(0, 3, n).astype(np.int32)
+    elif kind == "stripes":
+        col = np.minimum((np.argsort(np.argsort(grid642.v["latCell"])) * 4) // n, 3).astype(np.int32)
+    else:
+        col = np.zeros(n, np.int32); col[n // 2:] = 1; col[:3] = 2
+    world = int(col.max()) + 1
+    st = init_jw.make_state(grid642, L, _abi.INDEX_CORRECTED)
+    shards = parallel.make_shards(st, world, colours=col)
+    single = _single(grid642, st, 1)
+    backs = [_rank_backend(s) for s in shards]
+    ex = parallel.InProcessExchanger(backs, [s["lm"] for s in shards])
+    exchanges = parallel.exchanges_for(backs[0].cfg)
+    for b in backs:
+        b.atm_compute_solve_diagnostics(False, -1)
+    ex.exchange(exchanges["compute_solve_diagnostics"])
+    for name, args in _task_schedule(backs[0].cfg):
+        for b in backs:
+            b._call(name, *args)
+        spec = exchanges.get(parallel.exchange_key(name, args))
+        if spec:
+            ex.exchange(spec)
+    for b, s in zip(backs, shards):
+        _assert_owned_equal(single, b, s["lm"])
+        cc = s["static"]["cellClass"]
+        assert (cc == 2).sum() == len(s["lm"].cells) - s["lm"].n_owned[0]
