@@ -4,8 +4,8 @@ The reference computes the owned / ghost partitions (mesh_loading.rg:399-483) bu
 than one of them (main.rg:54-55; CURIS_2021_DependentPartitioning_BearE.md:50-58).  Here every rank
 holds [owned | ghost ring 1 | ghost ring 2] cells plus all their edges and vertices, runs every task
 on all of them (ghost entities are recomputed redundantly) and repairs the ghost values that the
-stencils invalidate with packed neighbour exchanges.  With 2 rings the literal dataflow needs three
-kinds of exchange per RK stage:
+stencils invalidate with packed neighbour exchanges.  With 2 rings the literal dataflow needs these
+exchanges per RK stage (10 per step):
 
     after the first acoustic step         cells    w                       (atm_compute_dyn_tend's w tendency; read at cellsOnEdge by the next stage's tend_u)
     after every atm_advance_acoustic_step cells    rtheta_pp, rtheta_pp_old (read at cellsOnEdge by divergence damping)
@@ -16,7 +16,9 @@ are bit-identical to the single-partition run: each entity sums over its own slo
 whatever rank computes it (tests/test_parallel.py, CPU: world_size-2 gloo; GPU: tests/test_parity_gpu.py).
 
 The wire is torch.distributed (NCCL send/recv over NVLink on the GPU box, gloo in the CPU tests);
-pack / unpack run in libmpas_b200 (k_pack / k_unpack) on the stream that carries the step.
+pack / unpack run in libmpas_b200 (k_pack / k_unpack).  DistributedDynamics.enable_overlap() moves the exchanges to a
+communication stream and hides them under interior compute (launch classes + TaskAPI.restrict); without it they run
+on the stream that carries the step.
 """
 from __future__ import annotations
 
