@@ -1522,6 +1522,140 @@ __global__ void k_rec_cell2(const View V, int nRelaxZone, int fix) {            
 }
 
 // ============================================================================================
+// EXPERIMENTAL, off by default (MpasConfig.chunk_tiles > 0): the same kernels with a different tile -> block mapping.
+// Shipped: one tile of blockDim.y consecutive entities per block, consecutive tiles land on different SMs, so L1 only
+// serves the reuse inside a tile (offline model and ncu agree on 54 % for k_dt_edge, profiles/r1_l1_locality_model.md).
+// Here a block walks `chunk` CONSECUTIVE tiles, so the neighbour columns gathered for one tile are still in L1 for the
+// next (model: 75-82 % hits).  Same arithmetic, same order: results are bit-identical.  Not yet measured on a GPU.
+#define PAIR_THREAD_TILE(n)                                     \
+  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;             \
+  const int x = tile * blockDim.y + threadIdx.y;                \
+  const bool inx = x < (n);                                     \
+  const int LP = V.LP; const int L = V.L;                       \
+  const size_t ix = (size_t)(inx ? x : 0) * LP + k0;            \
+  const bool m0 = inx && k0 < L, m1 = inx && k1 < L;            \
+  (void)ix; (void)m1; (void)k1;
+
+__global__ void k_dt_theta_flux_chunked(const View V, int chunk) {
+  const int ntile = (V.nEdges + (int)blockDim.y - 1) / (int)blockDim.y;
+  const int t_end = min((int)(blockIdx.x + 1) * chunk, ntile);
+  for (int tile = blockIdx.x * chunk; tile < t_end; ++tile) {
+    PAIR_THREAD_TILE(V.nEdges)
+    if (!m0) continue;
+    const int NA = V.nAdv;
+    const double* tm = FLD(theta_m);
+    const int na = V.nAdvCellsForEdge[x];
+    const D2 sg = sgn1(ld2(FLD(ru), ix));
+    D2 fa = bc(0.0);
+#pragma unroll 5
+    for (int j = 0; j < na; ++j) {
+      const D2 sw = V.adv_coefs[x * NA + j] + sg * V.adv_coefs_3rd[x * NA + j];
+      fa += sw * G2(tm, V.advCellsForEdge[x * NA + j]);
+    }
+    st2m(V.scr_flux, ix, fa, m0, m1);
+  }
+}
+
+// k_acoustic_gather with chunked tiles; honours mpasb200_set_range like the shipped kernel ([V.xoff, V.xend))
+__global__ void k_acoustic_gather_chunked(const View V, double dts, int chunk) {
+  const int ntile = (V.xend - V.xoff + (int)blockDim.y - 1) / (int)blockDim.y;
+  const int t_end = min((int)(blockIdx.x + 1) * chunk, ntile);
+  const int LP = V.LP, L = V.L;
+  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;
+  for (int tile = blockIdx.x * chunk; tile < t_end; ++tile) {
+    const int x = V.xoff + tile * blockDim.y + threadIdx.y;
+    if (x >= V.xend || k0 >= L) continue;
+    const bool m0 = true, m1 = k1 < L;
+    const size_t ix = (size_t)x * LP + k0;
+    if (V.specZoneMaskCell[x] != 0.0) continue;
+    const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
+    const double* ru_p = FLD(ru_p); const double* tm = FLD(theta_m);
+    const double inva = V.invAreaCell[x];
+    D2 rs = bc(0), ts = bc(0);
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {
+      const int e = V.edgesOnCell[x * V.MEP + i];
+      const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+      const D2 flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G2(ru_p, e) * inva;
+      rs -= flux;
+      ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
+    }
+    st2m(V.scr_rs, ix, rs, m0, m1); st2m(V.scr_ts, ix, ts, m0, m1);
+  }
+}
+
+__global__ void k_dt_edge_chunked(const View V, const DynTendParams P, int chunk) {
+  extern __shared__ double sm[];
+  const int ntile = (V.nEdges + (int)blockDim.y - 1) / (int)blockDim.y;
+  const int t_end = min((int)(blockIdx.x + 1) * chunk, ntile);
+  for (int tile = blockIdx.x * chunk; tile < t_end; ++tile) {
+  PAIR_THREAD_TILE(V.nEdges)
+  const int TS = LP + 2;
+  double* s_wduz = sm + (size_t)threadIdx.y * TS;
+  const double* u = FLD(u);
+  int4 cv = make_int4(0, 0, 0, 0);
+  D2 u2 = bc(0.0), wduz = bc(0.0);
+  if (m0) {
+    cv = V.ecv[x];
+    u2 = ld2(u, ix);
+    const double* rw = FLD(rw);
+    const D2 rwavg = 0.5 * (G2(rw, cv.x) + G2(rw, cv.y));
+    const D2 fzm = ld2(FLD(fzm), k0), fzp = ld2(FLD(fzp), k0);
+    const D2 um = (k0 >= 2) ? ld2(u, ix - 2) : bc(0.0);            // (u[k0-2], u[k0-1])
+    const double up = (k0 + 2 <= L) ? u[ix + 2] : 0.0;             // u[k1+1]
+    wduz.x = wduz_at(k0, L, rwavg.x, fzm.x, fzp.x, um.x, um.y, u2.x, u2.y);
+    if (m1) wduz.y = wduz_at(k1, L, rwavg.y, fzm.y, fzp.y, um.y, u2.x, u2.y, up);
+    s_wduz[k0] = wduz.x; if (m1) s_wduz[k1] = wduz.y;
+    st2m(FLD(wduz), ix, wduz, m0, m1);
+  }
+  if (inx && k0 == L) s_wduz[L] = FLD(wduz)[ix];          // level L: never written, read as stored
+  if (inx && k1 == L) s_wduz[L] = FLD(wduz)[ix + 1];
+  __syncthreads();
+  if (m0) {
+  const D2 rho_e = ld2(FLD(rho_edge), ix);
+  const double invDc = V.invDcEdge[x];
+  const D2 wduz_p = mk(s_wduz[k1], m1 ? s_wduz[k1 + 1] : 0.0);
+  D2 tend_u = -ld2(FLD(rdzw), k0) * (wduz_p - wduz);                                                // :987
+  // nonlinear Coriolis term :991-1001.  The reference adds each term nVertLevels times in a row
+  // (Q14); here it is added once, multiplied by nVertLevels (same value to O(L) ulp).
+  D2 q = bc(0.0);
+  {
+    const int ME2 = V.maxEdges2, n = V.nEdgesOnEdge[x];
+    const double* pv = FLD(pv_edge);
+    const D2 pv_k = ld2(pv, ix);
+    const double Ld = (double)L;
+#pragma unroll 2
+    for (int j = 0; j < n; ++j) {
+      const int eoe = V.edgesOnEdge[x * ME2 + j];
+      const D2 workpv = 0.5 * (pv_k + G2(pv, eoe));
+      q += Ld * (V.weightsOnEdge[x * ME2 + j] * G2(u, eoe) * workpv);
+    }
+  }
+  st2m(FLD(q), ix, q, m0, m1);
+  const double* ke = FLD(ke); const double* hd = FLD(h_divergence); const double* w = FLD(w);
+  tend_u += rho_e * (q - (G2(ke, cv.y) - G2(ke, cv.x)) * invDc) - u2 * 0.5 * (G2(hd, cv.x) + G2(hd, cv.y));   // :1005-1007
+  {
+    const D2 w1 = G2(w, cv.x), w2 = G2(w, cv.y);
+    const D2 w1p = mk(w1.y, m1 ? G1(w, cv.x, k0 + 2) : 0.0), w2p = mk(w2.y, m1 ? G1(w, cv.y, k0 + 2) : 0.0);
+    const D2 wsum = w1 + w1p + w2 + w2p;
+    tend_u -= (P.omega2 * V.cosAngleEdge[x] * V.cosLatEdge[x] * rho_e * 0.25 * wsum)
+              - (u2 * 0.25 * wsum * rho_e * P.inv_r_earth);                                        // :1011-1017
+  }
+  const D2 tue = ld2(FLD(tend_u_euler), ix);
+  if (P.rayleigh_u) {                                                                               // :1152-1159
+    const int lim = L - P.rayleigh_levels + 1;
+    if (k0 > lim) tend_u.x -= rho_e.x * u2.x * ((double)((double)k0 - (L - P.rayleigh_levels)) * P.rayleigh_coef_inverse);
+    if (k1 > lim) tend_u.y -= rho_e.y * u2.y * ((double)((double)k1 - (L - P.rayleigh_levels)) * P.rayleigh_coef_inverse);
+  }
+  tend_u += tue + ld2(FLD(tend_ru_physics), ix);                                                    // :1162
+  st2m(FLD(tend_u), ix, tend_u, m0, m1);
+  }
+  __syncthreads();      // s_wduz is reused by the next tile
+  }
+}
+
+
+// ============================================================================================
 // atm_rk_dynamics_substep_finish  :1951-2007
 __global__ void k_finish_cell(const View V, int lt_split, int first, int last, double inv_split) {
   PAIR_THREAD(V.nCells)

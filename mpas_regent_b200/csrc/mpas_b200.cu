@@ -220,6 +220,17 @@ void drain_kernel_times(mpasb200_t* h) {
     }                                                                                       \
   } while (0)
 
+// EXPERIMENTAL (MpasConfig.chunk_tiles > 0): a block walks `chunk` consecutive tiles (kernels.cuh, *_chunked)
+#define LAUNCH_CHUNKED(kernel, n, smem, ...)                                                \
+  do {                                                                                      \
+    if ((n) > 0) {                                                                          \
+      const int chunk_ = h->c.chunk_tiles;                                                  \
+      const int ntile_ = ((n) + h->CPB - 1) / h->CPB;                                       \
+      KTimer kt_(h, #kernel);                                                               \
+      kernel<<<(ntile_ + chunk_ - 1) / chunk_, dim3((unsigned)(h->LP / 2), (unsigned)h->CPB), (smem), h->stream>>>(__VA_ARGS__, chunk_); \
+      h->launches++;                                                                        \
+    }                                                                                       \
+  } while (0)
 size_t tile_bytes(const mpasb200_t* h, int tiles) { return (size_t)tiles * h->CPB * (h->LP + 2) * sizeof(double); }
 
 int post_launch(mpasb200_t* h) {
@@ -278,6 +289,7 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
   P.rayleigh_levels = C.config_number_rayleigh_damp_u_levels;
   P.rayleigh_coef_inverse = 1.0 / ((double)(C.config_number_rayleigh_damp_u_levels) * (C.config_rayleigh_damp_u_timescale_days * 86400.0));
   const size_t sm2 = tile_bytes(h, 2);
+  const bool chunked = C.chunk_tiles > 0;
   if (rk_step == 0) {
     LAUNCH(k_dt_cell0<true>, h->nCells, 0, h->V, P, C.config_len_disp, cam_coef);
     LAUNCH(k_dt_edge_delsq, h->nEdges, 0, h->V);
@@ -286,15 +298,19 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
       LAUNCH(k_dt_cell_delsq, h->nCells, 0, h->V);
     }
     LAUNCH(k_dt_edge_euler, h->nEdges, tile_bytes(h, 1), h->V, P);
-    LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
+    if (chunked) LAUNCH_CHUNKED(k_dt_edge_chunked, h->nEdges, tile_bytes(h, 1), h->V, P);
+    else LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
     LAUNCH(k_dt_cellA, h->nCells, 0, h->V, P);
     LAUNCH(k_dt_cellB, h->nCells, 0, h->V, P);
-    LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
+    if (chunked) LAUNCH_CHUNKED(k_dt_theta_flux_chunked, h->nEdges, 0, h->V);
+    else LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
     LAUNCH(k_dt_cellC<true>, h->nCells, sm2, h->V, P);
   } else {
     LAUNCH(k_dt_cell0<false>, h->nCells, 0, h->V, P, C.config_len_disp, cam_coef);
-    LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
-    LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
+    if (chunked) LAUNCH_CHUNKED(k_dt_edge_chunked, h->nEdges, tile_bytes(h, 1), h->V, P);
+    else LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
+    if (chunked) LAUNCH_CHUNKED(k_dt_theta_flux_chunked, h->nEdges, 0, h->V);
+    else LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
     LAUNCH(k_dt_cellC<false>, h->nCells, sm2, h->V, P);
   }
   return post_launch(h);
@@ -333,7 +349,10 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
 #undef AF
     F.p[AF_rs] = V.scr_rs; F.p[AF_ts] = V.scr_ts;
     const int split = h->c.acoustic_tma == 2;
-    if (split) LAUNCH(k_acoustic_gather, rc_.n, 0, Vc, dts);
+    if (split) {
+      if (h->c.chunk_tiles > 0) LAUNCH_CHUNKED(k_acoustic_gather_chunked, rc_.n, 0, Vc, dts);
+      else LAUNCH(k_acoustic_gather, rc_.n, 0, Vc, dts);
+    }
     const int T = h->LP / 2, NF = small_step == 0 ? (int)AF_rho_pp : (int)AF_COUNT;
     int C = 4;                               // columns per block: as many as fit the default 48 KB of dynamic shared memory
     auto smem_for = [&](int c) { return ((size_t)NF * c * h->LP + (size_t)4 * c * (h->LP + 2)) * sizeof(double) + 16; };
@@ -501,6 +520,7 @@ void mpasb200_default_config(MpasConfig* c) {
   c->index_policy = MPASB200_INDEX_CORRECTED; c->rkarg_policy = MPASB200_RKARG_SUBSTEP_TRUNC;
   c->sfc_renumber = 1; c->device = -1; c->use_graph = 0; c->acoustic_exact = 0; c->acoustic_tma = 2;
   c->physics_mode = MPASB200_PHYSICS_LITERAL;
+  c->chunk_tiles = 0;
 }
 
 const char* mpasb200_last_error(const mpasb200_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }

@@ -505,3 +505,23 @@ def test_range_restricted_launches_equal_whole(grid642, physics):
 
 
 from mpas_regent_b200._abi import CELL as parallel_CELL, EDGE as parallel_EDGE  # noqa: E402
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("MPASB200_TEST_EXPERIMENTAL"),
+                    reason="experimental chunk_tiles kernels: not yet run on a GPU; set MPASB200_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("chunk", [1, 3, 8])
+def test_experimental_chunked_tile_walk_is_bit_identical(grid2562, chunk):
+    """MpasConfig.chunk_tiles only changes which block handles which tile: every field must keep its bytes."""
+    from mpas_regent_b200 import dynamics, init_jw
+    st = init_jw.make_state(grid2562, L_SMALL, _abi.INDEX_CORRECTED)
+    outs = []
+    for c in (0, chunk):
+        g = dynamics.Dynamics(dynamics.dims_of(grid2562, L_SMALL), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, chunk_tiles=c))
+        g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
+        g.atm_compute_solve_diagnostics(False, -1)
+        for _ in range(2):
+            g.atm_srk3(DT)
+        outs.append(g.download_all())
+        g.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
