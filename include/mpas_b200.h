@@ -122,8 +122,8 @@ typedef struct {
   int32_t acoustic_tma;               /* acoustic step form: 0 = one fused kernel, plain loads; 1 = one fused kernel, own-column strips staged
                                          with cp.async.bulk (TMA); 2 (default) = lean gather kernel + TMA streaming/sweep kernel */
   int32_t physics_mode;               /* mpasb200_physics_mode_t; default LITERAL */
-  int32_t chunk_tiles;                /* EXPERIMENTAL, default 0 = off: > 0 makes the gather kernels k_dt_edge, k_dt_theta_flux and
-                                         k_acoustic_gather walk that many consecutive tiles per block (L1 reuse across tiles,
+  int32_t chunk_tiles;                /* EXPERIMENTAL, default 0 = off: > 0 makes the gather kernels k_dt_edge, k_dt_theta_flux,
+                                         k_acoustic_gather and k_divdamp walk that many consecutive tiles per block (L1 reuse across tiles,
                                          profiles/r1_l1_locality_model.md); results are bit-identical either way */
 } MpasConfig;
 

@@ -1556,6 +1556,37 @@ __global__ void k_dt_theta_flux_chunked(const View V, int chunk) {
   }
 }
 
+// k_divdamp with contiguous tiles per block instead of the grid stride (same next-tile prefetch); honours mpasb200_set_range
+__global__ void k_divdamp_chunked(const View V, double coef_divdamp, int chunk) {
+  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;
+  const int LP = V.LP, L = V.L;
+  if (k0 >= L) return;
+  const bool m1 = k1 < L;
+  const int stride = blockDim.y;
+  const int first = V.xoff + blockIdx.x * chunk * (int)blockDim.y;
+  const int nE = min(V.xend, first + chunk * (int)blockDim.y);
+  int x = first + threadIdx.y;
+  if (x >= nE) return;
+  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
+  int4 cv = V.ecv[x]; unsigned char skip = V.divdampSkip[x]; double sz = 1.0 - V.specZoneMaskEdge[x];
+  D2 r = ld2(FLD(ru_p), (size_t)x * LP + k0);
+  while (true) {
+    const int xn = x + stride;
+    const bool more = xn < nE;
+    const int xs = more ? xn : x;
+    const int4 cvn = V.ecv[xs]; const unsigned char skn = V.divdampSkip[xs]; const double szn = 1.0 - V.specZoneMaskEdge[xs];
+    const D2 rn = ld2(FLD(ru_p), (size_t)xs * LP + k0);
+    if (!skip) {
+      const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
+      const D2 divCell1 = -(a1 - b1);
+      const D2 divCell2 = -(a2 - b2);
+      st2m(FLD(ru_p), (size_t)x * LP + k0, r + coef_divdamp * (divCell2 - divCell1) * sz / (t1 + t2), true, m1);
+    }
+    if (!more) break;
+    x = xn; cv = cvn; skip = skn; sz = szn; r = rn;
+  }
+}
+
 // k_acoustic_gather with chunked tiles; honours mpasb200_set_range like the shipped kernel ([V.xoff, V.xend))
 __global__ void k_acoustic_gather_chunked(const View V, double dts, int chunk) {
   const int ntile = (V.xend - V.xoff + (int)blockDim.y - 1) / (int)blockDim.y;

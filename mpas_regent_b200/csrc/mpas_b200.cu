@@ -395,6 +395,13 @@ int t_divdamp(mpasb200_t* h, double dts) {
   const Range re_ = range_of(h, MPASB200_EDGE, h->nEdges);
   if (re_.n > 0) {            // persistent: 9 resident blocks per SM loop over the edge tiles
     const int tiles = (re_.n + h->CPB - 1) / h->CPB;
+    if (h->c.chunk_tiles > 0) {                       // EXPERIMENTAL: contiguous tiles per block (kernels.cuh)
+      const int chunk = h->c.chunk_tiles;
+      KTimer kt_(h, "k_divdamp_chunked");
+      k_divdamp_chunked<<<(tiles + chunk - 1) / chunk, dim3(h->LP / 2, h->CPB), 0, h->stream>>>(ranged(h, re_), coef_divdamp, chunk);
+      h->launches++;
+      return post_launch(h);
+    }
     KTimer kt_(h, "k_divdamp");
     k_divdamp<<<std::min(tiles, h->num_sms * 9), dim3(h->LP / 2, h->CPB), 0, h->stream>>>(ranged(h, re_), coef_divdamp);
     h->launches++;
