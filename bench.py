@@ -35,6 +35,10 @@ METRIC = "cell_level_updates_per_s"
 UNIT = "cell-levels/s"
 DT_REF = 720.0           # constants.rg:99, scaled with resolution to keep the CFL number
 E2E_FIELDS = ("u", "ru", "w", "theta_m", "rho_zz", "rw", "rho_p", "rtheta_p", "exner", "pressure_p")
+# fields scanned by the device form of summarize_timestep (rk_timestep.rg:29-359) after the timed loop: the prognostic state,
+# the acoustic perturbation variables and the tendencies / diagnostics every task of the step feeds into
+CHECK_FIELDS = ("u", "w", "theta_m", "rho_zz", "ru", "rw", "rho_p", "rtheta_p", "rtheta_pp", "rho_pp", "rw_p", "ru_p", "wwAvg",
+                "ruAvg", "tend_u", "tend_theta", "tend_rho", "pv_edge", "ke", "divergence", "vorticity", "v")
 
 
 def dt_for(n_cells: int) -> float:
@@ -119,6 +123,42 @@ def build_inputs(n_cells: int, L: int):
     except OSError:
         pass
     return st.mesh, st, time.time() - t0
+
+
+def run_check(g, lm=None, dist=None, world=1):
+    """min / max / NaN / Inf / bit checksum per field over the OWNED entities (mpasb200_summarize_field), merged over ranks.
+    Every merge is exact and order-independent, so the result must be identical at every N when the N-rank step is
+    bit-identical to the single-partition one."""
+    from mpas_regent_b200 import _abi
+    if lm is not None:
+        for ent, ids in ((_abi.CELL, lm.cells), (_abi.EDGE, lm.edges), (_abi.VERTEX, lm.vertices)):
+            g.set_global_ids(ent, ids)
+    loc = {}
+    for n in CHECK_FIELDS:
+        ent = _abi.FIELD_ENTITY[n]
+        loc[n] = g.summarize_field(n, None if lm is None else lm.n_owned[ent])
+    parts = [loc]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, loc)
+    return merge_checks(parts)
+
+
+def merge_checks(parts):
+    """merge per-rank summaries (owned entities, global ids): min / max with the first place, sums, checksum mod 2^64"""
+    out, comb, finite = {}, 0, True
+    for i, n in enumerate(CHECK_FIELDS):
+        ps = [p[n] for p in parts]
+        lo = min(ps, key=lambda p: (p["min"], p["min_at"] if p["min_at"][0] >= 0 else [1 << 62, 0]))
+        hi = min(ps, key=lambda p: (-p["max"], p["max_at"] if p["max_at"][0] >= 0 else [1 << 62, 0]))
+        cs = sum(int(p["checksum"], 16) for p in ps) & ((1 << 64) - 1)
+        out[n] = {"min": lo["min"], "min_at": lo["min_at"], "max": hi["max"], "max_at": hi["max_at"],
+                  "n_nan": sum(p["n_nan"] for p in ps), "n_inf": sum(p["n_inf"] for p in ps),
+                  "count": sum(p["count"] for p in ps), "checksum": f"{cs:016x}"}
+        finite = finite and out[n]["n_nan"] == 0 and out[n]["n_inf"] == 0
+        comb = (comb * 0x100000001b3 + cs + i) & ((1 << 64) - 1)
+    return {"what": "summarize_timestep (rk_timestep.rg:29-359) on the device over owned entities after the timed loop",
+            "finite": finite, "combined_checksum": f"{comb:016x}", "fields": out}
 
 
 def host_threads() -> int:
@@ -264,10 +304,10 @@ def main():
         for _ in range(max(args.warmup, 3)):
             step()
         g.sync()
-        g.reset_kernel_timing(); g.enable_kernel_timing(True)
         launches0 = g.launch_count
         sampler = ClockSampler(local_rank) if rank == 0 else None
         torch.cuda.synchronize(); barrier()
+        # ---- the timed region: K steps, nothing else on the stream (per-kernel events are a separate pass below) ----
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
@@ -277,10 +317,28 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize(); barrier()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler else {}
         launches = g.launch_count - launches0
+        # ---- the same K steps again with a CUDA-event pair around every launch (on the launching stream): per-kernel times.
+        # Kept out of the headline region because two event records per launch inflate a step of ~100 short kernels;
+        # graph replay is off here (events cannot bracket the nodes of a replayed graph).
+        k_steps = min(args.steps, 5)
+        if args.graph:
+            g.set_use_graph(False)
+        g.reset_kernel_timing(); g.enable_kernel_timing(True)
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        for _ in range(k_steps):
+            step()
+        if world > 1:
+            run.flush()
+        e3.record(stream)
+        torch.cuda.synchronize(); barrier()
+        ms_k = e2.elapsed_time(e3)
+        clocks = sampler.stop() if sampler else {}
         ktimes = g.kernel_times()
         g.enable_kernel_timing(False)
+        if args.graph:
+            g.set_use_graph(True)
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -289,6 +347,10 @@ def main():
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
         launches = int(tl.item())
     value = n_owned_total * L * args.steps / (ms * 1e-3)
+    # ---- the step's own sanity scan, before anything else touches the state ----
+    with torch.cuda.stream(stream):
+        check = run_check(g, run.lm if world > 1 else None, dist if world > 1 else None, world)
+    check["steps_from_initial_state"] = max(args.warmup, 3) + args.steps + k_steps
 
     # ---- roofline of the dominant kernel (rank 0's kernels; cells of this rank) ----
     peak, peak_src = peaks()
@@ -301,13 +363,19 @@ def main():
             u = traffic.units(key, scratch=False)
             bytes_per_launch = u * 8.0 * n_local * L
             achieved = bytes_per_launch / (kms / kn * 1e-3) / 1e9
-            traffic_bytes = None        # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch: NOT measured in this run (ncu cannot run under a bench) --
+            # taken from the committed ncu capture and stamped with where it came from, so a stale entry is visible
+            traffic_bytes, traffic_src = None, None
             tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if world == 1 and nC == 655362 and L == 55 and os.path.exists(tj):
-                traffic_bytes = json.load(open(tj))["bytes_per_launch"].get(name)
+                td = json.load(open(tj))
+                traffic_bytes = td["bytes_per_launch"].get(name)
+                traffic_src = {k: td.get(k) for k in ("source", "kernel_source_commit", "captured")}
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic_bytes, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                    "avg_launch_ms": kms / kn, "launches_timed": kn, "share_of_step": kms / ms}
+                    "traffic": traffic_bytes, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "avg_launch_ms": kms / kn, "launches_timed": kn, "share_of_step": kms / ms_k,
+                    "timed_over": f"{k_steps} steps with an event pair per launch ({ms_k / k_steps:.3f} ms/step; the headline "
+                                  f"region runs without them)"}
     step_units = traffic.step_units(True, scratch=False, corrected_physics=True) if corrected else traffic.SURVEY_STEP_UNITS_CANONICAL
     step_bytes = step_units * 8.0 * nC * L
     step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
@@ -384,8 +452,8 @@ def main():
             "roofline": roof,
             "step_hbm": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs_per_gpu": step_gbs / world,
                          "frac_of_peak": step_gbs / world / peak},
-            "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in top},
-            "e2e": e2e, "cpu_baseline": cpu,
+            "kernels_ms_per_step": {k: round(v[0] / k_steps, 4) for k, v in top},
+            "e2e": e2e, "cpu_baseline": cpu, "check": check,
         }
         _emit(line)
     if world > 1:

@@ -232,6 +232,25 @@ int  mpasb200_rk_dynamics_substep_finish(mpasb200_t *h, int dynamics_substep, in
 int  mpasb200_srk3(mpasb200_t *h, double dt);
 int  mpasb200_timestep(mpasb200_t *h, double dt);
 
+/* ---- summarize_timestep  rk_timestep.rg:29-359 --------------------------------------------------- *
+ * The reference's per-step sanity scan (global min / max of a field with the place they occur, NaN scan; every branch
+ * is disabled by configuration there) as a device reduction, extended by an order-independent 64-bit checksum of the
+ * bit patterns so that runs on 1 and N GPUs can be compared bit for bit without moving the fields.
+ * The scan covers entities [0, n_first) of the caller's numbering (the owned entities of a partition come first) and
+ * levels [0, nlevels).  min / max ignore NaN (a comparison with NaN is false, :64); the place is the first one in
+ * (id, level) order, id = global id if mpasb200_set_global_ids was called for the entity type, else the caller's index.
+ * checksum = sum mod 2^64 over the scanned points of mix64(bits(v) + 0x9e3779b97f4a7c15 * (id * nlevels + level + 1)),
+ * mix64 = the splitmix64 finaliser, every NaN counted as 0x7ff8000000000000.  Synchronous (host-visible point).       */
+typedef struct {
+  double   min, max;                 /* +inf / -inf when nothing compares */
+  int64_t  min_index, max_index;     /* -1 when nothing compares */
+  int32_t  min_level, max_level;
+  int64_t  n_nan, n_inf, count;
+  uint64_t checksum;
+} MpasFieldSummary;
+int  mpasb200_set_global_ids(mpasb200_t *h, int entity, const int32_t *global_id, int32_t n);   /* null: back to identity */
+int  mpasb200_summarize_field(mpasb200_t *h, int field, int32_t n_first, int32_t nlevels, MpasFieldSummary *out);
+
 /* ---- halo exchange building blocks (one process per GPU; the wire is the host's job) ------ *
  * Lists are LOCAL entity indices in the caller's (un-renumbered) numbering.  pack gathers
  * `n` columns x `nfields` fields x (nVertLevels+1) levels into the contiguous device
@@ -249,6 +268,7 @@ int  mpasb200_unpack(mpasb200_t *h, int list_id, const int32_t *fields, int32_t 
 int  mpasb200_class_range(mpasb200_t *h, int entity, int cls, int32_t *begin, int32_t *end);
 int  mpasb200_set_range(mpasb200_t *h, int entity, int32_t begin, int32_t end);
 int  mpasb200_set_stream(mpasb200_t *h, void *cuda_stream);  /* null = the handle's own stream */
+int  mpasb200_set_use_graph(mpasb200_t *h, int on);          /* MpasConfig.use_graph after creation */
 
 /* ---- introspection --------------------------------------------------------------------- */
 int64_t mpasb200_launch_count(const mpasb200_t *h);   /* kernels launched so far by this handle */

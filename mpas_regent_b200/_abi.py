@@ -96,6 +96,18 @@ MESH_MEMBERS = (
 )
 
 
+class MpasFieldSummary(C.Structure):
+    """image of MpasFieldSummary (mpas_b200.h): the device form of summarize_timestep, rk_timestep.rg:29-359"""
+    _fields_ = [("min", C.c_double), ("max", C.c_double), ("min_index", C.c_int64), ("max_index", C.c_int64),
+                ("min_level", C.c_int32), ("max_level", C.c_int32), ("n_nan", C.c_int64), ("n_inf", C.c_int64),
+                ("count", C.c_int64), ("checksum", C.c_uint64)]
+
+    def as_dict(self):
+        return {"min": self.min, "max": self.max, "min_at": [int(self.min_index), int(self.min_level)],
+                "max_at": [int(self.max_index), int(self.max_level)], "n_nan": int(self.n_nan), "n_inf": int(self.n_inf),
+                "count": int(self.count), "checksum": f"{int(self.checksum):016x}"}
+
+
 class MpasMeshPtrs(C.Structure):
     _fields_ = [(n, C.c_void_p) for (n, _, _, _) in MESH_MEMBERS]
 

@@ -806,10 +806,14 @@ __global__ void __launch_bounds__(256, LB_CELLC) k_dt_cellC(const View V, const 
 }
 
 // ============================================================================================
-// atm_set_smlstep_pert_variables_work  :1503-1528  (levels 0..L-1 of the cells of cpr; level -1 reads 0)
+// atm_set_smlstep_pert_variables_work  :1503-1528.  `for iCell in cpr` (:1516) visits EVERY point of the region, so the
+// levels are 0..L inclusive (regions hold L+1 levels, main.rg:21-24); level -1 reads 0 (M3), level L uses whatever the
+// mirror holds there for fzm/fzp/zz/zb_cell/u_tend (zero until uploaded, M1).
 __global__ void k_smlstep(const View V, int nRelaxZone) {
   PAIR_THREAD(V.nCells)
-  if (!m0) return;
+  const bool a0 = inx && k0 <= L, a1 = inx && k1 <= L;        // level L included
+  (void)m0;
+  if (!a0) return;
   if (!V.inCpr[x] || V.bdyMaskCell[x] > nRelaxZone) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
   const double* ut = FLD(u_tend); const double* zb = FLD(zb_cell); const double* zb3 = FLD(zb3_cell);
@@ -825,7 +829,7 @@ __global__ void k_smlstep(const View V, int nRelaxZone) {
   }
   const D2 zz2 = ld2(FLD(zz), ix);
   wv *= (fm * zz2 + fp * below(FLD(zz), ix, k0, zz2));
-  st2m(FLD(w), ix, wv, m0, m1);
+  st2m(FLD(w), ix, wv, a0, a1);
 }
 
 // ============================================================================================
@@ -1744,172 +1748,67 @@ __global__ void k_unpack(const PackArgs A, const int* __restrict__ idx, int n, i
 }
 
 // ============================================================================================
-// EXPERIMENTAL variants of k_divdamp used to measure which latency-hiding structure pays on B200
-// (profiles/r1_divdamp_variants.md).  Selected through mpasb200_debug_divdamp only.
-// V1: skip flag and ecv fetched together, own-column load issued before the dependent gathers
-__global__ void k_divdamp_v1(const View V, double coef_divdamp) {
-  PAIR_THREAD(V.nEdges)
-  if (!m0) return;
-  const unsigned char skip = V.divdampSkip[x];
-  const int4 cv = V.ecv[x];
-  const D2 r = ld2(FLD(ru_p), ix);
-  const double sz = 1.0 - V.specZoneMaskEdge[x];
-  if (skip) return;
-  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
-  const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
-  st2m(FLD(ru_p), ix, r + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), m0, m1);
+// summarize_timestep  rk_timestep.rg:29-359: global min / max of a field with the place they occur, plus what the
+// reference's (disabled) NaN scan looks for, plus an order-independent 64-bit checksum of the bit patterns.
+// The scan covers the first n caller-numbered entities (the owned ones of a partition) and levels [0, nlev).
+// Every reduction here is commutative and exact (min, max, integer add mod 2^64), so the result does not depend
+// on the block schedule, on the renumbering or on how many ranks share the mesh; atomics are therefore harmless
+// (this is the checker of the step, not one of its stencils).
+struct SumAcc { unsigned long long kmin, kmax, n_nan, n_inf, checksum, loc_min, loc_max; };
+DI unsigned long long ord_key(double v) {            // monotone map double -> uint64 (NaN never gets here)
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
 }
-// V2: V1 + every block prefetches the index words of the block that will run ~one wave later into L2
-__global__ void k_divdamp_v2(const View V, double coef_divdamp, int ahead) {
-  PAIR_THREAD(V.nEdges)
+DI unsigned long long mix64(unsigned long long z) {  // splitmix64 finaliser
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL; return z ^ (z >> 31);
+}
+__global__ void k_summarize(const double* __restrict__ field, const int* __restrict__ map, const int* __restrict__ gid,
+                            int n, int nlev, int LP, SumAcc* __restrict__ acc) {
+  __shared__ unsigned long long s[5][8];
+  unsigned long long kmin = ~0ULL, kmax = 0ULL, nn = 0, ni = 0, cs = 0;
+  const size_t total = (size_t)n * nlev;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / nlev), k = (int)(t % nlev);
+    const double v = field[(size_t)map[i] * LP + k];
+    unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    if (v != v) { nn++; bits = 0x7ff8000000000000ULL; }      // one canonical NaN: payloads differ between CPU and GPU
+    else {
+      if (isinf(v)) ni++;
+      const unsigned long long key = ord_key(v);
+      kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
+    }
+    const unsigned long long id = (unsigned long long)(gid ? gid[i] : i) * (unsigned long long)nlev + (unsigned long long)k + 1ULL;
+    cs += mix64(bits + 0x9e3779b97f4a7c15ULL * id);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long a = __shfl_down_sync(0xffffffffu, kmin, o), b = __shfl_down_sync(0xffffffffu, kmax, o);
+    kmin = a < kmin ? a : kmin; kmax = b > kmax ? b : kmax;
+    nn += __shfl_down_sync(0xffffffffu, nn, o); ni += __shfl_down_sync(0xffffffffu, ni, o); cs += __shfl_down_sync(0xffffffffu, cs, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s[0][w] = kmin; s[1][w] = kmax; s[2][w] = nn; s[3][w] = ni; s[4][w] = cs; }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    const long xa = (long)x + (long)ahead * blockDim.y;
-    if (xa < V.nEdges) { prefetch_l2(&V.ecv[xa]); prefetch_l2(&V.divdampSkip[xa]); prefetch_l2(&V.specZoneMaskEdge[xa]); }
-  }
-  if (!m0) return;
-  const unsigned char skip = V.divdampSkip[x];
-  const int4 cv = V.ecv[x];
-  const D2 r = ld2(FLD(ru_p), ix);
-  const double sz = 1.0 - V.specZoneMaskEdge[x];
-  if (skip) return;
-  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
-  const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
-  st2m(FLD(ru_p), ix, r + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), m0, m1);
-}
-// V3: two edges per thread (x and x + half), all 14 gathers in flight together
-__global__ void k_divdamp_v3(const View V, double coef_divdamp) {
-  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;
-  const int LP = V.LP, L = V.L;
-  const int half = (V.nEdges + 1) / 2;
-  const int xa = blockIdx.x * blockDim.y + threadIdx.y, xb = xa + half;
-  const bool ina = xa < half && k0 < L, inb = xb < V.nEdges && xa < half && k0 < L;
-  if (!ina) return;
-  const bool m1 = k1 < L;
-  const size_t ia = (size_t)xa * LP + k0, ib = (size_t)(inb ? xb : xa) * LP + k0;
-  const unsigned char sa = V.divdampSkip[xa], sb = inb ? V.divdampSkip[xb] : 1;
-  const int4 ca = V.ecv[xa], cb = V.ecv[inb ? xb : xa];
-  const D2 ra = ld2(FLD(ru_p), ia), rb = ld2(FLD(ru_p), ib);
-  const double za = 1.0 - V.specZoneMaskEdge[xa], zb = 1.0 - V.specZoneMaskEdge[inb ? xb : xa];
-  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
-  const D2 a1 = G2(rpp, ca.x), b1 = G2(rppo, ca.x), a2 = G2(rpp, ca.y), b2 = G2(rppo, ca.y), t1 = G2(tm, ca.x), t2 = G2(tm, ca.y);
-  const D2 c1 = G2(rpp, cb.x), d1 = G2(rppo, cb.x), c2 = G2(rpp, cb.y), d2 = G2(rppo, cb.y), u1 = G2(tm, cb.x), u2 = G2(tm, cb.y);
-  if (!sa) st2m(FLD(ru_p), ia, ra + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * za / (t1 + t2), true, m1);
-  if (!sb) st2m(FLD(ru_p), ib, rb + coef_divdamp * ((-(c2 - d2)) - (-(c1 - d1))) * zb / (u1 + u2), true, m1);
-}
-// V4: persistent blocks looping over edge tiles, the next tile's index words are loaded before the
-// current tile's gathers are consumed
-__global__ void k_divdamp_v4(const View V, double coef_divdamp) {
-  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;
-  const int LP = V.LP, L = V.L;
-  if (k0 >= L) return;
-  const bool m1 = k1 < L;
-  const int stride = gridDim.x * blockDim.y;
-  int x = blockIdx.x * blockDim.y + threadIdx.y;
-  if (x >= V.nEdges) return;
-  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
-  int4 cv = V.ecv[x]; unsigned char skip = V.divdampSkip[x]; double sz = 1.0 - V.specZoneMaskEdge[x];
-  D2 r = ld2(FLD(ru_p), (size_t)x * LP + k0);
-  while (true) {
-    const int xn = x + stride;
-    const bool more = xn < V.nEdges;
-    const int xs = more ? xn : x;
-    const int4 cvn = V.ecv[xs]; const unsigned char skn = V.divdampSkip[xs]; const double szn = 1.0 - V.specZoneMaskEdge[xs];
-    const D2 rn = ld2(FLD(ru_p), (size_t)xs * LP + k0);
-    if (!skip) {
-      const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
-      st2m(FLD(ru_p), (size_t)x * LP + k0, r + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), true, m1);
+    for (int j = 1; j < (int)(blockDim.x >> 5); ++j) {
+      kmin = s[0][j] < kmin ? s[0][j] : kmin; kmax = s[1][j] > kmax ? s[1][j] : kmax; nn += s[2][j]; ni += s[3][j]; cs += s[4][j];
     }
-    if (!more) break;
-    x = xn; cv = cvn; skip = skn; sz = szn; r = rn;
+    atomicMin(&acc->kmin, kmin); atomicMax(&acc->kmax, kmax);
+    atomicAdd(&acc->n_nan, nn); atomicAdd(&acc->n_inf, ni); atomicAdd(&acc->checksum, cs);
   }
 }
-// V5: four levels per thread (two 128-bit words), half the threads per column
-__global__ void k_divdamp_v5(const View V, double coef_divdamp) {
-  const int k0 = 4 * (int)threadIdx.x;
-  const int LP = V.LP, L = V.L;
-  const int x = blockIdx.x * blockDim.y + threadIdx.y;
-  if (x >= V.nEdges || k0 >= L) return;
-  const size_t ix = (size_t)x * LP + k0;
-  const unsigned char skip = V.divdampSkip[x];
-  const int4 cv = V.ecv[x];
-  const D2 r0 = ld2(FLD(ru_p), ix), r1 = ld2(FLD(ru_p), ix + 2);
-  const double sz = 1.0 - V.specZoneMaskEdge[x];
-  if (skip) return;
-  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
-  const size_t i1 = (size_t)cv.x * LP + k0, i2 = (size_t)cv.y * LP + k0;
-  const D2 a1 = ld2(rpp, i1), b1 = ld2(rppo, i1), a2 = ld2(rpp, i2), b2 = ld2(rppo, i2), t1 = ld2(tm, i1), t2 = ld2(tm, i2);
-  const D2 A1 = ld2(rpp, i1 + 2), B1 = ld2(rppo, i1 + 2), A2 = ld2(rpp, i2 + 2), B2 = ld2(rppo, i2 + 2), T1 = ld2(tm, i1 + 2), T2 = ld2(tm, i2 + 2);
-  st2m(FLD(ru_p), ix, r0 + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), true, k0 + 1 < L);
-  st2m(FLD(ru_p), ix + 2, r1 + coef_divdamp * ((-(A2 - B2)) - (-(A1 - B1))) * sz / (T1 + T2), k0 + 2 < L, k0 + 3 < L);
-}
-// V6: one-wave-ahead L2 prefetch of DATA as well as index words.  Exact: the index word of the tile `ahead`
-// blocks later (itself prefetched 2*ahead earlier) is loaded and the gather lines it points to are prefetched.
-DI void prefetch_col(const double* p, size_t col, int LP, int k0) { prefetch_l2(p + col * LP + k0); }
-__global__ void k_divdamp_v6(const View V, double coef_divdamp, int ahead) {
-  PAIR_THREAD(V.nEdges)
-  const bool pf_lane = (threadIdx.x & 7) == 0;          // one lane per 128-byte line of a column
-  const long xa = (long)x + (long)ahead * blockDim.y, xb = (long)x + 2L * ahead * blockDim.y;
-  unsigned char skip = 1; int4 cv = make_int4(0, 0, 0, 0); D2 r = bc(0); double sz = 0;
-  if (m0) {
-    skip = V.divdampSkip[x]; cv = V.ecv[x]; r = ld2(FLD(ru_p), ix); sz = 1.0 - V.specZoneMaskEdge[x];
-  }
-  if (pf_lane && k0 < V.L) {
-    if (xb < V.nEdges && threadIdx.x == 0) { prefetch_l2(&V.ecv[xb]); prefetch_l2(&V.divdampSkip[xb]); prefetch_l2(&V.specZoneMaskEdge[xb]); }
-    if (xa < V.nEdges) {
-      const int4 ca = V.ecv[xa];
-      prefetch_col(FLD(ru_p), xa, LP, k0);
-      prefetch_col(FLD(rtheta_pp), ca.x, LP, k0); prefetch_col(FLD(rtheta_pp_old), ca.x, LP, k0); prefetch_col(FLD(theta_m), ca.x, LP, k0);
-      prefetch_col(FLD(rtheta_pp), ca.y, LP, k0); prefetch_col(FLD(rtheta_pp_old), ca.y, LP, k0); prefetch_col(FLD(theta_m), ca.y, LP, k0);
-    }
-  }
-  if (!m0 || skip) return;
-  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
-  const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
-  st2m(FLD(ru_p), ix, r + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), m0, m1);
-}
-// V7: V4 (persistent, next tile's index words in registers) with four levels per thread
-__global__ void k_divdamp_v7(const View V, double coef_divdamp) {
-  const int k0 = 4 * (int)threadIdx.x;
-  const int LP = V.LP, L = V.L;
-  if (k0 >= L) return;
-  const int stride = gridDim.x * blockDim.y;
-  int x = blockIdx.x * blockDim.y + threadIdx.y;
-  if (x >= V.nEdges) return;
-  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
-  int4 cv = V.ecv[x]; unsigned char skip = V.divdampSkip[x]; double sz = 1.0 - V.specZoneMaskEdge[x];
-  D2 r0 = ld2(FLD(ru_p), (size_t)x * LP + k0), r1 = ld2(FLD(ru_p), (size_t)x * LP + k0 + 2);
-  while (true) {
-    const int xn = x + stride;
-    const bool more = xn < V.nEdges;
-    const int xs = more ? xn : x;
-    const int4 cvn = V.ecv[xs]; const unsigned char skn = V.divdampSkip[xs]; const double szn = 1.0 - V.specZoneMaskEdge[xs];
-    const D2 rn0 = ld2(FLD(ru_p), (size_t)xs * LP + k0), rn1 = ld2(FLD(ru_p), (size_t)xs * LP + k0 + 2);
-    if (!skip) {
-      const size_t i1 = (size_t)cv.x * LP + k0, i2 = (size_t)cv.y * LP + k0, ix = (size_t)x * LP + k0;
-      const D2 a1 = ld2(rpp, i1), b1 = ld2(rppo, i1), a2 = ld2(rpp, i2), b2 = ld2(rppo, i2), t1 = ld2(tm, i1), t2 = ld2(tm, i2);
-      const D2 A1 = ld2(rpp, i1 + 2), B1 = ld2(rppo, i1 + 2), A2 = ld2(rpp, i2 + 2), B2 = ld2(rppo, i2 + 2), T1 = ld2(tm, i1 + 2), T2 = ld2(tm, i2 + 2);
-      st2m(FLD(ru_p), ix, r0 + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), true, k0 + 1 < L);
-      st2m(FLD(ru_p), ix + 2, r1 + coef_divdamp * ((-(A2 - B2)) - (-(A1 - B1))) * sz / (T1 + T2), k0 + 2 < L, k0 + 3 < L);
-    }
-    if (!more) break;
-    x = xn; cv = cvn; skip = skn; sz = szn; r0 = rn0; r1 = rn1;
-  }
-}
-// V8: persistent tile loop WITHOUT next-tile prefetch (isolates the effect of block scheduling overhead)
-__global__ void k_divdamp_v8(const View V, double coef_divdamp) {
-  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;
-  const int LP = V.LP, L = V.L;
-  if (k0 >= L) return;
-  const bool m1 = k1 < L;
-  const int stride = gridDim.x * blockDim.y;
-  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
-  for (int x = blockIdx.x * blockDim.y + threadIdx.y; x < V.nEdges; x += stride) {
-    if (V.divdampSkip[x]) continue;
-    const int4 cv = V.ecv[x];
-    const size_t ix = (size_t)x * LP + k0;
-    const D2 r = ld2(FLD(ru_p), ix);
-    const double sz = 1.0 - V.specZoneMaskEdge[x];
-    const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
-    st2m(FLD(ru_p), ix, r + coef_divdamp * ((-(a2 - b2)) - (-(a1 - b1))) * sz / (t1 + t2), true, m1);
+// second pass: the FIRST place, in (entity id, level) order, where the extreme values occur (the reference keeps the
+// first hit of a strict comparison, rk_timestep.rg:62-72)
+__global__ void k_summarize_loc(const double* __restrict__ field, const int* __restrict__ map, const int* __restrict__ gid,
+                                int n, int nlev, int LP, SumAcc* __restrict__ acc) {
+  const unsigned long long kmin = acc->kmin, kmax = acc->kmax;
+  const size_t total = (size_t)n * nlev;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / nlev), k = (int)(t % nlev);
+    const double v = field[(size_t)map[i] * LP + k];
+    if (v != v) continue;
+    const unsigned long long key = ord_key(v);
+    const unsigned long long id = (unsigned long long)(gid ? gid[i] : i) * (unsigned long long)nlev + (unsigned long long)k;
+    if (key == kmin) atomicMin(&acc->loc_min, id);
+    if (key == kmax) atomicMin(&acc->loc_max, id);
   }
 }

@@ -18,6 +18,9 @@
 #include <vector>
 
 #include "kernels.cuh"
+#ifdef MPASB200_LAB
+#include "kernels_lab.cuh"
+#endif
 
 namespace {
 
@@ -48,7 +51,7 @@ struct mpasb200 {
   View V;                               // device pointers
   std::vector<void*> allocs;            // everything cudaMalloc'ed
   int64_t bytes = 0;
-  bool mesh_ok = false;
+  bool mesh_ok = false, mesh_started = false;
   // renumbering: newOf[entity][old] = internal index (size n+1, pad -> pad)
   std::vector<int> newOf[3];
   // launch classes (MpasMeshPtrs.cellClass / edgeClass): internal numbering is class-major, classBegin[ent][c] .. classBegin[ent][c+1]
@@ -79,6 +82,8 @@ struct mpasb200 {
   std::vector<KStat> kstats;
   std::map<double, std::pair<cudaGraphExec_t, int64_t>> graphs;   // dt -> (exec, kernel launches per replay)
   std::vector<HaloList> lists;
+  int* d_gid[3] = {nullptr, nullptr, nullptr}; int n_gid[3] = {0, 0, 0};   // mpasb200_set_global_ids
+  SumAcc* d_acc = nullptr;
   std::string err;
   std::mutex mu;
 };
@@ -200,13 +205,17 @@ struct KTimer {      // brackets one launch with an event pair when kernel timin
     if (h->ktiming && !h->capturing) { id = kstat_id(h, name); a = pool_event(h); cudaEventRecord(a, h->stream); }
   }
   ~KTimer() {
-    if (a) { cudaEvent_t b = pool_event(h); cudaEventRecord(b, h->stream); h->pending.push_back({id, a, b}); }
+    if (a) { cudaEvent_t b = pool_event(h); cudaEventRecord(b, h->stream); h->pending.push_back({id, a, b}); }   // same stream as `a`: one LAUNCH
   }
 };
 void drain_kernel_times(mpasb200_t* h) {
   if (h->pending.empty()) return;
-  cudaStreamSynchronize(h->stream);
-  for (auto& p : h->pending) { float ms = 0; cudaEventElapsedTime(&ms, p.a, p.b); h->kstats[p.stat].ms += ms; h->kstats[p.stat].n++; }
+  // events may sit on any stream the handle was pointed at (mpasb200_set_stream): wait for each pair itself
+  for (auto& p : h->pending) {
+    float ms = 0;
+    if (cudaEventSynchronize(p.b) != cudaSuccess || cudaEventElapsedTime(&ms, p.a, p.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    h->kstats[p.stat].ms += ms; h->kstats[p.stat].n++;
+  }
   h->pending.clear(); h->ev_used = 0;
 }
 
@@ -592,6 +601,8 @@ int mpasb200_destroy(mpasb200_t* h) {
   for (auto& l : h->lists) if (l.d_idx) cudaFree(l.d_idx);
   if (h->d_stage) cudaFree(h->d_stage);
   if (h->h_stage) cudaFreeHost(h->h_stage);
+  for (int e = 0; e < 3; ++e) if (h->d_gid[e]) cudaFree(h->d_gid[e]);
+  if (h->d_acc) cudaFree(h->d_acc);
   for (auto& pp : h->pipe) {
     if (pp.up) cudaFree(pp.up);
     if (pp.dn) cudaFree(pp.dn);
@@ -611,6 +622,9 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
   std::unique_lock<std::mutex> lk(h->mu);
   cudaSetDevice(h->device);
   if (h->mesh_ok) return fail(h, MPASB200_ESTATE, "upload_mesh may be called once per handle");
+  // a failed upload leaves a half-built mirror (its allocations are released by mpasb200_destroy): the handle is unusable
+  if (h->mesh_started) return fail(h, MPASB200_ESTATE, "a previous upload_mesh failed on this handle; destroy it and create a new one");
+  h->mesh_started = true;
   if (!m->nEdgesOnCell || !m->edgesOnCell || !m->cellsOnEdge || !m->verticesOnEdge || !m->edgesOnVertex)
     return fail(h, MPASB200_EINVAL, "nEdgesOnCell, edgesOnCell, cellsOnEdge, verticesOnEdge, edgesOnVertex are required");
   const int nC = h->nCells, nE = h->nEdges, nV = h->nVertices, pol = h->c.index_policy;
@@ -644,7 +658,7 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
         hk = hilbert3(q(x), q(y), q(z));
       }
       const int cls = m->cellClass ? m->cellClass[c] : 0;
-      if (cls > 3) return fail(h, MPASB200_EINVAL, "cellClass must be 0..3");
+      if (cls < 0 || cls > 3) return fail(h, MPASB200_EINVAL, "cellClass must be 0..3");
       key[c] = {{cls, hk}, c};
     }
     std::sort(key.begin(), key.end());
@@ -657,7 +671,7 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
     for (int e = 0; e < nE; ++e) {
       const uint64_t a = cNew[resolve(m->cellsOnEdge[e * 2], nC, pol)], b = cNew[resolve(m->cellsOnEdge[e * 2 + 1], nC, pol)];
       const int cls = m->edgeClass ? m->edgeClass[e] : 0;
-      if (cls > 3) return fail(h, MPASB200_EINVAL, "edgeClass must be 0..3");
+      if (cls < 0 || cls > 3) return fail(h, MPASB200_EINVAL, "edgeClass must be 0..3");
       ek[e] = {{cls, sfc ? ((std::min(a, b) << 32) | std::max(a, b)) : (uint64_t)e}, e};
     }
     std::sort(ek.begin(), ek.end());
@@ -977,8 +991,11 @@ int mpasb200_class_range(mpasb200_t* h, int entity, int cls, int32_t* begin, int
 int mpasb200_set_range(mpasb200_t* h, int entity, int32_t begin, int32_t end) {
   if (!h || entity < 0 || entity > 2) return MPASB200_EINVAL;
   std::unique_lock<std::mutex> lk(h->mu);
+  if (end >= 0 && begin >= 0 && end < begin) return fail(h, MPASB200_EINVAL, "set_range: end < begin");
+  // a captured atm_srk3 graph has the launch ranges baked in: drop the cache whenever a range changes
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.second.first);
+  h->graphs.clear();
   if (begin < 0 || end < 0) { h->rangeSet[entity] = false; return 0; }
-  if (end < begin) return fail(h, MPASB200_EINVAL, "set_range: end < begin");
   h->rangeB[entity] = begin; h->rangeE[entity] = end; h->rangeSet[entity] = true;
   return 0;
 }
@@ -986,6 +1003,13 @@ int mpasb200_set_stream(mpasb200_t* h, void* s) {
   if (!h) return MPASB200_EINVAL;
   std::unique_lock<std::mutex> lk(h->mu);
   h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return 0;
+}
+
+int mpasb200_set_use_graph(mpasb200_t* h, int on) {
+  if (!h) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  h->c.use_graph = on != 0;
   return 0;
 }
 
@@ -1083,6 +1107,56 @@ static int pack_unpack(mpasb200_t* h, int list_id, const int32_t* fields, int32_
 int mpasb200_pack(mpasb200_t* h, int list_id, const int32_t* fields, int32_t nfields, void* d_buf) { return pack_unpack(h, list_id, fields, nfields, d_buf, true); }
 int mpasb200_unpack(mpasb200_t* h, int list_id, const int32_t* fields, int32_t nfields, const void* d_buf) { return pack_unpack(h, list_id, fields, nfields, const_cast<void*>(d_buf), false); }
 
+// ---- summarize_timestep (rk_timestep.rg:29-359) as a device scan ------------------------------------------------------
+int mpasb200_set_global_ids(mpasb200_t* h, int entity, const int32_t* gid, int32_t n) {
+  REQUIRE_MESH();
+  if (entity < 0 || entity > MPASB200_VERTEX) return fail(h, MPASB200_EINVAL, "set_global_ids: bad entity");
+  std::unique_lock<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  if (h->d_gid[entity]) { cudaFree(h->d_gid[entity]); h->d_gid[entity] = nullptr; h->n_gid[entity] = 0; }
+  if (!gid) return 0;
+  if (n < 0 || n > entity_count(h, entity)) return fail(h, MPASB200_EINVAL, "set_global_ids: n out of range");
+  for (int i = 0; i < n; ++i) if (gid[i] < 0) return fail(h, MPASB200_EINVAL, "set_global_ids: negative id");
+  if (n > 0) {
+    CK(cudaMalloc((void**)&h->d_gid[entity], sizeof(int) * n));
+    CK(cudaMemcpy(h->d_gid[entity], gid, sizeof(int) * n, cudaMemcpyHostToDevice));
+  }
+  h->n_gid[entity] = n;
+  return 0;
+}
+int mpasb200_summarize_field(mpasb200_t* h, int field, int32_t n_first, int32_t nlevels, MpasFieldSummary* out) {
+  REQUIRE_MESH();
+  if (!out || field < 0 || field >= MPASB200_F_COUNT) return fail(h, MPASB200_EINVAL, "summarize_field: bad argument");
+  const FieldInfo& fi = kFields[field];
+  if (fi.entity == MPASB200_VERTICAL || fi.slots != 1) return fail(h, MPASB200_EINVAL, "summarize_field: scalar 3-D fields only");
+  std::unique_lock<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  if (h->capturing) return fail(h, MPASB200_ESTATE, "summarize_field during graph capture");
+  const int n = entity_count(h, fi.entity);
+  if (n_first < 0 || n_first > n || nlevels < 1 || nlevels > h->L1) return fail(h, MPASB200_EINVAL, "summarize_field: range");
+  const int* gid = h->d_gid[fi.entity];
+  if (gid && h->n_gid[fi.entity] < n_first) return fail(h, MPASB200_EINVAL, "summarize_field: fewer global ids than entities scanned");
+  if (!h->d_acc) CK(cudaMalloc((void**)&h->d_acc, sizeof(SumAcc)));
+  SumAcc a; a.kmin = ~0ULL; a.kmax = 0ULL; a.n_nan = a.n_inf = a.checksum = 0ULL; a.loc_min = a.loc_max = ~0ULL;
+  CK(cudaMemcpyAsync(h->d_acc, &a, sizeof(a), cudaMemcpyHostToDevice, h->stream));
+  const size_t total = (size_t)n_first * nlevels;
+  if (total > 0) {
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 16);
+    { KTimer kt_(h, "k_summarize"); k_summarize<<<blocks, 256, 0, h->stream>>>(h->V.f[field], h->d_newOf[fi.entity], gid, n_first, nlevels, h->LP, h->d_acc); h->launches++; }
+    { KTimer kt_(h, "k_summarize_loc"); k_summarize_loc<<<blocks, 256, 0, h->stream>>>(h->V.f[field], h->d_newOf[fi.entity], gid, n_first, nlevels, h->LP, h->d_acc); h->launches++; }
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(&a, h->d_acc, sizeof(a), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  auto unkey = [](unsigned long long k) { unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k; double v; std::memcpy(&v, &b, 8); return v; };
+  const bool any = a.kmin <= a.kmax;
+  out->min = any ? unkey(a.kmin) : INFINITY; out->max = any ? unkey(a.kmax) : -INFINITY;
+  out->min_index = any ? (int64_t)(a.loc_min / (unsigned long long)nlevels) : -1; out->min_level = any ? (int32_t)(a.loc_min % (unsigned long long)nlevels) : -1;
+  out->max_index = any ? (int64_t)(a.loc_max / (unsigned long long)nlevels) : -1; out->max_level = any ? (int32_t)(a.loc_max % (unsigned long long)nlevels) : -1;
+  out->n_nan = (int64_t)a.n_nan; out->n_inf = (int64_t)a.n_inf; out->count = (int64_t)total; out->checksum = a.checksum;
+  return 0;
+}
+
 // ---- introspection ------------------------------------------------------------------------------------------------
 int64_t mpasb200_launch_count(const mpasb200_t* h) { return h ? h->launches : 0; }
 int64_t mpasb200_device_bytes(const mpasb200_t* h) { return h ? h->bytes : 0; }
@@ -1098,6 +1172,7 @@ int mpasb200_field_by_name(const char* name) {
   for (int i = 0; i < MPASB200_F_COUNT; ++i) if (!std::strcmp(name, kFields[i].name)) return i;
   return -1;
 }
+#ifdef MPASB200_LAB
 // Experimental launch variants of the divergence-damping kernel (not part of the public header): used by
 // profiles/ scripts to measure latency-hiding structures.  variant 0 = production kernel.
 int mpasb200_debug_divdamp(mpasb200_t* h, int variant, double dts, int arg) {
@@ -1150,6 +1225,7 @@ int mpasb200_debug_acoustic(mpasb200_t* h, int abl, double dts) {
   h->launches++;
   return post_launch(h);
 }
+#endif  // MPASB200_LAB
 int mpasb200_enable_kernel_timing(mpasb200_t* h, int on) {
   if (!h) return MPASB200_EINVAL;
   std::unique_lock<std::mutex> lk(h->mu);
@@ -1177,14 +1253,16 @@ int mpasb200_kernel_time(mpasb200_t* h, int idx, const char** name, double* ms, 
   if (launches) *launches = h->kstats[idx].n;
   return 0;
 }
-int mpasb200_enable_timing(mpasb200_t* h, int on) { if (!h) return MPASB200_EINVAL; h->timing = on != 0; return 0; }
+int mpasb200_enable_timing(mpasb200_t* h, int on) { if (!h) return MPASB200_EINVAL; std::unique_lock<std::mutex> lk(h->mu); h->timing = on != 0; return 0; }
 int mpasb200_reset_timing(mpasb200_t* h) {
   if (!h) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
   for (int i = 0; i < MPASB200_T_COUNT; ++i) { h->task_ms[i] = 0; h->task_calls[i] = 0; }
   return 0;
 }
 int mpasb200_task_time(mpasb200_t* h, int task, double* ms, int64_t* calls, const char** name) {
   if (!h || task < 0 || task >= MPASB200_T_COUNT) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
   if (ms) *ms = h->task_ms[task];
   if (calls) *calls = h->task_calls[task];
   if (name) *name = kTaskNames[task];

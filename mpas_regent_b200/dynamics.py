@@ -83,9 +83,13 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         lib.mpasb200_pack.argtypes = [H, I, C.c_void_p, C.c_int32, C.c_void_p]
         lib.mpasb200_unpack.argtypes = [H, I, C.c_void_p, C.c_int32, C.c_void_p]
         lib.mpasb200_set_stream.argtypes = [H, C.c_void_p]
+        lib.mpasb200_set_use_graph.argtypes, lib.mpasb200_set_use_graph.restype = [H, I], I
         lib.mpasb200_class_range.argtypes = [H, I, I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         lib.mpasb200_set_range.argtypes = [H, I, C.c_int32, C.c_int32]
         lib.mpasb200_class_range.restype = lib.mpasb200_set_range.restype = I
+        lib.mpasb200_set_global_ids.argtypes, lib.mpasb200_set_global_ids.restype = [H, I, C.c_void_p, C.c_int32], I
+        lib.mpasb200_summarize_field.argtypes = [H, I, C.c_int32, C.c_int32, C.POINTER(_abi.MpasFieldSummary)]
+        lib.mpasb200_summarize_field.restype = I
         lib.mpasb200_launch_count.argtypes, lib.mpasb200_launch_count.restype = [H], C.c_int64
         lib.mpasb200_device_bytes.argtypes, lib.mpasb200_device_bytes.restype = [H], C.c_int64
         lib.mpasb200_field_info.argtypes = [I, C.POINTER(I), C.POINTER(I), C.POINTER(C.c_char_p)]
@@ -296,6 +300,10 @@ class Dynamics(TaskAPI):
     def set_stream(self, cuda_stream: int):
         self._check(self._lib.mpasb200_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")
 
+    def set_use_graph(self, on: bool):
+        self._check(self._lib.mpasb200_set_use_graph(self._h, int(bool(on))), "set_use_graph")
+        self.cfg.use_graph = int(bool(on))
+
     def class_range(self, entity: int, cls: int):
         """[begin, end) of a launch class (MpasMeshPtrs.cellClass / edgeClass) in the library's internal order."""
         b, e = C.c_int32(0), C.c_int32(0)
@@ -316,6 +324,24 @@ class Dynamics(TaskAPI):
     def set_range(self, entity: int, begin: int = -1, end: int = -1):
         """restrict atm_advance_acoustic_step (cells) / atm_divergence_damping_3d (edges) to [begin, end); no arguments = everything."""
         self._check(self._lib.mpasb200_set_range(self._h, entity, begin, end), "set_range")
+
+    # ---- summarize_timestep (rk_timestep.rg:29-359) as a device scan ------------------------------------
+    def set_global_ids(self, entity: int, gid: Optional[np.ndarray]):
+        """global id of every local entity (partitions): summaries then report places / checksums in global numbering."""
+        if gid is None:
+            self._check(self._lib.mpasb200_set_global_ids(self._h, entity, None, 0), "set_global_ids")
+            return
+        gid = np.ascontiguousarray(gid, dtype=np.int32)
+        self._check(self._lib.mpasb200_set_global_ids(self._h, entity, gid.ctypes.data, gid.shape[0]), "set_global_ids")
+
+    def summarize_field(self, name: str, n_first: Optional[int] = None, nlevels: Optional[int] = None) -> dict:
+        """min / max (+ place), NaN / Inf counts and the order-independent bit checksum of the first ``n_first``
+        entities (default all) and levels [0, nlevels) (default all nVertLevels+1) of a scalar 3-D field."""
+        out = _abi.MpasFieldSummary()
+        n = self.entity_count(FIELD_ENTITY[name]) if n_first is None else int(n_first)
+        nl = self.dims.nVertLevels + 1 if nlevels is None else int(nlevels)
+        self._check(self._lib.mpasb200_summarize_field(self._h, FIELD_ID[name], n, nl, C.byref(out)), "summarize_field")
+        return out.as_dict()
 
     # ---- halo building blocks ------------------------------------------------------------------------
     def register_list(self, entity: int, idx: np.ndarray) -> int:

@@ -756,7 +756,10 @@ int oracle_set_smlstep_pert_variables(oracle_t* o) {
   OMP_FOR
   for (int c = 0; c < nC; ++c) {
     if (!o->inCpr[c]) continue;
-    for (int k = 0; k < L; ++k) {
+    // `for iCell in cpr` (:1516) visits every point of the region, i.e. levels 0..nVertLevels INCLUSIVE (the index
+    // spaces have nVertLevels+1 levels, main.rg:21-24): level nVertLevels is processed with whatever fzm/fzp/zz/
+    // zb_cell/u_tend hold there (zero until written, rule M1 -- then w(:, nVertLevels) becomes 0 every stage).
+    for (int k = 0; k <= L; ++k) {
       if (o->bdyMaskCell[c] <= o->c.nRelaxZone) {
         for (int i = 0; i < o->nEdgesOnCell[c]; ++i) {
           int e = o->edgesOnCell[c * ME + i];

@@ -114,3 +114,51 @@ class Oracle(TaskAPI):
 
     def sync(self):
         pass
+
+    # ---- summarize_timestep (rk_timestep.rg:29-359): numpy restatement of mpasb200_summarize_field ---------------
+    def set_global_ids(self, entity: int, gid):
+        self._gid = getattr(self, "_gid", {})
+        self._gid[entity] = None if gid is None else np.asarray(gid, dtype=np.int64)
+
+    def summarize_field(self, name: str, n_first=None, nlevels=None) -> dict:
+        ent = _abi.FIELD_ENTITY[name]
+        a = self.download_field(name)
+        n = a.shape[0] if n_first is None else int(n_first)
+        nl = a.shape[1] if nlevels is None else int(nlevels)
+        gid = getattr(self, "_gid", {}).get(ent)
+        return summarize_np(a[:n, :nl], None if gid is None else gid[:n])
+
+
+_M64 = (1 << 64) - 1
+
+
+def _mix64(z: np.ndarray) -> np.ndarray:
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xbf58476d1ce4e5b9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94d049bb133111eb)
+    return z ^ (z >> np.uint64(31))
+
+
+def summarize_np(a: np.ndarray, gid=None) -> dict:
+    """the definition in include/mpas_b200.h (MpasFieldSummary), array-at-a-time"""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n, nl = a.shape
+    ids = (np.arange(n, dtype=np.uint64) if gid is None else np.asarray(gid).astype(np.uint64))[:, None] * np.uint64(nl) \
+        + np.arange(nl, dtype=np.uint64)[None, :]
+    bits = a.view(np.uint64).copy()
+    nan = np.isnan(a)
+    bits[nan] = np.uint64(0x7ff8000000000000)
+    with np.errstate(over="ignore"):
+        cs = int(_mix64(bits + np.uint64(0x9e3779b97f4a7c15) * (ids + np.uint64(1))).sum(dtype=np.uint64)) & _M64
+    raw = a.view(np.uint64)
+    key = np.where(raw >> np.uint64(63) != 0, ~raw, raw | np.uint64(1 << 63))        # monotone double -> uint64
+    ok = ~nan
+    out = {"n_nan": int(nan.sum()), "n_inf": int(np.isinf(a).sum()), "count": int(a.size), "checksum": f"{cs:016x}"}
+    if ok.any():
+        kmin, kmax = key[ok].min(), key[ok].max()
+        pmin, pmax = ids[ok & (key == kmin)].min(), ids[ok & (key == kmax)].min()
+        unkey = lambda k: np.array([k & np.uint64(_M64 >> 1) if k >> np.uint64(63) else ~k], dtype=np.uint64).view(np.float64)[0]
+        out.update(min=float(unkey(kmin)), max=float(unkey(kmax)), min_at=[int(pmin) // nl, int(pmin) % nl],
+                   max_at=[int(pmax) // nl, int(pmax) % nl])
+    else:
+        out.update(min=float("inf"), max=float("-inf"), min_at=[-1, -1], max_at=[-1, -1])
+    return out

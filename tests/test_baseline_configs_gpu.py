@@ -1,0 +1,204 @@
+"""Parity at the sizes BASELINE.json names, and the device form of summarize_timestep.
+
+config 2: x1.40962 synthetic icosahedral mesh, 41 levels, 100 RK3 steps, CUDA path vs the CPU oracle with the stated
+          growth bound 1e-12 * (1 + step) per field (north_star); plus one step under the literal reading
+          (LITERAL index policy, memory-model rule M1, literal rk_step argument).
+config 3: x1.163842 x 55 levels: one step, the device scan (mpasb200_summarize_field) against the oracle's fields --
+          min / max within tolerance, identical NaN / Inf counts (the largest mesh the oracle holds comfortably).
+The element-wise ulp histogram backs the "bit-identical" claims of DESIGN.md section 2 (tests/util.compare is norm-wise).
+
+Reference: dynamics/rk_timestep.rg:361-500 (atm_srk3), :29-359 (summarize_timestep).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from mpas_regent_b200 import _abi, icosa
+from tests.util import build_pair, compare, ulp_histogram
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _dt_for(n_cells):
+    return 720.0 * (2562.0 / n_cells) ** 0.5
+
+
+@pytest.fixture(scope="module")
+def mesh40962():
+    return icosa.make_icosahedral_mesh(40962)
+
+
+def test_config2_x1_40962_41_levels_100_steps(mesh40962):
+    """BASELINE.json configs[1]: 100 RK3 steps vs the reference restatement, bound 1e-12 * (1 + step)."""
+    L = 41
+    st, ora, g = build_pair(mesh40962, L, _abi.INDEX_CORRECTED, m5=True, rkarg=_abi.RKARG_STAGE_INDEX)
+    ora.set_threads(ora.max_threads())
+    dt = _dt_for(mesh40962.nCells)
+    for b in (ora, g):
+        b.atm_compute_solve_diagnostics(False, -1)
+    done, report = 0, {}
+    for upto in (1, 10, 50, 100):
+        for b in (ora, g):
+            for _ in range(upto - done):
+                b.atm_srk3(dt)
+        done = upto
+        worst = compare(g, ora, tol=1e-12 * (1 + upto), what=f"x1.40962 x 41 after {upto} steps")
+        report[upto] = {"worst_rel": worst[0], "field": worst[1], "bound": 1e-12 * (1 + upto)}
+        assert worst[0] <= 1e-12 * (1 + upto)
+    # the device scan sees what the oracle's fields hold
+    for name in ("w", "u", "theta_m", "rtheta_pp", "ru_p"):
+        s_g, s_o = g.summarize_field(name), ora.summarize_field(name)
+        assert s_g["n_nan"] == s_o["n_nan"] and s_g["n_inf"] == s_o["n_inf"], name
+        scale = max(abs(s_o["min"]), abs(s_o["max"]))
+        assert abs(s_g["min"] - s_o["min"]) <= 1e-10 * scale and abs(s_g["max"] - s_o["max"]) <= 1e-10 * scale, (name, s_g, s_o)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(report, open(os.path.join(ROOT, "gpurun_out", "config2_drift.json"), "w"), indent=1)
+    g.close(); ora.close()
+
+
+def test_config2_one_step_literal_reading(mesh40962):
+    """the closest statement of what the reference does: LITERAL ids, never-written fields zero (M1), literal rk_step argument."""
+    st, ora, g = build_pair(mesh40962, 41, _abi.INDEX_LITERAL, m5=False, rkarg=_abi.RKARG_SUBSTEP_TRUNC)
+    ora.set_threads(ora.max_threads())
+    for b in (ora, g):
+        b.atm_compute_solve_diagnostics(False, -1)
+        b.atm_srk3(_dt_for(mesh40962.nCells))
+    compare(g, ora, what="x1.40962 x 41, literal reading, 1 step")
+    g.close(); ora.close()
+
+
+def test_elementwise_ulp_histogram(grid2562):
+    """Element-wise ulp distances after one full step with the strictly ordered acoustic sweep (acoustic_exact=1):
+    every field is bit-identical to the oracle except the two that carry the nonlinear-Coriolis regrouping (Q14:
+    nVertLevels * term instead of nVertLevels additions) -- q and tend_u."""
+    st, ora, g = build_pair(grid2562, 26, _abi.INDEX_CORRECTED, m5=True, rkarg=_abi.RKARG_STAGE_INDEX, acoustic_exact=1)
+    for b in (ora, g):
+        b.atm_compute_solve_diagnostics(False, -1)
+        b.atm_srk3(720.0)
+    rep, not_exact = {}, []
+    for name, _, _ in _abi.FIELDS:
+        h = ulp_histogram(g.download_field(name), ora.download_field(name))
+        rep[name] = h
+        if h["max_ulp"] != 0:
+            not_exact.append(name)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "ulp_histogram_exact_mode.json"), "w"), indent=1)
+    assert set(not_exact) <= {"q", "tend_u"}, {n: rep[n] for n in not_exact}
+    for n in not_exact:
+        assert rep[n]["max_ulp"] <= 64, (n, rep[n])
+    g.close(); ora.close()
+
+
+def test_elementwise_ulp_histogram_default_mode(grid2562):
+    """the shipped configuration (affine acoustic sweep): histogram written for the record, element-wise bound asserted
+    on every element whose magnitude is within 1e-6 of the field's largest (smaller elements: absolute bound)."""
+    st, ora, g = build_pair(grid2562, 26, _abi.INDEX_CORRECTED, m5=True, rkarg=_abi.RKARG_STAGE_INDEX)
+    for b in (ora, g):
+        b.atm_compute_solve_diagnostics(False, -1)
+        b.atm_srk3(720.0)
+    rep = {}
+    for name, _, _ in _abi.FIELDS:
+        a, b = g.download_field(name), ora.download_field(name)
+        rep[name] = ulp_histogram(a, b)
+        fin = np.isfinite(b)
+        if fin.any():
+            ref = np.abs(b[fin]).max()
+            assert np.all(np.abs(a[fin] - b[fin]) <= 1e-12 * np.maximum(np.abs(b[fin]), 1e-6 * ref) + 1e-300), name
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "ulp_histogram_default_mode.json"), "w"), indent=1)
+    g.close(); ora.close()
+
+
+def test_smlstep_processes_level_L(grid642):
+    """atm_set_smlstep_pert_variables visits every point of cpr, level nVertLevels included (dynamics_tasks.rg:1516)."""
+    L = 10
+    st, ora, g = build_pair(grid642, L, _abi.INDEX_CORRECTED, m5=True)
+    rng = np.random.default_rng(11)
+    for b in (ora, g):
+        b.atm_compute_solve_diagnostics(False, -1)
+        b.atm_srk3(600.0)
+    for n in ("fzm", "fzp", "zz", "u_tend", "w", "zb_cell", "zb3_cell"):
+        a = ora.download_field(n)
+        if a.ndim == 1:
+            a[L] = 0.4
+        elif a.ndim == 2:
+            a[:, L] = 0.5 + rng.random(a.shape[0])
+        else:
+            a[:, L, :] = 0.5 + rng.random((a.shape[0], a.shape[2]))
+        for b in (ora, g):
+            b.upload_field(n, a)
+    w0 = ora.download_field("w")
+    for b in (ora, g):
+        b.atm_set_smlstep_pert_variables()
+    assert not np.array_equal(ora.download_field("w")[:, L], w0[:, L])
+    assert np.array_equal(g.download_field("w"), ora.download_field("w"))
+    g.close(); ora.close()
+
+
+def test_summarize_field_matches_numpy(grid642):
+    """mpasb200_summarize_field == its numpy restatement: min / max with place, NaN / Inf counts, bit checksum;
+    owned-prefix scans and global ids; invariant under the internal renumbering."""
+    from oracle.oracle import summarize_np
+    L = 10
+    outs = []
+    for sfc in (1, 0):
+        st, ora, g = build_pair(grid642, L, _abi.INDEX_CORRECTED, m5=True, sfc=sfc)
+        for b in (ora, g):
+            b.atm_compute_solve_diagnostics(False, -1)
+            b.atm_srk3(600.0)
+        a = g.download_field("w")
+        a[5, 3] = np.nan; a[17, 0] = np.inf; a[40, 2] = -np.inf; a[3, 1] = -0.0; a[9, 4] = a.max() if np.isfinite(a.max()) else 1.0
+        g.upload_field("w", a)
+        assert g.summarize_field("w") == summarize_np(a)
+        assert g.summarize_field("w", 100, L) == summarize_np(a[:100, :L])
+        gid = np.random.default_rng(3).permutation(10 * a.shape[0])[:a.shape[0]].astype(np.int32)
+        g.set_global_ids(_abi.CELL, gid)
+        assert g.summarize_field("w", 300) == summarize_np(a[:300], gid[:300])
+        g.set_global_ids(_abi.CELL, None)
+        e = g.download_field("u")
+        assert g.summarize_field("u") == summarize_np(e)
+        outs.append(g.summarize_field("theta_m"))
+        g.close(); ora.close()
+    assert outs[0] == outs[1]
+
+
+def test_graph_cache_dropped_when_range_changes(grid642):
+    """a captured atm_srk3 graph bakes the launch ranges in: mpasb200_set_range must invalidate it."""
+    from mpas_regent_b200 import dynamics, init_jw
+    st = init_jw.make_state(grid642, 10, _abi.INDEX_CORRECTED)
+    outs = []
+    for use_graph in (0, 1):
+        g = dynamics.Dynamics(dynamics.dims_of(grid642, 10), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, use_graph=use_graph))
+        g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
+        g.atm_compute_solve_diagnostics(False, -1)
+        g.atm_srk3(600.0)                              # whole range (captured when use_graph)
+        g.set_range(_abi.CELL, 0, 200); g.set_range(_abi.EDGE, 0, 500)
+        g.atm_srk3(600.0)                              # restricted ranges: a stale graph would replay the whole range
+        g.set_range(_abi.CELL); g.set_range(_abi.EDGE)
+        g.atm_srk3(600.0)
+        outs.append(g.download_all()); g.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
+
+
+def test_config3_x1_163842_55_levels_one_step_scan():
+    """BASELINE.json configs[2] at one partition: one RK3 step, every CHECK field scanned on the device and compared
+    with the oracle's fields (the multi-GPU runs of this config compare their checksums with this one, bench.py `check`)."""
+    mesh = icosa.make_icosahedral_mesh(163842)
+    st, ora, g = build_pair(mesh, 55, _abi.INDEX_CORRECTED, m5=True, rkarg=_abi.RKARG_STAGE_INDEX)
+    ora.set_threads(ora.max_threads())
+    dt = _dt_for(mesh.nCells)
+    for b in (ora, g):
+        b.atm_compute_solve_diagnostics(False, -1)
+        b.atm_srk3(dt)
+    import bench
+    for name in bench.CHECK_FIELDS:
+        s_g, s_o = g.summarize_field(name), ora.summarize_field(name)
+        assert s_g["n_nan"] == s_o["n_nan"] and s_g["n_inf"] == s_o["n_inf"] and s_g["count"] == s_o["count"], name
+        scale = max(abs(s_o["min"]), abs(s_o["max"]), 1e-300)
+        assert abs(s_g["min"] - s_o["min"]) <= 1e-12 * scale * 10 and abs(s_g["max"] - s_o["max"]) <= 1e-12 * scale * 10, (name, s_g, s_o)
+    compare(g, ora, names=[n for n in bench.CHECK_FIELDS], what="x1.163842 x 55, 1 step")
+    g.close(); ora.close()

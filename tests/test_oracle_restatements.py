@@ -70,24 +70,38 @@ def test_divergence_damping_3d(warmed):                                     # dy
     assert not np.array_equal(want, f["ru_p"])
 
 
-def test_set_smlstep_pert_variables(warmed):                                # dynamics_tasks.rg:1503-1528, every level incl. 0 (Q22)
+def test_set_smlstep_pert_variables(warmed):       # dynamics_tasks.rg:1503-1528, EVERY point of cpr: levels 0..L inclusive (Q22)
     st, ora, f = warmed
     _reset(ora, f)
     s, cfg = st.static, ora.cfg
     nE = s["cellsOnEdge"].shape[0]
-    fzm, fzp = f["fzm"][:L], f["fzp"][:L]
+    # make level L discriminating: the init leaves fzm/fzp/zz/u_tend/w of level L at zero (M1)
+    rng = np.random.default_rng(7)
+    f = dict(f)
+    for n in ("fzm", "fzp", "zz", "u_tend", "w", "zb_cell", "zb3_cell"):
+        a = f[n].copy()
+        if a.ndim == 1:
+            a[L] = 0.3 + rng.random()
+        elif a.ndim == 2:
+            a[:, L] = 0.5 + rng.random(a.shape[0])
+        else:
+            a[:, L, :] = 0.5 + rng.random((a.shape[0], a.shape[2]))
+        f[n] = a
+        ora.upload_field(n, a)
+    fzm, fzp = f["fzm"], f["fzp"]
     ut = _pad(f["u_tend"])
     w = f["w"].copy()
     act = (s["bdyMaskCell"] <= cfg.nRelaxZone)[:, None]
     for i in range(s["edgesOnCell"].shape[1]):
         on = act & (i < s["nEdgesOnCell"])[:, None]
         e = _idx(s["edgesOnCell"][:, i], nE)
-        u_k, u_m = ut[e][:, :L], _below(ut[e])[:, :L]
+        u_k, u_m = ut[e], _below(ut[e])
         flux = s["edgesOnCell_sign"][:, i][:, None] * (fzm * u_k + fzp * u_m)
-        w[:, :L] = np.where(on, w[:, :L] - (f["zb_cell"][:, :L, i] + np.copysign(1.0, u_k) * f["zb3_cell"][:, :L, i]) * flux, w[:, :L])
-    w[:, :L] = np.where(act, w[:, :L] * (fzm * f["zz"][:, :L] + fzp * _below(f["zz"])[:, :L]), w[:, :L])
+        w = np.where(on, w - (f["zb_cell"][:, :, i] + np.copysign(1.0, u_k) * f["zb3_cell"][:, :, i]) * flux, w)
+    w = np.where(act, w * (fzm * f["zz"] + fzp * _below(f["zz"])), w)
     ora.atm_set_smlstep_pert_variables()
     _check(ora, {"w": w})
+    assert np.abs(w[:, L]).max() > 0
 
 
 @pytest.mark.parametrize("small_step", [0, 1])

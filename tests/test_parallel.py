@@ -144,6 +144,30 @@ def test_n_ranks_equal_single_partition_bitwise(grid642, world, physics):
                 ex.exchange(spec)
     for b, s in zip(backs, shards):
         _assert_owned_equal(single, b, s["lm"])
+    # the step's sanity scan (summarize_timestep, rk_timestep.rg:29-359; bench.py `check`): per-rank summaries over the
+    # OWNED entities merge to exactly the single-partition summary -- min / max with place, counts, bit checksum
+    import bench
+    want = bench.run_check(single)
+    parts = [bench.run_check(b, s["lm"]) for b, s in zip(backs, shards)]
+    got = bench.merge_checks([p["fields"] for p in parts])
+    assert got["fields"] == want["fields"] and got["combined_checksum"] == want["combined_checksum"]
+
+
+def test_summarize_np_definition():
+    """the numpy restatement of MpasFieldSummary (include/mpas_b200.h) on a hand-checkable case"""
+    from oracle.oracle import summarize_np
+    a = np.array([[1.0, -0.0, 0.0], [np.nan, -3.5, np.inf]])
+    s = summarize_np(a)
+    assert (s["min"], s["min_at"], s["max"], s["max_at"], s["n_nan"], s["n_inf"], s["count"]) == (-3.5, [1, 1], np.inf, [1, 2], 1, 1, 6)
+    # checksum: order-independent (permuting rows together with their ids changes nothing), sensitive to a swap of values
+    g = np.array([7, 2])
+    assert summarize_np(a, g)["checksum"] == summarize_np(a[::-1], g[::-1])["checksum"]
+    assert summarize_np(a, g)["checksum"] != summarize_np(a[::-1], g)["checksum"]
+    assert summarize_np(a, g)["min_at"] == [2, 1]
+    # first place in (id, level) order on ties
+    b = np.array([[2.0, 2.0], [2.0, 1.0], [1.0, 5.0]])
+    assert summarize_np(b)["min_at"] == [1, 1] and summarize_np(b)["max_at"] == [2, 1]
+    assert summarize_np(np.full((2, 2), np.nan))["min_at"] == [-1, -1]
 
 
 def test_overlapped_schedule_in_process(grid642):

@@ -50,3 +50,24 @@ def compare(gpu, ora, names=None, tol=TOL, what=""):
             bad.append((n, f"rel {rel:.3e} (abs {err:.3e}, ref {ref:.3e})", int((np.abs(a - b) > tol * ref).sum())))
     assert not bad, f"{what}: {len(bad)} field(s) out of tolerance: {bad[:12]}"
     return worst
+
+
+def ulp_histogram(a, b):
+    """element-wise distance in units of the last place between two float64 arrays (the report behind the
+    bit-identical claims: compare() above is norm-wise per field and says nothing about small-magnitude elements)."""
+    a = np.ascontiguousarray(a, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    one_nan = np.isnan(a) ^ np.isnan(b)
+
+    def ordered(x):                                                     # monotone double -> uint64 (-0.0 sits 1 below +0.0)
+        u = x.view(np.uint64)
+        return np.where(u >> np.uint64(63) != 0, ~u, u | np.uint64(1 << 63))
+
+    ka, kb = ordered(a), ordered(b)
+    d = (np.maximum(ka, kb) - np.minimum(ka, kb)).astype(np.float64)       # exact below 2^53, which is all that matters here
+    d[both_nan] = 0
+    d[one_nan] = np.inf
+    h = {"0": int((d == 0).sum()), "1": int((d == 1).sum()), "2-4": int(((d >= 2) & (d <= 4)).sum()),
+         "5-16": int(((d > 4) & (d <= 16)).sum()), "17-256": int(((d > 16) & (d <= 256)).sum()),
+         ">256": int((d > 256).sum()), "max_ulp": float(d.max()) if d.size else 0.0, "n": int(d.size)}
+    return h
