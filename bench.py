@@ -240,7 +240,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--graph", type=int, default=0)
-    ap.add_argument("--chunk-tiles", type=int, default=0, help="EXPERIMENTAL (MpasConfig.chunk_tiles): consecutive tiles per block in the gather kernels")
+    ap.add_argument("--gather-stage", type=int, default=-1, help="MpasConfig.gather_stage bit mask (ablation: 0 = the plain gather kernels)")
+    ap.add_argument("--acoustic", type=int, default=3, help="MpasConfig.acoustic_tma (3 = exact streaming sweep, 2 = affine sweep)")
+    ap.add_argument("--acoustic-cols", type=int, default=0, help="MpasConfig.acoustic_cols")
     ap.add_argument("--physics", choices=("literal", "corrected"), default="literal",
                     help="literal = the reference as it executes (headline); corrected = acoustic u update + back-substitution + "
                          "recover wired in (SURVEY.md 8f rank 1, MPASB200_PHYSICS_CORRECTED)")
@@ -265,7 +267,7 @@ def main():
     dt = dt_for(nC)
     corrected = args.physics == "corrected"
     cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, device=local_rank, use_graph=args.graph,
-                              physics_mode=_abi.PHYSICS_CORRECTED if corrected else _abi.PHYSICS_LITERAL, chunk_tiles=args.chunk_tiles)
+                              physics_mode=_abi.PHYSICS_CORRECTED if corrected else _abi.PHYSICS_LITERAL, gather_stage=args.gather_stage, acoustic_tma=args.acoustic, acoustic_cols=args.acoustic_cols)
     stream = torch.cuda.Stream()
 
     if world == 1:
@@ -446,7 +448,7 @@ def main():
                                    + ("; CORRECTED physics mode (u update, back-substitution, recover wired in)" if corrected else ""),
                        "parallelism": parallelism, "l2": "working set (tens of GB) >> 126 MB L2; no flush needed",
                        "host_init_s": round(t_init, 1), "device_bytes": g.device_bytes, "cuda_graph": bool(args.graph),
-                       **({"chunk_tiles": args.chunk_tiles} if args.chunk_tiles else {})},
+                       "gather_stage": args.gather_stage, "acoustic_tma": args.acoustic},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,

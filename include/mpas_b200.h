@@ -119,12 +119,17 @@ typedef struct {
   int32_t use_graph;                  /* 1: mpasb200_srk3 replays a captured CUDA graph */
   int32_t acoustic_exact;             /* 1: evaluate the acoustic column sweep strictly left-to-right (two kernels, one
                                          thread per column); 0 (default): fused kernel, affine sweep (a few ulp apart) */
-  int32_t acoustic_tma;               /* acoustic step form: 0 = one fused kernel, plain loads; 1 = one fused kernel, own-column strips staged
-                                         with cp.async.bulk (TMA); 2 (default) = lean gather kernel + TMA streaming/sweep kernel */
+  int32_t acoustic_tma;               /* acoustic step form: 3 (default) = lean gather kernel + TMA streaming kernel whose column sweep is
+                                         evaluated strictly in the reference's order (bit-identical to the CPU restatement);
+                                         2 = the same with the affine two-level sweep (a few ulp of the largest term apart, faster sweep);
+                                         1 = one fused kernel, own-column strips staged with cp.async.bulk, affine sweep; 0 = fused, plain loads */
   int32_t physics_mode;               /* mpasb200_physics_mode_t; default LITERAL */
-  int32_t chunk_tiles;                /* EXPERIMENTAL, default 0 = off: > 0 makes the gather kernels k_dt_edge, k_dt_theta_flux,
-                                         k_acoustic_gather and k_divdamp walk that many consecutive tiles per block (L1 reuse across tiles,
-                                         profiles/r1_l1_locality_model.md); results are bit-identical either way */
+  int32_t gather_stage;               /* bit mask, default -1 = every staged kernel the handle's shape supports: the gather kernels request
+                                         all their neighbour level pairs at once with cp.async into per-thread shared-memory slots
+                                         (kernels_staged.cuh) instead of walking index -> gather chains.  bit 0 k_dt_edge, bit 1
+                                         k_acoustic_gather, bit 2 k_dt_theta_flux, bit 3 k_dt_cellC, bit 4 k_divdamp, bit 5 k_smlstep,
+                                         bit 6 k_diag_*; 0 = the plain round-1 kernels.  Results are bit-identical either way. */
+  int32_t acoustic_cols;              /* columns per block of the exact streaming acoustic kernel; 0 = default (4) */
 } MpasConfig;
 
 /* ---- level-0 ("static") region data -------------------------------------------- *

@@ -62,7 +62,7 @@ _CFG_D = ("gravity", "rgas", "cp", "cv", "omega", "sphere_radius", "prandtl", "c
           "config_h_theta_eddy_visc4", "config_rayleigh_damp_u_timescale_days", "config_mpas_cam_coef")
 _CFG_I = ("config_number_rayleigh_damp_u_levels", "config_horiz_mixing", "config_mix_full", "config_rayleigh_damp_u",
           "nRelaxZone", "number_of_sub_steps", "config_dynamics_split_steps", "index_policy", "rkarg_policy",
-          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma", "physics_mode", "chunk_tiles")
+          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma", "physics_mode", "gather_stage", "acoustic_cols")
 
 
 class MpasConfig(C.Structure):
@@ -134,9 +134,10 @@ def default_config(**over) -> MpasConfig:
     c.config_mix_full = c.config_rayleigh_damp_u = 0
     c.nRelaxZone, c.number_of_sub_steps, c.config_dynamics_split_steps = 5, 2, 1
     c.index_policy, c.rkarg_policy = INDEX_CORRECTED, RKARG_SUBSTEP_TRUNC
-    c.sfc_renumber, c.device, c.use_graph, c.acoustic_exact, c.acoustic_tma = 1, -1, 0, 0, 2
+    c.sfc_renumber, c.device, c.use_graph, c.acoustic_exact, c.acoustic_tma = 1, -1, 0, 0, 3
     c.physics_mode = PHYSICS_LITERAL
-    c.chunk_tiles = 0
+    c.gather_stage = -1
+    c.acoustic_cols = 0
     for k, v in over.items():
         if not hasattr(c, k):
             raise AttributeError(k)

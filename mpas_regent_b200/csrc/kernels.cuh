@@ -1272,6 +1272,109 @@ __global__ void __launch_bounds__(128, 5) k_acoustic_tma(const View V, const AcP
 #undef SIN
 }
 
+// EXACT streaming form (MpasConfig.acoustic_tma = 3, the default): same cp.async.bulk strips as k_acoustic_tma, but the
+// column arithmetic is evaluated strictly in the reference's order -- level by level, every expression as written at
+// :1657-1696 -- by ONE lane per column (the C columns of a block share lanes 0..C-1 of its first warp) out of shared
+// memory; the other lanes only move data (bulk strips in, coalesced 128-bit stores out).  Bit-identical to the oracle.
+// Why this is the default: the affine regrouping of k_acoustic_tma changes rw_p by a few ulp of its LARGEST term, which the
+// differences taken by atm_divergence_damping_3d amplify -- at BASELINE config 2 (x1.40962 x 41, dt = 180 s) ru_p then
+// misses the 1e-12 bound after one step (3.7e-12, gpurun_out/c1_pytest.log of round 2).  The recurrence is latency-bound
+// (~19 dependent fp64 operations per level), so the lanes that wait cost nothing: the kernel stays at the speed of the
+// strips as long as enough blocks are resident to overlap one block's sweep with its neighbours' copies.
+template <bool S0>
+__global__ void __launch_bounds__(128, 5) k_acoustic_seq(const View V, const AcPtrs F, double dts, double epssm, double resm) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  PAIR_THREAD_R()
+  const int C = blockDim.y, NF = S0 ? (int)AF_rho_pp : (int)AF_COUNT;
+  const int CL = C * LP;
+  double* in = reinterpret_cast<double*>(smraw);                 // [AF_COUNT][C*LP]; the last four strips double as outputs
+  double* s_v = in + (size_t)AF_COUNT * CL;                      // cofrz, rdzw, fzm, fzp  [4][LP]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_v + (size_t)4 * LP);
+  const int nthr = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  const size_t tile0 = ((size_t)V.xoff + (size_t)blockIdx.x * C) * LP;
+  if (tid == 0) mbar_expect_tx(bar, (uint32_t)(NF * CL * sizeof(double)));
+  for (int f = tid; f < NF; f += nthr) bulk_g2s(in + (size_t)f * CL, F.p[f] + tile0, (uint32_t)(CL * sizeof(double)), bar);
+  for (int i = tid; i < LP; i += nthr) {
+    s_v[i] = FLD(cofrz)[i]; s_v[LP + i] = FLD(rdzw)[i]; s_v[2 * LP + i] = FLD(fzm)[i]; s_v[3 * LP + i] = FLD(fzp)[i];
+  }
+  if (S0) for (int i = tid; i < 4 * CL; i += nthr) in[(size_t)AF_rho_pp * CL + i] = 0.0;   // :1625-1636: the old values are zero
+  if (S0 && inx) {                                                                                    // :1625-1630, level L
+    if (k0 == L) { FLD(wwAvg)[ix] = 0; FLD(rw_p)[ix] = 0; }
+    if (k1 == L) { FLD(wwAvg)[ix + 1] = 0; FLD(rw_p)[ix + 1] = 0; }
+  }
+  const size_t cl = (size_t)threadIdx.y * LP + k0;
+#define SIN(f) (in + (size_t)(f) * CL)
+  mbar_wait(bar, 0);
+  if (m0) st2m(FLD(rtheta_pp_old), ix, S0 ? bc(0.0) : ld2(SIN(AF_rtheta_pp), cl), m0, m1);           // :1615-1623
+  __syncthreads();
+  if (tid < C && V.xoff + (int)blockIdx.x * C + tid < V.xend) {
+    const int c = V.xoff + blockIdx.x * C + tid;
+    const size_t b = (size_t)tid * LP;
+    const double* cofrz = s_v; const double* rdzw = s_v + LP; const double* fzm = s_v + 2 * LP; const double* fzp = s_v + 3 * LP;
+    double* rho_pp = SIN(AF_rho_pp) + b; double* rtheta_pp = SIN(AF_rtheta_pp) + b; double* rw_p = SIN(AF_rw_p) + b; double* wwAvg = SIN(AF_wwAvg) + b;
+    const double* tend_rho = SIN(AF_tend_rho) + b; const double* theta_m = SIN(AF_theta_m) + b; const double* w = SIN(AF_w) + b;
+    const double* coftz = SIN(AF_coftz) + b; const double* cofwz = SIN(AF_cofwz) + b; const double* cofwr = SIN(AF_cofwr) + b;
+    const double* cofwt = SIN(AF_cofwt) + b; const double* a_tri = SIN(AF_a_tri) + b; const double* alpha_tri = SIN(AF_alpha_tri) + b;
+    const double* zz = SIN(AF_zz) + b; const double* rw_save = SIN(AF_rw_save) + b; const double* rw = SIN(AF_rw) + b;
+    const double* dss = SIN(AF_dss) + b; const double* rho_zz = SIN(AF_rho_zz) + b;
+    const double* srs = SIN(AF_rs) + b; const double* sts = SIN(AF_ts) + b;
+    const bool spec = V.specZoneMaskCell[c] != 0.0;
+    double rw_prev = 0, rho_prev = 0, rt_prev = 0;
+    double rw_old_k = rw_p[0];
+    double zz_m = 0.0, cofwt_m = 0.0, rz_m = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < L; ++k) {
+      const double rw_old_p = rw_p[k + 1];
+      const double rho_old = rho_pp[k];
+      const double rt_old = rtheta_pp[k];
+      const double ww_old = wwAvg[k];
+      const double zz_k = zz[k], cofwt_k = cofwt[k], rz_k = rho_zz[k];
+      double rw_new, rho_new, rt_new, ww_new = ww_old;
+      if (!spec) {
+        const double coftz_k = coftz[k], coftz_p = coftz[k + 1];
+        const double rs = rho_old + dts * tend_rho[k] + srs[k] - cofrz[k] * resm * (rw_old_p - rw_old_k);                       // :1657
+        const double ts = rt_old + dts * theta_m[k] + sts[k] - resm * rdzw[k] * (coftz_p * rw_old_p - coftz_k * rw_old_k);       // :1658
+        rw_new = rw_old_k;
+        if (k > 0) {
+          const double w_k = w[k];
+          ww_new += 0.5 * (1.0 - epssm) * rw_old_k;                                                                            // :1661
+          rw_new += dts * w_k - cofwz[k] * ((zz_k * ts - zz_m * 0.0) + resm * (zz_k * rt_old - zz_m * rt_prev))
+                    - cofwr[k] * ((rs + 0.0) + resm * (rho_old + rho_prev))
+                    + cofwt_k * (ts + resm * rt_old)
+                    + cofwt_m * (0.0 + resm * rt_prev);                                                                         // :1662-1667
+          rw_new -= a_tri[k] * rw_prev;                                                                                        // :1670
+          rw_new *= alpha_tri[k];                                                                                              // :1671
+          const double dsk = dss[k];
+          const double r3 = rw_save[k] - rw[k];
+          rw_new += r3 - dts * dsk * (fzm[k] * zz_k + fzp[k] * zz_m) * (fzm[k] * rz_k + fzp[k] * rz_m) * w_k;                   // :1682-1684
+          rw_new /= (1.0 + dts * dsk);                                                                                         // :1685
+          rw_new -= r3;                                                                                                        // :1686
+          ww_new += 0.5 * (1.0 + epssm) * rw_new;                                                                              // :1689
+        }
+        rho_new = rs - cofrz[k] * (rw_old_p - rw_new);                                                                         // :1694
+        rt_new = ts - rdzw[k] * (coftz_p * rw_old_p - coftz_k * rw_new);                                                       // :1695-1696
+      } else {                                                                                                                 // :1698-1703
+        rho_new = rho_old + dts * tend_rho[k];
+        rt_new = rt_old + dts * theta_m[k];
+        rw_new = rw_old_k + dts * w[k];
+        ww_new = ww_old + 0.5 * (1.0 + epssm) * rw_new;
+      }
+      rho_pp[k] = rho_new; rtheta_pp[k] = rt_new;
+      if (S0 || spec || k > 0) { rw_p[k] = rw_new; wwAvg[k] = ww_new; }
+      rw_prev = rw_new; rho_prev = rho_new; rt_prev = rt_new;
+      rw_old_k = rw_old_p; zz_m = zz_k; cofwt_m = cofwt_k; rz_m = rz_k;
+    }
+  }
+  __syncthreads();
+  if (!m0) return;
+  st2m(FLD(rho_pp), ix, ld2(SIN(AF_rho_pp), cl), m0, m1); st2m(FLD(rtheta_pp), ix, ld2(SIN(AF_rtheta_pp), cl), m0, m1);
+  const bool wr0 = S0 || k0 > 0 || V.specZoneMaskCell[x] != 0.0;
+  st2m(FLD(rw_p), ix, ld2(SIN(AF_rw_p), cl), wr0, m1); st2m(FLD(wwAvg), ix, ld2(SIN(AF_wwAvg), cl), wr0, m1);
+#undef SIN
+}
+
 // Two-kernel, strictly left-to-right form (MpasConfig.acoustic_exact = 1).  One thread per level in
 // phase 1, one thread per column in phase 2.
 __global__ void k_acoustic_flux(const View V, double dts, int small_step) {
@@ -1524,171 +1627,6 @@ __global__ void k_rec_cell2(const View V, int nRelaxZone, int fix) {            
   }
   st2m(FLD(w), ix, wv, m0, m1);
 }
-
-// ============================================================================================
-// EXPERIMENTAL, off by default (MpasConfig.chunk_tiles > 0): the same kernels with a different tile -> block mapping.
-// Shipped: one tile of blockDim.y consecutive entities per block, consecutive tiles land on different SMs, so L1 only
-// serves the reuse inside a tile (offline model and ncu agree on 54 % for k_dt_edge, profiles/r1_l1_locality_model.md).
-// Here a block walks `chunk` CONSECUTIVE tiles, so the neighbour columns gathered for one tile are still in L1 for the
-// next (model: 75-82 % hits).  Same arithmetic, same order: results are bit-identical.  Not yet measured on a GPU.
-#define PAIR_THREAD_TILE(n)                                     \
-  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;             \
-  const int x = tile * blockDim.y + threadIdx.y;                \
-  const bool inx = x < (n);                                     \
-  const int LP = V.LP; const int L = V.L;                       \
-  const size_t ix = (size_t)(inx ? x : 0) * LP + k0;            \
-  const bool m0 = inx && k0 < L, m1 = inx && k1 < L;            \
-  (void)ix; (void)m1; (void)k1;
-
-__global__ void k_dt_theta_flux_chunked(const View V, int chunk) {
-  const int ntile = (V.nEdges + (int)blockDim.y - 1) / (int)blockDim.y;
-  const int t_end = min((int)(blockIdx.x + 1) * chunk, ntile);
-  for (int tile = blockIdx.x * chunk; tile < t_end; ++tile) {
-    PAIR_THREAD_TILE(V.nEdges)
-    if (!m0) continue;
-    const int NA = V.nAdv;
-    const double* tm = FLD(theta_m);
-    const int na = V.nAdvCellsForEdge[x];
-    const D2 sg = sgn1(ld2(FLD(ru), ix));
-    D2 fa = bc(0.0);
-#pragma unroll 5
-    for (int j = 0; j < na; ++j) {
-      const D2 sw = V.adv_coefs[x * NA + j] + sg * V.adv_coefs_3rd[x * NA + j];
-      fa += sw * G2(tm, V.advCellsForEdge[x * NA + j]);
-    }
-    st2m(V.scr_flux, ix, fa, m0, m1);
-  }
-}
-
-// k_divdamp with contiguous tiles per block instead of the grid stride (same next-tile prefetch); honours mpasb200_set_range
-__global__ void k_divdamp_chunked(const View V, double coef_divdamp, int chunk) {
-  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;
-  const int LP = V.LP, L = V.L;
-  if (k0 >= L) return;
-  const bool m1 = k1 < L;
-  const int stride = blockDim.y;
-  const int first = V.xoff + blockIdx.x * chunk * (int)blockDim.y;
-  const int nE = min(V.xend, first + chunk * (int)blockDim.y);
-  int x = first + threadIdx.y;
-  if (x >= nE) return;
-  const double* rpp = FLD(rtheta_pp); const double* rppo = FLD(rtheta_pp_old); const double* tm = FLD(theta_m);
-  int4 cv = V.ecv[x]; unsigned char skip = V.divdampSkip[x]; double sz = 1.0 - V.specZoneMaskEdge[x];
-  D2 r = ld2(FLD(ru_p), (size_t)x * LP + k0);
-  while (true) {
-    const int xn = x + stride;
-    const bool more = xn < nE;
-    const int xs = more ? xn : x;
-    const int4 cvn = V.ecv[xs]; const unsigned char skn = V.divdampSkip[xs]; const double szn = 1.0 - V.specZoneMaskEdge[xs];
-    const D2 rn = ld2(FLD(ru_p), (size_t)xs * LP + k0);
-    if (!skip) {
-      const D2 a1 = G2(rpp, cv.x), b1 = G2(rppo, cv.x), a2 = G2(rpp, cv.y), b2 = G2(rppo, cv.y), t1 = G2(tm, cv.x), t2 = G2(tm, cv.y);
-      const D2 divCell1 = -(a1 - b1);
-      const D2 divCell2 = -(a2 - b2);
-      st2m(FLD(ru_p), (size_t)x * LP + k0, r + coef_divdamp * (divCell2 - divCell1) * sz / (t1 + t2), true, m1);
-    }
-    if (!more) break;
-    x = xn; cv = cvn; skip = skn; sz = szn; r = rn;
-  }
-}
-
-// k_acoustic_gather with chunked tiles; honours mpasb200_set_range like the shipped kernel ([V.xoff, V.xend))
-__global__ void k_acoustic_gather_chunked(const View V, double dts, int chunk) {
-  const int ntile = (V.xend - V.xoff + (int)blockDim.y - 1) / (int)blockDim.y;
-  const int t_end = min((int)(blockIdx.x + 1) * chunk, ntile);
-  const int LP = V.LP, L = V.L;
-  const int k0 = 2 * (int)threadIdx.x, k1 = k0 + 1;
-  for (int tile = blockIdx.x * chunk; tile < t_end; ++tile) {
-    const int x = V.xoff + tile * blockDim.y + threadIdx.y;
-    if (x >= V.xend || k0 >= L) continue;
-    const bool m0 = true, m1 = k1 < L;
-    const size_t ix = (size_t)x * LP + k0;
-    if (V.specZoneMaskCell[x] != 0.0) continue;
-    const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
-    const double* ru_p = FLD(ru_p); const double* tm = FLD(theta_m);
-    const double inva = V.invAreaCell[x];
-    D2 rs = bc(0), ts = bc(0);
-#pragma unroll 2
-    for (int i = 0; i < n; ++i) {
-      const int e = V.edgesOnCell[x * V.MEP + i];
-      const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
-      const D2 flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G2(ru_p, e) * inva;
-      rs -= flux;
-      ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
-    }
-    st2m(V.scr_rs, ix, rs, m0, m1); st2m(V.scr_ts, ix, ts, m0, m1);
-  }
-}
-
-__global__ void k_dt_edge_chunked(const View V, const DynTendParams P, int chunk) {
-  extern __shared__ double sm[];
-  const int ntile = (V.nEdges + (int)blockDim.y - 1) / (int)blockDim.y;
-  const int t_end = min((int)(blockIdx.x + 1) * chunk, ntile);
-  for (int tile = blockIdx.x * chunk; tile < t_end; ++tile) {
-  PAIR_THREAD_TILE(V.nEdges)
-  const int TS = LP + 2;
-  double* s_wduz = sm + (size_t)threadIdx.y * TS;
-  const double* u = FLD(u);
-  int4 cv = make_int4(0, 0, 0, 0);
-  D2 u2 = bc(0.0), wduz = bc(0.0);
-  if (m0) {
-    cv = V.ecv[x];
-    u2 = ld2(u, ix);
-    const double* rw = FLD(rw);
-    const D2 rwavg = 0.5 * (G2(rw, cv.x) + G2(rw, cv.y));
-    const D2 fzm = ld2(FLD(fzm), k0), fzp = ld2(FLD(fzp), k0);
-    const D2 um = (k0 >= 2) ? ld2(u, ix - 2) : bc(0.0);            // (u[k0-2], u[k0-1])
-    const double up = (k0 + 2 <= L) ? u[ix + 2] : 0.0;             // u[k1+1]
-    wduz.x = wduz_at(k0, L, rwavg.x, fzm.x, fzp.x, um.x, um.y, u2.x, u2.y);
-    if (m1) wduz.y = wduz_at(k1, L, rwavg.y, fzm.y, fzp.y, um.y, u2.x, u2.y, up);
-    s_wduz[k0] = wduz.x; if (m1) s_wduz[k1] = wduz.y;
-    st2m(FLD(wduz), ix, wduz, m0, m1);
-  }
-  if (inx && k0 == L) s_wduz[L] = FLD(wduz)[ix];          // level L: never written, read as stored
-  if (inx && k1 == L) s_wduz[L] = FLD(wduz)[ix + 1];
-  __syncthreads();
-  if (m0) {
-  const D2 rho_e = ld2(FLD(rho_edge), ix);
-  const double invDc = V.invDcEdge[x];
-  const D2 wduz_p = mk(s_wduz[k1], m1 ? s_wduz[k1 + 1] : 0.0);
-  D2 tend_u = -ld2(FLD(rdzw), k0) * (wduz_p - wduz);                                                // :987
-  // nonlinear Coriolis term :991-1001.  The reference adds each term nVertLevels times in a row
-  // (Q14); here it is added once, multiplied by nVertLevels (same value to O(L) ulp).
-  D2 q = bc(0.0);
-  {
-    const int ME2 = V.maxEdges2, n = V.nEdgesOnEdge[x];
-    const double* pv = FLD(pv_edge);
-    const D2 pv_k = ld2(pv, ix);
-    const double Ld = (double)L;
-#pragma unroll 2
-    for (int j = 0; j < n; ++j) {
-      const int eoe = V.edgesOnEdge[x * ME2 + j];
-      const D2 workpv = 0.5 * (pv_k + G2(pv, eoe));
-      q += Ld * (V.weightsOnEdge[x * ME2 + j] * G2(u, eoe) * workpv);
-    }
-  }
-  st2m(FLD(q), ix, q, m0, m1);
-  const double* ke = FLD(ke); const double* hd = FLD(h_divergence); const double* w = FLD(w);
-  tend_u += rho_e * (q - (G2(ke, cv.y) - G2(ke, cv.x)) * invDc) - u2 * 0.5 * (G2(hd, cv.x) + G2(hd, cv.y));   // :1005-1007
-  {
-    const D2 w1 = G2(w, cv.x), w2 = G2(w, cv.y);
-    const D2 w1p = mk(w1.y, m1 ? G1(w, cv.x, k0 + 2) : 0.0), w2p = mk(w2.y, m1 ? G1(w, cv.y, k0 + 2) : 0.0);
-    const D2 wsum = w1 + w1p + w2 + w2p;
-    tend_u -= (P.omega2 * V.cosAngleEdge[x] * V.cosLatEdge[x] * rho_e * 0.25 * wsum)
-              - (u2 * 0.25 * wsum * rho_e * P.inv_r_earth);                                        // :1011-1017
-  }
-  const D2 tue = ld2(FLD(tend_u_euler), ix);
-  if (P.rayleigh_u) {                                                                               // :1152-1159
-    const int lim = L - P.rayleigh_levels + 1;
-    if (k0 > lim) tend_u.x -= rho_e.x * u2.x * ((double)((double)k0 - (L - P.rayleigh_levels)) * P.rayleigh_coef_inverse);
-    if (k1 > lim) tend_u.y -= rho_e.y * u2.y * ((double)((double)k1 - (L - P.rayleigh_levels)) * P.rayleigh_coef_inverse);
-  }
-  tend_u += tue + ld2(FLD(tend_ru_physics), ix);                                                    // :1162
-  st2m(FLD(tend_u), ix, tend_u, m0, m1);
-  }
-  __syncthreads();      // s_wduz is reused by the next tile
-  }
-}
-
 
 // ============================================================================================
 // atm_rk_dynamics_substep_finish  :1951-2007

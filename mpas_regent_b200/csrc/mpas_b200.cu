@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "kernels_staged.cuh"
 #ifdef MPASB200_LAB
 #include "kernels_lab.cuh"
 #endif
@@ -48,6 +49,7 @@ struct mpasb200 {
   int device = 0;
   int nCells, nEdges, nVertices, L, LP, L1, CPB;
   int num_sms = 148;
+  int max_smem_optin = 48 * 1024;
   View V;                               // device pointers
   std::vector<void*> allocs;            // everything cudaMalloc'ed
   int64_t bytes = 0;
@@ -229,14 +231,21 @@ void drain_kernel_times(mpasb200_t* h) {
     }                                                                                       \
   } while (0)
 
-// EXPERIMENTAL (MpasConfig.chunk_tiles > 0): a block walks `chunk` consecutive tiles (kernels.cuh, *_chunked)
-#define LAUNCH_CHUNKED(kernel, n, smem, ...)                                                \
+// staged gather kernels (kernels_staged.cuh): `slots` 16-byte shared-memory slots per thread + `tiles` column tiles
+enum { GS_DT_EDGE = 1, GS_AC_GATHER = 2, GS_THETA_FLUX = 4, GS_CELLC = 8, GS_DIVDAMP = 16, GS_SMLSTEP = 32, GS_DIAG = 64 };
+size_t staged_bytes(const mpasb200_t* h, int slots, int tiles) {
+  const size_t tile = (((size_t)tiles * h->CPB * (h->LP + 2) + 1) & ~(size_t)1) * sizeof(double);
+  return tile + (size_t)slots * 16 * (size_t)(h->LP / 2) * h->CPB;
+}
+bool staged_on(const mpasb200_t* h, int bit, size_t smem) { return (h->c.gather_stage & bit) && smem <= (size_t)h->max_smem_optin; }
+#define LAUNCH_STAGED(kernel, n, smem, ...)                                                 \
   do {                                                                                      \
     if ((n) > 0) {                                                                          \
-      const int chunk_ = h->c.chunk_tiles;                                                  \
-      const int ntile_ = ((n) + h->CPB - 1) / h->CPB;                                       \
+      static bool attr_ = false;                                                            \
+      if (!attr_) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin); attr_ = true; } \
+      Cfg cf_ = cfg_for(h, (n));                                                            \
       KTimer kt_(h, #kernel);                                                               \
-      kernel<<<(ntile_ + chunk_ - 1) / chunk_, dim3((unsigned)(h->LP / 2), (unsigned)h->CPB), (smem), h->stream>>>(__VA_ARGS__, chunk_); \
+      kernel<<<cf_.grid, cf_.block, (smem), h->stream>>>(__VA_ARGS__);                      \
       h->launches++;                                                                        \
     }                                                                                       \
   } while (0)
@@ -298,7 +307,7 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
   P.rayleigh_levels = C.config_number_rayleigh_damp_u_levels;
   P.rayleigh_coef_inverse = 1.0 / ((double)(C.config_number_rayleigh_damp_u_levels) * (C.config_rayleigh_damp_u_timescale_days * 86400.0));
   const size_t sm2 = tile_bytes(h, 2);
-  const bool chunked = C.chunk_tiles > 0;
+  const size_t sm_edge = staged_bytes(h, 20, 1), sm_flux = staged_bytes(h, 10, 0);
   if (rk_step == 0) {
     LAUNCH(k_dt_cell0<true>, h->nCells, 0, h->V, P, C.config_len_disp, cam_coef);
     LAUNCH(k_dt_edge_delsq, h->nEdges, 0, h->V);
@@ -307,18 +316,18 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
       LAUNCH(k_dt_cell_delsq, h->nCells, 0, h->V);
     }
     LAUNCH(k_dt_edge_euler, h->nEdges, tile_bytes(h, 1), h->V, P);
-    if (chunked) LAUNCH_CHUNKED(k_dt_edge_chunked, h->nEdges, tile_bytes(h, 1), h->V, P);
+    if (staged_on(h, GS_DT_EDGE, sm_edge)) LAUNCH_STAGED(k_dt_edge_s<10>, h->nEdges, sm_edge, h->V, P);
     else LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
     LAUNCH(k_dt_cellA, h->nCells, 0, h->V, P);
     LAUNCH(k_dt_cellB, h->nCells, 0, h->V, P);
-    if (chunked) LAUNCH_CHUNKED(k_dt_theta_flux_chunked, h->nEdges, 0, h->V);
+    if (staged_on(h, GS_THETA_FLUX, sm_flux)) LAUNCH_STAGED(k_dt_theta_flux_s<10>, h->nEdges, sm_flux, h->V);
     else LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
     LAUNCH(k_dt_cellC<true>, h->nCells, sm2, h->V, P);
   } else {
     LAUNCH(k_dt_cell0<false>, h->nCells, 0, h->V, P, C.config_len_disp, cam_coef);
-    if (chunked) LAUNCH_CHUNKED(k_dt_edge_chunked, h->nEdges, tile_bytes(h, 1), h->V, P);
+    if (staged_on(h, GS_DT_EDGE, sm_edge)) LAUNCH_STAGED(k_dt_edge_s<10>, h->nEdges, sm_edge, h->V, P);
     else LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
-    if (chunked) LAUNCH_CHUNKED(k_dt_theta_flux_chunked, h->nEdges, 0, h->V);
+    if (staged_on(h, GS_THETA_FLUX, sm_flux)) LAUNCH_STAGED(k_dt_theta_flux_s<10>, h->nEdges, sm_flux, h->V);
     else LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
     LAUNCH(k_dt_cellC<false>, h->nCells, sm2, h->V, P);
   }
@@ -338,13 +347,48 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
   const double resm = (1.0 - epssm) / (1.0 + epssm);
   const Range rc_ = range_of(h, MPASB200_CELL, h->nCells), re_ = range_of(h, MPASB200_EDGE, h->nEdges);
   const View Vc = ranged(h, rc_), Ve = ranged(h, re_);
+  const size_t sm_gather = staged_bytes(h, 12, 0);
   if (h->c.physics_mode == MPASB200_PHYSICS_CORRECTED) {        // edge update, flux gather, column solve with back-substitution
     const double rcv = h->c.rgas / (h->c.cp - h->c.rgas), c2 = h->c.cp * rcv;
     if (small_step == 0) LAUNCH(k_acoustic_u<true>, re_.n, 0, Ve, dts, c2, h->c.gravity);
     else LAUNCH(k_acoustic_u<false>, re_.n, 0, Ve, dts, c2, h->c.gravity);
-    LAUNCH(k_acoustic_gather, rc_.n, 0, Vc, dts);
+    if (staged_on(h, GS_AC_GATHER, sm_gather)) LAUNCH_STAGED(k_acoustic_gather_s<6>, rc_.n, sm_gather, Vc, dts);
+    else LAUNCH(k_acoustic_gather, rc_.n, 0, Vc, dts);
     if (small_step == 0) LAUNCH(k_acoustic_col<true>, rc_.n, tile_bytes(h, 6), Vc, dts, epssm, resm);
     else LAUNCH(k_acoustic_col<false>, rc_.n, tile_bytes(h, 6), Vc, dts, epssm, resm);
+    return post_launch(h);
+  }
+  // default (acoustic_tma = 3): lean gather kernel + exact streaming kernel (strictly ordered sweep, bit-identical to the oracle)
+  if (!h->c.acoustic_exact && h->c.acoustic_tma == 3 && h->LP / 2 <= 128 &&
+      ((size_t)AF_COUNT * h->LP + (size_t)4 * h->LP) * sizeof(double) + 16 <= (size_t)h->max_smem_optin) {
+    if (rc_.n == 0) return 0;
+    const View& V = Vc;
+    AcPtrs F;
+#define AF(n) F.p[AF_##n] = V.f[MPASB200_F_##n]
+    AF(tend_rho); AF(theta_m); AF(w); AF(coftz); AF(cofwz); AF(cofwr); AF(cofwt); AF(a_tri); AF(alpha_tri); AF(zz); AF(rw_save); AF(rw);
+    AF(dss); AF(rho_zz); AF(rho_pp); AF(rtheta_pp); AF(rw_p); AF(wwAvg);
+#undef AF
+    F.p[AF_rs] = V.scr_rs; F.p[AF_ts] = V.scr_ts;
+    if (staged_on(h, GS_AC_GATHER, sm_gather)) LAUNCH_STAGED(k_acoustic_gather_s<6>, rc_.n, sm_gather, Vc, dts);
+    else LAUNCH(k_acoustic_gather, rc_.n, 0, Vc, dts);
+    const int T = h->LP / 2;
+    int C = std::max(1, h->c.acoustic_cols > 0 ? h->c.acoustic_cols : 4);
+    auto smem_for = [&](int c) { return ((size_t)AF_COUNT * c * h->LP + (size_t)4 * h->LP) * sizeof(double) + 16; };
+    while (C > 1 && (smem_for(C) > (size_t)h->max_smem_optin || C * T > 128)) C /= 2;
+    const size_t smem = smem_for(C);
+    static bool attr_ = false;
+    if (!attr_) {
+      cudaFuncSetAttribute(k_acoustic_seq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+      cudaFuncSetAttribute(k_acoustic_seq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+      attr_ = true;
+    }
+    dim3 block(T, C), grid((rc_.n + C - 1) / C);
+    {
+      KTimer kt_(h, small_step == 0 ? "k_acoustic_seq<true>" : "k_acoustic_seq<false>");
+      if (small_step == 0) k_acoustic_seq<true><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm);
+      else k_acoustic_seq<false><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm);
+    }
+    h->launches++;
     return post_launch(h);
   }
   const bool tma_fits = ((size_t)AF_COUNT * h->LP + (size_t)4 * (h->LP + 2)) * sizeof(double) + 16 <= 48 * 1024 && h->LP / 2 <= 128;
@@ -359,7 +403,7 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
     F.p[AF_rs] = V.scr_rs; F.p[AF_ts] = V.scr_ts;
     const int split = h->c.acoustic_tma == 2;
     if (split) {
-      if (h->c.chunk_tiles > 0) LAUNCH_CHUNKED(k_acoustic_gather_chunked, rc_.n, 0, Vc, dts);
+      if (staged_on(h, GS_AC_GATHER, sm_gather)) LAUNCH_STAGED(k_acoustic_gather_s<6>, rc_.n, sm_gather, Vc, dts);
       else LAUNCH(k_acoustic_gather, rc_.n, 0, Vc, dts);
     }
     const int T = h->LP / 2, NF = small_step == 0 ? (int)AF_rho_pp : (int)AF_COUNT;
@@ -404,13 +448,6 @@ int t_divdamp(mpasb200_t* h, double dts) {
   const Range re_ = range_of(h, MPASB200_EDGE, h->nEdges);
   if (re_.n > 0) {            // persistent: 9 resident blocks per SM loop over the edge tiles
     const int tiles = (re_.n + h->CPB - 1) / h->CPB;
-    if (h->c.chunk_tiles > 0) {                       // EXPERIMENTAL: contiguous tiles per block (kernels.cuh)
-      const int chunk = h->c.chunk_tiles;
-      KTimer kt_(h, "k_divdamp_chunked");
-      k_divdamp_chunked<<<(tiles + chunk - 1) / chunk, dim3(h->LP / 2, h->CPB), 0, h->stream>>>(ranged(h, re_), coef_divdamp, chunk);
-      h->launches++;
-      return post_launch(h);
-    }
     KTimer kt_(h, "k_divdamp");
     k_divdamp<<<std::min(tiles, h->num_sms * 9), dim3(h->LP / 2, h->CPB), 0, h->stream>>>(ranged(h, re_), coef_divdamp);
     h->launches++;
@@ -534,9 +571,10 @@ void mpasb200_default_config(MpasConfig* c) {
   c->config_horiz_mixing = MPASB200_MIX_2D_SMAGORINSKY;
   c->nRelaxZone = 5; c->number_of_sub_steps = 2; c->config_dynamics_split_steps = 1;
   c->index_policy = MPASB200_INDEX_CORRECTED; c->rkarg_policy = MPASB200_RKARG_SUBSTEP_TRUNC;
-  c->sfc_renumber = 1; c->device = -1; c->use_graph = 0; c->acoustic_exact = 0; c->acoustic_tma = 2;
+  c->sfc_renumber = 1; c->device = -1; c->use_graph = 0; c->acoustic_exact = 0; c->acoustic_tma = 3;
   c->physics_mode = MPASB200_PHYSICS_LITERAL;
-  c->chunk_tiles = 0;
+  c->gather_stage = -1;
+  c->acoustic_cols = 0;
 }
 
 const char* mpasb200_last_error(const mpasb200_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -561,6 +599,7 @@ int mpasb200_create(const MpasDims* dims, const MpasConfig* cfg, mpasb200_t** ou
     while (h->CPB * T > 256 && h->CPB > 1) h->CPB /= 2; }      // several kernels are compiled for <= 256 threads per block
   if (h->LP / 2 * h->CPB > 256) { g_create_error = "nVertLevels too large for one block per column group"; delete h; return MPASB200_EINVAL; }
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
+  cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
   cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   h->stream = h->own_stream;
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);

@@ -188,10 +188,10 @@ def test_error_paths(grid642):
     g.close()
 
 
-@pytest.mark.parametrize("exact", [0, 1, 2, 3], ids=["fused_affine", "two_kernel_exact", "fused_affine_tma", "split_gather_tma"])
+@pytest.mark.parametrize("exact", [0, 1, 2, 3, 4], ids=["fused_affine", "two_kernel_exact", "fused_affine_tma", "split_gather_tma", "split_gather_seq_default"])
 def test_acoustic_modes(grid2562, exact):
-    """both evaluations of the acoustic column sweep agree with the oracle (1e-12); the strictly
-    left-to-right one (acoustic_exact=1) is additionally bit-identical on the fields the sweep produces."""
+    """every evaluation of the acoustic column sweep agrees with the oracle (1e-12); the strictly ordered ones
+    (acoustic_exact=1, and the default acoustic_tma=3) are additionally bit-identical on the fields the sweep produces."""
     st, ora, g = build_pair(grid2562, L_SMALL, _abi.INDEX_CORRECTED, m5=True, acoustic_exact=int(exact == 1), acoustic_tma=(exact - 1 if exact >= 2 else 0))
     _warm(ora, g)
     for b in (ora, g):
@@ -199,10 +199,32 @@ def test_acoustic_modes(grid2562, exact):
             b.atm_advance_acoustic_step(dts, ss)
             b.atm_divergence_damping_3d(dts)
     compare(g, ora, what=f"acoustic exact={exact}")
-    if exact == 1:
+    if exact in (1, 4):
         for n in ("rw_p", "rho_pp", "rtheta_pp", "wwAvg", "rtheta_pp_old", "ru_p"):
             assert np.array_equal(g.download_field(n), ora.download_field(n)), n
     g.close(); ora.close()
+
+
+@pytest.mark.parametrize("mask", [0, 1, 2, 4, -1], ids=["plain", "dt_edge", "acoustic_gather", "theta_flux", "all"])
+def test_staged_gathers_bit_identical(grid2562, mask):
+    """MpasConfig.gather_stage only changes HOW neighbour columns reach the arithmetic (cp.async into shared-memory slots
+    instead of index -> gather chains): every field keeps its bytes, on the real mesh (pentagons) and with a range set."""
+    from mpas_regent_b200 import dynamics, init_jw
+    st = init_jw.make_state(grid2562, L_SMALL, _abi.INDEX_CORRECTED)
+    outs = []
+    for m in (0, mask):
+        g = dynamics.Dynamics(dynamics.dims_of(grid2562, L_SMALL), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, gather_stage=m))
+        g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
+        g.atm_compute_solve_diagnostics(False, -1)
+        for _ in range(2):
+            g.atm_srk3(DT)
+        g.set_range(_abi.CELL, 100, 1777)
+        g.atm_advance_acoustic_step(240.0, 1)
+        g.set_range(_abi.CELL)
+        outs.append(g.download_all())
+        g.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
 
 
 @pytest.mark.parametrize("physics,split", [(_abi.PHYSICS_LITERAL, False), (_abi.PHYSICS_CORRECTED, False), (_abi.PHYSICS_LITERAL, True)],
@@ -505,23 +527,3 @@ def test_range_restricted_launches_equal_whole(grid642, physics):
 
 
 from mpas_regent_b200._abi import CELL as parallel_CELL, EDGE as parallel_EDGE  # noqa: E402
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("MPASB200_TEST_EXPERIMENTAL"),
-                    reason="experimental chunk_tiles kernels: not yet run on a GPU; set MPASB200_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("chunk", [1, 3, 8])
-def test_experimental_chunked_tile_walk_is_bit_identical(grid2562, chunk):
-    """MpasConfig.chunk_tiles only changes which block handles which tile: every field must keep its bytes."""
-    from mpas_regent_b200 import dynamics, init_jw
-    st = init_jw.make_state(grid2562, L_SMALL, _abi.INDEX_CORRECTED)
-    outs = []
-    for c in (0, chunk):
-        g = dynamics.Dynamics(dynamics.dims_of(grid2562, L_SMALL), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, chunk_tiles=c))
-        g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
-        g.atm_compute_solve_diagnostics(False, -1)
-        for _ in range(2):
-            g.atm_srk3(DT)
-        outs.append(g.download_all())
-        g.close()
-    for n in outs[0]:
-        assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
