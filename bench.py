@@ -360,7 +360,7 @@ def main():
     roof = None
     if ktimes:
         name, (kms, kn) = max(ktimes.items(), key=lambda kv: kv[1][0])
-        key = name if name in traffic.K else None
+        key = traffic.lookup(name)
         if key is not None and kn > 0:
             u = traffic.units(key, scratch=False)
             bytes_per_launch = u * 8.0 * n_local * L

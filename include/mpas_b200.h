@@ -124,12 +124,14 @@ typedef struct {
                                          2 = the same with the affine two-level sweep (a few ulp of the largest term apart, faster sweep);
                                          1 = one fused kernel, own-column strips staged with cp.async.bulk, affine sweep; 0 = fused, plain loads */
   int32_t physics_mode;               /* mpasb200_physics_mode_t; default LITERAL */
-  int32_t gather_stage;               /* bit mask, default -1 = every staged kernel the handle's shape supports: the gather kernels request
-                                         all their neighbour level pairs at once with cp.async into per-thread shared-memory slots
-                                         (kernels_staged.cuh) instead of walking index -> gather chains.  bit 0 k_dt_edge, bit 1
-                                         k_acoustic_gather, bit 2 k_dt_theta_flux, bit 3 k_dt_cellC, bit 4 k_divdamp, bit 5 k_smlstep,
-                                         bit 6 k_diag_*; 0 = the plain round-1 kernels.  Results are bit-identical either way. */
+  int32_t gather_stage;               /* LABORATORY builds (-DMPASB200_LAB) only, ignored by the shipped library: bit mask selecting the
+                                         cp.async-staged forms of k_dt_edge (1), k_acoustic_gather (2), k_dt_theta_flux (4).  Measured
+                                         slower than the plain kernels on B200 (profiles/r2_staged_gathers.md); bit-identical results. */
   int32_t acoustic_cols;              /* columns per block of the exact streaming acoustic kernel; 0 = default (4) */
+  int32_t config_scalar_advection;    /* 0 (default): atm_srk3 skips scalar transport exactly like the reference (rk_timestep.rg:465);
+                                         1: atm_rk_integration_setup saves scalars_old and every RK stage calls atm_advance_scalars
+                                         with rk_timestep[rk_step] = dt/3, dt/2, dt (rk_timestep.rg:386-389)              */
+  double  config_coef_3rd_order;      /* 0.25, constants.rg:59 */
 } MpasConfig;
 
 /* ---- level-0 ("static") region data -------------------------------------------- *
@@ -229,6 +231,14 @@ int  mpasb200_divergence_damping_3d(mpasb200_t *h, double dts);
 int  mpasb200_recover_large_step_variables(mpasb200_t *h, int ns, int rk_step, double dt);
 /* atm_compute_solve_diagnostics       dynamics_tasks.rg:328-454   */
 int  mpasb200_compute_solve_diagnostics(mpasb200_t *h, int hollingsworth, int rk_step);
+/* atm_advance_scalars: NOT in the reference (its call sites are "SKIPPING" comments, rk_timestep.rg:465,485; the storage is
+ * cell_fs.scalars, data_structures.rg:36).  Implements atm_advance_scalars_work of MPAS-Atmosphere v7.0 (non-monotonic
+ * transport, no physics tendency): horizontal flux of every scalar through every edge with the advection stencil of
+ * atm_adv_coef_compression and the time-averaged mass flux ruAvg, cell-centric flux divergence over edgesOnCell with
+ * edgesOnCellSign, 3rd-order vertical flux with wwAvg (flux3, dynamics_tasks.rg:786-789; 2nd order at the two end levels),
+ * scalars = (scalars_old * rho_zz_old_split + dt * (tend - rdzw * d(wdtn))) / rho_zz.  Parity is against the oracle's
+ * restatement of that routine (unpinned: the reference cannot run it).                                                    */
+int  mpasb200_advance_scalars(mpasb200_t *h, double dt, int rk_step);
 /* atm_rk_dynamics_substep_finish      dynamics_tasks.rg:1951-2007 */
 int  mpasb200_rk_dynamics_substep_finish(mpasb200_t *h, int dynamics_substep, int dynamics_split);
 
@@ -260,7 +270,8 @@ int  mpasb200_summarize_field(mpasb200_t *h, int field, int32_t n_first, int32_t
  * Lists are LOCAL entity indices in the caller's (un-renumbered) numbering.  pack gathers
  * `n` columns x `nfields` fields x (nVertLevels+1) levels into the contiguous device
  * buffer `d_buf` laid out [i][field][level] (one contiguous row per listed entity, so a list that
- * concatenates several peers yields one contiguous slice per peer); unpack scatters the same layout back.
+ * concatenates several peers yields one contiguous slice per peer); unpack scatters the same layout back.  An array-typed
+ * field (scalars : double[8]) occupies one `field` entry per slot, in slot order.
  * A list is registered once and referred to by the returned id.                         */
 int  mpasb200_register_list(mpasb200_t *h, int entity, const int32_t *idx, int32_t n, int32_t *list_id);
 int  mpasb200_pack(mpasb200_t *h, int list_id, const int32_t *fields, int32_t nfields, void *d_buf);
@@ -291,7 +302,7 @@ int  mpasb200_enable_kernel_timing(mpasb200_t *h, int on);
 int  mpasb200_reset_kernel_timing(mpasb200_t *h);
 int  mpasb200_kernel_time(mpasb200_t *h, int idx, const char **name, double *ms, int64_t *launches);
 enum { MPASB200_T_SETUP = 0, MPASB200_T_MOIST, MPASB200_T_VERT_IMP, MPASB200_T_DYN_TEND, MPASB200_T_SMLSTEP,
-       MPASB200_T_ACOUSTIC, MPASB200_T_DIVDAMP, MPASB200_T_RECOVER, MPASB200_T_DIAG, MPASB200_T_FINISH, MPASB200_T_COUNT };
+       MPASB200_T_ACOUSTIC, MPASB200_T_DIVDAMP, MPASB200_T_RECOVER, MPASB200_T_DIAG, MPASB200_T_FINISH, MPASB200_T_SCALARS, MPASB200_T_COUNT };
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ E_OK, E_INVAL, E_CUDA, E_NODEVICE, E_STATE, E_NOMEM = 0, -1, -2, -3, -4, -5
 
 TASK_NAMES = ("rk_integration_setup", "compute_moist_coefficients", "compute_vert_imp_coefs", "compute_dyn_tend",
               "set_smlstep_pert_variables", "advance_acoustic_step", "divergence_damping_3d",
-              "recover_large_step_variables", "compute_solve_diagnostics", "rk_dynamics_substep_finish")
+              "recover_large_step_variables", "compute_solve_diagnostics", "rk_dynamics_substep_finish", "advance_scalars")
 
 
 def _parse_fields() -> List[Tuple[str, int, int]]:
@@ -62,11 +62,11 @@ _CFG_D = ("gravity", "rgas", "cp", "cv", "omega", "sphere_radius", "prandtl", "c
           "config_h_theta_eddy_visc4", "config_rayleigh_damp_u_timescale_days", "config_mpas_cam_coef")
 _CFG_I = ("config_number_rayleigh_damp_u_levels", "config_horiz_mixing", "config_mix_full", "config_rayleigh_damp_u",
           "nRelaxZone", "number_of_sub_steps", "config_dynamics_split_steps", "index_policy", "rkarg_policy",
-          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma", "physics_mode", "gather_stage", "acoustic_cols")
+          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma", "physics_mode", "gather_stage", "acoustic_cols", "config_scalar_advection")
 
 
 class MpasConfig(C.Structure):
-    _fields_ = [(n, C.c_double) for n in _CFG_D] + [(n, C.c_int32) for n in _CFG_I]
+    _fields_ = [(n, C.c_double) for n in _CFG_D] + [(n, C.c_int32) for n in _CFG_I] + [("config_coef_3rd_order", C.c_double)]
 
 
 # (member, ctype, entity, width-key)   width-key: 1 | "maxEdges" | "maxEdges2" | "vertexDegree" | "nAdvCells" | 2
@@ -136,8 +136,10 @@ def default_config(**over) -> MpasConfig:
     c.index_policy, c.rkarg_policy = INDEX_CORRECTED, RKARG_SUBSTEP_TRUNC
     c.sfc_renumber, c.device, c.use_graph, c.acoustic_exact, c.acoustic_tma = 1, -1, 0, 0, 3
     c.physics_mode = PHYSICS_LITERAL
-    c.gather_stage = -1
+    c.gather_stage = 0
     c.acoustic_cols = 0
+    c.config_scalar_advection = 0
+    c.config_coef_3rd_order = 0.25
     for k, v in over.items():
         if not hasattr(c, k):
             raise AttributeError(k)

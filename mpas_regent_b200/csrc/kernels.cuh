@@ -1653,6 +1653,85 @@ __global__ void k_finish_edge(const View V, int lt_split, int first, int last, d
 }
 
 // ============================================================================================
+// atm_advance_scalars -- absent from the reference (rk_timestep.rg:465,485 skip the call; storage data_structures.rg:36).
+// atm_advance_scalars_work of MPAS-Atmosphere v7.0, non-monotonic branch, no physics tendency (mpas_b200.h).  Two kernels:
+// the horizontal flux of every scalar through an edge is evaluated once per edge into library scratch (as for theta),
+// the cell kernel sums it over edgesOnCell in slot order (deterministic gather, no atomics), adds the vertical flux
+// divergence of its own column and updates the scalars in place (a block owns whole columns: reads, barrier, writes).
+template <int NS>
+__global__ void k_scalar_flux(const View V, double* __restrict__ sflux, size_t edgeSlot) {
+  PAIR_THREAD(V.nEdges)
+  if (!m0) return;
+  const int NA = V.nAdv;
+  const double* sc = FLD(scalars);
+  const int na = V.nAdvCellsForEdge[x];
+  const D2 sg = sgn1(ld2(FLD(ruAvg), ix));
+  D2 fa[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) fa[s] = bc(0.0);
+  for (int j = 0; j < na; ++j) {
+    const size_t ic = (size_t)V.advCellsForEdge[x * NA + j] * LP + k0;
+    const D2 sw = V.adv_coefs[x * NA + j] + sg * V.adv_coefs_3rd[x * NA + j];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) fa[s] += sw * ld2(sc + s * V.cellSlot, ic);
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) st2m(sflux + s * edgeSlot, ix, fa[s], m0, m1);
+}
+DI double wdtn_at(int k, int L, double ww, double fm, double fp, double qm2, double qm1, double q0, double qp1, double coef3) {
+  double r = 0.0;                                       // wdtn(0) = wdtn(L) = 0
+  if (k == 1 || k == L - 1) r = ww * (fm * q0 + fp * qm1);
+  if (k > 1 && k < L - 1) r = flux3(qm2, qm1, q0, qp1, ww, coef3);
+  return r;
+}
+template <int NS>
+__global__ void k_scalar_update(const View V, const double* __restrict__ sflux, size_t edgeSlot, double dt, double coef3) {
+  PAIR_THREAD(V.nCells)
+  D2 out[NS];
+  if (m0) {
+    const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
+    const double* ru = FLD(ruAvg);
+    D2 tend[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) tend[s] = bc(0.0);
+    for (int i = 0; i < n; ++i) {
+      const int e = V.edgesOnCell[x * V.MEP + i];
+      const D2 sr = V.edgesOnCellSign[x * ME + i] * G2(ru, e);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) tend[s] -= sr * G2(sflux + s * edgeSlot, e);
+    }
+    const double inv = V.invAreaCell[x];
+    const double* wwA = FLD(wwAvg);
+    const D2 ww = ld2(wwA, ix); const double ww2 = wwA[ix + 2 < (size_t)(x + 1) * LP ? ix + 2 : ix];     // wwAvg(k1+1)
+    const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0), rdzw = ld2(FLD(rdzw), k0);
+    const double fm2 = k0 + 2 < LP ? FLD(fzm)[k0 + 2] : 0.0, fp2 = k0 + 2 < LP ? FLD(fzp)[k0 + 2] : 0.0;
+    const D2 rz = ld2(FLD(rho_zz), ix), rzo = ld2(FLD(rho_zz_old_split), ix);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const double* q = FLD(scalars) + s * V.cellSlot;
+      const D2 qm = k0 >= 2 ? ld2(q, ix - 2) : bc(0.0), q2 = ld2(q, ix), qp = k0 + 2 < LP ? ld2(q, ix + 2) : bc(0.0);
+      const double wd0 = wdtn_at(k0, L, ww.x, fm.x, fp.x, qm.x, qm.y, q2.x, q2.y, coef3);
+      const double wd1 = wdtn_at(k1, L, ww.y, fm.y, fp.y, qm.y, q2.x, q2.y, qp.x, coef3);
+      const double wd2 = wdtn_at(k1 + 1, L, ww2, fm2, fp2, q2.x, q2.y, qp.x, qp.y, coef3);
+      const D2 old = ld2(FLD(scalars_old) + s * V.cellSlot, ix);
+      const D2 t = tend[s] * inv;
+      out[s] = mk((old.x * rzo.x + dt * (t.x - rdzw.x * (wd1 - wd0))) / rz.x, (old.y * rzo.y + dt * (t.y - rdzw.y * (wd2 - wd1))) / rz.y);
+    }
+  }
+  __syncthreads();                                     // every level pair of the block's columns has read its neighbours' levels
+  if (!m0) return;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) st2m(FLD(scalars) + s * V.cellSlot, ix, out[s], m0, m1);
+}
+// scalars_old = scalars (MPAS: scalars_2 = scalars_1 in atm_rk_integration_setup); grid.y = slot
+__global__ void k_setup_scalars(const View V) {
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
+  const size_t o = (size_t)blockIdx.y * V.cellSlot;
+  st2m(FLD(scalars_old) + o, ix, ld2(FLD(scalars) + o, ix), m0, m1);
+}
+
+// ============================================================================================
 // region <-> mirror transfers and halo pack/unpack.  `map[i]` = internal (SFC) index of caller index i.
 // staging layout: [i][L1][slots] (exactly the host array of an array-typed region field).
 __global__ void k_stage_to_field(double* __restrict__ field, const double* __restrict__ staging, const int* __restrict__ map,

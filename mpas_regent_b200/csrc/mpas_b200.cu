@@ -18,8 +18,8 @@
 #include <vector>
 
 #include "kernels.cuh"
-#include "kernels_staged.cuh"
 #ifdef MPASB200_LAB
+#include "kernels_staged.cuh"     // cp.async-staged gather kernels: measured slower than the plain ones (profiles/r2_staged_gathers.md)
 #include "kernels_lab.cuh"
 #endif
 
@@ -36,7 +36,7 @@ const FieldInfo kFields[] = {
 const char* kTaskNames[MPASB200_T_COUNT] = {
     "rk_integration_setup", "compute_moist_coefficients", "compute_vert_imp_coefs", "compute_dyn_tend",
     "set_smlstep_pert_variables", "advance_acoustic_step", "divergence_damping_3d", "recover_large_step_variables",
-    "compute_solve_diagnostics", "rk_dynamics_substep_finish"};
+    "compute_solve_diagnostics", "rk_dynamics_substep_finish", "advance_scalars"};
 
 std::string g_create_error;
 
@@ -86,6 +86,7 @@ struct mpasb200 {
   std::vector<HaloList> lists;
   int* d_gid[3] = {nullptr, nullptr, nullptr}; int n_gid[3] = {0, 0, 0};   // mpasb200_set_global_ids
   SumAcc* d_acc = nullptr;
+  double* d_sflux = nullptr;            // horiz_flux_arr of atm_advance_scalars: [nScalars][(nEdges+1)][LP], allocated on first use
   std::string err;
   std::mutex mu;
 };
@@ -237,7 +238,14 @@ size_t staged_bytes(const mpasb200_t* h, int slots, int tiles) {
   const size_t tile = (((size_t)tiles * h->CPB * (h->LP + 2) + 1) & ~(size_t)1) * sizeof(double);
   return tile + (size_t)slots * 16 * (size_t)(h->LP / 2) * h->CPB;
 }
-bool staged_on(const mpasb200_t* h, int bit, size_t smem) { return (h->c.gather_stage & bit) && smem <= (size_t)h->max_smem_optin; }
+#ifdef MPASB200_LAB
+bool staged_on(const mpasb200_t* h, int bit, size_t smem) { return (h->c.gather_stage & bit) && smem <= (size_t)h->max_smem_optin && h->LP / 2 * h->CPB <= 224; }
+#else
+// the staged kernels exist in -DMPASB200_LAB builds only; the shipped library always takes the plain kernels
+#define staged_on(h, bit, smem) false
+#define LAUNCH_STAGED(kernel, n, smem, ...) do { } while (0)
+#endif
+#ifdef MPASB200_LAB
 #define LAUNCH_STAGED(kernel, n, smem, ...)                                                 \
   do {                                                                                      \
     if ((n) > 0) {                                                                          \
@@ -249,6 +257,7 @@ bool staged_on(const mpasb200_t* h, int bit, size_t smem) { return (h->c.gather_
       h->launches++;                                                                        \
     }                                                                                       \
   } while (0)
+#endif
 size_t tile_bytes(const mpasb200_t* h, int tiles) { return (size_t)tiles * h->CPB * (h->LP + 2) * sizeof(double); }
 
 int post_launch(mpasb200_t* h) {
@@ -261,6 +270,34 @@ int post_launch(mpasb200_t* h) {
 int t_setup(mpasb200_t* h) {
   LAUNCH(k_setup_cell, h->nCells, 0, h->V);
   LAUNCH(k_setup_edge, h->nEdges, 0, h->V);
+  if (h->c.config_scalar_advection && h->nCells > 0) {             // MPAS: scalars_2 = scalars_1
+    Cfg cf = cfg_for(h, h->nCells); cf.grid.y = kFields[MPASB200_F_scalars].slots;
+    KTimer kt_(h, "k_setup_scalars");
+    k_setup_scalars<<<cf.grid, cf.block, 0, h->stream>>>(h->V);
+    h->launches++;
+  }
+  return post_launch(h);
+}
+int ensure_sflux(mpasb200_t* h) {      // horiz_flux_arr scratch of atm_advance_scalars, allocated on first use
+  if (h->d_sflux) return 0;
+  if (h->capturing) return fail(h, MPASB200_ESTATE, "scalar flux scratch must exist before a graph capture");
+  const size_t n = (size_t)(h->nEdges + 1) * h->LP * kFields[MPASB200_F_scalars].slots;
+  cudaError_t e = cudaMalloc((void**)&h->d_sflux, n * sizeof(double));
+  if (e != cudaSuccess) { h->err = std::string("cudaMalloc(scalar flux scratch): ") + cudaGetErrorString(e); return MPASB200_ENOMEM; }
+  cudaMemsetAsync(h->d_sflux, 0, n * sizeof(double), h->stream);
+  h->bytes += (int64_t)(n * sizeof(double));
+  return 0;
+}
+// atm_advance_scalars (mpas_b200.h): per-edge horizontal fluxes into scratch, then the cell update
+int t_scalars(mpasb200_t* h, double dt, int rk_step) {
+  (void)rk_step;
+  constexpr int NS = 8;
+  static_assert(NS == 8, "nScalars");
+  if (kFields[MPASB200_F_scalars].slots != NS) return fail(h, MPASB200_EINVAL, "advance_scalars is compiled for nScalars = 8 (constants.rg:42)");
+  const size_t edgeSlot = (size_t)(h->nEdges + 1) * h->LP;
+  if (int rc = ensure_sflux(h)) return rc;
+  LAUNCH(k_scalar_flux<NS>, h->nEdges, 0, h->V, h->d_sflux, edgeSlot);
+  LAUNCH(k_scalar_update<NS>, h->nCells, 0, h->V, h->d_sflux, edgeSlot, dt, h->c.config_coef_3rd_order);
   return post_launch(h);
 }
 int t_moist(mpasb200_t* h) { LAUNCH(k_moist, h->nCells, 0, h->V); return post_launch(h); }
@@ -479,6 +516,7 @@ int t_srk3(mpasb200_t* h, double dt) {
   const int number_of_sub_steps = C.number_of_sub_steps;
   const int dynamics_split = C.config_dynamics_split_steps;
   const double dt_dynamics = dt;
+  const double rk_timestep[3] = {dt_dynamics / 3, dt_dynamics / 2, dt_dynamics};                         // :386-389
   const double rk_sub_timestep[3] = {dt_dynamics / 3, dt_dynamics / number_of_sub_steps, dt_dynamics / number_of_sub_steps};
   const int number_sub_steps[3] = {std::max(1, number_of_sub_steps / 2), std::max(1, number_of_sub_steps / 2), number_of_sub_steps};
   int rc;
@@ -509,6 +547,8 @@ int t_srk3(mpasb200_t* h, double dt) {
     }
     // :459-460 atm_recover_large_step_variables is commented out in the reference (Q5); CORRECTED calls it as commented
     if (C.physics_mode == MPASB200_PHYSICS_CORRECTED) T(MPASB200_T_RECOVER, t_recover(h, number_sub_steps[rk_step], rk_step, dt));
+    // :465 "SKIPPING if (config_scalar_advection ...)": the call MPAS makes here, with rk_timestep[rk_step] (:386-389)
+    if (C.config_scalar_advection) T(MPASB200_T_SCALARS, t_scalars(h, rk_timestep[rk_step], rk_step));
     T(MPASB200_T_DIAG, t_diag(h, 0, rk_step));                             // :467
   }
   T(MPASB200_T_FINISH, t_finish(h, 1, dynamics_split));                    // :481
@@ -573,8 +613,9 @@ void mpasb200_default_config(MpasConfig* c) {
   c->index_policy = MPASB200_INDEX_CORRECTED; c->rkarg_policy = MPASB200_RKARG_SUBSTEP_TRUNC;
   c->sfc_renumber = 1; c->device = -1; c->use_graph = 0; c->acoustic_exact = 0; c->acoustic_tma = 3;
   c->physics_mode = MPASB200_PHYSICS_LITERAL;
-  c->gather_stage = -1;
+  c->gather_stage = 0;
   c->acoustic_cols = 0;
+  c->config_scalar_advection = 0; c->config_coef_3rd_order = 0.25;        // constants.rg:59
 }
 
 const char* mpasb200_last_error(const mpasb200_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -642,6 +683,7 @@ int mpasb200_destroy(mpasb200_t* h) {
   if (h->h_stage) cudaFreeHost(h->h_stage);
   for (int e = 0; e < 3; ++e) if (h->d_gid[e]) cudaFree(h->d_gid[e]);
   if (h->d_acc) cudaFree(h->d_acc);
+  if (h->d_sflux) cudaFree(h->d_sflux);
   for (auto& pp : h->pipe) {
     if (pp.up) cudaFree(pp.up);
     if (pp.dn) cudaFree(pp.dn);
@@ -1067,6 +1109,7 @@ int mpasb200_advance_acoustic_step(mpasb200_t* h, double dts, int small_step) { 
 int mpasb200_divergence_damping_3d(mpasb200_t* h, double dts) { REQUIRE_MESH(); Entry en(h, MPASB200_T_DIVDAMP); return en.done(t_divdamp(h, dts)); }
 int mpasb200_recover_large_step_variables(mpasb200_t* h, int ns, int rk_step, double dt) { REQUIRE_MESH(); Entry en(h, MPASB200_T_RECOVER); return en.done(t_recover(h, ns, rk_step, dt)); }
 int mpasb200_compute_solve_diagnostics(mpasb200_t* h, int hollingsworth, int rk_step) { REQUIRE_MESH(); Entry en(h, MPASB200_T_DIAG); return en.done(t_diag(h, hollingsworth, rk_step)); }
+int mpasb200_advance_scalars(mpasb200_t* h, double dt, int rk_step) { REQUIRE_MESH(); Entry en(h, MPASB200_T_SCALARS); return en.done(t_scalars(h, dt, rk_step)); }
 int mpasb200_rk_dynamics_substep_finish(mpasb200_t* h, int substep, int split) {
   REQUIRE_MESH();
   if (split < 1) return fail(h, MPASB200_EINVAL, "dynamics_split must be >= 1");
@@ -1077,6 +1120,7 @@ int mpasb200_rk_dynamics_substep_finish(mpasb200_t* h, int substep, int split) {
 int mpasb200_srk3(mpasb200_t* h, double dt) {
   REQUIRE_MESH();
   Entry en(h, -1);
+  if (h->c.config_scalar_advection) { if (int rc = ensure_sflux(h)) return rc; }
   if (!h->c.use_graph) return t_srk3(h, dt);
   auto it = h->graphs.find(dt);
   if (it == h->graphs.end()) {
@@ -1130,14 +1174,19 @@ static int pack_unpack(mpasb200_t* h, int list_id, const int32_t* fields, int32_
   if (list_id < 0 || list_id >= (int)h->lists.size() || !fields || nfields < 1 || nfields > 32 || !d_buf) return fail(h, MPASB200_EINVAL, "pack/unpack: bad argument");
   const HaloList& l = h->lists[list_id];
   if (l.n == 0) return 0;
-  PackArgs A; A.nf = nfields;
+  // an array-typed field (scalars : double[8]) travels as one buffer entry per slot, slots in order
+  PackArgs A; A.nf = 0;
+  const size_t slotStride = (size_t)(entity_count(h, l.entity) + 1) * h->LP;
   for (int i = 0; i < nfields; ++i) {
-    if (fields[i] < 0 || fields[i] >= MPASB200_F_COUNT || kFields[fields[i]].entity != l.entity || kFields[fields[i]].slots != 1)
-      return fail(h, MPASB200_EINVAL, "pack/unpack: field does not live on the list's entity type (scalar 3-D fields only)");
-    A.f[i] = h->V.f[fields[i]];
+    if (fields[i] < 0 || fields[i] >= MPASB200_F_COUNT || kFields[fields[i]].entity != l.entity)
+      return fail(h, MPASB200_EINVAL, "pack/unpack: field does not live on the list's entity type");
+    for (int sl = 0; sl < kFields[fields[i]].slots; ++sl) {
+      if (A.nf >= 32) return fail(h, MPASB200_EINVAL, "pack/unpack: more than 32 buffer entries (fields x slots)");
+      A.f[A.nf++] = h->V.f[fields[i]] + sl * slotStride;
+    }
   }
   const int rows = std::max(1, 128 / h->LP);
-  dim3 block(h->LP, rows), grid((l.n + rows - 1) / rows, nfields);
+  dim3 block(h->LP, rows), grid((l.n + rows - 1) / rows, A.nf);
   if (pack) k_pack<<<grid, block, 0, h->stream>>>(A, l.d_idx, l.n, h->L1, h->LP, (double*)d_buf);
   else k_unpack<<<grid, block, 0, h->stream>>>(A, l.d_idx, l.n, h->L1, h->LP, (const double*)d_buf);
   h->launches++;

@@ -63,6 +63,7 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         "recover_large_step_variables": ([H, I, I, D], I),
         "compute_solve_diagnostics": ([H, I, I], I),
         "rk_dynamics_substep_finish": ([H, I, I], I),
+        "advance_scalars": ([H, D, I], I),
         "srk3": ([H, D], I),
         "timestep": ([H, D], I),
     }
@@ -175,6 +176,10 @@ class TaskAPI:
     def atm_compute_solve_diagnostics(self, hollingsworth: bool, rk_step: int):
         self._call("compute_solve_diagnostics", int(bool(hollingsworth)), int(rk_step))
 
+    def atm_advance_scalars(self, dt: float, rk_step: int):
+        """not in the reference (rk_timestep.rg:465 skips it): atm_advance_scalars_work of MPAS-A v7 (mpas_b200.h)"""
+        self._call("advance_scalars", float(dt), int(rk_step))
+
     def atm_rk_dynamics_substep_finish(self, dynamics_substep: int, dynamics_split: int):
         self._call("rk_dynamics_substep_finish", int(dynamics_substep), int(dynamics_split))
 
@@ -193,6 +198,7 @@ class TaskAPI:
         c = self.cfg
         number_of_sub_steps = c.number_of_sub_steps
         dynamics_split = c.config_dynamics_split_steps
+        rk_timestep = [dt / 3, dt / 2, dt]                                        # rk_timestep.rg:386-389
         rk_sub_timestep = [dt / 3, dt / number_of_sub_steps, dt / number_of_sub_steps]
         number_sub_steps = [max(1, number_of_sub_steps // 2), max(1, number_of_sub_steps // 2), number_of_sub_steps]
         h = hook or (lambda name, *args: None)
@@ -213,6 +219,8 @@ class TaskAPI:
                 self.atm_divergence_damping_3d(rk_sub_timestep[rk_step]); h("divergence_damping_3d")
             if c.physics_mode == _abi.PHYSICS_CORRECTED:      # rk_timestep.rg:459-460, commented out in the reference
                 self.atm_recover_large_step_variables(number_sub_steps[rk_step], rk_step, dt); h("recover_large_step_variables")
+            if c.config_scalar_advection:                     # rk_timestep.rg:465 (skipped by the reference), :469 = the halo update
+                self.atm_advance_scalars(rk_timestep[rk_step], rk_step); h("advance_scalars")
             self.atm_compute_solve_diagnostics(False, rk_step); h("compute_solve_diagnostics", False, rk_step)
         self.atm_rk_dynamics_substep_finish(1, dynamics_split); h("rk_dynamics_substep_finish")
 

@@ -42,6 +42,8 @@ EXCHANGES: Dict[str, Dict[str, List[str]]] = {
     "advance_acoustic_step:first": {"cell": ["w", "rtheta_pp", "rtheta_pp_old"]},
     "advance_acoustic_step": {"cell": ["rtheta_pp", "rtheta_pp_old"]},
     "compute_solve_diagnostics": {"cell": ["ke", "divergence"], "edge": ["pv_edge", "v"], "vertex": ["vorticity"]},
+    # config_scalar_advection: the advection stencil reads `scalars` two rings out (rk_timestep.rg:469 = MPAS's halo update)
+    "advance_scalars": {"cell": ["scalars"]},
 }
 
 #: MPASB200_PHYSICS_CORRECTED: the acoustic edge update reads rho_pp across cells and atm_recover_large_step_variables runs,
@@ -52,6 +54,7 @@ EXCHANGES_CORRECTED: Dict[str, Dict[str, List[str]]] = {
     "advance_acoustic_step": {"cell": ["rtheta_pp", "rtheta_pp_old", "rho_pp", "rw_p", "wwAvg"]},
     "recover_large_step_variables": {"cell": ["w"], "edge": ["u", "ru", "ruAvg"]},
     "compute_solve_diagnostics": {"cell": ["ke", "divergence"], "edge": ["pv_edge", "v"], "vertex": ["vorticity"]},
+    "advance_scalars": {"cell": ["scalars"]},
 }
 
 
@@ -130,22 +133,24 @@ class HostDistExchanger(Exchanger):
             arrs = {n: self.b.download_field(n) for n in names}
             ops, recvs = [], []
             for peer in sorted(set(self.lm.send[ent]) | set(self.lm.recv[ent])):
+                width = [int(np.prod(arrs[n].shape[1:])) for n in names]       # levels x slots per listed entity
                 if peer in self.lm.send[ent]:
                     sidx = self.lm.send[ent][peer]
-                    buf = torch.from_numpy(np.ascontiguousarray(np.stack([arrs[n][sidx] for n in names])))
+                    buf = torch.from_numpy(np.ascontiguousarray(np.concatenate([arrs[n][sidx].reshape(len(sidx), -1) for n in names], axis=1)))
                     ops.append(dist.P2POp(dist.isend, buf, peer))
                 if peer in self.lm.recv[ent]:
                     ridx = self.lm.recv[ent][peer]
-                    rbuf = torch.empty((len(names), len(ridx), arrs[names[0]].shape[1]), dtype=torch.float64)
+                    rbuf = torch.empty((len(ridx), sum(width)), dtype=torch.float64)
                     ops.append(dist.P2POp(dist.irecv, rbuf, peer))
-                    recvs.append((ridx, rbuf))
+                    recvs.append((ridx, rbuf, width))
             if ops:
                 for r in dist.batch_isend_irecv(ops):
                     r.wait()
-            for ridx, rbuf in recvs:
-                a = rbuf.numpy()
-                for i, n in enumerate(names):
-                    arrs[n][ridx] = a[i]
+            for ridx, rbuf, width in recvs:
+                a, o = rbuf.numpy(), 0
+                for n, wd in zip(names, width):
+                    arrs[n][ridx] = a[:, o:o + wd].reshape((len(ridx),) + arrs[n].shape[1:])
+                    o += wd
             for n in names:
                 self.b.upload_field(n, arrs[n])
 
@@ -190,7 +195,7 @@ class NcclExchanger(Exchanger):
         torch, dist = self.torch, self.dist
         items, ops = [], []
         for ent, names in spec.items():
-            E, nf = self.ent[ent], len(names)
+            E, nf = self.ent[ent], sum(FIELD_SLOTS[n] for n in names)       # one buffer entry per slot of an array-typed field
             row = nf * self.L1
             sbuf = torch.empty(max(E["ns"] * row, 1), dtype=torch.float64, device="cuda")
             rbuf = torch.empty(max(E["nr"] * row, 1), dtype=torch.float64, device="cuda")

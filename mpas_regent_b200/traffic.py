@@ -88,7 +88,29 @@ K: Dict[str, Tuple[List[str], List[str]]] = {
     "k_rec_cell2": (["w", "ru", "zb_cell", "zb3_cell", "rho_zz"], ["w"]),
     "k_finish_cell": (["wwAvg", "rho_zz_old_split"], ["wwAvg_split", "wwAvg", "rho_zz"]),
     "k_finish_edge": (["ruAvg"], ["ruAvg_split", "ruAvg"]),
+    # atm_advance_scalars (8 scalars; horiz_flux_arr is library scratch: 8 edge fields = 24 units each way)
+    "k_setup_scalars": (["scalars"], ["scalars_old"]),
+    "k_scalar_flux<NS>": (["ruAvg", "scalars"], ["scr_e"] * 8),
+    "k_scalar_update<NS>": (["ruAvg", "scalars", "scalars_old", "wwAvg", "rho_zz", "rho_zz_old_split"] + ["scr_e"] * 8, ["scalars"]),
 }
+# the exact streaming acoustic kernel moves the same fields as the affine one
+K["k_acoustic_seq<true>"] = K["k_acoustic_tma<true>"]
+K["k_acoustic_seq<false>"] = K["k_acoustic_tma<false>"]
+# array-typed fields whose every slot is touched
+FULL_SLOTS = {"scalars": 8, "scalars_old": 8}
+
+
+def canon(kernel: str) -> str:
+    """name a launch is timed under (mpasb200_kernel_time) -> key of K: the staged forms (kernels_staged.cuh, `_s<slots>`)
+    move the same fields as the plain kernels."""
+    import re
+    m = re.match(r"(k_\w+?)_s<\d+>$", kernel)
+    return m.group(1) if m else kernel
+
+
+def lookup(kernel: str):
+    k = canon(kernel)
+    return k if k in K else None
 
 
 def _u(name: str) -> float:
@@ -97,12 +119,12 @@ def _u(name: str) -> float:
     if name == "scr_e":
         return 3.0
     s = FIELD_SLOTS[name]
-    return MULT[FIELD_ENTITY[name]] * (USED_SLOTS if s > 1 else 1)
+    return MULT[FIELD_ENTITY[name]] * (FULL_SLOTS.get(name, USED_SLOTS) if s > 1 else 1)
 
 
 def units(kernel: str, scratch: bool = True) -> float:
     """8-byte units per cell-level moved by one launch of ``kernel`` (reads + writes)."""
-    r, w = K[kernel]
+    r, w = K[canon(kernel)]
     return sum(_u(n) for n in r + w if scratch or not n.startswith("scr"))
 
 
@@ -123,7 +145,7 @@ def step_launches(canonical: bool = True, corrected_physics: bool = False) -> Li
             if corrected_physics:
                 seq += ["k_acoustic_u" + t, "k_acoustic_gather", "k_acoustic_col" + t, "k_divdamp"]
             else:
-                seq += ["k_acoustic_gather", "k_acoustic_tma" + t, "k_divdamp"]
+                seq += ["k_acoustic_gather", "k_acoustic_seq" + t, "k_divdamp"]
         if corrected_physics:
             seq += ["k_rec_pad", "k_rec_cell1", "k_rec_edge", "k_rec_cell2"]
         seq += ["k_diag_vertex", "k_diag_cell", "k_diag_edge<true>" if stage == 2 else "k_diag_edge<false>"]
@@ -153,8 +175,11 @@ TASK_KERNELS = {
                              "k_dt_cellA", "k_dt_cellB", "k_dt_theta_flux", "k_dt_cellC<true>"],
     "compute_dyn_tend:rk>0": ["k_dt_cell0<false>", "k_dt_edge", "k_dt_theta_flux", "k_dt_cellC<false>"],
     "set_smlstep_pert_variables": ["k_smlstep"],
-    "advance_acoustic_step:s0": ["k_acoustic_gather", "k_acoustic_tma<true>"],
-    "advance_acoustic_step": ["k_acoustic_gather", "k_acoustic_tma<false>"],
+    "advance_acoustic_step:s0": ["k_acoustic_gather", "k_acoustic_seq<true>"],
+    "advance_acoustic_step": ["k_acoustic_gather", "k_acoustic_seq<false>"],
+    "advance_acoustic_step:s0:affine": ["k_acoustic_gather", "k_acoustic_tma<true>"],
+    "advance_acoustic_step:affine": ["k_acoustic_gather", "k_acoustic_tma<false>"],
+    "advance_scalars": ["k_scalar_flux<NS>", "k_scalar_update<NS>"],
     "advance_acoustic_step:s0:fused": ["k_acoustic<true>"],
     "advance_acoustic_step:fused": ["k_acoustic<false>"],
     "advance_acoustic_step:s0:exact": ["k_acoustic_flux:s0", "k_acoustic_column:s0"],

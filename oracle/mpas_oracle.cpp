@@ -23,8 +23,8 @@
 //   M3  level -1 (dynamics_tasks.rg:1520,1525,1810,1855) is a zero pad row.
 //   M4  levels ascend within a column (the only order any hot-path loop depends on:
 //       rw_p[k-1], rtheta_pp[k-1], rho_pp[k-1] at dynamics_tasks.rg:1663-1670).
-//   `cpr` (private_1[i]) is a set of CELLS; atm_set_smlstep_pert_variables runs on levels
-//       0..nVertLevels-1 of them; atm_divergence_damping_3d indexes it with any cell.
+//   `cpr` (private_1[i]) is a set of CELLS; atm_set_smlstep_pert_variables runs on EVERY level
+//       0..nVertLevels of them (`for iCell in cpr`, dynamics_tasks.rg:1516); atm_divergence_damping_3d indexes it with any cell.
 //   Each 3-D field is stored [entity 0..N][level -1..nVertLevels][slot].
 //
 // Floating point: build with -O2 -ffp-contract=off (no FMA contraction; Terra/LLVM does not
@@ -246,6 +246,65 @@ int oracle_rk_integration_setup(oracle_t* o) {
   for (int c = 0; c < o->nCells; ++c) for (int k = 0; k < L; ++k) {
     rw_save(c, k) = rw(c, k); rtheta_p_save(c, k) = rtheta_p(c, k); rho_p_save(c, k) = rho_p(c, k);
     w_2(c, k) = w(c, k); theta_m_2(c, k) = theta_m(c, k); rho_zz_2(c, k) = rho_zz(c, k); rho_zz_old_split(c, k) = rho_zz(c, k);
+  }
+  if (o->c.config_scalar_advection) {      // MPAS: scalars_2 = scalars_1 (the reference's setup has no scalar line: it never advects)
+    F3A scalars = o->fa(MPASB200_F_scalars), scalars_old = o->fa(MPASB200_F_scalars_old);
+    OMP_FOR
+    for (int c = 0; c < o->nCells; ++c) for (int k = 0; k < L; ++k) for (int s = 0; s < scalars.S; ++s) scalars_old(c, k, s) = scalars(c, k, s);
+  }
+  return 0;
+}
+
+// atm_advance_scalars -- ABSENT from the reference (rk_timestep.rg:465,469,485 are "SKIPPING" comments; the storage is
+// cell_fs.scalars, data_structures.rg:36).  PARITY UNPINNED.  This restates atm_advance_scalars_work of MPAS-Atmosphere v7.0
+// (src/core_atmosphere/dynamics/mpas_atm_time_integration.F; upstream, not under /root/reference), loop by loop, non-monotonic
+// branch, scalar_tend_save = 0 (no physics), advance_density = false, in the reference's 0-based level convention:
+//   edges : horiz_flux_arr(s,k,e) = sum_j (adv_coefs(j,e) + sign(1, uhAvg(k,e)) * adv_coefs_3rd(j,e)) * scalar_new(s,k,advCellsForEdge(j,e))
+//   cells : tend(s,k) = -sum_i edgesOnCell_sign(i,c) * uhAvg(k,e_i) * horiz_flux_arr(s,k,e_i);  tend = tend * invAreaCell
+//           wdtn(s,0) = wdtn(s,L) = 0; wdtn(s,1) and wdtn(s,L-1) second order with fnm/fnp; flux3 with coef_3rd_order between
+//           scalar_new(s,k,c) = (scalar_old(s,k,c) * rho_zz_old(k,c) + dt * (tend(s,k) - rdnw(k) * (wdtn(s,k+1) - wdtn(s,k)))) / rho_zz_new(k,c)
+// Bindings: uhAvg = er.ruAvg, wwAvg = cr.wwAvg (data_structures.rg:184,514: "used in scalar transport"), fnm/fnp/rdnw =
+// vert_r.fzm/fzp/rdzw, edgesOnCell_sign = the field atm_compute_signs fills (cr.edgesOnCellSign, dynamics_tasks.rg:74-86),
+// scalar_new = cr.scalars, scalar_old = scalars_old (saved by the setup task), rho_zz_new = cr.rho_zz, rho_zz_old =
+// cr.rho_zz_old_split (the setup task's copy of rho_zz at the start of the step).
+int oracle_advance_scalars(oracle_t* o, double dt, int rk_step) {
+  (void)rk_step;
+  const int L = o->L, nC = o->nCells, nE = o->nEdges, ME = o->maxEdges, NA = o->nAdv;
+  const double coef_3rd_order = o->c.config_coef_3rd_order;
+  F3A scalars = o->fa(MPASB200_F_scalars), scalars_old = o->fa(MPASB200_F_scalars_old);
+  const int NS = scalars.S;
+  CF(ruAvg); CF(wwAvg); CF(rho_zz); CF(rho_zz_old_split);
+  VF(fzm); VF(fzp); VF(rdzw);
+  std::vector<double> flux((size_t)(nE + 1) * L * NS, 0.0);               // horiz_flux_arr; the pad edge carries no flux
+  OMP_FOR
+  for (int e = 0; e < nE; ++e)
+    for (int j = 0; j < o->nAdvCellsForEdge[e]; ++j) {
+      const int iAdvCell = o->advCellsForEdge[e * NA + j];
+      for (int k = 0; k < L; ++k) {
+        const double scalar_weight = o->adv_coefs[e * NA + j] + copysign(1.0, ruAvg(e, k)) * o->adv_coefs_3rd[e * NA + j];
+        for (int s = 0; s < NS; ++s) flux[((size_t)e * L + k) * NS + s] += scalar_weight * scalars(iAdvCell, k, s);
+      }
+    }
+  OMP_FOR
+  for (int c = 0; c < nC; ++c) {
+    std::vector<double> tend((size_t)L * NS, 0.0), wdtn((size_t)(L + 1) * NS, 0.0);
+    for (int i = 0; i < o->nEdgesOnCell[c]; ++i) {
+      const int e = o->edgesOnCell[c * ME + i];
+      for (int k = 0; k < L; ++k)
+        for (int s = 0; s < NS; ++s)
+          tend[(size_t)k * NS + s] -= o->edgesOnCellSign[c * ME + i] * ruAvg(e, k) * flux[((size_t)e * L + k) * NS + s];
+    }
+    for (int k = 0; k < L; ++k) for (int s = 0; s < NS; ++s) tend[(size_t)k * NS + s] = tend[(size_t)k * NS + s] * o->invAreaCell[c];
+    for (int s = 0; s < NS; ++s) {
+      if (L > 1) wdtn[(size_t)1 * NS + s] = wwAvg(c, 1) * (fzm[1] * scalars(c, 1, s) + fzp[1] * scalars(c, 0, s));
+      for (int k = 2; k < L - 1; ++k)
+        wdtn[(size_t)k * NS + s] = flux3(scalars(c, k - 2, s), scalars(c, k - 1, s), scalars(c, k, s), scalars(c, k + 1, s), wwAvg(c, k), coef_3rd_order);
+      if (L > 2) wdtn[(size_t)(L - 1) * NS + s] = wwAvg(c, L - 1) * (fzm[L - 1] * scalars(c, L - 1, s) + fzp[L - 1] * scalars(c, L - 2, s));
+    }
+    for (int k = 0; k < L; ++k)
+      for (int s = 0; s < NS; ++s)
+        scalars(c, k, s) = (scalars_old(c, k, s) * rho_zz_old_split(c, k)
+                            + dt * (tend[(size_t)k * NS + s] - rdzw[k] * (wdtn[(size_t)(k + 1) * NS + s] - wdtn[(size_t)k * NS + s]))) / rho_zz(c, k);
   }
   return 0;
 }
@@ -1063,7 +1122,7 @@ int oracle_srk3(oracle_t* o, double dt) {
   int number_of_sub_steps = C.number_of_sub_steps;                          // :378
   int dynamics_split = C.config_dynamics_split_steps;                       // :381
   double dt_dynamics = dt;
-  double rk_timestep[3] = {dt_dynamics / 3, dt_dynamics / 2, dt_dynamics}; (void)rk_timestep;
+  double rk_timestep[3] = {dt_dynamics / 3, dt_dynamics / 2, dt_dynamics};          // :386-389
   double rk_sub_timestep[3] = {dt_dynamics / 3, dt_dynamics / number_of_sub_steps, dt_dynamics / number_of_sub_steps};
   int number_sub_steps[3] = {std::max(1, number_of_sub_steps / 2), std::max(1, number_of_sub_steps / 2), number_of_sub_steps};
   oracle_rk_integration_setup(o);                                           // :404
@@ -1081,6 +1140,8 @@ int oracle_srk3(oracle_t* o, double dt) {
     }
     // :459-460 atm_recover_large_step_variables is commented out (Q5); CORRECTED calls it with the commented arguments
     if (C.physics_mode == MPASB200_PHYSICS_CORRECTED) oracle_recover_large_step_variables(o, number_sub_steps[rk_step], rk_step, dt);
+    // :465 "SKIPPING if (config_scalar_advection .and. (.not. config_split_dynamics_transport))": the call MPAS makes here
+    if (C.config_scalar_advection) oracle_advance_scalars(o, rk_timestep[rk_step], rk_step);
     oracle_compute_solve_diagnostics(o, 0, rk_step);                        // :467
   }
   oracle_rk_dynamics_substep_finish(o, 1, dynamics_split);                  // :481

@@ -577,3 +577,57 @@ def test_compute_dyn_tend(warmed, rk_step, mixing, cam, rayleigh):
             assert n in moved, n
         if mixing != _abi.MIX_OTHER:
             assert "kdiff" in moved
+
+
+def test_advance_scalars(warmed):
+    """atm_advance_scalars is ABSENT from the reference (rk_timestep.rg:465 skips it; storage data_structures.rg:36): the oracle
+    restates atm_advance_scalars_work of MPAS-A v7 loop by loop; this is the same routine array-at-a-time.  Parity unpinned."""
+    st, ora, f = warmed
+    _reset(ora, f)
+    s, cfg = st.static, ora.cfg
+    nC, nE = s["nEdgesOnCell"].shape[0], s["cellsOnEdge"].shape[0]
+    rng = np.random.default_rng(5)
+    NS = 8
+    q = 1e-3 * (1.0 + rng.random((nC, L + 1, NS))); q_old = 1e-3 * (1.0 + rng.random((nC, L + 1, NS)))
+    ru = (f["ru"] + 0.3 * rng.standard_normal(f["ru"].shape)); ww = 0.05 * rng.standard_normal(f["wwAvg"].shape)
+    rzo = f["rho_zz"] * (1.0 + 0.01 * rng.random(f["rho_zz"].shape))
+    for n, a in (("scalars", q), ("scalars_old", q_old), ("ruAvg", ru), ("wwAvg", ww), ("rho_zz_old_split", rzo)):
+        ora.upload_field(n, a)
+    dt = 200.0
+    coef3 = cfg.config_coef_3rd_order
+    fzm, fzp, rdzw = f["fzm"], f["fzp"], f["rdzw"]
+    qp, rup = _pad(q), _pad(ru)
+    flux = np.zeros((nE + 1, L, NS))
+    for j in range(s["advCellsForEdge"].shape[1]):
+        on = (j < s["nAdvCellsForEdge"])[:, None, None]
+        c = _idx(s["advCellsForEdge"][:, j], nC)
+        wgt = s["adv_coefs"][:, j][:, None] + np.copysign(1.0, ru[:, :L]) * s["adv_coefs_3rd"][:, j][:, None]
+        flux[:nE] += np.where(on, wgt[:, :, None] * qp[c][:, :L, :], 0.0)
+    tend = np.zeros((nC, L, NS))
+    for i in range(s["edgesOnCell"].shape[1]):
+        on = (i < s["nEdgesOnCell"])[:, None, None]
+        e = _idx(s["edgesOnCell"][:, i], nE)
+        tend -= np.where(on, (s["edgesOnCellSign"][:, i][:, None] * rup[e][:, :L])[:, :, None] * flux[e], 0.0)
+    tend *= s["invAreaCell"][:, None, None]
+    wdtn = np.zeros((nC, L + 1, NS))
+    for k in (1, L - 1):
+        wdtn[:, k] = ww[:, k, None] * (fzm[k] * q[:, k] + fzp[k] * q[:, k - 1])
+    for k in range(2, L - 1):
+        ua = ww[:, k, None]
+        f4 = ua * (7.0 * (q[:, k] + q[:, k - 1]) - (q[:, k + 1] + q[:, k - 2])) / 12.0
+        wdtn[:, k] = f4 + coef3 * np.abs(ua) * ((q[:, k + 1] - q[:, k - 2]) - 3.0 * (q[:, k] - q[:, k - 1])) / 12.0
+    want = q.copy()
+    want[:, :L] = (q_old[:, :L] * rzo[:, :L, None] + dt * (tend - rdzw[:L, None] * (wdtn[:, 1:] - wdtn[:, :-1]))) / f["rho_zz"][:, :L, None]
+    ora.atm_advance_scalars(dt, 1)
+    _check(ora, {"scalars": want})
+    assert not np.allclose(want[:, :L], q[:, :L])
+    # and the driver wiring: with config_scalar_advection on, the setup task saves scalars_old and every stage advances
+    from oracle.oracle import Oracle
+    from mpas_regent_b200 import dynamics
+    o2 = Oracle(dynamics.dims_of(st.mesh, L), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, config_scalar_advection=1))
+    o2.upload_mesh(st.static); o2.upload_state(st.f, st.vert); o2.upload_field("scalars", q)
+    o2.atm_compute_solve_diagnostics(False, -1)
+    o2.atm_srk3(600.0)
+    assert np.array_equal(o2.download_field("scalars_old")[:, :L], q[:, :L])
+    assert np.isfinite(o2.download_field("scalars")).all()
+    o2.close()

@@ -207,13 +207,17 @@ def test_acoustic_modes(grid2562, exact):
 
 @pytest.mark.parametrize("mask", [0, 1, 2, 4, -1], ids=["plain", "dt_edge", "acoustic_gather", "theta_flux", "all"])
 def test_staged_gathers_bit_identical(grid2562, mask):
-    """MpasConfig.gather_stage only changes HOW neighbour columns reach the arithmetic (cp.async into shared-memory slots
+    """(laboratory build only; measured slower, profiles/r2_staged_gathers.md)  MpasConfig.gather_stage only changes HOW neighbour columns reach the arithmetic (cp.async into shared-memory slots
     instead of index -> gather chains): every field keeps its bytes, on the real mesh (pentagons) and with a range set."""
+    import os
     from mpas_regent_b200 import dynamics, init_jw
+    lab = os.path.join(os.path.dirname(dynamics._LIB_PATH), "libmpas_b200_lab.so")
+    if not os.path.exists(lab):
+        pytest.skip("laboratory build absent (make -C mpas_regent_b200/csrc lab): the staged kernels are not in the shipped library")
     st = init_jw.make_state(grid2562, L_SMALL, _abi.INDEX_CORRECTED)
     outs = []
     for m in (0, mask):
-        g = dynamics.Dynamics(dynamics.dims_of(grid2562, L_SMALL), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, gather_stage=m))
+        g = dynamics.Dynamics(dynamics.dims_of(grid2562, L_SMALL), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, gather_stage=m), lib_path=lab)
         g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
         g.atm_compute_solve_diagnostics(False, -1)
         for _ in range(2):
@@ -527,3 +531,35 @@ def test_range_restricted_launches_equal_whole(grid642, physics):
 
 
 from mpas_regent_b200._abi import CELL as parallel_CELL, EDGE as parallel_EDGE  # noqa: E402
+
+
+# ---- atm_advance_scalars (absent from the reference, parity unpinned) ---------------------
+@pytest.mark.parametrize("policy", [_abi.INDEX_CORRECTED, _abi.INDEX_LITERAL], ids=["corrected", "literal"])
+def test_advance_scalars_parity(grid2562, policy):
+    """the task alone on a state where everything it reads is non-trivial, then the driver with config_scalar_advection on
+    (setup saves scalars_old, every RK stage advances; rk_timestep.rg:465), plain and as a CUDA graph: bit-identical."""
+    st, ora, g = build_pair(grid2562, L_SMALL, policy, m5=True, config_scalar_advection=1)
+    _warm(ora, g)
+    rng = np.random.default_rng(9)
+    nC = grid2562.nCells
+    q = 1e-3 * (1.0 + rng.random((nC, L_SMALL + 1, 8))); q_old = 1e-3 * (1.0 + rng.random((nC, L_SMALL + 1, 8)))
+    ru = ora.download_field("ru") + 0.3 * rng.standard_normal((grid2562.nEdges, L_SMALL + 1))
+    ww = 0.05 * rng.standard_normal((nC, L_SMALL + 1))
+    for b in (ora, g):
+        for n, a in (("scalars", q), ("scalars_old", q_old), ("ruAvg", ru), ("wwAvg", ww)):
+            b.upload_field(n, a)
+        b.atm_advance_scalars(240.0, 0)
+        b.atm_advance_scalars(720.0, 2)
+    a, b_ = g.download_field("scalars"), ora.download_field("scalars")
+    assert not np.array_equal(b_, q)
+    assert np.array_equal(a, b_), float(np.abs(a - b_).max())
+    for b in (ora, g):
+        b.atm_srk3(DT); b.atm_srk3(DT)
+    compare(g, ora, what="2 steps with scalar advection")
+    assert np.array_equal(g.download_field("scalars"), ora.download_field("scalars"))
+    assert np.array_equal(g.download_field("scalars_old"), ora.download_field("scalars_old"))
+    g.set_use_graph(True)
+    for b in (ora, g):
+        b.atm_srk3(DT)
+    assert np.array_equal(g.download_field("scalars"), ora.download_field("scalars"))
+    g.close(); ora.close()

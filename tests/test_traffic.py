@@ -33,9 +33,11 @@ def test_step_units():
 
 def test_every_kernel_in_the_library_is_declared():
     src = open(_abi.REPO_ROOT + "/mpas_regent_b200/csrc/mpas_b200.cu").read()
-    names = set(re.findall(r"LAUNCH\((k_\w+(?:<\w+>)?)", src))
+    names = set(re.findall(r"LAUNCH(?:_STAGED)?\((k_\w+(?:<\w+>)?)", src))
     assert names, "no launches found"
     for n in names:
-        if re.search(r"_v\d$", n):      # experimental variants behind mpasb200_debug_divdamp
+        if re.search(r"_v\d$", n):      # experimental variants behind mpasb200_debug_divdamp (MPASB200_LAB builds only)
             continue
-        assert n in T.K, n
+        assert T.lookup(n) is not None, n
+    for n in ("k_dt_edge_s<10>", "k_acoustic_gather_s<6>", "k_dt_theta_flux_s<10>"):
+        assert T.units(n) == T.units(T.canon(n)) and T.canon(n) != n
