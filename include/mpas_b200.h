@@ -286,6 +286,29 @@ int  mpasb200_set_range(mpasb200_t *h, int entity, int32_t begin, int32_t end);
 int  mpasb200_set_stream(mpasb200_t *h, void *cuda_stream);  /* null = the handle's own stream */
 int  mpasb200_set_use_graph(mpasb200_t *h, int on);          /* MpasConfig.use_graph after creation */
 
+/* ---- the distributed step: one process (or thread) per GPU, the whole exchange schedule inside the library ---------------- *
+ * Replaces what the reference computes but never runs: partition_regions (mesh_loading.rg:399-483) hands every rank its
+ * [owned | ghost ring 1 | ghost ring 2] cells; mpasb200_srk3_dist is atm_srk3 (rk_timestep.rg:361-500) on that local mesh
+ * with the halo exchanges the stencils need, issued by the library itself: k_pack -> ncclSend/ncclRecv (one ncclGroup per
+ * exchange, NVLink) -> k_unpack on a communication stream owned by the handle, ordered against the compute stream by events.
+ * When the mesh was uploaded with launch classes (MpasMeshPtrs.cellClass/edgeClass) every acoustic-loop exchange is hidden
+ * under interior compute (sent cells first, interior cells and interior edges under the exchange, edges next to ghosts after
+ * it; ghost cells are never advanced) and the exchanges after atm_compute_solve_diagnostics of stages 0 and 2 travel under the
+ * column work that follows.  Owned results are bit-identical to the single-partition run.
+ *   unique_id : 128 bytes from mpasb200_dist_unique_id on ONE rank, distributed by the host's own channel (Legion future,
+ *               MPI_Bcast, torch.distributed ...).  NCCL is dlopen'ed ("libnccl.so.2") on first use: single-GPU users need none.
+ *   halo      : per entity type, peers in any order; lists are LOCAL indices in the caller's numbering; for a pair of ranks
+ *               both sides list the same global entities in the same order (partition.build_halo_lists).                    */
+enum { MPASB200_X_ACOUSTIC_FIRST = 0, MPASB200_X_ACOUSTIC, MPASB200_X_DIAG, MPASB200_X_RECOVER, MPASB200_X_SCALARS, MPASB200_X_COUNT };
+int  mpasb200_dist_unique_id(void *id128);
+int  mpasb200_dist_init(mpasb200_t *h, int rank, int world, const void *id128);
+int  mpasb200_dist_set_halo(mpasb200_t *h, int entity,
+                            int32_t n_send_peers, const int32_t *send_peers, const int32_t *send_off /*[n+1]*/, const int32_t *send_idx,
+                            int32_t n_recv_peers, const int32_t *recv_peers, const int32_t *recv_off /*[n+1]*/, const int32_t *recv_idx);
+int  mpasb200_dist_exchange(mpasb200_t *h, int kind);     /* one exchange, complete on return of the stream order (init, tests) */
+int  mpasb200_srk3_dist(mpasb200_t *h, double dt);
+int  mpasb200_dist_flush(mpasb200_t *h);                  /* joins an exchange still travelling on the communication stream   */
+
 /* ---- introspection --------------------------------------------------------------------- */
 int64_t mpasb200_launch_count(const mpasb200_t *h);   /* kernels launched so far by this handle */
 int64_t mpasb200_device_bytes(const mpasb200_t *h);   /* bytes of HBM held by the mirror */

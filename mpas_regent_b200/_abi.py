@@ -23,6 +23,8 @@ MIX_2D_SMAGORINSKY, MIX_2D_FIXED, MIX_OTHER = 0, 1, 2
 RKARG_SUBSTEP_TRUNC, RKARG_STAGE_INDEX = 0, 1
 PHYSICS_LITERAL, PHYSICS_CORRECTED = 0, 1
 
+X_ACOUSTIC_FIRST, X_ACOUSTIC, X_DIAG, X_RECOVER, X_SCALARS = range(5)     # mpasb200_dist_exchange kinds
+
 E_OK, E_INVAL, E_CUDA, E_NODEVICE, E_STATE, E_NOMEM = 0, -1, -2, -3, -4, -5
 
 TASK_NAMES = ("rk_integration_setup", "compute_moist_coefficients", "compute_vert_imp_coefs", "compute_dyn_tend",

@@ -1375,6 +1375,172 @@ __global__ void __launch_bounds__(128, 5) k_acoustic_seq(const View V, const AcP
 #undef SIN
 }
 
+// ---- EXACT, column-per-lane streaming form (MpasConfig.acoustic_tma = 4) -------------------------------------------------
+// "The vertical implicit acoustic solve runs one thread per column" (north_star), at streaming speed: a block is a
+// warp-specialised pipeline over a tile of 32 consecutive columns.
+//   * warp 0, the SWEEPER: lane = column.  It walks the levels strictly in the reference's order (the body of
+//     k_acoustic_column, bit-identical to the oracle) with the recurrence state in registers, reading its inputs two
+//     levels at a time (one 128-bit shared-memory load per field) and writing its five outputs the same way.
+//   * warps 1..3, the MOVERS: stream the 20 (16 at small_step 0) input fields of the tile, chunk by chunk of 8 levels, from
+//     global memory into a two-stage shared-memory ring with cp.async (16 bytes per lane, 64 contiguous bytes per column
+//     and field; the two fields read one level ahead -- coftz(k+1), rw_p(k+1) -- come as 8-byte copies of the shifted
+//     strip), and write the finished chunks back with 128-bit stores.
+//   * stages are handed over with mbarriers (full/empty for inputs, ofull/oempty for outputs); a stage is laid out
+//     [field][column][8 levels] with the 16-byte pieces of a row XOR-swizzled by the column so that the sweeper's
+//     128-bit loads and the movers' 128-bit loads/stores are all bank-conflict free.
+// 32 recurrences advance per sweeper instruction (k_acoustic_seq: 4), two blocks are resident per SM, and while the
+// sweeper works on chunk j the copies of chunk j+1 are in flight: the kernel is bound by the strips, not by the chain.
+enum { AL_KC = 8, AL_COLS = 32, AL_NMOV = 96, AL_NOUT = 5 };
+DI void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+DI void cp_async_arrive_noinc(uint64_t* bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+DI void cp_async_16(void* dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory"); }
+DI void cp_async_8(void* dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory"); }
+DI int al_off(int c, int p) { return c * AL_KC + (((p ^ (c >> 1)) & 3) << 1); }      // doubles: row c, swizzled 16-byte piece p
+struct AcCarry { double rw_prev, rho_prev, rt_prev, zz_m, cofwt_m, rz_m; };
+// one level of :1657-1703, exactly the body of k_acoustic_column
+DI void ac_level(int k, bool spec, bool S0, double dts, double epssm, double resm, double cofrz_k, double rdzw_k, double fzm_k, double fzp_k,
+                 double tend_rho_k, double theta_m_k, double w_k, double coftz_k, double coftz_p, double cofwz_k, double cofwr_k,
+                 double cofwt_k, double a_k, double al_k, double zz_k, double rws_k, double rwv_k, double dsk, double rz_k, double srs_k,
+                 double sts_k, double rho_old, double rt_old, double rw_old_k, double rw_old_p, double ww_old, AcCarry& c,
+                 double& rho_new, double& rt_new, double& rw_new, double& ww_new) {
+  ww_new = ww_old;
+  if (!spec) {
+    const double rs = rho_old + dts * tend_rho_k + srs_k - cofrz_k * resm * (rw_old_p - rw_old_k);                       // :1657
+    const double ts = rt_old + dts * theta_m_k + sts_k - resm * rdzw_k * (coftz_p * rw_old_p - coftz_k * rw_old_k);       // :1658
+    rw_new = rw_old_k;
+    if (k > 0) {
+      ww_new += 0.5 * (1.0 - epssm) * rw_old_k;                                                                          // :1661
+      rw_new += dts * w_k - cofwz_k * ((zz_k * ts - c.zz_m * 0.0) + resm * (zz_k * rt_old - c.zz_m * c.rt_prev))
+                - cofwr_k * ((rs + 0.0) + resm * (rho_old + c.rho_prev))
+                + cofwt_k * (ts + resm * rt_old)
+                + c.cofwt_m * (0.0 + resm * c.rt_prev);                                                                   // :1662-1667
+      rw_new -= a_k * c.rw_prev;                                                                                         // :1670
+      rw_new *= al_k;                                                                                                    // :1671
+      const double r3 = rws_k - rwv_k;
+      rw_new += r3 - dts * dsk * (fzm_k * zz_k + fzp_k * c.zz_m) * (fzm_k * rz_k + fzp_k * c.rz_m) * w_k;                 // :1682-1684
+      const double r2 = 1.0 + dts * dsk;
+      if (r2 != 1.0) rw_new /= r2;                                     // x / 1.0 == x exactly: skip the division where dss = 0  :1685
+      rw_new -= r3;                                                                                                      // :1686
+      ww_new += 0.5 * (1.0 + epssm) * rw_new;                                                                            // :1689
+    }
+    rho_new = rs - cofrz_k * (rw_old_p - rw_new);                                                                        // :1694
+    rt_new = ts - rdzw_k * (coftz_p * rw_old_p - coftz_k * rw_new);                                                      // :1695-1696
+  } else {                                                                                                               // :1698-1703
+    rho_new = rho_old + dts * tend_rho_k;
+    rt_new = rt_old + dts * theta_m_k;
+    rw_new = rw_old_k + dts * w_k;
+    ww_new = ww_old + 0.5 * (1.0 + epssm) * rw_new;
+  }
+  c.rw_prev = rw_new; c.rho_prev = rho_new; c.rt_prev = rt_new; c.zz_m = zz_k; c.cofwt_m = cofwt_k; c.rz_m = rz_k;
+  (void)S0;
+}
+template <bool S0>
+__global__ void __launch_bounds__(32 + AL_NMOV, 2) k_acoustic_lane(const View V, const AcPtrs F, double dts, double epssm, double resm) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  constexpr int NS16 = S0 ? (int)AF_rho_pp : (int)AF_COUNT;      // fields copied 16 bytes at a time (AF_* order)
+  constexpr int NS8 = S0 ? 1 : 2;                                // shifted strips: coftz(k+1) [, rw_p(k+1)]
+  constexpr int NSTR = NS16 + NS8;
+  constexpr int STRIP = AL_COLS * AL_KC;                         // doubles per field per stage
+  double* in = reinterpret_cast<double*>(smraw);                 // [2][NSTR][STRIP]
+  double* out = in + (size_t)2 * NSTR * STRIP;                   // [2][AL_NOUT][STRIP]
+  double* s_v = out + (size_t)2 * AL_NOUT * STRIP;               // cofrz, rdzw, fzm, fzp  [4][LP]
+  const int L = V.L, LP = V.LP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + (size_t)4 * LP);
+  uint64_t* full = bars; uint64_t* empty = bars + 2; uint64_t* ofull = bars + 4; uint64_t* oempty = bars + 6;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int x0 = V.xoff + blockIdx.x * AL_COLS;
+  const int nch = (L + AL_KC - 1) / AL_KC;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(full + s, AL_NMOV); mbar_init(empty + s, 32); mbar_init(ofull + s, 32); mbar_init(oempty + s, AL_NMOV); }
+  }
+  for (int i = tid; i < LP; i += blockDim.x) {
+    s_v[i] = FLD(cofrz)[i]; s_v[LP + i] = FLD(rdzw)[i]; s_v[2 * LP + i] = FLD(fzm)[i]; s_v[3 * LP + i] = FLD(fzp)[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // ------------------------------------------------ sweeper: lane = column ------------------------------------------------
+    const int c = lane, x = x0 + c;
+    const bool on = x < V.xend;
+    const bool spec = on ? (V.specZoneMaskCell[x] != 0.0) : false;
+    AcCarry cr; cr.rw_prev = cr.rho_prev = cr.rt_prev = cr.zz_m = cr.cofwt_m = cr.rz_m = 0.0;
+    for (int j = 0; j < nch; ++j) {
+      const int s = j & 1, u = j >> 1;
+      mbar_wait(full + s, u & 1);
+      if (j >= 2) mbar_wait(oempty + s, (u - 1) & 1);
+      const double* __restrict__ si = in + (size_t)s * NSTR * STRIP;
+      double* __restrict__ so = out + (size_t)s * AL_NOUT * STRIP;
+#pragma unroll
+      for (int p = 0; p < AL_KC / 2; ++p) {
+        const int k0 = j * AL_KC + 2 * p;
+        const int o = al_off(c, p);
+#define LDP(f) (*reinterpret_cast<const D2*>(si + (size_t)(f) * STRIP + o))
+        const D2 tr = LDP(AF_tend_rho), tm = LDP(AF_theta_m), w2 = LDP(AF_w), cz = LDP(AF_coftz), cwz = LDP(AF_cofwz), cwr = LDP(AF_cofwr),
+                 cwt = LDP(AF_cofwt), at = LDP(AF_a_tri), al = LDP(AF_alpha_tri), zz = LDP(AF_zz), rws = LDP(AF_rw_save), rwv = LDP(AF_rw),
+                 ds = LDP(AF_dss), rz = LDP(AF_rho_zz), rsh = LDP(AF_rs), tsh = LDP(AF_ts);
+        const D2 czn = LDP(NS16);                                          // coftz(k+1)
+        D2 rho_o = bc(0.0), rt_o = bc(0.0), rwp = bc(0.0), wwo = bc(0.0), rwpn = bc(0.0);
+        if (!S0) { rho_o = LDP(AF_rho_pp); rt_o = LDP(AF_rtheta_pp); rwp = LDP(AF_rw_p); wwo = LDP(AF_wwAvg); rwpn = LDP(NS16 + 1); }
+#undef LDP
+        D2 rho_n = bc(0.0), rt_n = bc(0.0), rw_n = bc(0.0), ww_n = bc(0.0);
+        if (on && k0 < L)
+          ac_level(k0, spec, S0, dts, epssm, resm, s_v[k0], s_v[LP + k0], s_v[2 * LP + k0], s_v[3 * LP + k0], tr.x, tm.x, w2.x, cz.x, czn.x,
+                   cwz.x, cwr.x, cwt.x, at.x, al.x, zz.x, rws.x, rwv.x, ds.x, rz.x, rsh.x, tsh.x, rho_o.x, rt_o.x, rwp.x, rwpn.x, wwo.x, cr,
+                   rho_n.x, rt_n.x, rw_n.x, ww_n.x);
+        if (on && k0 + 1 < L)
+          ac_level(k0 + 1, spec, S0, dts, epssm, resm, s_v[k0 + 1], s_v[LP + k0 + 1], s_v[2 * LP + k0 + 1], s_v[3 * LP + k0 + 1], tr.y, tm.y, w2.y,
+                   cz.y, czn.y, cwz.y, cwr.y, cwt.y, at.y, al.y, zz.y, rws.y, rwv.y, ds.y, rz.y, rsh.y, tsh.y, rho_o.y, rt_o.y, rwp.y, rwpn.y,
+                   wwo.y, cr, rho_n.y, rt_n.y, rw_n.y, ww_n.y);
+        *reinterpret_cast<D2*>(so + (size_t)0 * STRIP + o) = rho_n;
+        *reinterpret_cast<D2*>(so + (size_t)1 * STRIP + o) = rt_n;
+        *reinterpret_cast<D2*>(so + (size_t)2 * STRIP + o) = rw_n;
+        *reinterpret_cast<D2*>(so + (size_t)3 * STRIP + o) = ww_n;
+        *reinterpret_cast<D2*>(so + (size_t)4 * STRIP + o) = rt_o;            // rtheta_pp_old  :1615-1623
+      }
+      mbar_arrive(empty + s);
+      mbar_arrive(ofull + s);
+    }
+    if (S0 && on) { FLD(wwAvg)[(size_t)x * LP + L] = 0; FLD(rw_p)[(size_t)x * LP + L] = 0; }            // :1625-1630, level L
+  } else {
+    // ------------------------------------------------ movers ------------------------------------------------
+    const int m = tid - 32;
+    double* const dst_f[AL_NOUT] = {FLD(rho_pp), FLD(rtheta_pp), FLD(rw_p), FLD(wwAvg), FLD(rtheta_pp_old)};
+    const int xl = V.xend - 1;                                     // columns past the range read the last valid one
+    for (int j = 0; j <= nch; ++j) {
+      if (j < nch) {
+        const int s = j & 1, u = j >> 1;
+        if (j >= 2) mbar_wait(empty + s, (u - 1) & 1);
+        double* si = in + (size_t)s * NSTR * STRIP;
+        const int kb = j * AL_KC;
+        for (int it = m; it < NS16 * (AL_COLS * 4); it += AL_NMOV) {
+          const int f = it >> 7, cp = it & 127, c = cp >> 2, p = cp & 3;
+          const int xc = min(x0 + c, xl);
+          cp_async_16(si + (size_t)f * STRIP + al_off(c, p), F.p[f] + (size_t)xc * LP + kb + 2 * p);
+        }
+        for (int it = m; it < NS8 * (AL_COLS * 8); it += AL_NMOV) {
+          const int f = it >> 8, ck = it & 255, c = ck >> 3, kk = ck & 7;
+          const int xc = min(x0 + c, xl);
+          const double* src = (f == 0 ? F.p[AF_coftz] : F.p[AF_rw_p]) + (size_t)xc * LP + kb + kk + 1;
+          cp_async_8(si + (size_t)(NS16 + f) * STRIP + al_off(c, kk >> 1) + (kk & 1), src);
+        }
+        cp_async_arrive_noinc(full + s);
+      }
+      if (j >= 1) {
+        const int jj = j - 1, s = jj & 1, u = jj >> 1;
+        mbar_wait(ofull + s, u & 1);
+        const double* so = out + (size_t)s * AL_NOUT * STRIP;
+        const int kb = jj * AL_KC;
+        for (int it = m; it < AL_NOUT * (AL_COLS * 4); it += AL_NMOV) {
+          const int f = it >> 7, cp = it & 127, c = cp >> 2, p = cp & 3;
+          const int x = x0 + c, k0 = kb + 2 * p;
+          const D2 v = *reinterpret_cast<const D2*>(so + (size_t)f * STRIP + al_off(c, p));
+          if (x < V.xend && k0 < L) st2m(dst_f[f], (size_t)x * LP + k0, v, true, k0 + 1 < L);
+        }
+        mbar_arrive(oempty + s);
+      }
+    }
+  }
+}
+
 // Two-kernel, strictly left-to-right form (MpasConfig.acoustic_exact = 1).  One thread per level in
 // phase 1, one thread per column in phase 2.
 __global__ void k_acoustic_flux(const View V, double dts, int small_step) {

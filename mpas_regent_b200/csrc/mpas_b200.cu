@@ -5,6 +5,7 @@
 // dynamics/dynamics_tasks.rg and of atm_srk3/atm_timestep in dynamics/rk_timestep.rg:361-519.
 // There is no host compute path in this file: every task entry launches kernels (kernels.cuh).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -86,6 +87,12 @@ struct mpasb200 {
   std::vector<HaloList> lists;
   int* d_gid[3] = {nullptr, nullptr, nullptr}; int n_gid[3] = {0, 0, 0};   // mpasb200_set_global_ids
   SumAcc* d_acc = nullptr;
+  // distributed step (mpasb200_dist_*): NCCL communicator, halo lists, packed buffers, communication stream
+  void* comm = nullptr; int rank = 0, world = 1;
+  struct Halo { std::vector<int> peers_s, off_s, peers_r, off_r; int* d_s = nullptr; int* d_r = nullptr; int ns = 0, nr = 0; bool set = false; } halo[3];
+  struct ExPart { int ent; std::vector<int> fields; int entries; double* sbuf = nullptr; double* rbuf = nullptr; };
+  std::vector<ExPart> xplan[MPASB200_X_COUNT]; bool xplan_built = false;
+  cudaStream_t comm_stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr; bool x_pending = false; bool has_classes = false;
   double* d_sflux = nullptr;            // horiz_flux_arr of atm_advance_scalars: [nScalars][(nEdges+1)][LP], allocated on first use
   std::string err;
   std::mutex mu;
@@ -395,7 +402,37 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
     else LAUNCH(k_acoustic_col<false>, rc_.n, tile_bytes(h, 6), Vc, dts, epssm, resm);
     return post_launch(h);
   }
-  // default (acoustic_tma = 3): lean gather kernel + exact streaming kernel (strictly ordered sweep, bit-identical to the oracle)
+  // acoustic_tma = 4: lean gather kernel + the column-per-lane exact pipeline (k_acoustic_lane)
+  {
+    const size_t smem_lane = ((size_t)2 * (AF_COUNT + 2) * AL_COLS * AL_KC + (size_t)2 * AL_NOUT * AL_COLS * AL_KC + (size_t)4 * h->LP) * sizeof(double) + 64;
+    if (!h->c.acoustic_exact && h->c.acoustic_tma == 4 && smem_lane <= (size_t)h->max_smem_optin) {
+      if (rc_.n == 0) return 0;
+      const View& V = Vc;
+      AcPtrs F;
+#define AF(n) F.p[AF_##n] = V.f[MPASB200_F_##n]
+      AF(tend_rho); AF(theta_m); AF(w); AF(coftz); AF(cofwz); AF(cofwr); AF(cofwt); AF(a_tri); AF(alpha_tri); AF(zz); AF(rw_save); AF(rw);
+      AF(dss); AF(rho_zz); AF(rho_pp); AF(rtheta_pp); AF(rw_p); AF(wwAvg);
+#undef AF
+      F.p[AF_rs] = V.scr_rs; F.p[AF_ts] = V.scr_ts;
+      LAUNCH(k_acoustic_gather, rc_.n, 0, Vc, dts);
+      static bool attr_ = false;
+      if (!attr_) {
+        cudaFuncSetAttribute(k_acoustic_lane<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+        cudaFuncSetAttribute(k_acoustic_lane<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
+        attr_ = true;
+      }
+      const size_t smem0 = ((size_t)2 * ((int)AF_rho_pp + 1) * AL_COLS * AL_KC + (size_t)2 * AL_NOUT * AL_COLS * AL_KC + (size_t)4 * h->LP) * sizeof(double) + 64;
+      const dim3 grid((rc_.n + AL_COLS - 1) / AL_COLS), block(32 + AL_NMOV);
+      {
+        KTimer kt_(h, small_step == 0 ? "k_acoustic_lane<true>" : "k_acoustic_lane<false>");
+        if (small_step == 0) k_acoustic_lane<true><<<grid, block, smem0, h->stream>>>(V, F, dts, epssm, resm);
+        else k_acoustic_lane<false><<<grid, block, smem_lane, h->stream>>>(V, F, dts, epssm, resm);
+      }
+      h->launches++;
+      return post_launch(h);
+    }
+  }
+  // acoustic_tma = 3: lean gather kernel + exact streaming kernel (strictly ordered sweep by one lane per column of a 4-column block)
   if (!h->c.acoustic_exact && h->c.acoustic_tma == 3 && h->LP / 2 <= 128 &&
       ((size_t)AF_COUNT * h->LP + (size_t)4 * h->LP) * sizeof(double) + 16 <= (size_t)h->max_smem_optin) {
     if (rc_.n == 0) return 0;
@@ -594,6 +631,191 @@ int ensure_hstage(mpasb200_t* h, size_t elems) {
   return 0;
 }
 
+
+// ---- NCCL, loaded on first use (dlopen): the single-GPU library has no NCCL dependency ---------------------------------------
+struct NcclId128 { char b[128]; };        // ncclUniqueId (passed BY VALUE to ncclCommInitRank)
+struct NcclApi {
+  void* lib = nullptr; bool tried = false; std::string err;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*GroupStart)() = nullptr; int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+bool nccl_load() {
+  std::unique_lock<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.tried) return g_nccl.lib != nullptr;
+  g_nccl.tried = true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { g_nccl.err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+#define SYM(member, name) *(void**)(&g_nccl.member) = dlsym(lib, name); if (!g_nccl.member) { g_nccl.err = std::string("dlsym ") + name; return false; }
+  SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+  SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.lib = lib;
+  return true;
+}
+#define NCK(call)                                                                                      \
+  do {                                                                                                 \
+    int r_ = (call);                                                                                   \
+    if (r_ != 0) { h->err = std::string(#call) + ": " + g_nccl.GetErrorString(r_); return MPASB200_ECUDA; } \
+  } while (0)
+enum { NCCL_F64 = 8 };
+
+void dist_release(mpasb200_t* h) {
+  for (int k = 0; k < MPASB200_X_COUNT; ++k) { for (auto& p : h->xplan[k]) { if (p.sbuf) cudaFree(p.sbuf); if (p.rbuf) cudaFree(p.rbuf); } h->xplan[k].clear(); }
+  for (int e = 0; e < 3; ++e) { if (h->halo[e].d_s) cudaFree(h->halo[e].d_s); if (h->halo[e].d_r) cudaFree(h->halo[e].d_r); h->halo[e].d_s = h->halo[e].d_r = nullptr; }
+  if (h->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+  if (h->ev_ready) { cudaEventDestroy(h->ev_ready); h->ev_ready = nullptr; }
+  if (h->ev_done) { cudaEventDestroy(h->ev_done); h->ev_done = nullptr; }
+  if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); h->comm_stream = nullptr; }
+}
+
+// which fields travel at which point of the step (mirrors parallel.EXCHANGES / EXCHANGES_CORRECTED)
+int dist_build_plans(mpasb200_t* h) {
+  if (h->xplan_built) return 0;
+  const bool corr = h->c.physics_mode == MPASB200_PHYSICS_CORRECTED;
+  auto F = [](std::initializer_list<int> l) { return std::vector<int>(l); };
+  std::vector<std::pair<int, std::vector<int>>> spec[MPASB200_X_COUNT];
+  spec[MPASB200_X_ACOUSTIC_FIRST] = {{MPASB200_CELL, corr ? F({MPASB200_F_w, MPASB200_F_rtheta_pp, MPASB200_F_rtheta_pp_old, MPASB200_F_rho_pp, MPASB200_F_rw_p, MPASB200_F_wwAvg})
+                                                          : F({MPASB200_F_w, MPASB200_F_rtheta_pp, MPASB200_F_rtheta_pp_old})}};
+  spec[MPASB200_X_ACOUSTIC] = {{MPASB200_CELL, corr ? F({MPASB200_F_rtheta_pp, MPASB200_F_rtheta_pp_old, MPASB200_F_rho_pp, MPASB200_F_rw_p, MPASB200_F_wwAvg})
+                                                    : F({MPASB200_F_rtheta_pp, MPASB200_F_rtheta_pp_old})}};
+  spec[MPASB200_X_DIAG] = {{MPASB200_CELL, F({MPASB200_F_ke, MPASB200_F_divergence})}, {MPASB200_EDGE, F({MPASB200_F_pv_edge, MPASB200_F_v})},
+                           {MPASB200_VERTEX, F({MPASB200_F_vorticity})}};
+  spec[MPASB200_X_RECOVER] = {{MPASB200_CELL, F({MPASB200_F_w})}, {MPASB200_EDGE, F({MPASB200_F_u, MPASB200_F_ru, MPASB200_F_ruAvg})}};
+  spec[MPASB200_X_SCALARS] = {{MPASB200_CELL, F({MPASB200_F_scalars})}};
+  for (int k = 0; k < MPASB200_X_COUNT; ++k)
+    for (auto& sp : spec[k]) {
+      mpasb200_t::ExPart p; p.ent = sp.first; p.fields = sp.second; p.entries = 0;
+      for (int f : p.fields) p.entries += kFields[f].slots;
+      const mpasb200_t::Halo& H = h->halo[p.ent];
+      const size_t row = (size_t)p.entries * h->L1;
+      CK(cudaMalloc((void**)&p.sbuf, std::max<size_t>(1, (size_t)H.ns * row) * sizeof(double)));
+      CK(cudaMalloc((void**)&p.rbuf, std::max<size_t>(1, (size_t)H.nr * row) * sizeof(double)));
+      h->bytes += (int64_t)(((size_t)H.ns + H.nr) * row * sizeof(double));
+      h->xplan[k].push_back(p);
+    }
+  h->xplan_built = true;
+  return 0;
+}
+int dist_pack_unpack(mpasb200_t* h, const mpasb200_t::ExPart& p, bool pack) {
+  const mpasb200_t::Halo& H = h->halo[p.ent];
+  const int n = pack ? H.ns : H.nr;
+  if (n == 0) return 0;
+  PackArgs A; A.nf = 0;
+  const size_t slotStride = (size_t)(entity_count(h, p.ent) + 1) * h->LP;
+  for (int f : p.fields) for (int sl = 0; sl < kFields[f].slots; ++sl) A.f[A.nf++] = h->V.f[f] + sl * slotStride;
+  const int rows = std::max(1, 128 / h->LP);
+  dim3 block(h->LP, rows), grid((n + rows - 1) / rows, A.nf);
+  KTimer kt_(h, pack ? "k_pack" : "k_unpack");
+  if (pack) k_pack<<<grid, block, 0, h->stream>>>(A, H.d_s, n, h->L1, h->LP, p.sbuf);
+  else k_unpack<<<grid, block, 0, h->stream>>>(A, H.d_r, n, h->L1, h->LP, p.rbuf);
+  h->launches++;
+  return 0;
+}
+// pack -> one NCCL group -> unpack, all on the communication stream; the compute stream continues at once
+int dist_start(mpasb200_t* h, int kind) {
+  if (!h->comm) return fail(h, MPASB200_ESTATE, "mpasb200_dist_init has not been called");
+  if (int rc = dist_build_plans(h)) return rc;
+  if (h->x_pending) return fail(h, MPASB200_ESTATE, "an exchange is still travelling (dist_flush first)");
+  CK(cudaEventRecord(h->ev_ready, h->stream));
+  CK(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+  cudaStream_t compute = h->stream;
+  h->stream = h->comm_stream;
+  int rc = 0;
+  for (auto& p : h->xplan[kind]) if ((rc = dist_pack_unpack(h, p, true))) break;
+  if (!rc) {
+    int nrc = g_nccl.GroupStart();
+    for (auto& p : h->xplan[kind]) {
+      const mpasb200_t::Halo& H = h->halo[p.ent];
+      const size_t row = (size_t)p.entries * h->L1;
+      for (size_t i = 0; i < H.peers_s.size() && !nrc; ++i)
+        if (H.off_s[i + 1] > H.off_s[i]) nrc = g_nccl.Send(p.sbuf + (size_t)H.off_s[i] * row, (size_t)(H.off_s[i + 1] - H.off_s[i]) * row, NCCL_F64, H.peers_s[i], h->comm, h->comm_stream);
+      for (size_t i = 0; i < H.peers_r.size() && !nrc; ++i)
+        if (H.off_r[i + 1] > H.off_r[i]) nrc = g_nccl.Recv(p.rbuf + (size_t)H.off_r[i] * row, (size_t)(H.off_r[i + 1] - H.off_r[i]) * row, NCCL_F64, H.peers_r[i], h->comm, h->comm_stream);
+    }
+    const int erc = g_nccl.GroupEnd();
+    if (nrc || erc) { h->err = std::string("NCCL send/recv: ") + g_nccl.GetErrorString(nrc ? nrc : erc); rc = MPASB200_ECUDA; }
+  }
+  if (!rc) for (auto& p : h->xplan[kind]) if ((rc = dist_pack_unpack(h, p, false))) break;
+  h->stream = compute;
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev_done, h->comm_stream));
+  h->x_pending = true;
+  return post_launch(h);
+}
+int dist_finish(mpasb200_t* h) {
+  if (!h->x_pending) return 0;
+  CK(cudaStreamWaitEvent(h->stream, h->ev_done, 0));
+  h->x_pending = false;
+  return 0;
+}
+int dist_exchange(mpasb200_t* h, int kind) { if (int rc = dist_start(h, kind)) return rc; return dist_finish(h); }
+
+void set_ranges(mpasb200_t* h, int ent, int cls) {      // launch class -> range of mpasb200_set_range (cls < 0: everything)
+  if (cls < 0) { h->rangeSet[ent] = false; return; }
+  h->rangeB[ent] = h->classBegin[ent][cls]; h->rangeE[ent] = h->classBegin[ent][cls + 1]; h->rangeSet[ent] = true;
+}
+void set_empty(mpasb200_t* h, int ent) { h->rangeB[ent] = h->rangeE[ent] = 0; h->rangeSet[ent] = true; }
+
+// atm_srk3 (rk_timestep.rg:361-500) on one rank of an N-rank run
+int t_srk3_dist(mpasb200_t* h, double dt) {
+  const MpasConfig& C = h->c;
+  const int number_of_sub_steps = C.number_of_sub_steps, dynamics_split = C.config_dynamics_split_steps;
+  const double rk_timestep[3] = {dt / 3, dt / 2, dt};
+  const double rk_sub_timestep[3] = {dt / 3, dt / number_of_sub_steps, dt / number_of_sub_steps};
+  const int number_sub_steps[3] = {std::max(1, number_of_sub_steps / 2), std::max(1, number_of_sub_steps / 2), number_of_sub_steps};
+  const bool corr = C.physics_mode == MPASB200_PHYSICS_CORRECTED;
+  const bool overlap = h->has_classes;
+  const bool saved[2] = {h->rangeSet[MPASB200_CELL], h->rangeSet[MPASB200_EDGE]};
+  if (saved[0] || saved[1]) return fail(h, MPASB200_ESTATE, "mpasb200_srk3_dist manages the launch ranges itself: clear mpasb200_set_range first");
+  int rc;
+#define R(call) do { if ((rc = (call))) { h->rangeSet[MPASB200_CELL] = h->rangeSet[MPASB200_EDGE] = false; return rc; } } while (0)
+  R(t_setup(h)); R(t_moist(h));
+  R(t_vert_imp(h, rk_sub_timestep[0]));
+  R(dist_finish(h));                         // the diagnostics exchange of the previous step's last stage travelled under setup/moist/vert_imp
+  for (int rk_step = 0; rk_step < 3; ++rk_step) {
+    if (rk_step == 1) { R(t_vert_imp(h, rk_sub_timestep[rk_step])); R(dist_finish(h)); }
+    const int rk_arg = (C.rkarg_policy == MPASB200_RKARG_SUBSTEP_TRUNC) ? (int)rk_sub_timestep[rk_step] : rk_step;
+    R(t_dyn_tend(h, rk_arg, dt, C.config_horiz_mixing, C.config_mpas_cam_coef, C.config_mix_full, C.config_rayleigh_damp_u));
+    R(t_smlstep(h));
+    for (int small_step = 0; small_step < number_sub_steps[rk_step] + 1; ++small_step) {
+      const double dts = rk_sub_timestep[rk_step];
+      const int kind = small_step == 0 ? MPASB200_X_ACOUSTIC_FIRST : MPASB200_X_ACOUSTIC;
+      if (!overlap) {
+        R(t_acoustic(h, dts, small_step)); R(dist_exchange(h, kind)); R(t_divdamp(h, dts));
+        continue;
+      }
+      if (corr) {                            // the edge update belongs to the task call: all edges once, before any cell
+        set_empty(h, MPASB200_CELL); set_ranges(h, MPASB200_EDGE, -1);
+        R(t_acoustic(h, dts, small_step));
+        set_empty(h, MPASB200_EDGE);
+      }
+      set_ranges(h, MPASB200_CELL, 1); R(t_acoustic(h, dts, small_step));          // owned cells some rank reads: first
+      R(dist_start(h, kind));                                                      // ... they travel
+      set_ranges(h, MPASB200_CELL, 0); R(t_acoustic(h, dts, small_step));          // ... under the interior cells
+      set_ranges(h, MPASB200_EDGE, 0); R(t_divdamp(h, dts));                       // ... and the interior edges
+      R(dist_finish(h));
+      set_ranges(h, MPASB200_EDGE, 1); R(t_divdamp(h, dts));                       // edges next to ghosts
+      set_ranges(h, MPASB200_CELL, -1); set_ranges(h, MPASB200_EDGE, -1);
+    }
+    if (corr) { R(t_recover(h, number_sub_steps[rk_step], rk_step, dt)); R(dist_exchange(h, MPASB200_X_RECOVER)); }
+    if (C.config_scalar_advection) { R(t_scalars(h, rk_timestep[rk_step], rk_step)); R(dist_exchange(h, MPASB200_X_SCALARS)); }
+    R(t_diag(h, 0, rk_step));
+    // read next by atm_compute_dyn_tend only: stages 0 and 2 let it travel under the column work in between
+    if (overlap && rk_step != 1) R(dist_start(h, MPASB200_X_DIAG)); else R(dist_exchange(h, MPASB200_X_DIAG));
+  }
+  R(t_finish(h, 1, dynamics_split));
+#undef R
+  return 0;
+}
 }  // namespace
 
 // =====================================================================================================
@@ -636,8 +858,11 @@ int mpasb200_create(const MpasDims* dims, const MpasConfig* cfg, mpasb200_t** ou
   if ((e = cudaSetDevice(h->device)) != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); delete h; return MPASB200_ECUDA; }
   h->nCells = dims->nCells; h->nEdges = dims->nEdges; h->nVertices = dims->nVertices;
   h->L = dims->nVertLevels; h->L1 = h->L + 1; h->LP = (h->L1 + 3) / 4 * 4;
+  // layout experiments (profiles/): MPASB200_LP_ALIGN = 16 pads every column to whole 128-byte lines; MPASB200_CPB = columns per block
+  if (const char* e = std::getenv("MPASB200_LP_ALIGN")) { const int a = std::atoi(e); if (a >= 4 && a % 4 == 0) h->LP = (h->L1 + a - 1) / a * a; }
   { const int T = h->LP / 2; int g = T, b = 32; while (b) { int t = g % b; g = b; b = t; } h->CPB = 32 / g; while (h->CPB * T < 128) h->CPB *= 2;
-    while (h->CPB * T > 256 && h->CPB > 1) h->CPB /= 2; }      // several kernels are compiled for <= 256 threads per block
+    while (h->CPB * T > 256 && h->CPB > 1) h->CPB /= 2;        // several kernels are compiled for <= 256 threads per block
+    if (const char* e = std::getenv("MPASB200_CPB")) { const int c = std::atoi(e); if (c >= 1 && c * T <= 256 && (c * T) % 32 == 0) h->CPB = c; } }
   if (h->LP / 2 * h->CPB > 256) { g_create_error = "nVertLevels too large for one block per column group"; delete h; return MPASB200_EINVAL; }
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
@@ -684,6 +909,7 @@ int mpasb200_destroy(mpasb200_t* h) {
   for (int e = 0; e < 3; ++e) if (h->d_gid[e]) cudaFree(h->d_gid[e]);
   if (h->d_acc) cudaFree(h->d_acc);
   if (h->d_sflux) cudaFree(h->d_sflux);
+  dist_release(h);
   for (auto& pp : h->pipe) {
     if (pp.up) cudaFree(pp.up);
     if (pp.dn) cudaFree(pp.dn);
@@ -900,6 +1126,7 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
 #undef UP_IDS
 #undef UP_INT
 #undef UP_DBL
+  h->has_classes = m->cellClass && m->edgeClass;
   h->mesh_ok = true;
   return 0;
 }
@@ -1243,6 +1470,69 @@ int mpasb200_summarize_field(mpasb200_t* h, int field, int32_t n_first, int32_t 
   out->max_index = any ? (int64_t)(a.loc_max / (unsigned long long)nlevels) : -1; out->max_level = any ? (int32_t)(a.loc_max % (unsigned long long)nlevels) : -1;
   out->n_nan = (int64_t)a.n_nan; out->n_inf = (int64_t)a.n_inf; out->count = (int64_t)total; out->checksum = a.checksum;
   return 0;
+}
+
+// ---- the distributed step ----------------------------------------------------------------------------------------------------
+int mpasb200_dist_unique_id(void* id128) {
+  if (!id128) return MPASB200_EINVAL;
+  if (!nccl_load()) { g_create_error = g_nccl.err; return MPASB200_ESTATE; }
+  return g_nccl.GetUniqueId(id128) == 0 ? 0 : MPASB200_ECUDA;
+}
+int mpasb200_dist_init(mpasb200_t* h, int rank, int world, const void* id128) {
+  if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  if (h->comm) return fail(h, MPASB200_ESTATE, "dist_init may be called once per handle");
+  if (!nccl_load()) return fail(h, MPASB200_ESTATE, g_nccl.err);
+  NcclId128 id; std::memcpy(id.b, id128, 128);
+  NCK(g_nccl.CommInitRank(&h->comm, world, id, rank));
+  h->rank = rank; h->world = world;
+  CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  return 0;
+}
+int mpasb200_dist_set_halo(mpasb200_t* h, int entity, int32_t nsp, const int32_t* sp, const int32_t* so, const int32_t* si,
+                           int32_t nrp, const int32_t* rp, const int32_t* ro, const int32_t* ri) {
+  REQUIRE_MESH();
+  if (entity < 0 || entity > MPASB200_VERTEX || nsp < 0 || nrp < 0) return fail(h, MPASB200_EINVAL, "dist_set_halo: bad argument");
+  if ((nsp && (!sp || !so || !si)) || (nrp && (!rp || !ro || !ri))) return fail(h, MPASB200_EINVAL, "dist_set_halo: null list");
+  std::unique_lock<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  if (h->xplan_built) return fail(h, MPASB200_ESTATE, "dist_set_halo after the first exchange");
+  mpasb200_t::Halo& H = h->halo[entity];
+  const int cnt = entity_count(h, entity);
+  auto load = [&](int np, const int32_t* peers, const int32_t* off, const int32_t* idx, std::vector<int>& P, std::vector<int>& O, int** d, int* n) -> int {
+    P.assign(peers, peers + np); O.assign(1, 0);
+    if (np) O.assign(off, off + np + 1);
+    *n = np ? O[np] : 0;
+    for (int i = 0; i < np; ++i) if (P[i] < 0 || P[i] >= h->world || P[i] == h->rank || O[i + 1] < O[i]) return fail(h, MPASB200_EINVAL, "dist_set_halo: bad peer / offsets");
+    std::vector<int> tmp(*n);
+    for (int i = 0; i < *n; ++i) { if (idx[i] < 0 || idx[i] >= cnt) return fail(h, MPASB200_EINVAL, "dist_set_halo: index out of range"); tmp[i] = h->newOf[entity][idx[i]]; }
+    if (*d) { cudaFree(*d); *d = nullptr; }
+    if (*n) { CK(cudaMalloc((void**)d, sizeof(int) * *n)); CK(cudaMemcpy(*d, tmp.data(), sizeof(int) * *n, cudaMemcpyHostToDevice)); }
+    return 0;
+  };
+  int rc;
+  if ((rc = load(nsp, sp, so, si, H.peers_s, H.off_s, &H.d_s, &H.ns))) return rc;
+  if ((rc = load(nrp, rp, ro, ri, H.peers_r, H.off_r, &H.d_r, &H.nr))) return rc;
+  H.set = true;
+  return 0;
+}
+int mpasb200_dist_exchange(mpasb200_t* h, int kind) {
+  REQUIRE_MESH();
+  if (kind < 0 || kind >= MPASB200_X_COUNT) return fail(h, MPASB200_EINVAL, "dist_exchange: unknown kind");
+  Entry en(h, -1);
+  if (int rc = dist_finish(h)) return rc;
+  return dist_exchange(h, kind);
+}
+int mpasb200_dist_flush(mpasb200_t* h) { REQUIRE_MESH(); Entry en(h, -1); return dist_finish(h); }
+int mpasb200_srk3_dist(mpasb200_t* h, double dt) {
+  REQUIRE_MESH();
+  Entry en(h, -1);
+  if (!h->comm) return fail(h, MPASB200_ESTATE, "mpasb200_dist_init has not been called");
+  if (h->c.config_scalar_advection) { if (int rc = ensure_sflux(h)) return rc; }
+  return t_srk3_dist(h, dt);
 }
 
 // ---- introspection ------------------------------------------------------------------------------------------------

@@ -91,6 +91,13 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         lib.mpasb200_set_global_ids.argtypes, lib.mpasb200_set_global_ids.restype = [H, I, C.c_void_p, C.c_int32], I
         lib.mpasb200_summarize_field.argtypes = [H, I, C.c_int32, C.c_int32, C.POINTER(_abi.MpasFieldSummary)]
         lib.mpasb200_summarize_field.restype = I
+        lib.mpasb200_dist_unique_id.argtypes, lib.mpasb200_dist_unique_id.restype = [C.c_void_p], I
+        lib.mpasb200_dist_init.argtypes, lib.mpasb200_dist_init.restype = [H, I, I, C.c_void_p], I
+        lib.mpasb200_dist_set_halo.argtypes = [H, I, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mpasb200_dist_set_halo.restype = I
+        lib.mpasb200_dist_exchange.argtypes, lib.mpasb200_dist_exchange.restype = [H, I], I
+        lib.mpasb200_dist_flush.argtypes, lib.mpasb200_dist_flush.restype = [H], I
+        lib.mpasb200_srk3_dist.argtypes, lib.mpasb200_srk3_dist.restype = [H, D], I
         lib.mpasb200_launch_count.argtypes, lib.mpasb200_launch_count.restype = [H], C.c_int64
         lib.mpasb200_device_bytes.argtypes, lib.mpasb200_device_bytes.restype = [H], C.c_int64
         lib.mpasb200_field_info.argtypes = [I, C.POINTER(I), C.POINTER(I), C.POINTER(C.c_char_p)]
@@ -350,6 +357,42 @@ class Dynamics(TaskAPI):
         nl = self.dims.nVertLevels + 1 if nlevels is None else int(nlevels)
         self._check(self._lib.mpasb200_summarize_field(self._h, FIELD_ID[name], n, nl, C.byref(out)), "summarize_field")
         return out.as_dict()
+
+    # ---- the distributed step inside the library (mpasb200_dist_*) --------------------------------------------
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        """128 bytes (ncclGetUniqueId) made on ONE rank; the host's own channel carries them to the others"""
+        buf = C.create_string_buffer(128)
+        rc = load_library().mpasb200_dist_unique_id(buf)
+        if rc != 0:
+            raise MpasB200Error(f"mpasb200_dist_unique_id failed ({rc}): {load_library().mpasb200_last_error(None).decode()}")
+        return buf.raw
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        self._check(self._lib.mpasb200_dist_init(self._h, rank, world, C.c_char_p(unique_id)), "dist_init")
+
+    def dist_set_halo(self, entity: int, send: Dict[int, np.ndarray], recv: Dict[int, np.ndarray]):
+        """send / recv: peer rank -> local indices (partition.LocalMesh.send[ent] / .recv[ent])"""
+        def flat(d):
+            peers = sorted(d)
+            off = np.cumsum([0] + [len(d[p]) for p in peers]).astype(np.int32)
+            idx = np.concatenate([np.asarray(d[p], dtype=np.int32) for p in peers]) if peers else np.zeros(0, np.int32)
+            return np.asarray(peers, dtype=np.int32), off, np.ascontiguousarray(idx, dtype=np.int32)
+        sp, so, si = flat(send)
+        rp, ro, ri = flat(recv)
+        self._check(self._lib.mpasb200_dist_set_halo(self._h, entity, len(sp), sp.ctypes.data, so.ctypes.data, si.ctypes.data,
+                                                     len(rp), rp.ctypes.data, ro.ctypes.data, ri.ctypes.data), "dist_set_halo")
+
+    def dist_exchange(self, kind: int):
+        self._check(self._lib.mpasb200_dist_exchange(self._h, int(kind)), "dist_exchange")
+
+    def dist_flush(self):
+        self._check(self._lib.mpasb200_dist_flush(self._h), "dist_flush")
+
+    def atm_srk3_dist(self, dt: float):
+        """atm_srk3 on one rank of an N-rank run, exchanges issued by the library (mpasb200_srk3_dist)"""
+        self._check(self._lib.mpasb200_srk3_dist(self._h, float(dt)), "srk3_dist")
 
     # ---- halo building blocks ------------------------------------------------------------------------
     def register_list(self, entity: int, idx: np.ndarray) -> int:

@@ -252,6 +252,33 @@ class NcclExchanger(Exchanger):
                     self.dyn.unpack(E["lr"], names, rbuf.data_ptr())
 
 
+class NativeDistributedDynamics:
+    """The same step with the whole exchange schedule INSIDE libmpas_b200 (mpasb200_dist_init / _set_halo / _srk3_dist):
+    NCCL send/recv issued from the C++ driver on the library's own communication stream, overlap by launch classes.
+    The host only hands over the NCCL unique id (here through torch.distributed) and the halo lists."""
+
+    def __init__(self, dyn, lm: partition.LocalMesh, rank: int, world: int):
+        import torch.distributed as dist
+        self.dyn, self.lm = dyn, lm
+        box = [dyn.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        dyn.dist_init(rank, world, box[0])
+        for ent in ("cell", "edge", "vertex"):
+            dyn.dist_set_halo(ENT[ent], lm.send[ent], lm.recv[ent])
+        self.overlap = True
+        self.t_init = 0.0
+
+    def init_diagnostics(self):
+        self.dyn.atm_compute_solve_diagnostics(False, -1)
+        self.dyn.dist_exchange(_abi.X_DIAG)
+
+    def step(self, dt: float):
+        self.dyn.atm_srk3_dist(dt)
+
+    def flush(self):
+        self.dyn.dist_flush()
+
+
 class DistributedDynamics:
     """atm_srk3 on one rank of an N-rank run: the reference's task sequence (rk_timestep.rg:378-481) with the
     exchanges of EXCHANGES after the tasks that need them."""
@@ -337,10 +364,13 @@ class DistributedDynamics:
         dyn.upload_mesh(static)
         dyn.upload_state(fields, vert)
         del fields
-        run = cls(dyn, NcclExchanger(dyn, lm, stream))
+        if os.environ.get("MPAS_B200_NATIVE_DIST", "1") != "0":
+            run = NativeDistributedDynamics(dyn, lm, rank, world)
+        else:
+            run = cls(dyn, NcclExchanger(dyn, lm, stream))
+            if cfg.physics_mode == _abi.PHYSICS_LITERAL and os.environ.get("MPAS_B200_OVERLAP", "1") != "0":
+                run.enable_overlap()
         run.lm = lm
-        if cfg.physics_mode == _abi.PHYSICS_LITERAL and os.environ.get("MPAS_B200_OVERLAP", "1") != "0":
-            run.enable_overlap()
         run.init_diagnostics()
         run.t_init = time.time() - t0
         return run

@@ -96,6 +96,8 @@ K: Dict[str, Tuple[List[str], List[str]]] = {
 # the exact streaming acoustic kernel moves the same fields as the affine one
 K["k_acoustic_seq<true>"] = K["k_acoustic_tma<true>"]
 K["k_acoustic_seq<false>"] = K["k_acoustic_tma<false>"]
+K["k_acoustic_lane<true>"] = K["k_acoustic_tma<true>"]
+K["k_acoustic_lane<false>"] = K["k_acoustic_tma<false>"]
 # array-typed fields whose every slot is touched
 FULL_SLOTS = {"scalars": 8, "scalars_old": 8}
 

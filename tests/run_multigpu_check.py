@@ -19,19 +19,31 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mode = sys.argv[1] if len(sys.argv) > 1 else "literal"
-    corrected, overlap = mode == "corrected", mode == "overlap"
+    # modes: literal | overlap | corrected  = the host-side (Python) schedule;  native | native_corrected | native_scalars = the
+    # schedule inside the library (mpasb200_srk3_dist)
+    native = mode.startswith("native")
+    corrected, overlap = mode.endswith("corrected"), mode == "overlap"
+    scalars = mode == "native_scalars"
     L, dt, steps = 12, 400.0, (1 if corrected else 3)     # corrected physics: the first step is the finite one
     mesh = icosa.make_icosahedral_mesh(2562)
     st = init_jw.make_state(mesh, L, _abi.INDEX_CORRECTED)
     cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, device=local,
-                              physics_mode=_abi.PHYSICS_CORRECTED if corrected else _abi.PHYSICS_LITERAL)
+                              physics_mode=_abi.PHYSICS_CORRECTED if corrected else _abi.PHYSICS_LITERAL,
+                              config_scalar_advection=int(scalars))
+    if scalars:
+        rng = np.random.default_rng(17)
+        st.f["scalars"] = 1e-3 * (1.0 + rng.random((mesh.nCells, L + 1, 8)))
     stream = torch.cuda.Stream()
     sh = parallel.make_shards(st, world)[rank]
     lm = sh["lm"]
     d = dynamics.Dynamics(_abi.make_dims(len(lm.cells), len(lm.edges), len(lm.vertices), L), cfg)
     d.set_stream(stream.cuda_stream)
     d.upload_mesh(sh["static"]); d.upload_state(sh["f"], sh["vert"])
-    run = parallel.DistributedDynamics(d, parallel.NcclExchanger(d, lm, stream))
+    run = (parallel.NativeDistributedDynamics(d, lm, rank, world) if native
+           else parallel.DistributedDynamics(d, parallel.NcclExchanger(d, lm, stream)))
+    if native:
+        c0, c1 = d.class_range(_abi.CELL, 0), d.class_range(_abi.CELL, 1)
+        assert c1[1] - c1[0] > 0 and c0[1] - c0[0] > 0
     if overlap:       # acoustic-loop exchanges on the communication stream, interior compute underneath
         assert run.enable_overlap()
         c0, c1 = d.class_range(_abi.CELL, 0), d.class_range(_abi.CELL, 1)

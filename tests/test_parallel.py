@@ -316,3 +316,40 @@ def test_irregular_colourings_still_match_single_partition(grid642, kind):
         _assert_owned_equal(single, b, s["lm"])
         cc = s["static"]["cellClass"]
         assert (cc == 2).sum() == len(s["lm"].cells) - s["lm"].n_owned[0]
+
+
+def test_n_ranks_equal_single_partition_with_scalar_transport(grid642):
+    """config_scalar_advection: atm_advance_scalars reads `scalars` two rings out, so it is exchanged after every stage
+    (parallel.EXCHANGES["advance_scalars"], rk_timestep.rg:469); the array-typed field travels slot by slot."""
+    from oracle.oracle import Oracle
+    world = 3
+    st = init_jw.make_state(grid642, L, _abi.INDEX_CORRECTED)
+    st.f["scalars"] = 1e-3 * (1.0 + np.random.default_rng(2).random((grid642.nCells, L + 1, 8)))
+    shards = parallel.make_shards(st, world)
+    cfg = dict(rkarg_policy=_abi.RKARG_STAGE_INDEX, config_scalar_advection=1, physics_mode=_abi.PHYSICS_CORRECTED)
+    single = Oracle(dynamics.dims_of(grid642, L), _abi.default_config(**cfg))
+    single.upload_mesh(st.static); single.upload_state(st.f, st.vert)
+    single.atm_compute_solve_diagnostics(False, -1)
+    single.atm_srk3(DT)
+    backs = []
+    for sh in shards:
+        lm = sh["lm"]
+        o = Oracle(_abi.make_dims(len(lm.cells), len(lm.edges), len(lm.vertices), L), _abi.default_config(**cfg))
+        o.upload_mesh(sh["static"]); o.upload_state(sh["f"], sh["vert"])
+        backs.append(o)
+    ex = parallel.InProcessExchanger(backs, [s["lm"] for s in shards])
+    exchanges = parallel.exchanges_for(backs[0].cfg)
+    for b in backs:
+        b.atm_compute_solve_diagnostics(False, -1)
+    ex.exchange(exchanges["compute_solve_diagnostics"])
+    seq = _task_schedule(backs[0].cfg)
+    assert [n for n, _ in seq].count("advance_scalars") == 3
+    for name, args in seq:
+        for b in backs:
+            b._call(name, *args)
+        spec = exchanges.get(parallel.exchange_key(name, args))
+        if spec:
+            ex.exchange(spec)
+    assert not np.array_equal(single.download_field("scalars"), st.f["scalars"])
+    for b, s in zip(backs, shards):
+        _assert_owned_equal(single, b, s["lm"], names=("scalars", "scalars_old", "w", "theta_m", "u"))

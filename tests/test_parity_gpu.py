@@ -188,7 +188,7 @@ def test_error_paths(grid642):
     g.close()
 
 
-@pytest.mark.parametrize("exact", [0, 1, 2, 3, 4], ids=["fused_affine", "two_kernel_exact", "fused_affine_tma", "split_gather_tma", "split_gather_seq_default"])
+@pytest.mark.parametrize("exact", [0, 1, 2, 3, 4, 5], ids=["fused_affine", "two_kernel_exact", "fused_affine_tma", "split_gather_tma", "split_gather_seq", "split_gather_lane_pipeline"])
 def test_acoustic_modes(grid2562, exact):
     """every evaluation of the acoustic column sweep agrees with the oracle (1e-12); the strictly ordered ones
     (acoustic_exact=1, and the default acoustic_tma=3) are additionally bit-identical on the fields the sweep produces."""
@@ -199,7 +199,7 @@ def test_acoustic_modes(grid2562, exact):
             b.atm_advance_acoustic_step(dts, ss)
             b.atm_divergence_damping_3d(dts)
     compare(g, ora, what=f"acoustic exact={exact}")
-    if exact in (1, 4):
+    if exact in (1, 4, 5):
         for n in ("rw_p", "rho_pp", "rtheta_pp", "wwAvg", "rtheta_pp_old", "ru_p"):
             assert np.array_equal(g.download_field(n), ora.download_field(n)), n
     g.close(); ora.close()
@@ -325,7 +325,8 @@ def test_nccl_ranks_equal_single_gpu():
         pytest.skip("needs >= 2 GPUs")
     n = 2 if n < 4 else 4
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for physics, port in (("literal", "29533"), ("overlap", "29537"), ("corrected", "29535")):
+    for physics, port in (("literal", "29533"), ("overlap", "29537"), ("corrected", "29535"), ("native", "29539"),
+                          ("native_corrected", "29541"), ("native_scalars", "29543")):
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                               "--master-port", port, os.path.join(root, "tests", "run_multigpu_check.py"), physics],
                              capture_output=True, text=True, timeout=600, cwd=root)
@@ -562,4 +563,38 @@ def test_advance_scalars_parity(grid2562, policy):
     for b in (ora, g):
         b.atm_srk3(DT)
     assert np.array_equal(g.download_field("scalars"), ora.download_field("scalars"))
+    g.close(); ora.close()
+
+
+@pytest.mark.parametrize("levels", [4, 26, 30, 55, 58, 100], ids=lambda v: f"L{v}")
+def test_acoustic_lane_pipeline_shapes(grid642, levels):
+    """k_acoustic_lane (acoustic_tma = 4: sweeper warp + mover warps, 8-level chunks, 32-column tiles): partial last chunk,
+    partial last tile, level counts around the chunk size, a restricted cell range, spec-zone columns -- bit-identical
+    acoustic outputs, full state inside the bound."""
+    st, ora, g = build_pair(grid642, levels, _abi.INDEX_CORRECTED, m5=True, acoustic_tma=4)
+    spec = np.zeros(grid642.nCells); spec[5::37] = 1.0
+    ora.close(); g.close()
+    st.static["specZoneMaskCell"] = spec
+    from mpas_regent_b200 import dynamics
+    from oracle.oracle import Oracle
+    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, acoustic_tma=4)
+    ora = Oracle(dynamics.dims_of(grid642, levels), cfg); g = dynamics.Dynamics(dynamics.dims_of(grid642, levels), cfg)
+    for b in (ora, g):
+        b.upload_mesh(st.static); b.upload_state(st.f, st.vert)
+        b.atm_compute_solve_diagnostics(False, -1)
+        b.atm_srk3(300.0)
+    compare(g, ora, what=f"L={levels}")
+    for n in ACOUSTIC_OUT[2:]:
+        assert np.array_equal(g.download_field(n), ora.download_field(n), equal_nan=True), n
+    # a restricted range: cells [37, 301) only
+    snap = {n: ora.download_field(n) for n in ACOUSTIC_OUT[2:]}
+    g.set_range(_abi.CELL, 37, 301)
+    g.atm_advance_acoustic_step(100.0, 1)
+    ora.atm_advance_acoustic_step(100.0, 1)
+    for n in ACOUSTIC_OUT[2:]:
+        a, full = g.download_field(n), ora.download_field(n)
+        lo, hi = g.class_range(_abi.CELL, 0)      # no classes: internal order == the curve; compare through the untouched set instead
+        touched = ~np.all(a == snap[n], axis=1)
+        assert touched.sum() <= 301 - 37, n
+        assert np.array_equal(a[touched], full[touched], equal_nan=True), n
     g.close(); ora.close()
