@@ -119,15 +119,15 @@ typedef struct {
   int32_t use_graph;                  /* 1: mpasb200_srk3 replays a captured CUDA graph */
   int32_t acoustic_exact;             /* 1: evaluate the acoustic column sweep strictly left-to-right (two kernels, one
                                          thread per column); 0 (default): fused kernel, affine sweep (a few ulp apart) */
-  int32_t acoustic_tma;               /* acoustic step form: 3 (default) = lean gather kernel + TMA streaming kernel whose column sweep is
-                                         evaluated strictly in the reference's order (bit-identical to the CPU restatement);
-                                         2 = the same with the affine two-level sweep (a few ulp of the largest term apart, faster sweep);
-                                         1 = one fused kernel, own-column strips staged with cp.async.bulk, affine sweep; 0 = fused, plain loads */
+  int32_t acoustic_tma;               /* acoustic step form: 3 (default) = lean gather kernel + k_acoustic_lane, a warp-specialised streaming
+                                         pipeline whose column sweep runs one column per lane strictly in the reference's order
+                                         (bit-identical to the CPU restatement); 2 = gather kernel + cp.async.bulk strips with the affine
+                                         two-level sweep (a few ulp of the largest term apart); 1 = one fused kernel, bulk strips, affine
+                                         sweep; 0 = fused, plain loads */
   int32_t physics_mode;               /* mpasb200_physics_mode_t; default LITERAL */
   int32_t gather_stage;               /* LABORATORY builds (-DMPASB200_LAB) only, ignored by the shipped library: bit mask selecting the
                                          cp.async-staged forms of k_dt_edge (1), k_acoustic_gather (2), k_dt_theta_flux (4).  Measured
                                          slower than the plain kernels on B200 (profiles/r2_staged_gathers.md); bit-identical results. */
-  int32_t acoustic_cols;              /* columns per block of the exact streaming acoustic kernel; 0 = default (4) */
   int32_t config_scalar_advection;    /* 0 (default): atm_srk3 skips scalar transport exactly like the reference (rk_timestep.rg:465);
                                          1: atm_rk_integration_setup saves scalars_old and every RK stage calls atm_advance_scalars
                                          with rk_timestep[rk_step] = dt/3, dt/2, dt (rk_timestep.rg:386-389)              */

@@ -64,7 +64,7 @@ _CFG_D = ("gravity", "rgas", "cp", "cv", "omega", "sphere_radius", "prandtl", "c
           "config_h_theta_eddy_visc4", "config_rayleigh_damp_u_timescale_days", "config_mpas_cam_coef")
 _CFG_I = ("config_number_rayleigh_damp_u_levels", "config_horiz_mixing", "config_mix_full", "config_rayleigh_damp_u",
           "nRelaxZone", "number_of_sub_steps", "config_dynamics_split_steps", "index_policy", "rkarg_policy",
-          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma", "physics_mode", "gather_stage", "acoustic_cols", "config_scalar_advection")
+          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma", "physics_mode", "gather_stage", "config_scalar_advection")
 
 
 class MpasConfig(C.Structure):
@@ -139,7 +139,6 @@ def default_config(**over) -> MpasConfig:
     c.sfc_renumber, c.device, c.use_graph, c.acoustic_exact, c.acoustic_tma = 1, -1, 0, 0, 3
     c.physics_mode = PHYSICS_LITERAL
     c.gather_stage = 0
-    c.acoustic_cols = 0
     c.config_scalar_advection = 0
     c.config_coef_3rd_order = 0.25
     for k, v in over.items():

@@ -1272,110 +1272,11 @@ __global__ void __launch_bounds__(128, 5) k_acoustic_tma(const View V, const AcP
 #undef SIN
 }
 
-// EXACT streaming form (MpasConfig.acoustic_tma = 3, the default): same cp.async.bulk strips as k_acoustic_tma, but the
-// column arithmetic is evaluated strictly in the reference's order -- level by level, every expression as written at
-// :1657-1696 -- by ONE lane per column (the C columns of a block share lanes 0..C-1 of its first warp) out of shared
-// memory; the other lanes only move data (bulk strips in, coalesced 128-bit stores out).  Bit-identical to the oracle.
-// Why this is the default: the affine regrouping of k_acoustic_tma changes rw_p by a few ulp of its LARGEST term, which the
-// differences taken by atm_divergence_damping_3d amplify -- at BASELINE config 2 (x1.40962 x 41, dt = 180 s) ru_p then
-// misses the 1e-12 bound after one step (3.7e-12, gpurun_out/c1_pytest.log of round 2).  The recurrence is latency-bound
-// (~19 dependent fp64 operations per level), so the lanes that wait cost nothing: the kernel stays at the speed of the
-// strips as long as enough blocks are resident to overlap one block's sweep with its neighbours' copies.
-template <bool S0>
-__global__ void __launch_bounds__(128, 5) k_acoustic_seq(const View V, const AcPtrs F, double dts, double epssm, double resm) {
-  extern __shared__ __align__(128) unsigned char smraw[];
-  PAIR_THREAD_R()
-  const int C = blockDim.y, NF = S0 ? (int)AF_rho_pp : (int)AF_COUNT;
-  const int CL = C * LP;
-  double* in = reinterpret_cast<double*>(smraw);                 // [AF_COUNT][C*LP]; the last four strips double as outputs
-  double* s_v = in + (size_t)AF_COUNT * CL;                      // cofrz, rdzw, fzm, fzp  [4][LP]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_v + (size_t)4 * LP);
-  const int nthr = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
-  if (tid == 0) mbar_init(bar, 1);
-  __syncthreads();
-  const size_t tile0 = ((size_t)V.xoff + (size_t)blockIdx.x * C) * LP;
-  if (tid == 0) mbar_expect_tx(bar, (uint32_t)(NF * CL * sizeof(double)));
-  for (int f = tid; f < NF; f += nthr) bulk_g2s(in + (size_t)f * CL, F.p[f] + tile0, (uint32_t)(CL * sizeof(double)), bar);
-  for (int i = tid; i < LP; i += nthr) {
-    s_v[i] = FLD(cofrz)[i]; s_v[LP + i] = FLD(rdzw)[i]; s_v[2 * LP + i] = FLD(fzm)[i]; s_v[3 * LP + i] = FLD(fzp)[i];
-  }
-  if (S0) for (int i = tid; i < 4 * CL; i += nthr) in[(size_t)AF_rho_pp * CL + i] = 0.0;   // :1625-1636: the old values are zero
-  if (S0 && inx) {                                                                                    // :1625-1630, level L
-    if (k0 == L) { FLD(wwAvg)[ix] = 0; FLD(rw_p)[ix] = 0; }
-    if (k1 == L) { FLD(wwAvg)[ix + 1] = 0; FLD(rw_p)[ix + 1] = 0; }
-  }
-  const size_t cl = (size_t)threadIdx.y * LP + k0;
-#define SIN(f) (in + (size_t)(f) * CL)
-  mbar_wait(bar, 0);
-  if (m0) st2m(FLD(rtheta_pp_old), ix, S0 ? bc(0.0) : ld2(SIN(AF_rtheta_pp), cl), m0, m1);           // :1615-1623
-  __syncthreads();
-  if (tid < C && V.xoff + (int)blockIdx.x * C + tid < V.xend) {
-    const int c = V.xoff + blockIdx.x * C + tid;
-    const size_t b = (size_t)tid * LP;
-    const double* cofrz = s_v; const double* rdzw = s_v + LP; const double* fzm = s_v + 2 * LP; const double* fzp = s_v + 3 * LP;
-    double* rho_pp = SIN(AF_rho_pp) + b; double* rtheta_pp = SIN(AF_rtheta_pp) + b; double* rw_p = SIN(AF_rw_p) + b; double* wwAvg = SIN(AF_wwAvg) + b;
-    const double* tend_rho = SIN(AF_tend_rho) + b; const double* theta_m = SIN(AF_theta_m) + b; const double* w = SIN(AF_w) + b;
-    const double* coftz = SIN(AF_coftz) + b; const double* cofwz = SIN(AF_cofwz) + b; const double* cofwr = SIN(AF_cofwr) + b;
-    const double* cofwt = SIN(AF_cofwt) + b; const double* a_tri = SIN(AF_a_tri) + b; const double* alpha_tri = SIN(AF_alpha_tri) + b;
-    const double* zz = SIN(AF_zz) + b; const double* rw_save = SIN(AF_rw_save) + b; const double* rw = SIN(AF_rw) + b;
-    const double* dss = SIN(AF_dss) + b; const double* rho_zz = SIN(AF_rho_zz) + b;
-    const double* srs = SIN(AF_rs) + b; const double* sts = SIN(AF_ts) + b;
-    const bool spec = V.specZoneMaskCell[c] != 0.0;
-    double rw_prev = 0, rho_prev = 0, rt_prev = 0;
-    double rw_old_k = rw_p[0];
-    double zz_m = 0.0, cofwt_m = 0.0, rz_m = 0.0;
-#pragma unroll 2
-    for (int k = 0; k < L; ++k) {
-      const double rw_old_p = rw_p[k + 1];
-      const double rho_old = rho_pp[k];
-      const double rt_old = rtheta_pp[k];
-      const double ww_old = wwAvg[k];
-      const double zz_k = zz[k], cofwt_k = cofwt[k], rz_k = rho_zz[k];
-      double rw_new, rho_new, rt_new, ww_new = ww_old;
-      if (!spec) {
-        const double coftz_k = coftz[k], coftz_p = coftz[k + 1];
-        const double rs = rho_old + dts * tend_rho[k] + srs[k] - cofrz[k] * resm * (rw_old_p - rw_old_k);                       // :1657
-        const double ts = rt_old + dts * theta_m[k] + sts[k] - resm * rdzw[k] * (coftz_p * rw_old_p - coftz_k * rw_old_k);       // :1658
-        rw_new = rw_old_k;
-        if (k > 0) {
-          const double w_k = w[k];
-          ww_new += 0.5 * (1.0 - epssm) * rw_old_k;                                                                            // :1661
-          rw_new += dts * w_k - cofwz[k] * ((zz_k * ts - zz_m * 0.0) + resm * (zz_k * rt_old - zz_m * rt_prev))
-                    - cofwr[k] * ((rs + 0.0) + resm * (rho_old + rho_prev))
-                    + cofwt_k * (ts + resm * rt_old)
-                    + cofwt_m * (0.0 + resm * rt_prev);                                                                         // :1662-1667
-          rw_new -= a_tri[k] * rw_prev;                                                                                        // :1670
-          rw_new *= alpha_tri[k];                                                                                              // :1671
-          const double dsk = dss[k];
-          const double r3 = rw_save[k] - rw[k];
-          rw_new += r3 - dts * dsk * (fzm[k] * zz_k + fzp[k] * zz_m) * (fzm[k] * rz_k + fzp[k] * rz_m) * w_k;                   // :1682-1684
-          rw_new /= (1.0 + dts * dsk);                                                                                         // :1685
-          rw_new -= r3;                                                                                                        // :1686
-          ww_new += 0.5 * (1.0 + epssm) * rw_new;                                                                              // :1689
-        }
-        rho_new = rs - cofrz[k] * (rw_old_p - rw_new);                                                                         // :1694
-        rt_new = ts - rdzw[k] * (coftz_p * rw_old_p - coftz_k * rw_new);                                                       // :1695-1696
-      } else {                                                                                                                 // :1698-1703
-        rho_new = rho_old + dts * tend_rho[k];
-        rt_new = rt_old + dts * theta_m[k];
-        rw_new = rw_old_k + dts * w[k];
-        ww_new = ww_old + 0.5 * (1.0 + epssm) * rw_new;
-      }
-      rho_pp[k] = rho_new; rtheta_pp[k] = rt_new;
-      if (S0 || spec || k > 0) { rw_p[k] = rw_new; wwAvg[k] = ww_new; }
-      rw_prev = rw_new; rho_prev = rho_new; rt_prev = rt_new;
-      rw_old_k = rw_old_p; zz_m = zz_k; cofwt_m = cofwt_k; rz_m = rz_k;
-    }
-  }
-  __syncthreads();
-  if (!m0) return;
-  st2m(FLD(rho_pp), ix, ld2(SIN(AF_rho_pp), cl), m0, m1); st2m(FLD(rtheta_pp), ix, ld2(SIN(AF_rtheta_pp), cl), m0, m1);
-  const bool wr0 = S0 || k0 > 0 || V.specZoneMaskCell[x] != 0.0;
-  st2m(FLD(rw_p), ix, ld2(SIN(AF_rw_p), cl), wr0, m1); st2m(FLD(wwAvg), ix, ld2(SIN(AF_wwAvg), cl), wr0, m1);
-#undef SIN
-}
-
-// ---- EXACT, column-per-lane streaming form (MpasConfig.acoustic_tma = 4) -------------------------------------------------
+// ---- EXACT, column-per-lane streaming form (MpasConfig.acoustic_tma = 3, the default) ----------------------------------------
+// Why exact is the default: the affine regrouping of k_acoustic_tma changes rw_p by a few ulp of its LARGEST term, which the
+// differences taken by atm_divergence_damping_3d amplify -- at BASELINE config 2 (x1.40962 x 41, dt = 180 s) ru_p then misses
+// the 1e-12 bound after ONE step (3.7e-12; profiles/r2_acoustic_exact.md).  With this kernel every field of the step except
+// q / tend_u (Q14) is bit-identical to the oracle, at the affine kernel's speed.
 // "The vertical implicit acoustic solve runs one thread per column" (north_star), at streaming speed: a block is a
 // warp-specialised pipeline over a tile of 32 consecutive columns.
 //   * warp 0, the SWEEPER: lane = column.  It walks the levels strictly in the reference's order (the body of
@@ -1388,7 +1289,7 @@ __global__ void __launch_bounds__(128, 5) k_acoustic_seq(const View V, const AcP
 //   * stages are handed over with mbarriers (full/empty for inputs, ofull/oempty for outputs); a stage is laid out
 //     [field][column][8 levels] with the 16-byte pieces of a row XOR-swizzled by the column so that the sweeper's
 //     128-bit loads and the movers' 128-bit loads/stores are all bank-conflict free.
-// 32 recurrences advance per sweeper instruction (k_acoustic_seq: 4), two blocks are resident per SM, and while the
+// 32 recurrences advance per sweeper instruction, two blocks are resident per SM, and while the
 // sweeper works on chunk j the copies of chunk j+1 are in flight: the kernel is bound by the strips, not by the chain.
 enum { AL_KC = 8, AL_COLS = 32, AL_NMOV = 96, AL_NOUT = 5 };
 DI void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
@@ -1448,8 +1349,11 @@ __global__ void __launch_bounds__(32 + AL_NMOV, 2) k_acoustic_lane(const View V,
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + (size_t)4 * LP);
   uint64_t* full = bars; uint64_t* empty = bars + 2; uint64_t* ofull = bars + 4; uint64_t* oempty = bars + 6;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int x0 = V.xoff + blockIdx.x * AL_COLS;
   const int nch = (L + AL_KC - 1) / AL_KC;
+  // persistent: a block walks the tiles blockIdx.x, + gridDim.x, ... as ONE stream of chunks, so the ring never drains between tiles
+  const int ntile = (V.xend - V.xoff + AL_COLS - 1) / AL_COLS;
+  const int my_tiles = ((int)blockIdx.x < ntile) ? (ntile - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int ng = my_tiles * nch;                                 // chunks this block streams
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(full + s, AL_NMOV); mbar_init(empty + s, 32); mbar_init(ofull + s, 32); mbar_init(oempty + s, AL_NMOV); }
   }
@@ -1459,14 +1363,20 @@ __global__ void __launch_bounds__(32 + AL_NMOV, 2) k_acoustic_lane(const View V,
   __syncthreads();
   if (warp == 0) {
     // ------------------------------------------------ sweeper: lane = column ------------------------------------------------
-    const int c = lane, x = x0 + c;
-    const bool on = x < V.xend;
-    const bool spec = on ? (V.specZoneMaskCell[x] != 0.0) : false;
+    const int c = lane;
+    int x = 0; bool on = false, spec = false;
     AcCarry cr; cr.rw_prev = cr.rho_prev = cr.rt_prev = cr.zz_m = cr.cofwt_m = cr.rz_m = 0.0;
-    for (int j = 0; j < nch; ++j) {
-      const int s = j & 1, u = j >> 1;
+    for (int g = 0; g < ng; ++g) {
+      const int j = g % nch;
+      if (j == 0) {                                              // next tile: new columns, recurrence state back to level -1
+        x = V.xoff + ((int)blockIdx.x + (g / nch) * (int)gridDim.x) * AL_COLS + c;
+        on = x < V.xend;
+        spec = on ? (V.specZoneMaskCell[x] != 0.0) : false;
+        cr.rw_prev = cr.rho_prev = cr.rt_prev = cr.zz_m = cr.cofwt_m = cr.rz_m = 0.0;
+      }
+      const int s = g & 1, u = g >> 1;
       mbar_wait(full + s, u & 1);
-      if (j >= 2) mbar_wait(oempty + s, (u - 1) & 1);
+      if (g >= 2) mbar_wait(oempty + s, (u - 1) & 1);
       const double* __restrict__ si = in + (size_t)s * NSTR * STRIP;
       double* __restrict__ so = out + (size_t)s * AL_NOUT * STRIP;
 #pragma unroll
@@ -1498,19 +1408,20 @@ __global__ void __launch_bounds__(32 + AL_NMOV, 2) k_acoustic_lane(const View V,
       }
       mbar_arrive(empty + s);
       mbar_arrive(ofull + s);
+      if (S0 && on && j == nch - 1) { FLD(wwAvg)[(size_t)x * LP + L] = 0; FLD(rw_p)[(size_t)x * LP + L] = 0; }   // :1625-1630, level L
     }
-    if (S0 && on) { FLD(wwAvg)[(size_t)x * LP + L] = 0; FLD(rw_p)[(size_t)x * LP + L] = 0; }            // :1625-1630, level L
   } else {
     // ------------------------------------------------ movers ------------------------------------------------
     const int m = tid - 32;
     double* const dst_f[AL_NOUT] = {FLD(rho_pp), FLD(rtheta_pp), FLD(rw_p), FLD(wwAvg), FLD(rtheta_pp_old)};
     const int xl = V.xend - 1;                                     // columns past the range read the last valid one
-    for (int j = 0; j <= nch; ++j) {
-      if (j < nch) {
-        const int s = j & 1, u = j >> 1;
-        if (j >= 2) mbar_wait(empty + s, (u - 1) & 1);
+    for (int g = 0; g <= ng; ++g) {
+      if (g < ng) {
+        const int s = g & 1, u = g >> 1;
+        if (g >= 2) mbar_wait(empty + s, (u - 1) & 1);
         double* si = in + (size_t)s * NSTR * STRIP;
-        const int kb = j * AL_KC;
+        const int kb = (g % nch) * AL_KC;
+        const int x0 = V.xoff + ((int)blockIdx.x + (g / nch) * (int)gridDim.x) * AL_COLS;
         for (int it = m; it < NS16 * (AL_COLS * 4); it += AL_NMOV) {
           const int f = it >> 7, cp = it & 127, c = cp >> 2, p = cp & 3;
           const int xc = min(x0 + c, xl);
@@ -1524,11 +1435,12 @@ __global__ void __launch_bounds__(32 + AL_NMOV, 2) k_acoustic_lane(const View V,
         }
         cp_async_arrive_noinc(full + s);
       }
-      if (j >= 1) {
-        const int jj = j - 1, s = jj & 1, u = jj >> 1;
+      if (g >= 1) {
+        const int gg = g - 1, s = gg & 1, u = gg >> 1;
         mbar_wait(ofull + s, u & 1);
         const double* so = out + (size_t)s * AL_NOUT * STRIP;
-        const int kb = jj * AL_KC;
+        const int kb = (gg % nch) * AL_KC;
+        const int x0 = V.xoff + ((int)blockIdx.x + (gg / nch) * (int)gridDim.x) * AL_COLS;
         for (int it = m; it < AL_NOUT * (AL_COLS * 4); it += AL_NMOV) {
           const int f = it >> 7, cp = it & 127, c = cp >> 2, p = cp & 3;
           const int x = x0 + c, k0 = kb + 2 * p;

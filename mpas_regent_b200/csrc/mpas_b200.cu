@@ -402,10 +402,10 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
     else LAUNCH(k_acoustic_col<false>, rc_.n, tile_bytes(h, 6), Vc, dts, epssm, resm);
     return post_launch(h);
   }
-  // acoustic_tma = 4: lean gather kernel + the column-per-lane exact pipeline (k_acoustic_lane)
+  // acoustic_tma = 3 (default): lean gather kernel + the column-per-lane exact pipeline (k_acoustic_lane)
   {
     const size_t smem_lane = ((size_t)2 * (AF_COUNT + 2) * AL_COLS * AL_KC + (size_t)2 * AL_NOUT * AL_COLS * AL_KC + (size_t)4 * h->LP) * sizeof(double) + 64;
-    if (!h->c.acoustic_exact && h->c.acoustic_tma == 4 && smem_lane <= (size_t)h->max_smem_optin) {
+    if (!h->c.acoustic_exact && h->c.acoustic_tma == 3 && smem_lane <= (size_t)h->max_smem_optin) {
       if (rc_.n == 0) return 0;
       const View& V = Vc;
       AcPtrs F;
@@ -422,7 +422,8 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
         attr_ = true;
       }
       const size_t smem0 = ((size_t)2 * ((int)AF_rho_pp + 1) * AL_COLS * AL_KC + (size_t)2 * AL_NOUT * AL_COLS * AL_KC + (size_t)4 * h->LP) * sizeof(double) + 64;
-      const dim3 grid((rc_.n + AL_COLS - 1) / AL_COLS), block(32 + AL_NMOV);
+      const int tiles = (rc_.n + AL_COLS - 1) / AL_COLS;
+      const dim3 grid(std::min(tiles, 2 * h->num_sms)), block(32 + AL_NMOV);      // persistent: two resident blocks per SM walk the tiles
       {
         KTimer kt_(h, small_step == 0 ? "k_acoustic_lane<true>" : "k_acoustic_lane<false>");
         if (small_step == 0) k_acoustic_lane<true><<<grid, block, smem0, h->stream>>>(V, F, dts, epssm, resm);
@@ -431,39 +432,6 @@ int t_acoustic(mpasb200_t* h, double dts, int small_step) {
       h->launches++;
       return post_launch(h);
     }
-  }
-  // acoustic_tma = 3: lean gather kernel + exact streaming kernel (strictly ordered sweep by one lane per column of a 4-column block)
-  if (!h->c.acoustic_exact && h->c.acoustic_tma == 3 && h->LP / 2 <= 128 &&
-      ((size_t)AF_COUNT * h->LP + (size_t)4 * h->LP) * sizeof(double) + 16 <= (size_t)h->max_smem_optin) {
-    if (rc_.n == 0) return 0;
-    const View& V = Vc;
-    AcPtrs F;
-#define AF(n) F.p[AF_##n] = V.f[MPASB200_F_##n]
-    AF(tend_rho); AF(theta_m); AF(w); AF(coftz); AF(cofwz); AF(cofwr); AF(cofwt); AF(a_tri); AF(alpha_tri); AF(zz); AF(rw_save); AF(rw);
-    AF(dss); AF(rho_zz); AF(rho_pp); AF(rtheta_pp); AF(rw_p); AF(wwAvg);
-#undef AF
-    F.p[AF_rs] = V.scr_rs; F.p[AF_ts] = V.scr_ts;
-    if (staged_on(h, GS_AC_GATHER, sm_gather)) LAUNCH_STAGED(k_acoustic_gather_s<6>, rc_.n, sm_gather, Vc, dts);
-    else LAUNCH(k_acoustic_gather, rc_.n, 0, Vc, dts);
-    const int T = h->LP / 2;
-    int C = std::max(1, h->c.acoustic_cols > 0 ? h->c.acoustic_cols : 4);
-    auto smem_for = [&](int c) { return ((size_t)AF_COUNT * c * h->LP + (size_t)4 * h->LP) * sizeof(double) + 16; };
-    while (C > 1 && (smem_for(C) > (size_t)h->max_smem_optin || C * T > 128)) C /= 2;
-    const size_t smem = smem_for(C);
-    static bool attr_ = false;
-    if (!attr_) {
-      cudaFuncSetAttribute(k_acoustic_seq<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
-      cudaFuncSetAttribute(k_acoustic_seq<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin);
-      attr_ = true;
-    }
-    dim3 block(T, C), grid((rc_.n + C - 1) / C);
-    {
-      KTimer kt_(h, small_step == 0 ? "k_acoustic_seq<true>" : "k_acoustic_seq<false>");
-      if (small_step == 0) k_acoustic_seq<true><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm);
-      else k_acoustic_seq<false><<<grid, block, smem, h->stream>>>(V, F, dts, epssm, resm);
-    }
-    h->launches++;
-    return post_launch(h);
   }
   const bool tma_fits = ((size_t)AF_COUNT * h->LP + (size_t)4 * (h->LP + 2)) * sizeof(double) + 16 <= 48 * 1024 && h->LP / 2 <= 128;
   if (!h->c.acoustic_exact && h->c.acoustic_tma && h->nCells > 0 && tma_fits) {
@@ -836,7 +804,6 @@ void mpasb200_default_config(MpasConfig* c) {
   c->sfc_renumber = 1; c->device = -1; c->use_graph = 0; c->acoustic_exact = 0; c->acoustic_tma = 3;
   c->physics_mode = MPASB200_PHYSICS_LITERAL;
   c->gather_stage = 0;
-  c->acoustic_cols = 0;
   c->config_scalar_advection = 0; c->config_coef_3rd_order = 0.25;        // constants.rg:59
 }
 
@@ -858,11 +825,8 @@ int mpasb200_create(const MpasDims* dims, const MpasConfig* cfg, mpasb200_t** ou
   if ((e = cudaSetDevice(h->device)) != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); delete h; return MPASB200_ECUDA; }
   h->nCells = dims->nCells; h->nEdges = dims->nEdges; h->nVertices = dims->nVertices;
   h->L = dims->nVertLevels; h->L1 = h->L + 1; h->LP = (h->L1 + 3) / 4 * 4;
-  // layout experiments (profiles/): MPASB200_LP_ALIGN = 16 pads every column to whole 128-byte lines; MPASB200_CPB = columns per block
-  if (const char* e = std::getenv("MPASB200_LP_ALIGN")) { const int a = std::atoi(e); if (a >= 4 && a % 4 == 0) h->LP = (h->L1 + a - 1) / a * a; }
   { const int T = h->LP / 2; int g = T, b = 32; while (b) { int t = g % b; g = b; b = t; } h->CPB = 32 / g; while (h->CPB * T < 128) h->CPB *= 2;
-    while (h->CPB * T > 256 && h->CPB > 1) h->CPB /= 2;        // several kernels are compiled for <= 256 threads per block
-    if (const char* e = std::getenv("MPASB200_CPB")) { const int c = std::atoi(e); if (c >= 1 && c * T <= 256 && (c * T) % 32 == 0) h->CPB = c; } }
+    while (h->CPB * T > 256 && h->CPB > 1) h->CPB /= 2; }      // several kernels are compiled for <= 256 threads per block
   if (h->LP / 2 * h->CPB > 256) { g_create_error = "nVertLevels too large for one block per column group"; delete h; return MPASB200_EINVAL; }
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
   cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);

@@ -94,8 +94,6 @@ K: Dict[str, Tuple[List[str], List[str]]] = {
     "k_scalar_update<NS>": (["ruAvg", "scalars", "scalars_old", "wwAvg", "rho_zz", "rho_zz_old_split"] + ["scr_e"] * 8, ["scalars"]),
 }
 # the exact streaming acoustic kernel moves the same fields as the affine one
-K["k_acoustic_seq<true>"] = K["k_acoustic_tma<true>"]
-K["k_acoustic_seq<false>"] = K["k_acoustic_tma<false>"]
 K["k_acoustic_lane<true>"] = K["k_acoustic_tma<true>"]
 K["k_acoustic_lane<false>"] = K["k_acoustic_tma<false>"]
 # array-typed fields whose every slot is touched
@@ -147,7 +145,7 @@ def step_launches(canonical: bool = True, corrected_physics: bool = False) -> Li
             if corrected_physics:
                 seq += ["k_acoustic_u" + t, "k_acoustic_gather", "k_acoustic_col" + t, "k_divdamp"]
             else:
-                seq += ["k_acoustic_gather", "k_acoustic_seq" + t, "k_divdamp"]
+                seq += ["k_acoustic_gather", "k_acoustic_lane" + t, "k_divdamp"]
         if corrected_physics:
             seq += ["k_rec_pad", "k_rec_cell1", "k_rec_edge", "k_rec_cell2"]
         seq += ["k_diag_vertex", "k_diag_cell", "k_diag_edge<true>" if stage == 2 else "k_diag_edge<false>"]
@@ -177,8 +175,8 @@ TASK_KERNELS = {
                              "k_dt_cellA", "k_dt_cellB", "k_dt_theta_flux", "k_dt_cellC<true>"],
     "compute_dyn_tend:rk>0": ["k_dt_cell0<false>", "k_dt_edge", "k_dt_theta_flux", "k_dt_cellC<false>"],
     "set_smlstep_pert_variables": ["k_smlstep"],
-    "advance_acoustic_step:s0": ["k_acoustic_gather", "k_acoustic_seq<true>"],
-    "advance_acoustic_step": ["k_acoustic_gather", "k_acoustic_seq<false>"],
+    "advance_acoustic_step:s0": ["k_acoustic_gather", "k_acoustic_lane<true>"],
+    "advance_acoustic_step": ["k_acoustic_gather", "k_acoustic_lane<false>"],
     "advance_acoustic_step:s0:affine": ["k_acoustic_gather", "k_acoustic_tma<true>"],
     "advance_acoustic_step:affine": ["k_acoustic_gather", "k_acoustic_tma<false>"],
     "advance_scalars": ["k_scalar_flux<NS>", "k_scalar_update<NS>"],
