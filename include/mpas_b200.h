@@ -192,6 +192,16 @@ int  mpasb200_destroy(mpasb200_t *h);
 const char *mpasb200_last_error(const mpasb200_t *h);   /* h may be null: last create error */
 int  mpasb200_upload_mesh(mpasb200_t *h, const MpasMeshPtrs *mesh);
 
+/* Strided form for a Legion caller: the static data of the reference sits at level 0 of the 2-D regions (cr[{iCell, 0}].edgesOnCell,
+ * mesh_loading.rg:228-344), i.e. one element (or one int[w] / double[w] array, elements contiguous) per x with a BYTE stride
+ * between consecutive x -- offsets[0] of legion_accessor_array_2d_raw_rect_ptr.  mpasb200_mesh_member copies one member of
+ * MpasMeshPtrs (by its name, e.g. "edgesOnCell") out of such an instance into a dense staging copy owned by the handle;
+ * mpasb200_upload_mesh_staged then does what mpasb200_upload_mesh does with the staged members (members never staged are null =
+ * "never written").  `base` addresses the element of x = 0, level 0.  isShared / inCpr / cellClass / edgeClass are uint8_t (a
+ * Regent bool is one byte).                                                                                                */
+int  mpasb200_mesh_member(mpasb200_t *h, const char *member, const void *base, int64_t stride_x);
+int  mpasb200_upload_mesh_staged(mpasb200_t *h);
+
 /* ---- region <-> device mirror ---------------------------------------------------- *
  * `base` addresses element (x=0, level=0, slot=0) of the field instance; stride_x /
  * stride_k are BYTE strides in x and level exactly as legion_accessor_array_2d_raw_rect_ptr

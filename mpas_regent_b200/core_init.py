@@ -5,8 +5,10 @@ These stay on the host in the drop-in design (they are CPU Regent tasks that run
 the GPU library only consumes their outputs through ``mpasb200_upload_mesh`` /
 ``mpasb200_upload_field``.  They are vectorised re-statements that keep the reference's
 quirks (SURVEY.md 8a Q-list), so that the harness feeds the kernels what the reference's
-regions would hold.  The literal loop-by-loop versions live in ``oracle/`` and the two are
-compared in tests/test_core_init.py.
+regions would hold.  tests/test_core_init.py checks them two ways: geometric properties under the
+CORRECTED policy, and -- for ``atm_compute_signs`` and ``atm_couple_coef_3rd_order`` -- a literal loop-by-loop
+restatement of the reference text under BOTH index policies on the bundled x1.2562 mesh (the oracle itself
+has no init-chain functions: it starts from the uploaded static data).
 
 Index policy: ``raw`` ids are the stored 1-based values.  ``R(raw, n)`` resolves them to
 array indices with a zero pad entity at index n (mesh.resolve_ids).  Under LITERAL the

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -55,6 +56,7 @@ struct mpasb200 {
   std::vector<void*> allocs;            // everything cudaMalloc'ed
   int64_t bytes = 0;
   bool mesh_ok = false, mesh_started = false;
+  std::map<std::string, std::vector<char>> mesh_stage;      // mpasb200_mesh_member: dense host copies of strided region members
   // renumbering: newOf[entity][old] = internal index (size n+1, pad -> pad)
   std::vector<int> newOf[3];
   // launch classes (MpasMeshPtrs.cellClass / edgeClass): internal numbering is class-major, classBegin[ent][c] .. classBegin[ent][c+1]
@@ -1093,6 +1095,62 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
   h->has_classes = m->cellClass && m->edgeClass;
   h->mesh_ok = true;
   return 0;
+}
+
+// ---- strided members of the static region data (mpas_b200.h) -----------------------------------------------------------------
+namespace {
+struct MemberInfo { const char* name; size_t offset; int elem; int entity; int wkind; };   // wkind: 1, 2, -1 maxEdges, -2 maxEdges2, -3 vertexDegree, -4 nAdvCells
+#define MM(name, T, ent, w) {#name, offsetof(MpasMeshPtrs, name), (int)sizeof(T), MPASB200_##ent, w}
+const MemberInfo kMembers[] = {
+    MM(nEdgesOnCell, int32_t, CELL, 1), MM(edgesOnCell, int32_t, CELL, -1), MM(verticesOnCell, int32_t, CELL, -1), MM(kiteForCell, int32_t, CELL, -1),
+    MM(edgesOnCellSign, double, CELL, -1), MM(edgesOnCell_sign, double, CELL, -1), MM(invAreaCell, double, CELL, 1), MM(latCell, double, CELL, 1),
+    MM(defc_a, double, CELL, -1), MM(defc_b, double, CELL, -1), MM(bdyMaskCell, int32_t, CELL, 1), MM(specZoneMaskCell, double, CELL, 1),
+    MM(isShared, uint8_t, CELL, 1), MM(inCpr, uint8_t, CELL, 1),
+    MM(cellsOnEdge, int32_t, EDGE, 2), MM(verticesOnEdge, int32_t, EDGE, 2), MM(nEdgesOnEdge, int32_t, EDGE, 1), MM(edgesOnEdge_ECP, int32_t, EDGE, -2),
+    MM(edgesOnEdge, int32_t, EDGE, -2), MM(weightsOnEdge, double, EDGE, -2), MM(dcEdge, double, EDGE, 1), MM(dvEdge, double, EDGE, 1),
+    MM(invDcEdge, double, EDGE, 1), MM(invDvEdge, double, EDGE, 1), MM(angleEdge, double, EDGE, 1), MM(latEdge, double, EDGE, 1),
+    MM(nAdvCellsForEdge, int32_t, EDGE, 1), MM(advCellsForEdge, int32_t, EDGE, -4), MM(adv_coefs, double, EDGE, -4), MM(adv_coefs_3rd, double, EDGE, -4),
+    MM(meshScalingDel2, double, EDGE, 1), MM(meshScalingDel4, double, EDGE, 1), MM(specZoneMaskEdge, double, EDGE, 1),
+    MM(edgesOnVertex, int32_t, VERTEX, -3), MM(edgesOnVertexSign, double, VERTEX, -3), MM(edgesOnVertex_sign, double, VERTEX, -3),
+    MM(kiteAreasOnVertex, double, VERTEX, -3), MM(fVertex, double, VERTEX, 1), MM(invAreaTriangle, double, VERTEX, 1),
+    MM(xCell, double, CELL, 1), MM(yCell, double, CELL, 1), MM(zCell, double, CELL, 1), MM(cellClass, uint8_t, CELL, 1), MM(edgeClass, uint8_t, EDGE, 1),
+};
+#undef MM
+int member_width(const mpasb200_t* h, int wkind) {
+  switch (wkind) { case -1: return h->d.maxEdges; case -2: return h->d.maxEdges2; case -3: return h->d.vertexDegree; case -4: return h->d.nAdvCells; default: return wkind; }
+}
+}  // namespace
+int mpasb200_mesh_member(mpasb200_t* h, const char* member, const void* base, int64_t stride_x) {
+  if (!h || !member || !base) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  if (h->mesh_ok) return fail(h, MPASB200_ESTATE, "mesh_member after upload_mesh");
+  for (const MemberInfo& mi : kMembers)
+    if (!std::strcmp(mi.name, member)) {
+      const int n = entity_count(h, mi.entity), w = member_width(h, mi.wkind);
+      const size_t row = (size_t)w * mi.elem;
+      if (stride_x == 0) stride_x = (int64_t)row;
+      if (stride_x > 0 && (size_t)stride_x < row) return fail(h, MPASB200_EINVAL, "mesh_member: stride smaller than one element row");
+      std::vector<char>& v = h->mesh_stage[member];
+      v.resize((size_t)n * row);
+      for (int x = 0; x < n; ++x) std::memcpy(v.data() + (size_t)x * row, (const char*)base + (int64_t)x * stride_x, row);
+      return 0;
+    }
+  return fail(h, MPASB200_EINVAL, std::string("mesh_member: unknown member ") + member);
+}
+int mpasb200_upload_mesh_staged(mpasb200_t* h) {
+  if (!h) return MPASB200_EINVAL;
+  MpasMeshPtrs m;
+  std::memset(&m, 0, sizeof(m));
+  {
+    std::unique_lock<std::mutex> lk(h->mu);
+    for (const MemberInfo& mi : kMembers) {
+      auto it = h->mesh_stage.find(mi.name);
+      if (it != h->mesh_stage.end()) *(const void**)((char*)&m + mi.offset) = it->second.data();
+    }
+  }
+  const int rc = mpasb200_upload_mesh(h, &m);
+  if (rc == 0) { std::unique_lock<std::mutex> lk(h->mu); h->mesh_stage.clear(); }
+  return rc;
 }
 
 // ---- field transfers ---------------------------------------------------------------------------------

@@ -73,6 +73,8 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
     if prefix == "mpasb200_":
         lib.mpasb200_default_config.argtypes, lib.mpasb200_default_config.restype = [C.POINTER(MpasConfig)], None
         lib.mpasb200_last_error.argtypes, lib.mpasb200_last_error.restype = [H], C.c_char_p
+        lib.mpasb200_mesh_member.argtypes, lib.mpasb200_mesh_member.restype = [H, C.c_char_p, C.c_void_p, C.c_int64], I
+        lib.mpasb200_upload_mesh_staged.argtypes, lib.mpasb200_upload_mesh_staged.restype = [H], I
         lib.mpasb200_upload_field.argtypes = [H, I, C.c_void_p, C.c_int64, C.c_int64]
         lib.mpasb200_download_field.argtypes = [H, I, C.c_void_p, C.c_int64, C.c_int64]
         lib.mpasb200_zero_field.argtypes = [H, I]

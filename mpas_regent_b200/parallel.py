@@ -363,6 +363,7 @@ class DistributedDynamics:
         dyn.set_stream(stream.cuda_stream)
         dyn.upload_mesh(static)
         dyn.upload_state(fields, vert)
+        host_fields = {n: fields[n] for n in getattr(cls, "KEEP_HOST_FIELDS", ()) if n in fields}     # bench.py's end-to-end leg
         del fields
         if os.environ.get("MPAS_B200_NATIVE_DIST", "1") != "0":
             run = NativeDistributedDynamics(dyn, lm, rank, world)
@@ -371,6 +372,7 @@ class DistributedDynamics:
             if cfg.physics_mode == _abi.PHYSICS_LITERAL and os.environ.get("MPAS_B200_OVERLAP", "1") != "0":
                 run.enable_overlap()
         run.lm = lm
+        run.host_fields = host_fields
         run.init_diagnostics()
         run.t_init = time.time() - t0
         return run

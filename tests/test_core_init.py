@@ -88,3 +88,84 @@ def test_advection_lists_contain_both_cells_and_reproduce_a_constant(grid642):
 def test_mesh_scaling_is_one_on_a_uniform_mesh(grid642):
     st = _state(grid642)
     assert np.allclose(st.static["meshScalingDel2"], 1.0) and np.allclose(st.static["meshScalingDel4"], 1.0)
+
+
+# ---- literal loop-by-loop restatement of atm_compute_signs (dynamics_tasks.rg:46-130) under BOTH index policies ----------------
+def _literal_compute_signs(m, policy):
+    """The reference text, one loop at a time.  Memory model: stored ids are 1-based; LITERAL uses the stored id as
+    the index (id == N reads the zero pad entity), CORRECTED uses id - 1 (id 0 reads the pad); `iCell.x == stored id` compares a
+    0-based loop index with a stored id as written under LITERAL (Q33) and with id - 1 under CORRECTED."""
+    v = m.v
+    nC, nE, nV = m.nCells, m.nEdges, m.nVertices
+    lit = policy == _abi.INDEX_LITERAL
+
+    def idx(raw, n):
+        i = raw if lit else raw - 1
+        return n if (i < 0 or i > n) else i
+
+    def same(loop_index, stored):
+        return loop_index == (stored if lit else stored - 1)
+
+    voe = np.vstack([v["verticesOnEdge"], np.zeros((1, 2), v["verticesOnEdge"].dtype)])
+    coe = np.vstack([v["cellsOnEdge"], np.zeros((1, 2), v["cellsOnEdge"].dtype)])
+    cov = np.vstack([v["cellsOnVertex"], np.zeros((1, 3), v["cellsOnVertex"].dtype)])
+    evs = np.zeros((nV, 3)); ecs = np.zeros((nC, 10)); kite = np.zeros((nC, 10), np.int32)
+    for iVtx in range(nV):                                                   # :60-72
+        for i in range(3):
+            e = v["edgesOnVertex"][iVtx, i]
+            if e <= nE:
+                evs[iVtx, i] = 1.0 if same(iVtx, voe[idx(e, nE), 1]) else -1.0
+            else:
+                evs[iVtx, i] = 0.0
+    for iCell in range(nC):                                                  # :74-86
+        for i in range(v["nEdgesOnCell"][iCell]):
+            e = v["edgesOnCell"][iCell, i]
+            if e <= nE:
+                ecs[iCell, i] = 1.0 if same(iCell, coe[idx(e, nE), 0]) else -1.0
+            else:
+                ecs[iCell, i] = 0.0
+    for iCell in range(nC):                                                  # :113-129, j = 1 .. vertexDegree-1, first match wins
+        for i in range(v["nEdgesOnCell"][iCell]):
+            iv = v["verticesOnCell"][iCell, i]
+            if iv <= nV:
+                for j in range(1, 3):
+                    if same(iCell, cov[idx(iv, nV), j]):
+                        kite[iCell, i] = j
+                        break
+            else:
+                kite[iCell, i] = 1
+    return evs, ecs, kite
+
+
+def test_compute_signs_equals_the_literal_loops_under_both_policies(grid2562):
+    for policy in (_abi.INDEX_LITERAL, _abi.INDEX_CORRECTED):
+        out = core_init.atm_compute_signs(grid2562, policy)
+        evs, ecs, kite = _literal_compute_signs(grid2562, policy)
+        assert np.array_equal(out["edgesOnVertexSign"], evs), policy
+        assert np.array_equal(out["edgesOnCellSign"], ecs), policy
+        assert np.array_equal(out["kiteForCell"], kite), policy
+    # the two policies really differ on this mesh (Q32/Q33): the literal reading gets most signs "wrong"
+    a = core_init.atm_compute_signs(grid2562, _abi.INDEX_LITERAL)["edgesOnCellSign"]
+    b = core_init.atm_compute_signs(grid2562, _abi.INDEX_CORRECTED)["edgesOnCellSign"]
+    assert (a != b).any()
+
+
+def test_zb_cell_selection_equals_the_literal_loops(grid642):
+    """:88-110: zb_cell(i) = zb[0] of the slot's edge if this cell is its first cell, else zb[1]; every level 0..nVertLevels."""
+    m, L1 = grid642, 4
+    rng = np.random.default_rng(1)
+    zb, zb3 = rng.random((m.nEdges, L1, 2)), rng.random((m.nEdges, L1, 2))
+    for policy in (_abi.INDEX_LITERAL, _abi.INDEX_CORRECTED):
+        out = core_init.atm_compute_signs(m, policy, zb=zb, zb3=zb3, nlev1=L1)
+        lit = policy == _abi.INDEX_LITERAL
+        zbp = np.concatenate([zb, np.zeros((1, L1, 2))]); coe = np.vstack([m.v["cellsOnEdge"], np.zeros((1, 2), np.int64)])
+        want = np.zeros((m.nCells, L1, 10))
+        for c in range(m.nCells):
+            for i in range(m.v["nEdgesOnCell"][c]):
+                raw = m.v["edgesOnCell"][c, i]
+                if raw <= m.nEdges:
+                    e = raw if lit else raw - 1
+                    e = m.nEdges if (e < 0 or e > m.nEdges) else e
+                    first = c == (coe[e, 0] if lit else coe[e, 0] - 1)
+                    want[c, :, i] = zbp[e, :, 0 if first else 1]
+        assert np.array_equal(out["zb_cell"], want), policy

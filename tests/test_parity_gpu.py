@@ -598,3 +598,38 @@ def test_acoustic_lane_pipeline_shapes(grid642, levels):
         assert touched.sum() <= 301 - 37, n
         assert np.array_equal(a[touched], full[touched], equal_nan=True), n
     g.close(); ora.close()
+
+
+def test_strided_mesh_members_equal_dense_upload(grid642):
+    """mpasb200_mesh_member + mpasb200_upload_mesh_staged (the Legion-instance form: one array per x with a byte stride between x,
+    level 0 of a 2-D region) build the same mirror as the dense mpasb200_upload_mesh."""
+    import ctypes as C
+    from mpas_regent_b200 import dynamics, init_jw
+    L = 8
+    st = init_jw.make_state(grid642, L, _abi.INDEX_CORRECTED)
+    cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX)
+    outs = []
+    for staged in (False, True):
+        g = dynamics.Dynamics(dynamics.dims_of(grid642, L), cfg)
+        if not staged:
+            g.upload_mesh(st.static)
+        else:
+            keep = []
+            for name, dt, ent, wkey in _abi.MESH_MEMBERS:
+                a = st.static.get(name)
+                if a is None:
+                    continue
+                a = np.ascontiguousarray(a, dtype=dt).reshape(a.shape[0], -1)
+                pad = np.zeros((a.shape[0], a.shape[1] + 3), dtype=dt)            # a wider instance: byte stride > row size
+                pad[:, :a.shape[1]] = a
+                keep.append(pad)
+                rc = g._lib.mpasb200_mesh_member(g._h, name.encode(), pad.ctypes.data, pad.strides[0])
+                assert rc == 0, name
+            assert g._lib.mpasb200_mesh_member(g._h, b"noSuchMember", keep[0].ctypes.data, 8) != 0
+            assert g._lib.mpasb200_upload_mesh_staged(g._h) == 0
+        g.upload_state(st.f, st.vert)
+        g.atm_compute_solve_diagnostics(False, -1)
+        g.atm_srk3(600.0)
+        outs.append(g.download_all()); g.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
