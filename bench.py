@@ -504,7 +504,7 @@ def main():
                "single_thread_value": v1}
 
     if rank == 0:
-        top = sorted(ktimes.items(), key=lambda kv: -kv[1][0])[:8]
+        top = sorted(ktimes.items(), key=lambda kv: -kv[1][0])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

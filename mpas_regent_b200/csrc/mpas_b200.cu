@@ -1509,7 +1509,11 @@ int mpasb200_dist_init(mpasb200_t* h, int rank, int world, const void* id128) {
   NcclId128 id; std::memcpy(id.b, id128, 128);
   NCK(g_nccl.CommInitRank(&h->comm, world, id, rank));
   h->rank = rank; h->world = world;
-  CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  // highest priority: when the compute stream fills the GPU, the blocks of k_pack / the NCCL kernels / k_unpack are scheduled
+  // ahead of the interior compute's pending blocks, so an exchange starts as soon as SMs drain instead of behind the whole kernel
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  CK(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi));
   CK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
   return 0;
