@@ -183,6 +183,9 @@ typedef struct {
    * cells: 0 = owned, not sent to any rank; 1 = owned, sent; 2 = ghost.  edges: 0 = both cells owned; 1 = the rest. */
   const uint8_t *cellClass;         /* [nCells] */
   const uint8_t *edgeClass;         /* [nEdges] */
+  /* init chain on the device (mpasb200_reconstruct_2d); may be null */
+  const double  *lonCell;           /* [nCells]                                      */
+  const double  *coeffs_reconstruct;/* [nCells][maxEdges][3]  (data_structures.rg: coeffs_reconstruct : double[maxEdges][3]) */
 } MpasMeshPtrs;
 
 /* ---- lifecycle ------------------------------------------------------------------ */
@@ -251,6 +254,14 @@ int  mpasb200_compute_solve_diagnostics(mpasb200_t *h, int hollingsworth, int rk
 int  mpasb200_advance_scalars(mpasb200_t *h, double dt, int rk_step);
 /* atm_rk_dynamics_substep_finish      dynamics_tasks.rg:1951-2007 */
 int  mpasb200_rk_dynamics_substep_finish(mpasb200_t *h, int dynamics_substep, int dynamics_split);
+
+/* ---- init chain on the device: the two one-time tasks of atm_core_init that are stencils over 3-D fields ---- */
+/* atm_init_coupled_diagnostics        dynamics_tasks.rg:651-725  (rho_zz /= zz; ru; rw from w and ru; rho_p, rtheta_base, rtheta_p,
+ *                                     exner, exner_base, pressure_p, pressure_base; levels 0..nVertLevels-1)                        */
+int  mpasb200_init_coupled_diagnostics(mpasb200_t *h);
+/* mpas_reconstruct_2d                 dynamics_tasks.rg:1894-1948 (uReconstructX/Y/Z from u with coeffs_reconstruct, then
+ *                                     uReconstructZonal / uReconstructMeridional; also MPAS's end-of-step call, rk_timestep.rg:487) */
+int  mpasb200_reconstruct_2d(mpasb200_t *h, int includeHalos, int on_a_sphere);
 
 /* ---- the driver: atm_srk3 / atm_timestep  rk_timestep.rg:361-519 ------------------------- *
  * Replays the reference's call sequence on the device (control flow + scalars only).    */

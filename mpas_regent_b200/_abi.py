@@ -95,6 +95,7 @@ MESH_MEMBERS = (
     ("fVertex", np.float64, VERTEX, 1), ("invAreaTriangle", np.float64, VERTEX, 1),
     ("xCell", np.float64, CELL, 1), ("yCell", np.float64, CELL, 1), ("zCell", np.float64, CELL, 1),
     ("cellClass", np.uint8, CELL, 1), ("edgeClass", np.uint8, EDGE, 1),
+    ("lonCell", np.float64, CELL, 1), ("coeffs_reconstruct", np.float64, CELL, "maxEdges3"),
 )
 
 
@@ -158,8 +159,10 @@ def mesh_ptrs(static: Dict[str, np.ndarray], dims: MpasDims):
         if a is None:
             setattr(m, name, None)
             continue
-        w = wkey if isinstance(wkey, int) else getattr(dims, wkey)
+        w = wkey if isinstance(wkey, int) else (3 * dims.maxEdges if wkey == "maxEdges3" else getattr(dims, wkey))
         a = np.ascontiguousarray(a, dtype=dt)
+        if wkey == "maxEdges3":
+            a = a.reshape(a.shape[0], -1)
         want = (counts[ent],) if w == 1 else (counts[ent], w)
         if a.shape != want:
             raise ValueError(f"{name}: shape {a.shape}, expected {want}")

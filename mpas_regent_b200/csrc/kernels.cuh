@@ -1810,6 +1810,75 @@ __global__ void k_setup_scalars(const View V) {
 }
 
 // ============================================================================================
+// Init chain on the device.
+// atm_init_coupled_diagnostics  :651-725.  Three passes with the reference's grid-wide dependencies between them:
+// rho_zz /= zz on every cell (:676), ru on every edge from both cells' rho_zz (:679-683), then everything cell-local.
+__global__ void k_icd_cell1(const View V) {
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
+  st2m(FLD(rho_zz), ix, ld2(FLD(rho_zz), ix) / ld2(FLD(zz), ix), m0, m1);
+}
+__global__ void k_icd_edge(const View V) {
+  PAIR_THREAD(V.nEdges)
+  if (!m0) return;
+  const int4 cv = V.ecv[x];
+  const double* rz = FLD(rho_zz);
+  st2m(FLD(ru), ix, 0.5 * ld2(FLD(u), ix) * (G2(rz, cv.x) + G2(rz, cv.y)), m0, m1);
+}
+__global__ void k_icd_cell2(const View V, double rgas, double rcv) {
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
+  const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
+  const double* ru = FLD(ru); const double* zb = FLD(zb_cell); const double* zb3 = FLD(zb3_cell);
+  const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0);
+  const D2 rz = ld2(FLD(rho_zz), ix), rzm = below(FLD(rho_zz), ix, k0, rz);
+  const D2 zz = ld2(FLD(zz), ix), zzm = below(FLD(zz), ix, k0, zz);
+  const D2 zf = fp * zzm + fm * zz;
+  D2 rw = ld2(FLD(w), ix) * (fp * rzm + fm * rz) * zf;                                                 // :691-694
+  if (k0 == 0) rw.x = 0.0;
+  for (int i = 0; i < n; ++i) {                                                                       // :698-709
+    const int e = V.edgesOnCell[x * V.MEP + i];
+    const D2 r2 = G2(ru, e);
+    const D2 flux = fm * r2 + fp * below(ru, (size_t)e * LP + k0, k0, r2);
+    const D2 t = V.edgesOnCellSign[x * ME + i] * (ld2(zb, i * V.cellSlot + ix) + sgn1(flux) * ld2(zb3, i * V.cellSlot + ix)) * flux * zf;
+    if (k0 > 0) rw.x -= t.x;
+    rw.y -= t.y;
+  }
+  st2m(FLD(rw), ix, rw, m0, m1);
+  const int p0 = 100000;
+  const D2 rb = ld2(FLD(rho_base), ix), tb = ld2(FLD(theta_base), ix), tm = ld2(FLD(theta_m), ix);
+  const D2 rho_p = rz - rb, rtb = tb * rb;
+  const D2 rtp = tm * rho_p + rb * (tm - tb);
+  const D2 a = zz * (rgas / p0) * (rtp + rtb), b = zz * (rgas / p0) * (rtb);
+  const D2 ex = mk(pow(a.x, rcv), pow(a.y, rcv)), exb = mk(pow(b.x, rcv), pow(b.y, rcv));
+  st2m(FLD(rho_p), ix, rho_p, m0, m1); st2m(FLD(rtheta_base), ix, rtb, m0, m1); st2m(FLD(rtheta_p), ix, rtp, m0, m1);
+  st2m(FLD(exner), ix, ex, m0, m1); st2m(FLD(exner_base), ix, exb, m0, m1);
+  st2m(FLD(pressure_p), ix, zz * rgas * (ex * rtp + rtb * (ex - exb)), m0, m1);
+  st2m(FLD(pressure_base), ix, zz * rgas * exb * rtb, m0, m1);
+}
+// mpas_reconstruct_2d  :1894-1948
+__global__ void k_reconstruct(const View V, int on_a_sphere) {
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
+  const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
+  const double* u = FLD(u);
+  D2 ux = bc(0.0), uy = bc(0.0), uz = bc(0.0);
+  for (int i = 0; i < n; ++i) {
+    const D2 ue = G2(u, V.edgesOnCell[x * V.MEP + i]);
+    const double* cf = V.coeffsRecon + ((size_t)x * ME + i) * 3;
+    ux += cf[0] * ue; uy += cf[1] * ue; uz += cf[2] * ue;
+  }
+  st2m(FLD(uReconstructX), ix, ux, m0, m1); st2m(FLD(uReconstructY), ix, uy, m0, m1); st2m(FLD(uReconstructZ), ix, uz, m0, m1);
+  if (on_a_sphere) {
+    const double clat = V.cosLatCell[x], slat = V.sinLatCell[x], clon = V.cosLonCell[x], slon = V.sinLonCell[x];
+    st2m(FLD(uReconstructZonal), ix, -ux * slon + uy * clon, m0, m1);
+    st2m(FLD(uReconstructMeridional), ix, -(ux * clon + uy * slon) * slat + uz * clat, m0, m1);
+  } else {
+    st2m(FLD(uReconstructZonal), ix, ux, m0, m1); st2m(FLD(uReconstructMeridional), ix, uy, m0, m1);
+  }
+}
+
+// ============================================================================================
 // region <-> mirror transfers and halo pack/unpack.  `map[i]` = internal (SFC) index of caller index i.
 // staging layout: [i][L1][slots] (exactly the host array of an array-typed region field).
 __global__ void k_stage_to_field(double* __restrict__ field, const double* __restrict__ staging, const int* __restrict__ map,

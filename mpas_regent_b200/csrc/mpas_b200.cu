@@ -297,6 +297,15 @@ int ensure_sflux(mpasb200_t* h) {      // horiz_flux_arr scratch of atm_advance_
   h->bytes += (int64_t)(n * sizeof(double));
   return 0;
 }
+// init chain on the device: atm_init_coupled_diagnostics (:651-725), mpas_reconstruct_2d (:1894-1948)
+int t_init_coupled(mpasb200_t* h) {
+  const double rcv = h->c.rgas / (h->c.cp - h->c.rgas);
+  LAUNCH(k_icd_cell1, h->nCells, 0, h->V);
+  LAUNCH(k_icd_edge, h->nEdges, 0, h->V);
+  LAUNCH(k_icd_cell2, h->nCells, 0, h->V, h->c.rgas, rcv);
+  return post_launch(h);
+}
+int t_reconstruct(mpasb200_t* h, int on_a_sphere) { LAUNCH(k_reconstruct, h->nCells, 0, h->V, on_a_sphere); return post_launch(h); }
 // atm_advance_scalars (mpas_b200.h): per-edge horizontal fluxes into scratch, then the cell update
 int t_scalars(mpasb200_t* h, double dt, int rk_step) {
   (void)rk_step;
@@ -1046,10 +1055,19 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
   UP_DBL(defc_b, m->defc_b, nC, ME, cNew);
   UP_INT(bdyMaskCell, m->bdyMaskCell, nC, 1, cNew);
   UP_DBL(specZoneMaskCell, m->specZoneMaskCell, nC, 1, cNew);
+  UP_DBL(coeffsRecon, m->coeffs_reconstruct, nC, ME * 3, cNew);
   {
     std::vector<double> cl((size_t)nC + 1, 1.0);        // cos(0) for the pad
     for (int c = 0; c < nC; ++c) cl[cNew[c]] = std::cos(m->latCell ? m->latCell[c] : 0.0);
     if ((rc = dev_upload<double>(h, &V.cosLatCell, cl))) return rc;
+    std::vector<double> sl((size_t)nC + 1, 0.0), clo((size_t)nC + 1, 1.0), slo((size_t)nC + 1, 0.0);
+    for (int c = 0; c < nC; ++c) {
+      sl[cNew[c]] = std::sin(m->latCell ? m->latCell[c] : 0.0);
+      clo[cNew[c]] = std::cos(m->lonCell ? m->lonCell[c] : 0.0); slo[cNew[c]] = std::sin(m->lonCell ? m->lonCell[c] : 0.0);
+    }
+    if ((rc = dev_upload<double>(h, &V.sinLatCell, sl))) return rc;
+    if ((rc = dev_upload<double>(h, &V.cosLonCell, clo))) return rc;
+    if ((rc = dev_upload<double>(h, &V.sinLonCell, slo))) return rc;
     std::vector<unsigned char> sh = build_vals<unsigned char, uint8_t>(m->isShared, nC, 1, cNew);
     std::vector<unsigned char> cp((size_t)nC + 1, 1); cp[nC] = 0;
     if (m->inCpr) for (int c = 0; c < nC; ++c) cp[cNew[c]] = m->inCpr[c];
@@ -1114,10 +1132,11 @@ const MemberInfo kMembers[] = {
     MM(edgesOnVertex, int32_t, VERTEX, -3), MM(edgesOnVertexSign, double, VERTEX, -3), MM(edgesOnVertex_sign, double, VERTEX, -3),
     MM(kiteAreasOnVertex, double, VERTEX, -3), MM(fVertex, double, VERTEX, 1), MM(invAreaTriangle, double, VERTEX, 1),
     MM(xCell, double, CELL, 1), MM(yCell, double, CELL, 1), MM(zCell, double, CELL, 1), MM(cellClass, uint8_t, CELL, 1), MM(edgeClass, uint8_t, EDGE, 1),
+    MM(lonCell, double, CELL, 1), MM(coeffs_reconstruct, double, CELL, -5),
 };
 #undef MM
 int member_width(const mpasb200_t* h, int wkind) {
-  switch (wkind) { case -1: return h->d.maxEdges; case -2: return h->d.maxEdges2; case -3: return h->d.vertexDegree; case -4: return h->d.nAdvCells; default: return wkind; }
+  switch (wkind) { case -1: return h->d.maxEdges; case -2: return h->d.maxEdges2; case -3: return h->d.vertexDegree; case -4: return h->d.nAdvCells; case -5: return 3 * h->d.maxEdges; default: return wkind; }
 }
 }  // namespace
 int mpasb200_mesh_member(mpasb200_t* h, const char* member, const void* base, int64_t stride_x) {
@@ -1359,6 +1378,8 @@ int mpasb200_divergence_damping_3d(mpasb200_t* h, double dts) { REQUIRE_MESH(); 
 int mpasb200_recover_large_step_variables(mpasb200_t* h, int ns, int rk_step, double dt) { REQUIRE_MESH(); Entry en(h, MPASB200_T_RECOVER); return en.done(t_recover(h, ns, rk_step, dt)); }
 int mpasb200_compute_solve_diagnostics(mpasb200_t* h, int hollingsworth, int rk_step) { REQUIRE_MESH(); Entry en(h, MPASB200_T_DIAG); return en.done(t_diag(h, hollingsworth, rk_step)); }
 int mpasb200_advance_scalars(mpasb200_t* h, double dt, int rk_step) { REQUIRE_MESH(); Entry en(h, MPASB200_T_SCALARS); return en.done(t_scalars(h, dt, rk_step)); }
+int mpasb200_init_coupled_diagnostics(mpasb200_t* h) { REQUIRE_MESH(); Entry en(h, -1); return t_init_coupled(h); }
+int mpasb200_reconstruct_2d(mpasb200_t* h, int includeHalos, int on_a_sphere) { (void)includeHalos; REQUIRE_MESH(); Entry en(h, -1); return t_reconstruct(h, on_a_sphere); }
 int mpasb200_rk_dynamics_substep_finish(mpasb200_t* h, int substep, int split) {
   REQUIRE_MESH();
   if (split < 1) return fail(h, MPASB200_EINVAL, "dynamics_split must be >= 1");

@@ -33,6 +33,8 @@ struct View {
   const double* dvOnCell; const double* invDcOnCell; const double* ms2OnCell; const double* ms4OnCell;   // [c][maxEdges]
   const double* defc_a; const double* defc_b; const int* bdyMaskCell; const double* specZoneMaskCell;
   const unsigned char* isShared; const unsigned char* inCpr;
+  const double* sinLatCell; const double* cosLonCell; const double* sinLonCell;   // host-evaluated (glibc), like cosLatCell
+  const double* coeffsRecon;   // [c][maxEdges][3]  coeffs_reconstruct
   const int* nAdvOnCell;       // [c][maxEdges]
   const int* advCellOnCell;    // [c][maxEdges][NAP]
   const double* advCoefOnCell; const double* adv3OnCell;   // [c][maxEdges][NAP]

@@ -64,6 +64,8 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         "compute_solve_diagnostics": ([H, I, I], I),
         "rk_dynamics_substep_finish": ([H, I, I], I),
         "advance_scalars": ([H, D, I], I),
+        "init_coupled_diagnostics": ([H], I),
+        "reconstruct_2d": ([H, I, I], I),
         "srk3": ([H, D], I),
         "timestep": ([H, D], I),
     }
@@ -188,6 +190,14 @@ class TaskAPI:
     def atm_advance_scalars(self, dt: float, rk_step: int):
         """not in the reference (rk_timestep.rg:465 skips it): atm_advance_scalars_work of MPAS-A v7 (mpas_b200.h)"""
         self._call("advance_scalars", float(dt), int(rk_step))
+
+    def atm_init_coupled_diagnostics(self):
+        """dynamics_tasks.rg:651-725 (one-time task of atm_core_init) on the device"""
+        self._call("init_coupled_diagnostics")
+
+    def mpas_reconstruct_2d(self, includeHalos: bool = False, on_a_sphere: bool = True):
+        """dynamics_tasks.rg:1894-1948"""
+        self._call("reconstruct_2d", int(bool(includeHalos)), int(bool(on_a_sphere)))
 
     def atm_rk_dynamics_substep_finish(self, dynamics_substep: int, dynamics_split: int):
         self._call("rk_dynamics_substep_finish", int(dynamics_substep), int(dynamics_split))

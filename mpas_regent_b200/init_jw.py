@@ -335,6 +335,10 @@ def make_state(mesh_unit: Mesh, nVertLevels: int, policy: int = CORRECTED, m5: b
             F[k] = zero_e()
         coeffs = np.zeros((nC, MAX_EDGES, 3))
     st.extras = dict(coeffs_reconstruct=coeffs, theta_base=theta_base, zb=zb, zb3=zb3, deriv_two=deriv_two)
+    # inputs of the device-side init chain (mpasb200_init_coupled_diagnostics / mpasb200_reconstruct_2d)
+    S["lonCell"] = v["lonCell"]
+    S["coeffs_reconstruct"] = coeffs
+    F["theta_base"] = theta_base
     F["uReconstructZonal"], F["uReconstructMeridional"] = core_init.mpas_reconstruct_2d(mesh, policy, F["u"], coeffs, L)
     # v is produced by atm_compute_solve_diagnostics(rk_step=-1) at init (atm_core.rg:31): that is a
     # hot-path task and is run through the library (or the oracle) by the caller.  For callers that

@@ -167,8 +167,8 @@ class LocalMesh:
 
 
 _CELL_ROWS_1D = ("nEdgesOnCell", "latCell", "invAreaCell", "bdyMaskCell", "specZoneMaskCell", "isShared", "inCpr",
-                 "xCell", "yCell", "zCell")
-_CELL_ROWS_ME = ("kiteForCell", "edgesOnCellSign", "edgesOnCell_sign", "defc_a", "defc_b")
+                 "xCell", "yCell", "zCell", "lonCell")
+_CELL_ROWS_ME = ("kiteForCell", "edgesOnCellSign", "edgesOnCell_sign", "defc_a", "defc_b", "coeffs_reconstruct")
 _EDGE_ROWS = ("nEdgesOnEdge", "weightsOnEdge", "dcEdge", "dvEdge", "invDcEdge", "invDvEdge", "angleEdge", "latEdge",
               "nAdvCellsForEdge", "adv_coefs", "adv_coefs_3rd", "meshScalingDel2", "meshScalingDel4", "specZoneMaskEdge")
 _VERTEX_ROWS = ("edgesOnVertexSign", "edgesOnVertex_sign", "kiteAreasOnVertex", "fVertex", "invAreaTriangle")

@@ -89,6 +89,11 @@ K: Dict[str, Tuple[List[str], List[str]]] = {
     "k_finish_cell": (["wwAvg", "rho_zz_old_split"], ["wwAvg_split", "wwAvg", "rho_zz"]),
     "k_finish_edge": (["ruAvg"], ["ruAvg_split", "ruAvg"]),
     # atm_advance_scalars (8 scalars; horiz_flux_arr is library scratch: 8 edge fields = 24 units each way)
+    "k_icd_cell1": (["rho_zz", "zz"], ["rho_zz"]),
+    "k_icd_edge": (["u", "rho_zz"], ["ru"]),
+    "k_icd_cell2": (["w", "rho_zz", "zz", "ru", "zb_cell", "zb3_cell", "rho_base", "theta_base", "theta_m"],
+                    ["rw", "rho_p", "rtheta_base", "rtheta_p", "exner", "exner_base", "pressure_p", "pressure_base"]),
+    "k_reconstruct": (["u"], ["uReconstructX", "uReconstructY", "uReconstructZ", "uReconstructZonal", "uReconstructMeridional"]),
     "k_setup_scalars": (["scalars"], ["scalars_old"]),
     "k_scalar_flux<NS>": (["ruAvg", "scalars"], ["scr_e"] * 8),
     "k_scalar_update<NS>": (["ruAvg", "scalars", "scalars_old", "wwAvg", "rho_zz", "rho_zz_old_split"] + ["scr_e"] * 8, ["scalars"]),

@@ -71,7 +71,7 @@ struct Oracle {
   std::vector<std::vector<double>> store;   // per field id
   // static data, [N+1] rows, resolved ids
   std::vector<int> nEdgesOnCell, edgesOnCell, verticesOnCell, kiteForCell, bdyMaskCell;
-  std::vector<double> edgesOnCellSign, edgesOnCell_sign, invAreaCell, latCell, defc_a, defc_b, specZoneMaskCell;
+  std::vector<double> edgesOnCellSign, edgesOnCell_sign, invAreaCell, latCell, defc_a, defc_b, specZoneMaskCell, lonCell, coeffs_reconstruct;
   std::vector<uint8_t> isShared, inCpr;
   std::vector<uint8_t> cellClass, edgeClass;      // launch classes of MpasMeshPtrs (all 0 when absent)
   int onlyClass[2] = {-1, -1};                   // oracle_set_class: restrict the acoustic step (cells) / divergence damping (edges)
@@ -200,6 +200,8 @@ int oracle_upload_mesh(oracle_t* o, const MpasMeshPtrs* m) {
   fill_rows(o->kiteAreasOnVertex, m->kiteAreasOnVertex, nV, VD);
   fill_rows(o->fVertex, m->fVertex, nV, 1);
   fill_rows(o->invAreaTriangle, m->invAreaTriangle, nV, 1);
+  fill_rows(o->lonCell, m->lonCell, nC, 1);
+  fill_rows(o->coeffs_reconstruct, m->coeffs_reconstruct, nC, ME * 3);
   o->mesh_ok = true;
   return 0;
 }
@@ -305,6 +307,81 @@ int oracle_advance_scalars(oracle_t* o, double dt, int rk_step) {
       for (int s = 0; s < NS; ++s)
         scalars(c, k, s) = (scalars_old(c, k, s) * rho_zz_old_split(c, k)
                             + dt * (tend[(size_t)k * NS + s] - rdzw[k] * (wdtn[(size_t)(k + 1) * NS + s] - wdtn[(size_t)k * NS + s]))) / rho_zz(c, k);
+  }
+  return 0;
+}
+
+// atm_init_coupled_diagnostics -- dynamics_tasks.rg:651-725 (one-time task of atm_core_init; levels 0..nVertLevels-1)
+int oracle_init_coupled_diagnostics(oracle_t* o) {
+  const int L = o->L, nC = o->nCells, nE = o->nEdges, ME = o->maxEdges;
+  const double rgas = o->c.rgas, rcv = rgas / (o->c.cp - rgas);
+  const int p0 = 100000;                                                        // an integer in the reference (:668)
+  CF(rho_zz); CF(zz); CF(ru); CF(u); CF(rw); CF(w); CF(rho_p); CF(rho_base); CF(rtheta_base); CF(theta_base); CF(rtheta_p); CF(theta_m);
+  CF(exner); CF(exner_base); CF(pressure_p); CF(pressure_base);
+  F3A zb_cell = o->fa(MPASB200_F_zb_cell), zb3_cell = o->fa(MPASB200_F_zb3_cell);
+  VF(fzm); VF(fzp);
+  OMP_FOR
+  for (int c = 0; c < nC; ++c) for (int k = 0; k < L; ++k) rho_zz(c, k) /= zz(c, k);                                    // :676
+  OMP_FOR
+  for (int e = 0; e < nE; ++e) {
+    const int cell1 = o->cellsOnEdge[e * 2], cell2 = o->cellsOnEdge[e * 2 + 1];
+    for (int k = 0; k < L; ++k) ru(e, k) = 0.5 * u(e, k) * (rho_zz(cell1, k) + rho_zz(cell2, k));                        // :679-683
+  }
+  OMP_FOR
+  for (int c = 0; c < nC; ++c) {
+    for (int k = 0; k < L; ++k) {
+      rw(c, k) = 0;
+      if (k > 0 && k < L)                                                                                               // :691-694
+        rw(c, k) = w(c, k) * (fzp[k] * rho_zz(c, k - 1) + fzm[k] * rho_zz(c, k)) * (fzp[k] * zz(c, k - 1) + fzm[k] * zz(c, k));
+    }
+    for (int k = 0; k < L; ++k)                                                                                          // :698-709
+      for (int i = 0; i < o->nEdgesOnCell[c]; ++i) {
+        const int e = o->edgesOnCell[c * ME + i];
+        if (k > 0) {
+          const double flux = fzm[k] * ru(e, k) + fzp[k] * ru(e, k - 1);
+          rw(c, k) -= o->edgesOnCellSign[c * ME + i] * (zb_cell(c, k, i) + copysign(1.0, flux) * zb3_cell(c, k, i)) * flux
+                      * (fzp[k] * zz(c, k - 1) + fzm[k] * zz(c, k));
+        }
+      }
+    for (int k = 0; k < L; ++k) {                                                                                        // :711-718
+      rho_p(c, k) = rho_zz(c, k) - rho_base(c, k);
+      rtheta_base(c, k) = theta_base(c, k) * rho_base(c, k);
+      rtheta_p(c, k) = theta_m(c, k) * rho_p(c, k) + rho_base(c, k) * (theta_m(c, k) - theta_base(c, k));
+      exner(c, k) = pow(zz(c, k) * (rgas / p0) * (rtheta_p(c, k) + rtheta_base(c, k)), rcv);
+      exner_base(c, k) = pow(zz(c, k) * (rgas / p0) * (rtheta_base(c, k)), rcv);
+      pressure_p(c, k) = zz(c, k) * rgas * (exner(c, k) * rtheta_p(c, k) + rtheta_base(c, k) * (exner(c, k) - exner_base(c, k)));
+      pressure_base(c, k) = zz(c, k) * rgas * exner_base(c, k) * rtheta_base(c, k);
+    }
+  }
+  return 0;
+}
+
+// mpas_reconstruct_2d -- dynamics_tasks.rg:1894-1948
+int oracle_reconstruct_2d(oracle_t* o, int includeHalos, int on_a_sphere) {
+  (void)includeHalos;                                                           // nCellsReconstruct = nCells either way (:1909-1912)
+  const int L = o->L, nC = o->nCells, ME = o->maxEdges;
+  CF(u); CF(uReconstructX); CF(uReconstructY); CF(uReconstructZ); CF(uReconstructZonal); CF(uReconstructMeridional);
+  OMP_FOR
+  for (int c = 0; c < nC; ++c) {
+    for (int k = 0; k < L; ++k) {
+      uReconstructX(c, k) = 0.0; uReconstructY(c, k) = 0.0; uReconstructZ(c, k) = 0.0;
+      for (int i = 0; i < o->nEdgesOnCell[c]; ++i) {
+        const int e = o->edgesOnCell[c * ME + i];
+        const double* cf = &o->coeffs_reconstruct[((size_t)c * ME + i) * 3];
+        uReconstructX(c, k) += cf[0] * u(e, k);
+        uReconstructY(c, k) += cf[1] * u(e, k);
+        uReconstructZ(c, k) += cf[2] * u(e, k);
+      }
+    }
+    if (on_a_sphere) {
+      const double clat = cos(o->latCell[c]), slat = sin(o->latCell[c]), clon = cos(o->lonCell[c]), slon = sin(o->lonCell[c]);
+      for (int k = 0; k < L; ++k) {
+        uReconstructZonal(c, k) = -uReconstructX(c, k) * slon + uReconstructY(c, k) * clon;
+        uReconstructMeridional(c, k) = -(uReconstructX(c, k) * clon + uReconstructY(c, k) * slon) * slat + uReconstructZ(c, k) * clat;
+      }
+    } else {
+      for (int k = 0; k < L; ++k) { uReconstructZonal(c, k) = uReconstructX(c, k); uReconstructMeridional(c, k) = uReconstructY(c, k); }
+    }
   }
   return 0;
 }

@@ -631,3 +631,48 @@ def test_advance_scalars(warmed):
     assert np.array_equal(o2.download_field("scalars_old")[:, :L], q[:, :L])
     assert np.isfinite(o2.download_field("scalars")).all()
     o2.close()
+
+
+def test_init_coupled_diagnostics_and_reconstruct_2d(warmed):
+    """the two one-time tasks of atm_core_init that are stencils over 3-D fields, array-at-a-time:
+    atm_init_coupled_diagnostics dynamics_tasks.rg:651-725, mpas_reconstruct_2d :1894-1948 (the latter also against the
+    vectorised host producer core_init.mpas_reconstruct_2d the harness uses)."""
+    from mpas_regent_b200 import core_init
+    st, ora, f = warmed
+    _reset(ora, f)
+    s, cfg = st.static, ora.cfg
+    nC, nE = s["nEdgesOnCell"].shape[0], s["cellsOnEdge"].shape[0]
+    rgas = cfg.rgas; rcv = rgas / (cfg.cp - rgas)
+    fzm, fzp = f["fzm"], f["fzp"]
+    lev = np.arange(L + 1)[None, :] < L
+    rho_zz = np.where(lev, f["rho_zz"] / np.where(lev, f["zz"], 1.0), f["rho_zz"])
+    c1, c2 = _idx(s["cellsOnEdge"][:, 0], nC), _idx(s["cellsOnEdge"][:, 1], nC)
+    rzp = _pad(rho_zz)
+    ru = np.where(lev, 0.5 * f["u"] * (rzp[c1] + rzp[c2]), f["ru"])
+    zz = f["zz"]
+    zf = fzp * _below(zz) + fzm * zz
+    rw = f["w"] * (fzp * _below(rho_zz) + fzm * rho_zz) * zf
+    rw[:, 0] = 0.0
+    rup = _pad(ru)
+    for i in range(s["edgesOnCell"].shape[1]):
+        on = (i < s["nEdgesOnCell"])[:, None] & (np.arange(L + 1)[None, :] > 0)
+        e = _idx(s["edgesOnCell"][:, i], nE)
+        flux = fzm * rup[e] + fzp * _below(rup[e])
+        rw = np.where(on, rw - s["edgesOnCellSign"][:, i][:, None] * (f["zb_cell"][:, :, i] + np.copysign(1.0, flux) * f["zb3_cell"][:, :, i]) * flux * zf, rw)
+    rho_p = rho_zz - f["rho_base"]
+    rtb = f["theta_base"] * f["rho_base"]
+    rtp = f["theta_m"] * rho_p + f["rho_base"] * (f["theta_m"] - f["theta_base"])
+    with np.errstate(invalid="ignore"):
+        ex = np.power(zz * (rgas / 100000) * (rtp + rtb), rcv); exb = np.power(zz * (rgas / 100000) * rtb, rcv)
+    want = {"rho_zz": rho_zz, "ru": ru, "rw": np.where(lev, rw, f["rw"])}
+    for n, a in (("rho_p", rho_p), ("rtheta_base", rtb), ("rtheta_p", rtp), ("exner", ex), ("exner_base", exb),
+                 ("pressure_p", zz * rgas * (ex * rtp + rtb * (ex - exb))), ("pressure_base", zz * rgas * exb * rtb)):
+        want[n] = np.where(lev, a, f[n])
+    ora.atm_init_coupled_diagnostics()
+    _check(ora, want)
+    # reconstruct
+    _reset(ora, f)
+    ora.mpas_reconstruct_2d(False, True)
+    zonal, merid = core_init.mpas_reconstruct_2d(st.mesh, _abi.INDEX_CORRECTED, f["u"], s["coeffs_reconstruct"], L)
+    _check(ora, {"uReconstructZonal": np.where(lev, zonal, f["uReconstructZonal"]), "uReconstructMeridional": np.where(lev, merid, f["uReconstructMeridional"])})
+    assert np.abs(ora.download_field("uReconstructX")).max() > 0

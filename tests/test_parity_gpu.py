@@ -633,3 +633,22 @@ def test_strided_mesh_members_equal_dense_upload(grid642):
         outs.append(g.download_all()); g.close()
     for n in outs[0]:
         assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
+
+
+@pytest.mark.parametrize("policy", [_abi.INDEX_CORRECTED, _abi.INDEX_LITERAL], ids=["corrected", "literal"])
+def test_init_chain_on_the_device(grid2562, policy):
+    """atm_init_coupled_diagnostics (dynamics_tasks.rg:651-725) and mpas_reconstruct_2d (:1894-1948) as
+    device kernels: 1e-12 against the oracle (the two pow() calls are the only non-exact operations), everything else bitwise."""
+    st, ora, g = build_pair(grid2562, L_SMALL, policy, m5=True)
+    for b in (ora, g):
+        b.atm_init_coupled_diagnostics()
+        b.mpas_reconstruct_2d(False, True)
+    compare(g, ora, what="init chain")
+    for n in ("rho_zz", "ru", "rw", "rho_p", "rtheta_base", "rtheta_p", "uReconstructX", "uReconstructY", "uReconstructZ",
+              "uReconstructZonal", "uReconstructMeridional"):
+        assert np.array_equal(g.download_field(n), ora.download_field(n), equal_nan=True), n
+    for b in (ora, g):
+        b.mpas_reconstruct_2d(False, False)
+    for n in ("uReconstructZonal", "uReconstructMeridional"):
+        assert np.array_equal(g.download_field(n), ora.download_field(n), equal_nan=True), n
+    g.close(); ora.close()
