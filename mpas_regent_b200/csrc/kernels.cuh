@@ -504,11 +504,32 @@ __global__ void k_dt_edge(const View V, const DynTendParams P) {
     const double* pv = FLD(pv_edge);
     const D2 pv_k = ld2(pv, ix);
     const double Ld = (double)L;
+    // The static rows (ids, weights) are the same address for every lane of a column: each scalar load costs an L1 wavefront per
+    // column in the warp, and the L1 data pipe is this kernel's busiest unit.  Read them two ids / two weights
+    // at a time (rows are 8- / 16-byte aligned when maxEdges2 is even): 10 wide loads instead of 20 narrow ones per 10 slots.
+    if ((ME2 & 1) == 0) {
+      const int2* idr = reinterpret_cast<const int2*>(V.edgesOnEdge + (size_t)x * ME2);
+      const double2* wr = reinterpret_cast<const double2*>(V.weightsOnEdge + (size_t)x * ME2);
+#pragma unroll 1
+      for (int j0 = 0; j0 < n; j0 += 2) {
+        const int2 id = idr[j0 >> 1];
+        const double2 wt = wr[j0 >> 1];
+        {
+          const D2 workpv = 0.5 * (pv_k + G2(pv, id.x));
+          q += Ld * (wt.x * G2(u, id.x) * workpv);
+        }
+        if (j0 + 1 < n) {
+          const D2 workpv = 0.5 * (pv_k + G2(pv, id.y));
+          q += Ld * (wt.y * G2(u, id.y) * workpv);
+        }
+      }
+    } else {
 #pragma unroll 2
-    for (int j = 0; j < n; ++j) {
-      const int eoe = V.edgesOnEdge[x * ME2 + j];
-      const D2 workpv = 0.5 * (pv_k + G2(pv, eoe));
-      q += Ld * (V.weightsOnEdge[x * ME2 + j] * G2(u, eoe) * workpv);
+      for (int j = 0; j < n; ++j) {
+        const int eoe = V.edgesOnEdge[x * ME2 + j];
+        const D2 workpv = 0.5 * (pv_k + G2(pv, eoe));
+        q += Ld * (V.weightsOnEdge[x * ME2 + j] * G2(u, eoe) * workpv);
+      }
     }
   }
   st2m(FLD(q), ix, q, m0, m1);
@@ -620,15 +641,26 @@ __global__ void k_dt_cellB(const View V, const DynTendParams P) {
 __global__ void k_dt_theta_flux(const View V) {
   PAIR_THREAD(V.nEdges)
   if (!m0) return;
-  const int NA = V.nAdv;
   const double* tm = FLD(theta_m);
   const int na = V.nAdvCellsForEdge[x];
   const D2 sg = sgn1(ld2(FLD(ru), ix));
   D2 fa = bc(0.0);
-#pragma unroll 5
-  for (int j = 0; j < na; ++j) {
-    const D2 sw = V.adv_coefs[x * NA + j] + sg * V.adv_coefs_3rd[x * NA + j];
-    fa += sw * G2(tm, V.advCellsForEdge[x * NA + j]);
+  // per-edge advection rows repacked at upload_mesh: ids [e][NAE] (NAE a multiple of 4) and {adv_coefs, adv_coefs_3rd} pairs
+  // [e][NAE], so four ids come with one 128-bit load and a coefficient pair with one -- 14 wide loads instead of 30 scalar ones
+  // for a 10-cell stencil (every lane of a column reads the same address: each load is an L1 wavefront per column in the warp)
+  const int NAE = V.NAE;
+  const int4* idr = reinterpret_cast<const int4*>(V.advCellE + (size_t)x * NAE);
+  const double2* cr = V.advCoefE + (size_t)x * NAE;
+  for (int j0 = 0; j0 < na; j0 += 4) {
+    const int4 id = idr[j0 >> 2];
+    const int ids[4] = {id.x, id.y, id.z, id.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (j0 + t < na) {
+        const double2 c = cr[j0 + t];
+        const D2 sw = c.x + sg * c.y;
+        fa += sw * G2(tm, ids[t]);
+      }
   }
   st2m(V.scr_flux, ix, fa, m0, m1);
 }
@@ -979,13 +1011,38 @@ __global__ void k_acoustic_gather(const View V, double dts) {
   const double* ru_p = FLD(ru_p); const double* tm = FLD(theta_m);
   const double inva = V.invAreaCell[x];
   D2 rs = bc(0), ts = bc(0);
+  if ((ME & 1) == 0) {
+    // static rows read two slots at a time (every lane of a column reads the same address; the L1 data pipe is the busiest unit,
+    // DESIGN.md 4.2): per 2 slots 3 int2 + 2 double2 loads instead of 10 scalar ones.  MEP is a multiple of 4, ME even.
+    const int2* er = reinterpret_cast<const int2*>(V.edgesOnCell + (size_t)x * V.MEP);
+    const int2* c1r = reinterpret_cast<const int2*>(V.c1OnCell + (size_t)x * V.MEP);
+    const int2* c2r = reinterpret_cast<const int2*>(V.c2OnCell + (size_t)x * V.MEP);
+    const double2* sr = reinterpret_cast<const double2*>(V.edgesOnCellSign + (size_t)x * ME);
+    const double2* dr = reinterpret_cast<const double2*>(V.dvOnCell + (size_t)x * ME);
 #pragma unroll 2
-  for (int i = 0; i < n; ++i) {
-    const int e = V.edgesOnCell[x * V.MEP + i];
-    const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
-    const D2 flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G2(ru_p, e) * inva;
-    rs -= flux;
-    ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
+    for (int i0 = 0; i0 < n; i0 += 2) {
+      const int2 e2 = er[i0 >> 1], a2 = c1r[i0 >> 1], b2 = c2r[i0 >> 1];
+      const double2 sg = sr[i0 >> 1], dv = dr[i0 >> 1];
+      {
+        const D2 flux = sg.x * dts * dv.x * G2(ru_p, e2.x) * inva;
+        rs -= flux;
+        ts -= flux * 0.5 * (G2(tm, b2.x) + G2(tm, a2.x));
+      }
+      if (i0 + 1 < n) {
+        const D2 flux = sg.y * dts * dv.y * G2(ru_p, e2.y) * inva;
+        rs -= flux;
+        ts -= flux * 0.5 * (G2(tm, b2.y) + G2(tm, a2.y));
+      }
+    }
+  } else {
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {
+      const int e = V.edgesOnCell[x * V.MEP + i];
+      const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+      const D2 flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G2(ru_p, e) * inva;
+      rs -= flux;
+      ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
+    }
   }
   st2m(V.scr_rs, ix, rs, m0, m1); st2m(V.scr_ts, ix, ts, m0, m1);
 }

@@ -94,7 +94,7 @@ struct mpasb200 {
   struct Halo { std::vector<int> peers_s, off_s, peers_r, off_r; int* d_s = nullptr; int* d_r = nullptr; int ns = 0, nr = 0; bool set = false; } halo[3];
   struct ExPart { int ent; std::vector<int> fields; int entries; double* sbuf = nullptr; double* rbuf = nullptr; };
   std::vector<ExPart> xplan[MPASB200_X_COUNT]; bool xplan_built = false;
-  cudaStream_t comm_stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr; bool x_pending = false; bool has_classes = false;
+  cudaStream_t comm_stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_side = nullptr; bool x_pending = false; bool has_classes = false;
   double* d_sflux = nullptr;            // horiz_flux_arr of atm_advance_scalars: [nScalars][(nEdges+1)][LP], allocated on first use
   std::string err;
   std::mutex mu;
@@ -653,6 +653,7 @@ void dist_release(mpasb200_t* h) {
   if (h->comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
   if (h->ev_ready) { cudaEventDestroy(h->ev_ready); h->ev_ready = nullptr; }
   if (h->ev_done) { cudaEventDestroy(h->ev_done); h->ev_done = nullptr; }
+  if (h->ev_side) { cudaEventDestroy(h->ev_side); h->ev_side = nullptr; }
   if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); h->comm_stream = nullptr; }
 }
 
@@ -700,12 +701,17 @@ int dist_pack_unpack(mpasb200_t* h, const mpasb200_t::ExPart& p, bool pack) {
   return 0;
 }
 // pack -> one NCCL group -> unpack, all on the communication stream; the compute stream continues at once
-int dist_start(mpasb200_t* h, int kind) {
+// the communication stream joins the compute stream's order here (everything enqueued on compute so far is visible to it)
+int dist_fork(mpasb200_t* h) {
+  CK(cudaEventRecord(h->ev_ready, h->stream));
+  CK(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+  return 0;
+}
+int dist_start(mpasb200_t* h, int kind, bool forked = false) {
   if (!h->comm) return fail(h, MPASB200_ESTATE, "mpasb200_dist_init has not been called");
   if (int rc = dist_build_plans(h)) return rc;
   if (h->x_pending) return fail(h, MPASB200_ESTATE, "an exchange is still travelling (dist_flush first)");
-  CK(cudaEventRecord(h->ev_ready, h->stream));
-  CK(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+  if (!forked) { if (int rc = dist_fork(h)) return rc; }
   cudaStream_t compute = h->stream;
   h->stream = h->comm_stream;
   int rc = 0;
@@ -777,9 +783,22 @@ int t_srk3_dist(mpasb200_t* h, double dt) {
         R(t_acoustic(h, dts, small_step));
         set_empty(h, MPASB200_EDGE);
       }
-      set_ranges(h, MPASB200_CELL, 1); R(t_acoustic(h, dts, small_step));          // owned cells some rank reads: first
-      R(dist_start(h, kind));                                                      // ... they travel
+      // the owned cells some rank reads (a small launch) are advanced ON THE COMMUNICATION STREAM, at its high priority and
+      // concurrently with the interior cells on the compute stream: the small launch does not leave the GPU half empty, and the
+      // exchange starts as soon as those cells are done
+      R(dist_fork(h));
+      {
+        cudaStream_t compute = h->stream;
+        h->stream = h->comm_stream;
+        set_ranges(h, MPASB200_CELL, 1);
+        rc = t_acoustic(h, dts, small_step);
+        h->stream = compute;
+        if (rc) { h->rangeSet[MPASB200_CELL] = h->rangeSet[MPASB200_EDGE] = false; return rc; }
+        CK(cudaEventRecord(h->ev_side, h->comm_stream));
+      }
+      R(dist_start(h, kind, true));                                                // ... they travel
       set_ranges(h, MPASB200_CELL, 0); R(t_acoustic(h, dts, small_step));          // ... under the interior cells
+      CK(cudaStreamWaitEvent(h->stream, h->ev_side, 0));                           // interior edges touch sent cells too
       set_ranges(h, MPASB200_EDGE, 0); R(t_divdamp(h, dts));                       // ... and the interior edges
       R(dist_finish(h));
       set_ranges(h, MPASB200_EDGE, 1); R(t_divdamp(h, dts));                       // edges next to ghosts
@@ -1017,6 +1036,19 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
           advS[d] = advE[(size_t)e * NA + j]; acS[d] = acE[(size_t)e * NA + j]; a3S[d] = a3E[(size_t)e * NA + j];
         }
       }
+    {   // per-edge advection rows with a 16-byte pitch (k_dt_theta_flux)
+      const int nae = (NA + 3) / 4 * 4;
+      V.NAE = nae;
+      std::vector<int> idE((size_t)(nE + 1) * nae, nC);
+      std::vector<double2> cfE((size_t)(nE + 1) * nae, make_double2(0.0, 0.0));
+      for (int e = 0; e <= nE; ++e)
+        for (int j = 0; j < NA; ++j) {
+          idE[(size_t)e * nae + j] = advE[(size_t)e * NA + j];
+          cfE[(size_t)e * nae + j] = make_double2(acE[(size_t)e * NA + j], a3E[(size_t)e * NA + j]);
+        }
+      if ((rc = dev_upload<int>(h, &V.advCellE, idE))) return rc;
+      if ((rc = dev_upload<double2>(h, &V.advCoefE, cfE))) return rc;
+    }
     if ((rc = dev_upload<int>(h, &V.edgesOnCell, eoc))) return rc;
     if ((rc = dev_upload<int>(h, &V.c1OnCell, c1))) return rc;
     if ((rc = dev_upload<int>(h, &V.c2OnCell, c2))) return rc;
@@ -1537,6 +1569,7 @@ int mpasb200_dist_init(mpasb200_t* h, int rank, int world, const void* id128) {
   CK(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi));
   CK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
   return 0;
 }
 int mpasb200_dist_set_halo(mpasb200_t* h, int entity, int32_t nsp, const int32_t* sp, const int32_t* so, const int32_t* si,

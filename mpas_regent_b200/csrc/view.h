@@ -14,6 +14,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <vector_types.h>
 #include "../../include/mpas_b200.h"
 
 struct View {
@@ -44,6 +45,7 @@ struct View {
   const double* weightsOnEdge; const double* dcEdge; const double* dvEdge; const double* invDcEdge; const double* invDvEdge;
   const double* cosAngleEdge; const double* sinAngleEdge; const double* cosLatEdge;
   const int* nAdvCellsForEdge; const int* advCellsForEdge; const double* adv_coefs; const double* adv_coefs_3rd;
+  int NAE; const int* advCellE /* [e][NAE] */; const double2* advCoefE /* [e][NAE] {adv_coefs, adv_coefs_3rd} */;   // 16-byte rows for k_dt_theta_flux
   const double* meshScalingDel2; const double* meshScalingDel4; const double* specZoneMaskEdge;
   const unsigned char* divdampSkip;   // isShared[cell1] && isShared[cell2]   (dynamics_tasks.rg:1750)
   // vertex statics
