@@ -274,6 +274,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--graph", type=int, default=0)
     ap.add_argument("--gather-stage", type=int, default=-1, help="MpasConfig.gather_stage bit mask (ablation: 0 = the plain gather kernels)")
+    ap.add_argument("--edge-tiles", type=int, default=None, help="MpasConfig.edge_tiles (0 = plain k_dt_edge; 8 / 16 = tile-staged form)")
     ap.add_argument("--acoustic", type=int, default=3, help="MpasConfig.acoustic_tma (3 = exact column-per-lane pipeline, 2 = affine sweep)")
     ap.add_argument("--physics", choices=("literal", "corrected"), default="literal",
                     help="literal = the reference as it executes (headline); corrected = acoustic u update + back-substitution + "
@@ -299,7 +300,8 @@ def main():
     dt = dt_for(nC)
     corrected = args.physics == "corrected"
     cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, device=local_rank, use_graph=args.graph,
-                              physics_mode=_abi.PHYSICS_CORRECTED if corrected else _abi.PHYSICS_LITERAL, gather_stage=args.gather_stage, acoustic_tma=args.acoustic)
+                              physics_mode=_abi.PHYSICS_CORRECTED if corrected else _abi.PHYSICS_LITERAL, gather_stage=args.gather_stage, acoustic_tma=args.acoustic,
+                              **({} if args.edge_tiles is None else {"edge_tiles": args.edge_tiles}))
     stream = torch.cuda.Stream()
 
     if world == 1:
@@ -511,7 +513,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(nC, L, world, corrected),
             "run_info": {"parallelism_detail": parallelism, "host_init_s": round(t_init, 1), "device_bytes": g.device_bytes,
-                         "cuda_graph": bool(args.graph), "acoustic_tma": args.acoustic, "ms_per_step_with_kernel_events": ms_k / k_steps},
+                         "cuda_graph": bool(args.graph), "acoustic_tma": args.acoustic, "edge_tiles": int(cfg.edge_tiles), "ms_per_step_with_kernel_events": ms_k / k_steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,

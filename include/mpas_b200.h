@@ -131,6 +131,10 @@ typedef struct {
   int32_t config_scalar_advection;    /* 0 (default): atm_srk3 skips scalar transport exactly like the reference (rk_timestep.rg:465);
                                          1: atm_rk_integration_setup saves scalars_old and every RK stage calls atm_advance_scalars
                                          with rk_timestep[rk_step] = dt/3, dt/2, dt (rk_timestep.rg:386-389)              */
+  int32_t edge_tiles;                 /* LABORATORY builds (-DMPASB200_LAB) only, ignored by the shipped library: 8 / 16 = k_dt_edge as a
+                                         tile kernel (a block owns 8 / 16 consecutive edges and stages the DISTINCT edgesOnEdge columns of
+                                         the tile once in shared memory with cp.async.bulk, lists built at upload_mesh).  Bit-identical
+                                         results, measured slower than the plain kernel on B200 (profiles/r2_edge_tiles.md). */
   double  config_coef_3rd_order;      /* 0.25, constants.rg:59 */
 } MpasConfig;
 
@@ -262,6 +266,39 @@ int  mpasb200_init_coupled_diagnostics(mpasb200_t *h);
 /* mpas_reconstruct_2d                 dynamics_tasks.rg:1894-1948 (uReconstructX/Y/Z from u with coeffs_reconstruct, then
  *                                     uReconstructZonal / uReconstructMeridional; also MPAS's end-of-step call, rk_timestep.rg:487) */
 int  mpasb200_reconstruct_2d(mpasb200_t *h, int includeHalos, int on_a_sphere);
+
+/* ---- the mesh-only producers of atm_core_init on the device ------------------------------------------- *
+ * atm_compute_signs (dynamics_tasks.rg:46-130), atm_adv_coef_compression (:133-269) and atm_couple_coef_3rd_order (:303-325) run
+ * once, before the first step, on connectivity alone.  Their inputs are the RAW stored ids of the static region fields in the
+ * caller's numbering (host pointers, row-major [entity][slot] like MpasMeshPtrs; index_policy of the handle resolves them), their
+ * outputs are exactly the MpasMeshPtrs members / 3-D fields the hot path consumes.  The two list builders may be called before
+ * mpasb200_upload_mesh (their outputs feed it); the 3-D part of atm_compute_signs (zb_cell, zb3_cell from the edge fields zb, zb3)
+ * works on the device mirror and therefore comes after mpasb200_upload_mesh + the upload of zb, zb3.                             */
+typedef struct {
+  const int32_t *nEdgesOnCell;      /* [nCells]                    */
+  const int32_t *edgesOnCell;       /* [nCells][maxEdges]          */
+  const int32_t *verticesOnCell;    /* [nCells][maxEdges]          */
+  const int32_t *cellsOnCell;       /* [nCells][maxEdges]          */
+  const int32_t *cellsOnEdge;       /* [nEdges][2]                 */
+  const int32_t *verticesOnEdge;    /* [nEdges][2]                 */
+  const int32_t *cellsOnVertex;     /* [nVertices][vertexDegree]   */
+  const int32_t *edgesOnVertex;     /* [nVertices][vertexDegree]   */
+  const double  *dcEdge, *dvEdge;   /* [nEdges]                    */
+  const double  *deriv_two;         /* [nEdges][2*FIFTEEN]; null = never written upstream = all zero (rule M1) */
+} MpasInitMesh;
+/* atm_compute_signs, level-0 part     dynamics_tasks.rg:60-86, 113-129: edgesOnVertexSign [nVertices][vertexDegree],
+ *                                     edgesOnCellSign [nCells][maxEdges], kiteForCell [nCells][maxEdges] (host, caller's numbering) */
+int  mpasb200_compute_signs(mpasb200_t *h, const MpasInitMesh *m, double *edgesOnVertexSign, double *edgesOnCellSign, int32_t *kiteForCell);
+/* atm_compute_signs, 3-D part         dynamics_tasks.rg:88-110: zb_cell, zb3_cell from zb, zb3 (levels 0..nVertLevels) */
+int  mpasb200_compute_zb_cell(mpasb200_t *h);
+/* atm_adv_coef_compression            dynamics_tasks.rg:133-269: nAdvCellsForEdge [nEdges], advCellsForEdge (raw ids) / adv_coefs /
+ *                                     adv_coefs_3rd [nEdges][FIFTEEN]; quirks kept (the list index n, the cap at maxEdges-1)       */
+int  mpasb200_adv_coef_compression(mpasb200_t *h, const MpasInitMesh *m, int32_t *nAdvCellsForEdge, int32_t *advCellsForEdge,
+                                   double *adv_coefs, double *adv_coefs_3rd);
+/* atm_couple_coef_3rd_order           dynamics_tasks.rg:303-325: adv_coefs_3rd [nEdges][FIFTEEN] (host array, scaled on the device,
+ *                                     may be null) *= coef; zb3_cell *= coef at LEVEL 0 only (the device field; skipped before
+ *                                     mpasb200_upload_mesh)                                                                        */
+int  mpasb200_couple_coef_3rd_order(mpasb200_t *h, double config_coef_3rd_order, double *adv_coefs_3rd);
 
 /* ---- the driver: atm_srk3 / atm_timestep  rk_timestep.rg:361-519 ------------------------- *
  * Replays the reference's call sequence on the device (control flow + scalars only).    */

@@ -64,7 +64,7 @@ _CFG_D = ("gravity", "rgas", "cp", "cv", "omega", "sphere_radius", "prandtl", "c
           "config_h_theta_eddy_visc4", "config_rayleigh_damp_u_timescale_days", "config_mpas_cam_coef")
 _CFG_I = ("config_number_rayleigh_damp_u_levels", "config_horiz_mixing", "config_mix_full", "config_rayleigh_damp_u",
           "nRelaxZone", "number_of_sub_steps", "config_dynamics_split_steps", "index_policy", "rkarg_policy",
-          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma", "physics_mode", "gather_stage", "config_scalar_advection")
+          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma", "physics_mode", "gather_stage", "config_scalar_advection", "edge_tiles")
 
 
 class MpasConfig(C.Structure):
@@ -111,12 +111,47 @@ class MpasFieldSummary(C.Structure):
                 "count": int(self.count), "checksum": f"{int(self.checksum):016x}"}
 
 
+INIT_MESH_MEMBERS = (
+    ("nEdgesOnCell", np.int32, CELL, 1), ("edgesOnCell", np.int32, CELL, "maxEdges"), ("verticesOnCell", np.int32, CELL, "maxEdges"),
+    ("cellsOnCell", np.int32, CELL, "maxEdges"), ("cellsOnEdge", np.int32, EDGE, 2), ("verticesOnEdge", np.int32, EDGE, 2),
+    ("cellsOnVertex", np.int32, VERTEX, "vertexDegree"), ("edgesOnVertex", np.int32, VERTEX, "vertexDegree"),
+    ("dcEdge", np.float64, EDGE, 1), ("dvEdge", np.float64, EDGE, 1), ("deriv_two", np.float64, EDGE, "twoFifteen"),
+)
+
+
+class MpasInitMesh(C.Structure):
+    """image of MpasInitMesh (mpas_b200.h): raw connectivity for the mesh-only producers of atm_core_init"""
+    _fields_ = [(n, C.c_void_p) for (n, _, _, _) in INIT_MESH_MEMBERS]
+
+
+def init_mesh_ptrs(arrays: Dict[str, np.ndarray], dims: "MpasDims"):
+    """MpasInitMesh over numpy arrays (missing members stay null); the keep-alive list must outlive the call"""
+    m, keep = MpasInitMesh(), []
+    counts = {CELL: dims.nCells, EDGE: dims.nEdges, VERTEX: dims.nVertices}
+    for name, dt, ent, wkey in INIT_MESH_MEMBERS:
+        a = arrays.get(name)
+        if a is None:
+            setattr(m, name, None)
+            continue
+        w = wkey if isinstance(wkey, int) else (2 * dims.nAdvCells if wkey == "twoFifteen" else getattr(dims, wkey))
+        a = np.ascontiguousarray(a, dtype=dt)
+        want = (counts[ent],) if w == 1 else (counts[ent], w)
+        if a.shape != want:
+            raise ValueError(f"{name}: shape {a.shape}, expected {want}")
+        keep.append(a)
+        setattr(m, name, a.ctypes.data)
+    return m, keep
+
+
 class MpasMeshPtrs(C.Structure):
     _fields_ = [(n, C.c_void_p) for (n, _, _, _) in MESH_MEMBERS]
 
 
 def make_dims(nCells, nEdges, nVertices, nVertLevels, maxEdges=10, maxEdges2=20, vertexDegree=3, nAdvCells=15) -> MpasDims:
     return MpasDims(nCells, nEdges, nVertices, nVertLevels, maxEdges, maxEdges2, vertexDegree, nAdvCells)
+
+
+EDGE_TILES_DEFAULT = 0
 
 
 def default_config(**over) -> MpasConfig:
@@ -141,6 +176,7 @@ def default_config(**over) -> MpasConfig:
     c.physics_mode = PHYSICS_LITERAL
     c.gather_stage = 0
     c.config_scalar_advection = 0
+    c.edge_tiles = EDGE_TILES_DEFAULT
     c.config_coef_3rd_order = 0.25
     for k, v in over.items():
         if not hasattr(c, k):

@@ -28,6 +28,9 @@
 #ifndef LB_AC
 #define LB_AC 3
 #endif
+#ifndef KDE_PREFETCH
+#define KDE_PREFETCH 0
+#endif
 #ifndef LB_MISC
 #define LB_MISC 1
 #endif
@@ -477,6 +480,16 @@ __global__ void k_dt_edge(const View V, const DynTendParams P) {
   D2 u2 = bc(0.0), wduz = bc(0.0);
   if (m0) {
     cv = V.ecv[x];
+#if KDE_PREFETCH
+    // (laboratory variant) the loads of the kernel's tail -- own-column strips and the cell columns that depend only on `cv` -- are
+    // requested into L2 now, one request per 128-byte line, so that they later cost an L2 round trip instead of a DRAM one
+    if ((threadIdx.x & 7) == 0) {
+      prefetch_l2(FLD(rho_edge) + ix); prefetch_l2(FLD(tend_u_euler) + ix); prefetch_l2(FLD(tend_ru_physics) + ix); prefetch_l2(FLD(pv_edge) + ix);
+      const size_t a = (size_t)cv.x * LP + k0, b = (size_t)cv.y * LP + k0;
+      prefetch_l2(FLD(ke) + a); prefetch_l2(FLD(ke) + b); prefetch_l2(FLD(h_divergence) + a); prefetch_l2(FLD(h_divergence) + b);
+      prefetch_l2(FLD(w) + a); prefetch_l2(FLD(w) + b);
+    }
+#endif
     u2 = ld2(u, ix);
     const double* rw = FLD(rw);
     const D2 rwavg = 0.5 * (G2(rw, cv.x) + G2(rw, cv.y));
@@ -504,32 +517,13 @@ __global__ void k_dt_edge(const View V, const DynTendParams P) {
     const double* pv = FLD(pv_edge);
     const D2 pv_k = ld2(pv, ix);
     const double Ld = (double)L;
-    // The static rows (ids, weights) are the same address for every lane of a column: each scalar load costs an L1 wavefront per
-    // column in the warp, and the L1 data pipe is this kernel's busiest unit.  Read them two ids / two weights
-    // at a time (rows are 8- / 16-byte aligned when maxEdges2 is even): 10 wide loads instead of 20 narrow ones per 10 slots.
-    if ((ME2 & 1) == 0) {
-      const int2* idr = reinterpret_cast<const int2*>(V.edgesOnEdge + (size_t)x * ME2);
-      const double2* wr = reinterpret_cast<const double2*>(V.weightsOnEdge + (size_t)x * ME2);
-#pragma unroll 1
-      for (int j0 = 0; j0 < n; j0 += 2) {
-        const int2 id = idr[j0 >> 1];
-        const double2 wt = wr[j0 >> 1];
-        {
-          const D2 workpv = 0.5 * (pv_k + G2(pv, id.x));
-          q += Ld * (wt.x * G2(u, id.x) * workpv);
-        }
-        if (j0 + 1 < n) {
-          const D2 workpv = 0.5 * (pv_k + G2(pv, id.y));
-          q += Ld * (wt.y * G2(u, id.y) * workpv);
-        }
-      }
-    } else {
+    // (reading the static rows two slots at a time -- int2 ids, double2 weights -- was measured: 64 registers instead of 56,
+    // 28 resident warps instead of 35, 2.94 -> 3.52 ms per launch on x1.655362; profiles/r2_ncu_gather_kernels.md)
 #pragma unroll 2
-      for (int j = 0; j < n; ++j) {
-        const int eoe = V.edgesOnEdge[x * ME2 + j];
-        const D2 workpv = 0.5 * (pv_k + G2(pv, eoe));
-        q += Ld * (V.weightsOnEdge[x * ME2 + j] * G2(u, eoe) * workpv);
-      }
+    for (int j = 0; j < n; ++j) {
+      const int eoe = V.edgesOnEdge[x * ME2 + j];
+      const D2 workpv = 0.5 * (pv_k + G2(pv, eoe));
+      q += Ld * (V.weightsOnEdge[x * ME2 + j] * G2(u, eoe) * workpv);
     }
   }
   st2m(FLD(q), ix, q, m0, m1);
@@ -1011,38 +1005,13 @@ __global__ void k_acoustic_gather(const View V, double dts) {
   const double* ru_p = FLD(ru_p); const double* tm = FLD(theta_m);
   const double inva = V.invAreaCell[x];
   D2 rs = bc(0), ts = bc(0);
-  if ((ME & 1) == 0) {
-    // static rows read two slots at a time (every lane of a column reads the same address; the L1 data pipe is the busiest unit,
-    // DESIGN.md 4.2): per 2 slots 3 int2 + 2 double2 loads instead of 10 scalar ones.  MEP is a multiple of 4, ME even.
-    const int2* er = reinterpret_cast<const int2*>(V.edgesOnCell + (size_t)x * V.MEP);
-    const int2* c1r = reinterpret_cast<const int2*>(V.c1OnCell + (size_t)x * V.MEP);
-    const int2* c2r = reinterpret_cast<const int2*>(V.c2OnCell + (size_t)x * V.MEP);
-    const double2* sr = reinterpret_cast<const double2*>(V.edgesOnCellSign + (size_t)x * ME);
-    const double2* dr = reinterpret_cast<const double2*>(V.dvOnCell + (size_t)x * ME);
 #pragma unroll 2
-    for (int i0 = 0; i0 < n; i0 += 2) {
-      const int2 e2 = er[i0 >> 1], a2 = c1r[i0 >> 1], b2 = c2r[i0 >> 1];
-      const double2 sg = sr[i0 >> 1], dv = dr[i0 >> 1];
-      {
-        const D2 flux = sg.x * dts * dv.x * G2(ru_p, e2.x) * inva;
-        rs -= flux;
-        ts -= flux * 0.5 * (G2(tm, b2.x) + G2(tm, a2.x));
-      }
-      if (i0 + 1 < n) {
-        const D2 flux = sg.y * dts * dv.y * G2(ru_p, e2.y) * inva;
-        rs -= flux;
-        ts -= flux * 0.5 * (G2(tm, b2.y) + G2(tm, a2.y));
-      }
-    }
-  } else {
-#pragma unroll 2
-    for (int i = 0; i < n; ++i) {
-      const int e = V.edgesOnCell[x * V.MEP + i];
-      const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
-      const D2 flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G2(ru_p, e) * inva;
-      rs -= flux;
-      ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
-    }
+  for (int i = 0; i < n; ++i) {
+    const int e = V.edgesOnCell[x * V.MEP + i];
+    const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
+    const D2 flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G2(ru_p, e) * inva;
+    rs -= flux;
+    ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
   }
   st2m(V.scr_rs, ix, rs, m0, m1); st2m(V.scr_ts, ix, ts, m0, m1);
 }

@@ -21,6 +21,10 @@
 
 #include "kernels.cuh"
 #ifdef MPASB200_LAB
+#include "kernels_tiles.cuh"     // tile-staged k_dt_edge (TMA, de-duplicated columns): bit-identical, measured slower (profiles/r2_edge_tiles.md)
+#endif
+#include "kernels_init.cuh"
+#ifdef MPASB200_LAB
 #include "kernels_staged.cuh"     // cp.async-staged gather kernels: measured slower than the plain ones (profiles/r2_staged_gathers.md)
 #include "kernels_lab.cuh"
 #endif
@@ -95,6 +99,9 @@ struct mpasb200 {
   struct ExPart { int ent; std::vector<int> fields; int entries; double* sbuf = nullptr; double* rbuf = nullptr; };
   std::vector<ExPart> xplan[MPASB200_X_COUNT]; bool xplan_built = false;
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_side = nullptr; bool x_pending = false; bool has_classes = false;
+#ifdef MPASB200_LAB
+  EdgeTiles et = {nullptr, nullptr, nullptr, 0, 0, 0}; size_t et_smem = 0; int et_minb = 0, et_abl = 0;     // k_dt_edge_tile (MpasConfig.edge_tiles), built by upload_mesh
+#endif
   double* d_sflux = nullptr;            // horiz_flux_arr of atm_advance_scalars: [nScalars][(nEdges+1)][LP], allocated on first use
   std::string err;
   std::mutex mu;
@@ -269,6 +276,33 @@ bool staged_on(const mpasb200_t* h, int bit, size_t smem) { return (h->c.gather_
 #endif
 size_t tile_bytes(const mpasb200_t* h, int tiles) { return (size_t)tiles * h->CPB * (h->LP + 2) * sizeof(double); }
 
+#ifdef MPASB200_LAB
+// k_dt_edge_tile (kernels_tiles.cuh): compiled for at most ET_MAXT threads per block, ET_MINB resident blocks
+enum { ET_MAXT16 = 448, ET_MINB16 = 3, ET_MAXT8 = 224, ET_MINB8 = 5 };
+void launch_dt_edge(mpasb200_t* h, const DynTendParams& P) {
+  if (h->et.TE == 0) return;
+  const int nT = (h->nEdges + h->et.TE - 1) / h->et.TE;
+  const dim3 block((unsigned)(h->LP / 2), (unsigned)h->et.TE);
+  KTimer kt_(h, "k_dt_edge_tile");
+#define ET_GO(TE_, MT_, MB_) k_dt_edge_tile<TE_, MT_, MB_><<<nT, block, h->et_smem, h->stream>>>(h->V, P, h->et)
+#ifdef MPASB200_LAB
+  if (h->et_abl && h->et.TE == 16) { if (h->et_abl == 1) k_dt_edge_tile<16, ET_MAXT16, 2, 1><<<nT, block, h->et_smem, h->stream>>>(h->V, P, h->et); else k_dt_edge_tile<16, ET_MAXT16, 2, 2><<<nT, block, h->et_smem, h->stream>>>(h->V, P, h->et); }
+  else if (h->et_abl) { if (h->et_abl == 1) k_dt_edge_tile<8, ET_MAXT8, ET_MINB8, 1><<<nT, block, h->et_smem, h->stream>>>(h->V, P, h->et); else k_dt_edge_tile<8, ET_MAXT8, ET_MINB8, 2><<<nT, block, h->et_smem, h->stream>>>(h->V, P, h->et); }
+  else
+#endif
+  if (h->et.TE == 16 && h->et_minb == 2) ET_GO(16, ET_MAXT16, 2);
+  else if (h->et.TE == 16) ET_GO(16, ET_MAXT16, ET_MINB16);
+  else if (h->et_minb == 4) ET_GO(8, ET_MAXT8, 4);
+  else ET_GO(8, ET_MAXT8, ET_MINB8);
+#undef ET_GO
+  h->launches++;
+}
+#define ET_ON(h) ((h)->et.TE != 0)
+#else
+#define ET_ON(h) false
+#define launch_dt_edge(h, P) do { } while (0)
+#endif
+
 int post_launch(mpasb200_t* h) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = std::string("kernel launch: ") + cudaGetErrorString(e); return MPASB200_ECUDA; }
@@ -372,6 +406,7 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
     }
     LAUNCH(k_dt_edge_euler, h->nEdges, tile_bytes(h, 1), h->V, P);
     if (staged_on(h, GS_DT_EDGE, sm_edge)) LAUNCH_STAGED(k_dt_edge_s<10>, h->nEdges, sm_edge, h->V, P);
+    else if (ET_ON(h)) launch_dt_edge(h, P);
     else LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
     LAUNCH(k_dt_cellA, h->nCells, 0, h->V, P);
     LAUNCH(k_dt_cellB, h->nCells, 0, h->V, P);
@@ -381,6 +416,7 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
   } else {
     LAUNCH(k_dt_cell0<false>, h->nCells, 0, h->V, P, C.config_len_disp, cam_coef);
     if (staged_on(h, GS_DT_EDGE, sm_edge)) LAUNCH_STAGED(k_dt_edge_s<10>, h->nEdges, sm_edge, h->V, P);
+    else if (ET_ON(h)) launch_dt_edge(h, P);
     else LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
     if (staged_on(h, GS_THETA_FLUX, sm_flux)) LAUNCH_STAGED(k_dt_theta_flux_s<10>, h->nEdges, sm_flux, h->V);
     else LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
@@ -835,6 +871,7 @@ void mpasb200_default_config(MpasConfig* c) {
   c->physics_mode = MPASB200_PHYSICS_LITERAL;
   c->gather_stage = 0;
   c->config_scalar_advection = 0; c->config_coef_3rd_order = 0.25;        // constants.rg:59
+  c->edge_tiles = 0;
 }
 
 const char* mpasb200_last_error(const mpasb200_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -917,6 +954,68 @@ int mpasb200_destroy(mpasb200_t* h) {
   delete h;
   return 0;
 }
+
+#ifdef MPASB200_LAB
+// ---- tile lists of k_dt_edge_tile (kernels_tiles.cuh): per tile of TE consecutive internal edges the distinct columns to stage
+// (own edges first, then edgesOnEdge neighbours in first-use order, at most `cap`), per edge the staged slot of every neighbour.
+namespace {
+int build_edge_tiles(mpasb200_t* h, const std::vector<int>& eoe, const std::vector<int>& nEoE) {
+  const int TE = h->c.edge_tiles % 100, minb_over = h->c.edge_tiles / 100 % 10, nE = h->nEdges, ME2 = h->d.maxEdges2, LP = h->LP;
+  if (TE == 0 || nE == 0) return 0;
+  if (TE != 8 && TE != 16) return fail(h, MPASB200_EINVAL, "edge_tiles must be 0, 8 or 16");
+  const int maxt = TE == 16 ? ET_MAXT16 : ET_MAXT8, minb = (TE == 16 && minb_over == 2) ? 2 : (TE == 8 && minb_over == 4) ? 4 : (TE == 16 ? ET_MINB16 : ET_MINB8);
+  h->et_minb = minb; h->et_abl = h->c.edge_tiles / 1000;      // ablations: laboratory build only
+  if ((ME2 & 1) || LP / 2 * TE > maxt) { h->c.edge_tiles = 0; return 0; }      // shapes the tile kernel is not compiled for: plain kernel
+  int smem_sm = 0;
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device);
+  const size_t fixed = ((size_t)TE * ME2 + (size_t)TE * (LP + 2)) * sizeof(double) + 16;
+  const size_t per_block = std::min<size_t>((size_t)smem_sm / minb - 1024, (size_t)h->max_smem_optin);
+  if (per_block < fixed + (size_t)TE * 2 * LP * sizeof(double)) { h->c.edge_tiles = 0; return 0; }
+  int cap = (int)((per_block - fixed) / ((size_t)2 * LP * sizeof(double)));
+  cap = std::min(cap, std::min(254, TE * (ME2 + 1)));
+  const int SP = (ME2 + 15) / 16 * 16;
+  const int nT = (nE + TE - 1) / TE;
+  std::vector<int> cols((size_t)nT * cap, nE), ncols(nT, 0);
+  std::vector<unsigned char> slot((size_t)(nE + 1) * SP, 255);
+  std::vector<int> slotOf((size_t)nE + 1, -1);
+  for (int t = 0; t < nT; ++t) {
+    int* cl = cols.data() + (size_t)t * cap;
+    int nc = TE;                                        // own edges: slot = local index (entries past nEdges stay the pad column)
+    for (int i = 0; i < TE; ++i) { const int e = t * TE + i; if (e < nE) { cl[i] = e; slotOf[e] = i; } }
+    for (int i = 0; i < TE; ++i) {
+      const int e = t * TE + i;
+      if (e >= nE) break;
+      const int n = std::min(nEoE[e], ME2);
+      for (int j = 0; j < n; ++j) {
+        const int id = eoe[(size_t)e * ME2 + j];
+        if (slotOf[id] < 0 && nc < cap) { slotOf[id] = nc; cl[nc++] = id; }
+        if (slotOf[id] >= 0) slot[(size_t)e * SP + j] = (unsigned char)slotOf[id];
+      }
+    }
+    ncols[t] = nc;
+    for (int i = 0; i < nc; ++i) slotOf[cl[i]] = -1;
+  }
+  int rc;
+  if ((rc = dev_upload<int>(h, &h->et.cols, cols))) return rc;
+  if ((rc = dev_upload<int>(h, &h->et.ncols, ncols))) return rc;
+  if ((rc = dev_upload<unsigned char>(h, &h->et.slot, slot))) return rc;
+  h->et.cap = cap; h->et.SP = SP; h->et.TE = TE;
+  h->et_smem = fixed + (size_t)cap * 2 * LP * sizeof(double);
+#define ET_ATTR(TE_, MT_, MB_) cudaFuncSetAttribute(k_dt_edge_tile<TE_, MT_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->et_smem)
+  cudaError_t e = (TE == 16 && minb == 2) ? ET_ATTR(16, ET_MAXT16, 2) : (TE == 16) ? ET_ATTR(16, ET_MAXT16, ET_MINB16)
+                  : (minb == 4) ? ET_ATTR(8, ET_MAXT8, 4) : ET_ATTR(8, ET_MAXT8, ET_MINB8);
+#undef ET_ATTR
+#ifdef MPASB200_LAB
+  cudaFuncSetAttribute(k_dt_edge_tile<16, ET_MAXT16, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->et_smem);
+  cudaFuncSetAttribute(k_dt_edge_tile<16, ET_MAXT16, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->et_smem);
+  cudaFuncSetAttribute(k_dt_edge_tile<8, ET_MAXT8, ET_MINB8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->et_smem);
+  cudaFuncSetAttribute(k_dt_edge_tile<8, ET_MAXT8, ET_MINB8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->et_smem);
+#endif
+  if (e != cudaSuccess) return fail(h, MPASB200_ECUDA, std::string("k_dt_edge_tile shared memory: ") + cudaGetErrorString(e));
+  return 0;
+}
+}  // namespace
+#endif
 
 int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
   if (!h || !m) return MPASB200_EINVAL;
@@ -1111,6 +1210,11 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
   UP_INT(nEdgesOnEdge, m->nEdgesOnEdge, nE, 1, eNew);
   UP_IDS(edgesOnEdge_ECP, m->edgesOnEdge_ECP, nE, ME2, eNew, nE, eNew);
   UP_IDS(edgesOnEdge, m->edgesOnEdge, nE, ME2, eNew, nE, eNew);
+#ifdef MPASB200_LAB
+  if (h->c.edge_tiles) {
+    if ((rc = build_edge_tiles(h, build_ids(m->edgesOnEdge, nE, ME2, eNew, nE, eNew, pol), build_vals<int, int32_t>(m->nEdgesOnEdge, nE, 1, eNew)))) return rc;
+  }
+#endif
   UP_DBL(weightsOnEdge, m->weightsOnEdge, nE, ME2, eNew);
   UP_DBL(dcEdge, m->dcEdge, nE, 1, eNew);
   UP_DBL(dvEdge, m->dvEdge, nE, 1, eNew);
@@ -1412,6 +1516,129 @@ int mpasb200_compute_solve_diagnostics(mpasb200_t* h, int hollingsworth, int rk_
 int mpasb200_advance_scalars(mpasb200_t* h, double dt, int rk_step) { REQUIRE_MESH(); Entry en(h, MPASB200_T_SCALARS); return en.done(t_scalars(h, dt, rk_step)); }
 int mpasb200_init_coupled_diagnostics(mpasb200_t* h) { REQUIRE_MESH(); Entry en(h, -1); return t_init_coupled(h); }
 int mpasb200_reconstruct_2d(mpasb200_t* h, int includeHalos, int on_a_sphere) { (void)includeHalos; REQUIRE_MESH(); Entry en(h, -1); return t_reconstruct(h, on_a_sphere); }
+}  // extern "C"
+// ---- the mesh-only producers of atm_core_init on the device (kernels_init.cuh) ---------------------------------------------------
+namespace {
+struct TempDev {                       // device scratch of one call, released on return
+  std::vector<void*> p;
+  ~TempDev() { for (void* q : p) cudaFree(q); }
+  template <class T> T* up(const T* src, size_t n, cudaStream_t st, cudaError_t* err) {
+    if (!src || n == 0) return nullptr;
+    T* d = nullptr;
+    if ((*err = cudaMalloc(&d, n * sizeof(T))) != cudaSuccess) return nullptr;
+    p.push_back(d);
+    *err = cudaMemcpyAsync(d, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    return d;
+  }
+  template <class T> T* out(size_t n, cudaError_t* err) {
+    T* d = nullptr;
+    if ((*err = cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T))) != cudaSuccess) return nullptr;
+    p.push_back(d);
+    return d;
+  }
+};
+#define TD(expr) do { expr; if (err != cudaSuccess) return fail(h, MPASB200_ECUDA, std::string("init producers: ") + cudaGetErrorString(err)); } while (0)
+int init_mesh_dev(mpasb200_t* h, const MpasInitMesh* m, TempDev& t, InitMeshDev& M) {
+  const size_t nC = h->nCells, nE = h->nEdges, nV = h->nVertices, ME = h->d.maxEdges, VD = h->d.vertexDegree, NA = h->d.nAdvCells;
+  cudaError_t err = cudaSuccess;
+  std::memset(&M, 0, sizeof(M));
+  M.nC = (int)nC; M.nE = (int)nE; M.nV = (int)nV; M.ME = (int)ME; M.VD = (int)VD; M.NA = (int)NA; M.pol = h->c.index_policy;
+  TD(M.nEdgesOnCell = t.up<int>(m->nEdgesOnCell, nC, h->stream, &err));
+  TD(M.edgesOnCell = t.up<int>(m->edgesOnCell, nC * ME, h->stream, &err));
+  TD(M.verticesOnCell = t.up<int>(m->verticesOnCell, nC * ME, h->stream, &err));
+  TD(M.cellsOnCell = t.up<int>(m->cellsOnCell, nC * ME, h->stream, &err));
+  TD(M.cellsOnEdge = t.up<int>(m->cellsOnEdge, nE * 2, h->stream, &err));
+  TD(M.verticesOnEdge = t.up<int>(m->verticesOnEdge, nE * 2, h->stream, &err));
+  TD(M.cellsOnVertex = t.up<int>(m->cellsOnVertex, nV * VD, h->stream, &err));
+  TD(M.edgesOnVertex = t.up<int>(m->edgesOnVertex, nV * VD, h->stream, &err));
+  TD(M.dcEdge = t.up<double>(m->dcEdge, nE, h->stream, &err));
+  TD(M.dvEdge = t.up<double>(m->dvEdge, nE, h->stream, &err));
+  TD(M.deriv_two = t.up<double>(m->deriv_two, nE * 2 * NA, h->stream, &err));
+  return 0;
+}
+template <class T> int fetch(mpasb200_t* h, T* host, const T* dev, size_t n) {
+  if (!host || n == 0) return 0;
+  CK(cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+int mpasb200_compute_signs(mpasb200_t* h, const MpasInitMesh* m, double* edgesOnVertexSign, double* edgesOnCellSign, int32_t* kiteForCell) {
+  if (!h || !m) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  if (!m->nEdgesOnCell || !m->edgesOnCell || !m->verticesOnCell || !m->cellsOnEdge || !m->verticesOnEdge || !m->cellsOnVertex || !m->edgesOnVertex)
+    return fail(h, MPASB200_EINVAL, "compute_signs: nEdgesOnCell, edgesOnCell, verticesOnCell, cellsOnEdge, verticesOnEdge, cellsOnVertex, edgesOnVertex are required");
+  TempDev t; InitMeshDev M;
+  if (int rc = init_mesh_dev(h, m, t, M)) return rc;
+  cudaError_t err = cudaSuccess;
+  const size_t nC = h->nCells, nV = h->nVertices, ME = h->d.maxEdges, VD = h->d.vertexDegree;
+  double* d_eov = nullptr; double* d_eoc = nullptr; int* d_kite = nullptr;
+  TD(d_eov = t.out<double>(nV * VD, &err)); TD(d_eoc = t.out<double>(nC * ME, &err)); TD(d_kite = t.out<int>(nC * ME, &err));
+  if (nV) { KTimer kt_(h, "k_signs_vertex"); k_signs_vertex<<<(unsigned)((nV + 127) / 128), 128, 0, h->stream>>>(M, d_eov); h->launches++; }
+  if (nC) { KTimer kt_(h, "k_signs_cell"); k_signs_cell<<<(unsigned)((nC + 127) / 128), 128, 0, h->stream>>>(M, d_eoc, d_kite); h->launches++; }
+  if (int rc = post_launch(h)) return rc;
+  if (int rc = fetch(h, edgesOnVertexSign, d_eov, nV * VD)) return rc;
+  if (int rc = fetch(h, edgesOnCellSign, d_eoc, nC * ME)) return rc;
+  if (int rc = fetch(h, (int*)kiteForCell, d_kite, nC * ME)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int mpasb200_adv_coef_compression(mpasb200_t* h, const MpasInitMesh* m, int32_t* nAdvCellsForEdge, int32_t* advCellsForEdge,
+                                  double* adv_coefs, double* adv_coefs_3rd) {
+  if (!h || !m) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  if (!m->nEdgesOnCell || !m->cellsOnCell || !m->cellsOnEdge || !m->dcEdge || !m->dvEdge)
+    return fail(h, MPASB200_EINVAL, "adv_coef_compression: nEdgesOnCell, cellsOnCell, cellsOnEdge, dcEdge, dvEdge are required");
+  if (!nAdvCellsForEdge || !advCellsForEdge || !adv_coefs || !adv_coefs_3rd) return fail(h, MPASB200_EINVAL, "adv_coef_compression: null output");
+  enum { WMAX = 34 };                                   // 2 + 2*maxEdges, maxEdges <= 16 (mpasb200_create)
+  if (2 + 2 * h->d.maxEdges > WMAX) return fail(h, MPASB200_EINVAL, "adv_coef_compression: maxEdges too large");
+  TempDev t; InitMeshDev M;
+  if (int rc = init_mesh_dev(h, m, t, M)) return rc;
+  cudaError_t err = cudaSuccess;
+  const size_t nE = h->nEdges, NA = h->d.nAdvCells;
+  int* d_n = nullptr; int* d_adv = nullptr; double* d_a = nullptr; double* d_a3 = nullptr;
+  TD(d_n = t.out<int>(nE, &err)); TD(d_adv = t.out<int>(nE * NA, &err)); TD(d_a = t.out<double>(nE * NA, &err)); TD(d_a3 = t.out<double>(nE * NA, &err));
+  if (nE) { KTimer kt_(h, "k_adv_coef"); k_adv_coef<WMAX><<<(unsigned)((nE + 127) / 128), 128, 0, h->stream>>>(M, d_n, d_adv, d_a, d_a3); h->launches++; }
+  if (int rc = post_launch(h)) return rc;
+  if (int rc = fetch(h, (int*)nAdvCellsForEdge, d_n, nE)) return rc;
+  if (int rc = fetch(h, (int*)advCellsForEdge, d_adv, nE * NA)) return rc;
+  if (int rc = fetch(h, adv_coefs, d_a, nE * NA)) return rc;
+  if (int rc = fetch(h, adv_coefs_3rd, d_a3, nE * NA)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int mpasb200_compute_zb_cell(mpasb200_t* h) {
+  REQUIRE_MESH();
+  Entry en(h, -1);
+  LAUNCH(k_zb_cell, h->nCells, 0, h->V);
+  return post_launch(h);
+}
+
+int mpasb200_couple_coef_3rd_order(mpasb200_t* h, double coef, double* adv_coefs_3rd) {
+  if (!h) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  TempDev t;
+  cudaError_t err = cudaSuccess;
+  const size_t n = (size_t)h->nEdges * h->d.nAdvCells;
+  if (adv_coefs_3rd && n) {
+    double* d = nullptr;
+    TD(d = t.up<double>(adv_coefs_3rd, n, h->stream, &err));
+    { KTimer kt_(h, "k_scale"); k_scale<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d, n, coef); h->launches++; }
+    if (int rc = fetch(h, adv_coefs_3rd, d, n)) return rc;
+  }
+  if (h->mesh_ok && h->nCells) { KTimer kt_(h, "k_zb3_level0"); k_zb3_level0<<<(unsigned)((h->nCells + 127) / 128), 128, 0, h->stream>>>(h->V, coef); h->launches++; }
+  if (int rc = post_launch(h)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+#undef TD
+
 int mpasb200_rk_dynamics_substep_finish(mpasb200_t* h, int substep, int split) {
   REQUIRE_MESH();
   if (split < 1) return fail(h, MPASB200_EINVAL, "dynamics_split must be >= 1");

@@ -23,7 +23,7 @@ from . import _abi
 from ._abi import (CELL, EDGE, FIELD_ENTITY, FIELD_ID, FIELD_SLOTS, FIELDS, VERTEX, VERTICAL, MpasConfig, MpasDims,
                    MpasMeshPtrs)
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libmpas_b200.so")
+_LIB_PATH = os.environ.get("MPAS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libmpas_b200.so")   # the override selects a laboratory build (profiles/ scripts only)
 _lib = None
 
 
@@ -68,6 +68,10 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         "reconstruct_2d": ([H, I, I], I),
         "srk3": ([H, D], I),
         "timestep": ([H, D], I),
+        "compute_signs": ([H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], I),
+        "compute_zb_cell": ([H], I),
+        "adv_coef_compression": ([H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], I),
+        "couple_coef_3rd_order": ([H, D, C.c_void_p], I),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, prefix + name)
@@ -198,6 +202,39 @@ class TaskAPI:
     def mpas_reconstruct_2d(self, includeHalos: bool = False, on_a_sphere: bool = True):
         """dynamics_tasks.rg:1894-1948"""
         self._call("reconstruct_2d", int(bool(includeHalos)), int(bool(on_a_sphere)))
+
+    # ---- the mesh-only producers of atm_core_init (SURVEY.md 8f rank 3); `mesh` holds RAW ids in the caller's numbering ----
+    def atm_compute_signs(self, mesh: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+        """dynamics_tasks.rg:60-86, 113-129: edgesOnVertexSign, edgesOnCellSign, kiteForCell (the 3-D part is atm_compute_zb_cell)"""
+        d = self.dims
+        m, keep = _abi.init_mesh_ptrs(mesh, d)
+        out = dict(edgesOnVertexSign=np.zeros((d.nVertices, d.vertexDegree)), edgesOnCellSign=np.zeros((d.nCells, d.maxEdges)),
+                   kiteForCell=np.zeros((d.nCells, d.maxEdges), dtype=np.int32))
+        self._call("compute_signs", C.addressof(m), out["edgesOnVertexSign"].ctypes.data, out["edgesOnCellSign"].ctypes.data,
+                   out["kiteForCell"].ctypes.data)
+        del keep
+        return out
+
+    def atm_compute_zb_cell(self):
+        """dynamics_tasks.rg:88-110: fields zb, zb3 -> zb_cell, zb3_cell (after upload_mesh)"""
+        self._call("compute_zb_cell")
+
+    def atm_adv_coef_compression(self, mesh: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+        """dynamics_tasks.rg:133-269"""
+        d = self.dims
+        m, keep = _abi.init_mesh_ptrs(mesh, d)
+        out = dict(nAdvCellsForEdge=np.zeros(d.nEdges, dtype=np.int32), advCellsForEdge=np.zeros((d.nEdges, d.nAdvCells), dtype=np.int32),
+                   adv_coefs=np.zeros((d.nEdges, d.nAdvCells)), adv_coefs_3rd=np.zeros((d.nEdges, d.nAdvCells)))
+        self._call("adv_coef_compression", C.addressof(m), out["nAdvCellsForEdge"].ctypes.data, out["advCellsForEdge"].ctypes.data,
+                   out["adv_coefs"].ctypes.data, out["adv_coefs_3rd"].ctypes.data)
+        del keep
+        return out
+
+    def atm_couple_coef_3rd_order(self, config_coef_3rd_order: float, adv_coefs_3rd: Optional[np.ndarray] = None):
+        """dynamics_tasks.rg:303-325: adv_coefs_3rd (in place, C-contiguous float64) and zb3_cell at level 0"""
+        if adv_coefs_3rd is not None:
+            assert adv_coefs_3rd.dtype == np.float64 and adv_coefs_3rd.flags.c_contiguous
+        self._call("couple_coef_3rd_order", float(config_coef_3rd_order), None if adv_coefs_3rd is None else adv_coefs_3rd.ctypes.data)
 
     def atm_rk_dynamics_substep_finish(self, dynamics_substep: int, dynamics_split: int):
         self._call("rk_dynamics_substep_finish", int(dynamics_substep), int(dynamics_split))

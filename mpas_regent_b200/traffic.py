@@ -94,15 +94,17 @@ K: Dict[str, Tuple[List[str], List[str]]] = {
     "k_icd_cell2": (["w", "rho_zz", "zz", "ru", "zb_cell", "zb3_cell", "rho_base", "theta_base", "theta_m"],
                     ["rw", "rho_p", "rtheta_base", "rtheta_p", "exner", "exner_base", "pressure_p", "pressure_base"]),
     "k_reconstruct": (["u"], ["uReconstructX", "uReconstructY", "uReconstructZ", "uReconstructZonal", "uReconstructMeridional"]),
+    "k_zb_cell": (["zb", "zb3"], ["zb_cell", "zb3_cell"]),          # atm_compute_signs, 3-D part (one-time)
     "k_setup_scalars": (["scalars"], ["scalars_old"]),
     "k_scalar_flux<NS>": (["ruAvg", "scalars"], ["scr_e"] * 8),
     "k_scalar_update<NS>": (["ruAvg", "scalars", "scalars_old", "wwAvg", "rho_zz", "rho_zz_old_split"] + ["scr_e"] * 8, ["scalars"]),
 }
 # the exact streaming acoustic kernel moves the same fields as the affine one
+K["k_dt_edge_tile"] = K["k_dt_edge"]          # tile-staged form (kernels_tiles.cuh): same fields
 K["k_acoustic_lane<true>"] = K["k_acoustic_tma<true>"]
 K["k_acoustic_lane<false>"] = K["k_acoustic_tma<false>"]
 # array-typed fields whose every slot is touched
-FULL_SLOTS = {"scalars": 8, "scalars_old": 8}
+FULL_SLOTS = {"scalars": 8, "scalars_old": 8, "zb": 2, "zb3": 2}
 
 
 def canon(kernel: str) -> str:

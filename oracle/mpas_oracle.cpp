@@ -387,6 +387,139 @@ int oracle_reconstruct_2d(oracle_t* o, int includeHalos, int on_a_sphere) {
 }
 
 // atm_compute_moist_coefficients -- dynamics_tasks.rg:460-502  (edge loop is empty: cqu never written)
+// ---- the mesh-only producers of atm_core_init --------------------------------------------------------------
+// Literal loops over the RAW stored ids in the caller's numbering.  `R(id, n)` is rule M2 (the pad entity n reads as zero).
+namespace {
+struct RawMesh {
+  const MpasInitMesh* m; int nC, nE, nV, ME, VD, pol;
+  long R(long id, int n) const { long idx = (pol == MPASB200_INDEX_LITERAL) ? id : id - 1; if (idx < 0 || idx > n) idx = n; return idx; }
+  int off() const { return pol == MPASB200_INDEX_LITERAL ? 0 : 1; }       // what a 0-based loop index is offset by to equal a stored id
+  int nEdgesOnCell(long c) const { return c < nC ? m->nEdgesOnCell[c] : 0; }
+  int cellsOnCell(long c, int i) const { return c < nC ? m->cellsOnCell[c * ME + i] : 0; }
+  int cellsOnEdge(long e, int i) const { return e < nE ? m->cellsOnEdge[e * 2 + i] : 0; }
+  int verticesOnEdge(long e, int i) const { return e < nE ? m->verticesOnEdge[e * 2 + i] : 0; }
+  int cellsOnVertex(long v, int i) const { return v < nV ? m->cellsOnVertex[v * VD + i] : 0; }
+};
+RawMesh raw_of(const Oracle* o, const MpasInitMesh* m) { return RawMesh{m, o->nCells, o->nEdges, o->nVertices, o->maxEdges, o->vertexDegree, o->c.index_policy}; }
+}  // namespace
+
+// atm_compute_signs, level-0 part   dynamics_tasks.rg:60-86, 113-129
+int oracle_compute_signs(oracle_t* o, const MpasInitMesh* m, double* edgesOnVertexSign, double* edgesOnCellSign, int32_t* kiteForCell) {
+  if (!o || !m || !m->edgesOnVertex || !m->verticesOnEdge || !m->nEdgesOnCell || !m->edgesOnCell || !m->cellsOnEdge || !m->verticesOnCell || !m->cellsOnVertex)
+    return MPASB200_EINVAL;
+  const RawMesh r = raw_of(o, m);
+  const int nC = r.nC, nE = r.nE, nV = r.nV, ME = r.ME, VD = r.VD;
+  if (edgesOnVertexSign)
+    for (int iVtx = 0; iVtx < nV; ++iVtx)                                                          // :60-72
+      for (int i = 0; i < VD; ++i) {
+        const int e = m->edgesOnVertex[(size_t)iVtx * VD + i];
+        if (e <= nE) edgesOnVertexSign[(size_t)iVtx * VD + i] = (iVtx + r.off() == r.verticesOnEdge(r.R(e, nE), 1)) ? 1.0 : -1.0;
+        else edgesOnVertexSign[(size_t)iVtx * VD + i] = 0.0;
+      }
+  if (edgesOnCellSign)
+    for (int iCell = 0; iCell < nC; ++iCell) {                                                     // :74-86
+      for (int i = 0; i < ME; ++i) edgesOnCellSign[(size_t)iCell * ME + i] = 0.0;                  // rule M1: never written = 0
+      for (int i = 0; i < m->nEdgesOnCell[iCell] && i < ME; ++i) {
+        const int e = m->edgesOnCell[(size_t)iCell * ME + i];
+        if (e <= nE) edgesOnCellSign[(size_t)iCell * ME + i] = (iCell + r.off() == r.cellsOnEdge(r.R(e, nE), 0)) ? 1.0 : -1.0;
+        else edgesOnCellSign[(size_t)iCell * ME + i] = 0.0;
+      }
+    }
+  if (kiteForCell)
+    for (int iCell = 0; iCell < nC; ++iCell) {                                                     // :113-129
+      for (int i = 0; i < ME; ++i) kiteForCell[(size_t)iCell * ME + i] = 0;
+      for (int i = 0; i < m->nEdgesOnCell[iCell] && i < ME; ++i) {
+        const int iVtx = m->verticesOnCell[(size_t)iCell * ME + i];
+        if (iVtx <= nV) {
+          for (int j = 1; j < VD; ++j)
+            if (iCell + r.off() == r.cellsOnVertex(r.R(iVtx, nV), j)) { kiteForCell[(size_t)iCell * ME + i] = j; break; }
+        } else kiteForCell[(size_t)iCell * ME + i] = 1;
+      }
+    }
+  return 0;
+}
+
+// atm_compute_signs, 3-D part   dynamics_tasks.rg:88-110 (resolved numbering: `iCell.x == cellsOnEdge[0]` is `iCell == resolved cell1`
+// under either index policy; an edge id that resolves to the pad copies the pad's zeros)
+int oracle_compute_zb_cell(oracle_t* o) {
+  if (!o->mesh_ok) return MPASB200_ESTATE;
+  const int nC = o->nCells, L = o->L, ME = o->maxEdges;
+  F3A zb = o->fa(MPASB200_F_zb), zb3 = o->fa(MPASB200_F_zb3), zb_cell = o->fa(MPASB200_F_zb_cell), zb3_cell = o->fa(MPASB200_F_zb3_cell);
+  OMP_FOR
+  for (int iCell = 0; iCell < nC; ++iCell)
+    for (int k = 0; k <= L; ++k)
+      for (int i = 0; i < o->nEdgesOnCell[iCell]; ++i) {
+        const int e = o->edgesOnCell[(size_t)iCell * ME + i];
+        const int side = (iCell == o->cellsOnEdge[(size_t)e * 2]) ? 0 : 1;
+        zb_cell(iCell, k, i) = zb(e, k, side);
+        zb3_cell(iCell, k, i) = zb3(e, k, side);
+      }
+  return 0;
+}
+
+// atm_adv_coef_compression   dynamics_tasks.rg:133-269
+int oracle_adv_coef_compression(oracle_t* o, const MpasInitMesh* m, int32_t* nAdvCellsForEdge, int32_t* advCellsForEdge,
+                                double* adv_coefs, double* adv_coefs_3rd) {
+  if (!o || !m || !m->cellsOnEdge || !m->cellsOnCell || !m->nEdgesOnCell || !m->dcEdge || !m->dvEdge || !nAdvCellsForEdge || !advCellsForEdge || !adv_coefs || !adv_coefs_3rd)
+    return MPASB200_EINVAL;
+  const RawMesh r = raw_of(o, m);
+  const int nC = r.nC, nE = r.nE, ME = r.ME, NA = o->nAdv;
+  const int W = 2 + 2 * ME;
+  std::vector<int> cell_list(W);
+  std::vector<double> a(W), a3(W);
+  for (int iEdge = 0; iEdge < nE; ++iEdge) {
+    nAdvCellsForEdge[iEdge] = 0;
+    for (int j = 0; j < NA; ++j) { advCellsForEdge[(size_t)iEdge * NA + j] = 0; adv_coefs[(size_t)iEdge * NA + j] = 0.0; adv_coefs_3rd[(size_t)iEdge * NA + j] = 0.0; }
+    const int cell1 = m->cellsOnEdge[(size_t)iEdge * 2], cell2 = m->cellsOnEdge[(size_t)iEdge * 2 + 1];
+    if (!(cell1 <= nC || cell2 <= nC)) continue;
+    const long i1 = r.R(cell1, nC), i2 = r.R(cell2, nC);
+    auto d2 = [&](int idx) { return (m->deriv_two && idx < 2 * NA) ? m->deriv_two[(size_t)iEdge * 2 * NA + idx] : 0.0; };   // past the array: 0
+    cell_list[0] = cell1; cell_list[1] = cell2;
+    int n = 1;
+    for (int i = 0; i < r.nEdgesOnCell(i1); ++i)
+      if (r.cellsOnCell(i1, i) != cell2) { n += 1; cell_list[n] = r.cellsOnCell(i1, i); }
+    for (int iCell = 0; iCell < r.nEdgesOnCell(i2); ++iCell) {
+      bool addcell = true;
+      for (int i = 0; i < n; ++i) if (cell_list[i] == r.cellsOnCell(i2, iCell)) addcell = false;
+      if (addcell && n < ME - 1) { n += 1; cell_list[n] = r.cellsOnCell(i2, iCell); }
+    }
+    nAdvCellsForEdge[iEdge] = n;
+    for (int iCell = 0; iCell < n && iCell < NA; ++iCell) advCellsForEdge[(size_t)iEdge * NA + iCell] = cell_list[iCell];
+    std::fill(a.begin(), a.end(), 0.0); std::fill(a3.begin(), a3.end(), 0.0);
+    auto j_in_of = [&](int target) { int j_in = 0; for (int j = 0; j < n; ++j) if (cell_list[j] == target) j_in = j; return j_in; };
+    int j_in = j_in_of(cell1);
+    a[j_in] += d2(0); a3[j_in] += d2(0);
+    for (int iCell = 0; iCell < r.nEdgesOnCell(i1); ++iCell) {
+      j_in = j_in_of(r.cellsOnCell(i1, iCell));
+      a[j_in] += d2(iCell * NA + 0); a3[j_in] += d2(iCell * NA + 0);
+    }
+    j_in = j_in_of(cell2);
+    a[j_in] += d2(1); a3[j_in] += d2(1);
+    for (int iCell = 0; iCell < r.nEdgesOnCell(i2); ++iCell) {
+      j_in = j_in_of(r.cellsOnCell(i2, iCell));
+      a[j_in] += d2(iCell * NA + 1); a3[j_in] += d2(iCell * NA + 1);
+    }
+    const double dc = m->dcEdge[iEdge], dv = m->dvEdge[iEdge];
+    for (int j = 0; j < n; ++j) {
+      a[j] = -1.0 * pow(dc, 2) * a[j] / 12;
+      a3[j] = -1.0 * pow(dc, 2) * a3[j] / 12;
+    }
+    a[j_in_of(cell1)] += 0.5;
+    a[j_in_of(cell2)] += 0.5;
+    for (int j = 0; j < n; ++j) { a[j] *= dv; a3[j] *= dv; }
+    for (int j = 0; j < NA && j < W; ++j) { adv_coefs[(size_t)iEdge * NA + j] = a[j]; adv_coefs_3rd[(size_t)iEdge * NA + j] = a3[j]; }
+  }
+  return 0;
+}
+
+// atm_couple_coef_3rd_order   dynamics_tasks.rg:303-325 (zb3_cell: `cr[{iCell, 0}]` is LEVEL 0 only)
+int oracle_couple_coef_3rd_order(oracle_t* o, double coef, double* adv_coefs_3rd) {
+  if (adv_coefs_3rd) for (size_t i = 0; i < (size_t)o->nEdges * o->nAdv; ++i) adv_coefs_3rd[i] *= coef;
+  F3A zb3_cell = o->fa(MPASB200_F_zb3_cell);
+  for (int iCell = 0; iCell < o->nCells; ++iCell) for (int j = 0; j < o->maxEdges; ++j) zb3_cell(iCell, 0, j) *= coef;
+  return 0;
+}
+
 int oracle_compute_moist_coefficients(oracle_t* o) {
   const int L = o->L;
   CF(qtot); CF(cqw);

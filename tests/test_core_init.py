@@ -169,3 +169,52 @@ def test_zb_cell_selection_equals_the_literal_loops(grid642):
                     first = c == (coe[e, 0] if lit else coe[e, 0] - 1)
                     want[c, :, i] = zbp[e, :, 0 if first else 1]
         assert np.array_equal(out["zb_cell"], want), policy
+
+
+# ---- the oracle's literal loops of the mesh-only producers (dynamics_tasks.rg:46-325) against the vectorised host producers ----
+import pytest
+
+
+def _raw_mesh(mesh, scaled, deriv_two=None):
+    v = mesh.v
+    d = {k: v[k] for k in ("nEdgesOnCell", "edgesOnCell", "verticesOnCell", "cellsOnCell", "cellsOnEdge", "verticesOnEdge", "cellsOnVertex", "edgesOnVertex")}
+    d["dcEdge"], d["dvEdge"] = scaled.v["dcEdge"], scaled.v["dvEdge"]
+    if deriv_two is not None:
+        d["deriv_two"] = deriv_two
+    return d
+
+
+@pytest.mark.parametrize("policy", [_abi.INDEX_CORRECTED, _abi.INDEX_LITERAL], ids=["corrected", "literal"])
+@pytest.mark.parametrize("which", ["x1.2562", "icosa642"])
+def test_oracle_init_producers_equal_host_producers(grid2562, grid642, policy, which):
+    """oracle_compute_signs / oracle_adv_coef_compression / oracle_compute_zb_cell / oracle_couple_coef_3rd_order (loop by loop from
+    the reference text) against core_init.py (array at a time): integer lists and signs identical, coefficients bit-identical
+    (same operation order), under both index policies, on the bundled mesh (pentagons) and a generated one."""
+    from mpas_regent_b200 import dynamics
+    from oracle.oracle import Oracle
+    mesh = grid2562 if which == "x1.2562" else grid642
+    L = 6
+    st = init_jw.make_state(mesh, L, policy)                     # runs the host chain; extras keep zb, zb3, deriv_two
+    scaled = st.mesh
+    ora = Oracle(dynamics.dims_of(mesh, L), _abi.default_config(index_policy=policy))
+    raw = _raw_mesh(mesh, scaled, st.extras["deriv_two"])
+    sg_h = core_init.atm_compute_signs(scaled, policy, zb=st.extras["zb"], zb3=st.extras["zb3"], nlev1=L + 1)
+    sg_o = ora.atm_compute_signs(raw)
+    for k in ("edgesOnVertexSign", "edgesOnCellSign", "kiteForCell"):
+        assert np.array_equal(sg_o[k], sg_h[k]), k
+    adv_h = core_init.atm_adv_coef_compression(scaled, policy, st.extras["deriv_two"])
+    adv_o = ora.atm_adv_coef_compression(raw)
+    for k in ("nAdvCellsForEdge", "advCellsForEdge", "adv_coefs", "adv_coefs_3rd"):
+        assert np.array_equal(adv_o[k], adv_h[k]), k
+    # 3-D part + coupling: needs the uploaded mesh (resolved numbering)
+    ora.upload_mesh(st.static)
+    ora.upload_field("zb", st.extras["zb"]); ora.upload_field("zb3", st.extras["zb3"])
+    ora.atm_compute_zb_cell()
+    assert np.array_equal(ora.download_field("zb_cell"), sg_h["zb_cell"])
+    a3 = adv_o["adv_coefs_3rd"].copy()
+    ora.atm_couple_coef_3rd_order(0.25, a3)
+    a3_h, zb3c_h = core_init.atm_couple_coef_3rd_order(0.25, adv_h["adv_coefs_3rd"].copy(), sg_h["zb3_cell"].copy())
+    assert np.array_equal(a3, a3_h)
+    assert np.array_equal(ora.download_field("zb3_cell"), zb3c_h)
+    assert np.array_equal(a3, st.static["adv_coefs_3rd"]) and np.array_equal(ora.download_field("zb3_cell"), st.f["zb3_cell"])
+    ora.close()

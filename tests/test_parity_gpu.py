@@ -205,6 +205,33 @@ def test_acoustic_modes(grid2562, exact):
     g.close(); ora.close()
 
 
+@pytest.mark.parametrize("policy", [_abi.INDEX_CORRECTED, _abi.INDEX_LITERAL], ids=["corrected", "literal"])
+@pytest.mark.parametrize("tiles", [8, 408, 16, 216], ids=["te8_5blocks", "te8_4blocks", "te16_3blocks", "te16_2blocks"])
+@pytest.mark.parametrize("levels", [L_SMALL, 55], ids=lambda v: f"L{v}")
+def test_edge_tiles_bit_identical(grid2562, tiles, policy, levels):
+    """(laboratory build only; measured slower, profiles/r2_edge_tiles.md)  MpasConfig.edge_tiles only changes HOW the edgesOnEdge columns reach k_dt_edge's arithmetic (the distinct columns of a tile of
+    edges staged once in shared memory with cp.async.bulk instead of per-thread gathers): every field keeps its bytes on the real mesh
+    (pentagons, the last tile partial), under both index policies (LITERAL ids scatter the neighbours: the not-staged fallback runs)."""
+    import os
+    from mpas_regent_b200 import dynamics, init_jw
+    lab = os.path.join(os.path.dirname(dynamics._LIB_PATH), "libmpas_b200_lab.so")
+    if not os.path.exists(lab):
+        pytest.skip("laboratory build absent (make -C mpas_regent_b200/csrc lab): the tile-staged kernel is not in the shipped library")
+    st = init_jw.make_state(grid2562, levels, policy)
+    outs = []
+    for t in (0, tiles):
+        g = dynamics.Dynamics(dynamics.dims_of(grid2562, levels), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, index_policy=policy, edge_tiles=t), lib_path=lab)
+        g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
+        g.atm_compute_solve_diagnostics(False, -1)
+        for _ in range(2):
+            g.atm_srk3(DT)
+        g.atm_compute_dyn_tend(1, DT, config_rayleigh_damp_u=True)
+        outs.append(g.download_all())
+        g.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
+
+
 @pytest.mark.parametrize("mask", [0, 1, 2, 4, -1], ids=["plain", "dt_edge", "acoustic_gather", "theta_flux", "all"])
 def test_staged_gathers_bit_identical(grid2562, mask):
     """(laboratory build only; measured slower, profiles/r2_staged_gathers.md)  MpasConfig.gather_stage only changes HOW neighbour columns reach the arithmetic (cp.async into shared-memory slots
@@ -651,4 +678,43 @@ def test_init_chain_on_the_device(grid2562, policy):
         b.mpas_reconstruct_2d(False, False)
     for n in ("uReconstructZonal", "uReconstructMeridional"):
         assert np.array_equal(g.download_field(n), ora.download_field(n), equal_nan=True), n
+    g.close(); ora.close()
+
+
+@pytest.mark.parametrize("policy", [_abi.INDEX_CORRECTED, _abi.INDEX_LITERAL], ids=["corrected", "literal"])
+@pytest.mark.parametrize("which", ["x1.2562", "icosa642"])
+def test_mesh_only_init_producers_on_the_device(grid2562, grid642, policy, which):
+    """atm_compute_signs (dynamics_tasks.rg:46-130), atm_adv_coef_compression (:133-269) and
+    atm_couple_coef_3rd_order (:303-325) as device kernels, through the C ABI with the RAW stored ids: integer lists, signs and
+    coefficients are bit-identical to the oracle's literal loops (and therefore to what the host chain fed every other test)."""
+    from mpas_regent_b200 import dynamics, init_jw
+    from oracle.oracle import Oracle
+    from tests.test_core_init import _raw_mesh
+    mesh = grid2562 if which == "x1.2562" else grid642
+    st = init_jw.make_state(mesh, L_SMALL, policy)
+    raw = _raw_mesh(mesh, st.mesh, st.extras["deriv_two"])
+    cfg = _abi.default_config(index_policy=policy)
+    g = dynamics.Dynamics(dynamics.dims_of(mesh, L_SMALL), cfg)
+    ora = Oracle(dynamics.dims_of(mesh, L_SMALL), cfg)
+    sg, so = g.atm_compute_signs(raw), ora.atm_compute_signs(raw)           # before upload_mesh: their outputs feed it
+    for k in so:
+        assert np.array_equal(sg[k], so[k]), k
+        assert np.array_equal(sg[k], st.static[k]), k
+    ag, ao = g.atm_adv_coef_compression(raw), ora.atm_adv_coef_compression(raw)
+    for k in ao:
+        assert np.array_equal(ag[k], ao[k]), k
+    raw0 = dict(raw); raw0.pop("deriv_two")                                  # deriv_two never written upstream: null = zeros
+    a0g, a0o = g.atm_adv_coef_compression(raw0), ora.atm_adv_coef_compression(raw0)
+    for k in a0o:
+        assert np.array_equal(a0g[k], a0o[k]), k
+    for b in (g, ora):
+        b.upload_mesh(st.static)
+        b.upload_field("zb", st.extras["zb"]); b.upload_field("zb3", st.extras["zb3"])
+        b.atm_compute_zb_cell()
+    a3g, a3o = ag["adv_coefs_3rd"].copy(), ao["adv_coefs_3rd"].copy()
+    g.atm_couple_coef_3rd_order(0.25, a3g); ora.atm_couple_coef_3rd_order(0.25, a3o)
+    assert np.array_equal(a3g, a3o) and np.array_equal(a3g, st.static["adv_coefs_3rd"])
+    for n in ("zb_cell", "zb3_cell"):
+        assert np.array_equal(g.download_field(n), ora.download_field(n)), n
+        assert np.array_equal(g.download_field(n), st.f[n]), n
     g.close(); ora.close()
