@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--graph", type=int, default=0)
     ap.add_argument("--gather-stage", type=int, default=-1, help="MpasConfig.gather_stage bit mask (ablation: 0 = the plain gather kernels)")
     ap.add_argument("--edge-tiles", type=int, default=None, help="MpasConfig.edge_tiles (0 = plain k_dt_edge; 8 / 16 = tile-staged form)")
+    ap.add_argument("--kernel-forms", type=int, default=None, help="MpasConfig.kernel_forms bit mask (1 = k_dt_cellC as two launches)")
     ap.add_argument("--acoustic", type=int, default=3, help="MpasConfig.acoustic_tma (3 = exact column-per-lane pipeline, 2 = affine sweep)")
     ap.add_argument("--physics", choices=("literal", "corrected"), default="literal",
                     help="literal = the reference as it executes (headline); corrected = acoustic u update + back-substitution + "
@@ -301,7 +302,8 @@ def main():
     corrected = args.physics == "corrected"
     cfg = _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, device=local_rank, use_graph=args.graph,
                               physics_mode=_abi.PHYSICS_CORRECTED if corrected else _abi.PHYSICS_LITERAL, gather_stage=args.gather_stage, acoustic_tma=args.acoustic,
-                              **({} if args.edge_tiles is None else {"edge_tiles": args.edge_tiles}))
+                              **({} if args.edge_tiles is None else {"edge_tiles": args.edge_tiles}),
+                              **({} if args.kernel_forms is None else {"kernel_forms": args.kernel_forms}))
     stream = torch.cuda.Stream()
 
     if world == 1:
@@ -513,7 +515,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(nC, L, world, corrected),
             "run_info": {"parallelism_detail": parallelism, "host_init_s": round(t_init, 1), "device_bytes": g.device_bytes,
-                         "cuda_graph": bool(args.graph), "acoustic_tma": args.acoustic, "edge_tiles": int(cfg.edge_tiles), "ms_per_step_with_kernel_events": ms_k / k_steps},
+                         "cuda_graph": bool(args.graph), "acoustic_tma": args.acoustic, "edge_tiles": int(cfg.edge_tiles), "kernel_forms": int(cfg.kernel_forms), "ms_per_step_with_kernel_events": ms_k / k_steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,

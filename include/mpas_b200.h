@@ -135,6 +135,9 @@ typedef struct {
                                          tile kernel (a block owns 8 / 16 consecutive edges and stages the DISTINCT edgesOnEdge columns of
                                          the tile once in shared memory with cp.async.bulk, lists built at upload_mesh).  Bit-identical
                                          results, measured slower than the plain kernel on B200 (profiles/r2_edge_tiles.md). */
+  int32_t kernel_forms;               /* bit mask of alternative launch forms with bit-identical results: 1 = k_dt_cellC as two launches
+                                         (the w pass, then the theta pass) instead of one fused kernel */
+  int32_t reserved0;
   double  config_coef_3rd_order;      /* 0.25, constants.rg:59 */
 } MpasConfig;
 
@@ -299,6 +302,19 @@ int  mpasb200_adv_coef_compression(mpasb200_t *h, const MpasInitMesh *m, int32_t
  *                                     may be null) *= coef; zb3_cell *= coef at LEVEL 0 only (the device field; skipped before
  *                                     mpasb200_upload_mesh)                                                                        */
 int  mpasb200_couple_coef_3rd_order(mpasb200_t *h, double config_coef_3rd_order, double *adv_coefs_3rd);
+
+/* init_atm_case_jw                    vertical_init/init_atm_cases.rg:24-743 -- the Jablonowski-Williamson baroclinic-wave initial
+ * state on the device, CORRECTED reading (the reference text indexes regions with swapped, out-of-range (level, cell) pairs and cannot
+ * be restated literally; this is the formula-by-formula equivalent of the host generator mpas_regent_b200/init_jw.py, dry case, parity
+ * against it at 1e-12).  After mpasb200_upload_mesh.  Inputs: host arrays in the caller's numbering, geometry already scaled to the
+ * sphere (init_atm_cases.rg:87-111).  Writes the vertical fields rdzw, rdzu, fzm, fzp, cf1, cf2, cf3 and the 3-D fields zgrid, zz,
+ * zxu, rho_base, theta_base, pressure_p, rho_p, exner, theta_m, rtheta_p, rho_zz, u, ru, zb, zb3 (= 0), rw, w.                       */
+typedef struct {
+  const double *latCell, *areaCell;   /* [nCells]    */
+  const double *latVertex;            /* [nVertices] */
+  int32_t n_lat_table;                /* rows of the (z, lat) section the columns are balanced on; 0 = 4097 */
+} MpasJwGeometry;
+int  mpasb200_init_atm_case_jw(mpasb200_t *h, const MpasJwGeometry *g);
 
 /* ---- the driver: atm_srk3 / atm_timestep  rk_timestep.rg:361-519 ------------------------- *
  * Replays the reference's call sequence on the device (control flow + scalars only).    */

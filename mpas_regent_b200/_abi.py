@@ -64,7 +64,7 @@ _CFG_D = ("gravity", "rgas", "cp", "cv", "omega", "sphere_radius", "prandtl", "c
           "config_h_theta_eddy_visc4", "config_rayleigh_damp_u_timescale_days", "config_mpas_cam_coef")
 _CFG_I = ("config_number_rayleigh_damp_u_levels", "config_horiz_mixing", "config_mix_full", "config_rayleigh_damp_u",
           "nRelaxZone", "number_of_sub_steps", "config_dynamics_split_steps", "index_policy", "rkarg_policy",
-          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma", "physics_mode", "gather_stage", "config_scalar_advection", "edge_tiles")
+          "sfc_renumber", "device", "use_graph", "acoustic_exact", "acoustic_tma", "physics_mode", "gather_stage", "config_scalar_advection", "edge_tiles", "kernel_forms", "reserved0")
 
 
 class MpasConfig(C.Structure):
@@ -143,6 +143,11 @@ def init_mesh_ptrs(arrays: Dict[str, np.ndarray], dims: "MpasDims"):
     return m, keep
 
 
+class MpasJwGeometry(C.Structure):
+    """image of MpasJwGeometry (mpas_b200.h)"""
+    _fields_ = [("latCell", C.c_void_p), ("areaCell", C.c_void_p), ("latVertex", C.c_void_p), ("n_lat_table", C.c_int32)]
+
+
 class MpasMeshPtrs(C.Structure):
     _fields_ = [(n, C.c_void_p) for (n, _, _, _) in MESH_MEMBERS]
 
@@ -152,6 +157,8 @@ def make_dims(nCells, nEdges, nVertices, nVertLevels, maxEdges=10, maxEdges2=20,
 
 
 EDGE_TILES_DEFAULT = 0
+KERNEL_FORMS_DEFAULT = 0
+KF_SPLIT_CELLC = 1
 
 
 def default_config(**over) -> MpasConfig:
@@ -177,6 +184,8 @@ def default_config(**over) -> MpasConfig:
     c.gather_stage = 0
     c.config_scalar_advection = 0
     c.edge_tiles = EDGE_TILES_DEFAULT
+    c.kernel_forms = KERNEL_FORMS_DEFAULT
+    c.reserved0 = 0
     c.config_coef_3rd_order = 0.25
     for k, v in over.items():
         if not hasattr(c, k):

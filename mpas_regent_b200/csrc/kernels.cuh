@@ -25,6 +25,9 @@
 #ifndef LB_CELLC
 #define LB_CELLC 4
 #endif
+#ifndef LB_CELLC_SPLIT
+#define LB_CELLC_SPLIT 5
+#endif
 #ifndef LB_AC
 #define LB_AC 3
 #endif
@@ -674,8 +677,10 @@ DI double wdtz_at(int k, int L, double rws, double rw, double fzm, double fzp, d
 }
 
 // final cell pass: w (:1256-1322) and theta (:1328-1479)
-template <bool RK0>
-__global__ void __launch_bounds__(256, LB_CELLC) k_dt_cellC(const View V, const DynTendParams P) {
+// PART 0: both passes in one launch; 1: the w pass alone; 2: the theta pass alone.  The two passes share only `rw` (one unit re-read):
+// launched separately each needs fewer registers and fewer barriers than the fused kernel (64 registers with 80-96 B of spills).
+template <bool RK0, int PART = 0>
+__global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_dt_cellC(const View V, const DynTendParams P) {
   extern __shared__ double sm[];
   PAIR_THREAD(V.nCells)
   const int TS = LP + 2;
@@ -688,6 +693,7 @@ __global__ void __launch_bounds__(256, LB_CELLC) k_dt_cellC(const View V, const 
   if (m0) {
     fzm = ld2(FLD(fzm), k0); fzp = ld2(FLD(fzp), k0); rdzu = ld2(FLD(rdzu), k0); rdzw = ld2(FLD(rdzw), k0);
     rw2 = ld2(rw, ix); rwm = below(rw, ix, k0, rw2);
+    if (PART != 2) {
     if (RK0) {
       w2 = ld2(FLD(w), ix);
       twe = ld2(FLD(tend_w_euler), ix);
@@ -707,7 +713,9 @@ __global__ void __launch_bounds__(256, LB_CELLC) k_dt_cellC(const View V, const 
       w2 = w_adv_curv(V, P, x, k0, ix, LP, m0, m1);
     }
     s_a[k0] = w2.x; if (m1) s_a[k1] = w2.y;
+    }
   }
+  if (PART != 2) {
   if (inx && k0 == L) { s_a[L] = FLD(w)[ix]; s_b[L] = FLD(wdwz)[ix]; }          // level L keeps its stored value
   if (inx && k1 == L) { s_a[L] = FLD(w)[ix + 1]; s_b[L] = FLD(wdwz)[ix + 1]; }
   __syncthreads();
@@ -752,6 +760,8 @@ __global__ void __launch_bounds__(256, LB_CELLC) k_dt_cellC(const View V, const 
     w2 = mk(k0 > 0 ? w2.x + twe.x : w2.x, w2.y + twe.y);                                            // :1320
     st2m(FLD(w), ix, w2, m0, m1);
   }
+  }
+  if (PART == 1) return;
   // ---------------- theta ----------------
   const double* tm = FLD(theta_m); const double* tms = FLD(theta_m_save);
   D2 tt = bc(0.0), wdtz = bc(0.0);

@@ -11,12 +11,6 @@
 #pragma once
 #include "kernels.cuh"
 
-struct EdgeTiles {
-  const int* cols;             // [tile][cap]  internal edge ids of the staged columns; the tile's own edges come first (slot = local index)
-  const int* ncols;            // [tile]
-  const unsigned char* slot;   // [edge][SP]   byte j = staged slot of edgesOnEdge[j], 255 = not staged (read from global memory)
-  int cap, SP, TE;
-};
 
 DI int slot_byte(const uint4& a, int j) {      // byte j (0..15) of a 16-byte row held in four registers
   const unsigned w = (j < 8) ? ((j < 4) ? a.x : a.y) : ((j < 12) ? a.z : a.w);

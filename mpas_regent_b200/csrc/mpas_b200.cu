@@ -24,6 +24,7 @@
 #include "kernels_tiles.cuh"     // tile-staged k_dt_edge (TMA, de-duplicated columns): bit-identical, measured slower (profiles/r2_edge_tiles.md)
 #endif
 #include "kernels_init.cuh"
+#include "kernels_jw.cuh"
 #ifdef MPASB200_LAB
 #include "kernels_staged.cuh"     // cp.async-staged gather kernels: measured slower than the plain ones (profiles/r2_staged_gathers.md)
 #include "kernels_lab.cuh"
@@ -99,9 +100,7 @@ struct mpasb200 {
   struct ExPart { int ent; std::vector<int> fields; int entries; double* sbuf = nullptr; double* rbuf = nullptr; };
   std::vector<ExPart> xplan[MPASB200_X_COUNT]; bool xplan_built = false;
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_side = nullptr; bool x_pending = false; bool has_classes = false;
-#ifdef MPASB200_LAB
-  EdgeTiles et = {nullptr, nullptr, nullptr, 0, 0, 0}; size_t et_smem = 0; int et_minb = 0, et_abl = 0;     // k_dt_edge_tile (MpasConfig.edge_tiles), built by upload_mesh
-#endif
+  EdgeTiles et = {nullptr, nullptr, nullptr, 0, 0, 0}; size_t et_smem = 0; int et_minb = 0, et_abl = 0;     // k_dt_edge_tile (MpasConfig.edge_tiles; laboratory builds), built by upload_mesh
   double* d_sflux = nullptr;            // horiz_flux_arr of atm_advance_scalars: [nScalars][(nEdges+1)][LP], allocated on first use
   std::string err;
   std::mutex mu;
@@ -412,7 +411,8 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
     LAUNCH(k_dt_cellB, h->nCells, 0, h->V, P);
     if (staged_on(h, GS_THETA_FLUX, sm_flux)) LAUNCH_STAGED(k_dt_theta_flux_s<10>, h->nEdges, sm_flux, h->V);
     else LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
-    LAUNCH(k_dt_cellC<true>, h->nCells, sm2, h->V, P);
+    if (h->c.kernel_forms & 1) { LAUNCH((k_dt_cellC<true, 1>), h->nCells, sm2, h->V, P); LAUNCH((k_dt_cellC<true, 2>), h->nCells, sm2, h->V, P); }
+    else LAUNCH(k_dt_cellC<true>, h->nCells, sm2, h->V, P);
   } else {
     LAUNCH(k_dt_cell0<false>, h->nCells, 0, h->V, P, C.config_len_disp, cam_coef);
     if (staged_on(h, GS_DT_EDGE, sm_edge)) LAUNCH_STAGED(k_dt_edge_s<10>, h->nEdges, sm_edge, h->V, P);
@@ -420,7 +420,8 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
     else LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
     if (staged_on(h, GS_THETA_FLUX, sm_flux)) LAUNCH_STAGED(k_dt_theta_flux_s<10>, h->nEdges, sm_flux, h->V);
     else LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
-    LAUNCH(k_dt_cellC<false>, h->nCells, sm2, h->V, P);
+    if (h->c.kernel_forms & 1) { LAUNCH((k_dt_cellC<false, 1>), h->nCells, sm2, h->V, P); LAUNCH((k_dt_cellC<false, 2>), h->nCells, sm2, h->V, P); }
+    else LAUNCH(k_dt_cellC<false>, h->nCells, sm2, h->V, P);
   }
   return post_launch(h);
 }
@@ -871,7 +872,7 @@ void mpasb200_default_config(MpasConfig* c) {
   c->physics_mode = MPASB200_PHYSICS_LITERAL;
   c->gather_stage = 0;
   c->config_scalar_advection = 0; c->config_coef_3rd_order = 0.25;        // constants.rg:59
-  c->edge_tiles = 0;
+  c->edge_tiles = 0; c->kernel_forms = 0; c->reserved0 = 0;
 }
 
 const char* mpasb200_last_error(const mpasb200_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -1638,6 +1639,54 @@ int mpasb200_couple_coef_3rd_order(mpasb200_t* h, double coef, double* adv_coefs
   return 0;
 }
 #undef TD
+
+// init_atm_case_jw on the device (kernels_jw.cuh)
+int mpasb200_init_atm_case_jw(mpasb200_t* h, const MpasJwGeometry* g) {
+  REQUIRE_MESH();
+  if (!g || !g->latCell || !g->areaCell || !g->latVertex) return fail(h, MPASB200_EINVAL, "init_atm_case_jw: latCell, areaCell, latVertex are required");
+  Entry en(h, -1);
+  const int L = h->L, L1 = h->L1, nC = h->nCells, nV = h->nVertices;
+  if (L < 3) return fail(h, MPASB200_EINVAL, "init_atm_case_jw: nVertLevels >= 3");
+  // ---- vertical grid (init_atm_cases.rg:165-237, corrected indexing: zw[k] = k*dz), on the host: L+1 numbers per array
+  const double zt = 45000.0, strf = 1.5, pii = 3.141592653589793;
+  std::vector<double> zw(L1), sh(L1), ah(L1), dzw(L1, 0.0), dzu(L1, 0.0), rdzw(L1, 0.0), rdzu(L1, 0.0), fzm(L1, 0.0), fzp(L1, 0.0), cf1(L1, 0.0), cf2(L1, 0.0), cf3(L1, 0.0);
+  const double dz = zt / L;
+  for (int k = 0; k <= L; ++k) { zw[k] = k * dz; sh[k] = std::pow(k * dz / zt, strf); ah[k] = 1.0 - std::pow(std::cos(0.5 * pii * k * dz / zt), 6.0); }
+  for (int k = 0; k < L; ++k) { dzw[k] = zw[k + 1] - zw[k]; rdzw[k] = 1.0 / dzw[k]; }
+  for (int k = 1; k < L; ++k) { dzu[k] = 0.5 * (dzw[k] + dzw[k - 1]); rdzu[k] = 1.0 / dzu[k]; fzp[k] = 0.5 * dzw[k] / dzu[k]; fzm[k] = 0.5 * dzw[k - 1] / dzu[k]; }
+  { const double cof1 = (2.0 * dzu[1] + dzu[2]) / (dzu[1] + dzu[2]) * dzw[0] / dzu[1], cof2 = dzu[1] / (dzu[1] + dzu[2]) * dzw[0] / dzu[2];
+    cf1[0] = fzp[1] + cof1; cf2[0] = fzm[1] - cof1 - cof2; cf3[0] = cof2; }
+  auto putv = [&](int id, const std::vector<double>& v) { return cudaMemcpyAsync(h->V.f[id], v.data(), sizeof(double) * L1, cudaMemcpyHostToDevice, h->stream); };
+  CK(putv(MPASB200_F_rdzw, rdzw)); CK(putv(MPASB200_F_rdzu, rdzu)); CK(putv(MPASB200_F_fzm, fzm)); CK(putv(MPASB200_F_fzp, fzp));
+  CK(putv(MPASB200_F_cf1, cf1)); CK(putv(MPASB200_F_cf2, cf2)); CK(putv(MPASB200_F_cf3, cf3));
+  // ---- device scratch: vertical helpers, geometry in internal numbering, the (z, lat) section
+  TempDev t;
+  cudaError_t err = cudaSuccess;
+#define TDJ(expr) do { expr; if (err != cudaSuccess) return fail(h, MPASB200_ECUDA, std::string("init_atm_case_jw: ") + cudaGetErrorString(err)); } while (0)
+  JwParams J;
+  std::memset(&J, 0, sizeof(J));
+  J.nlat = g->n_lat_table > 1 ? g->n_lat_table : 4097;
+  J.u0 = 35.0; J.t0 = 288.0; J.t0b = 250.0; J.dtdz = 0.005; J.eta_t = 0.2; J.delta_t = 4.8e5; J.etavs0 = (1.0 - 0.252) * pii / 2.0; J.p0 = 1.0e5; J.zt = zt;
+  J.r_earth = h->c.sphere_radius; J.omega = h->c.omega; J.rgas = h->c.rgas; J.cp = h->c.cp; J.gravity = h->c.gravity; J.pii = pii;
+  TDJ(J.sh = t.up<double>(sh.data(), L1, h->stream, &err)); TDJ(J.ah = t.up<double>(ah.data(), L1, h->stream, &err));
+  TDJ(J.dzw = t.up<double>(dzw.data(), L1, h->stream, &err)); TDJ(J.dzu = t.up<double>(dzu.data(), L1, h->stream, &err));
+  std::vector<double> latC((size_t)nC + 1, 0.0), areaC((size_t)nC + 1, 1.0), latV((size_t)nV + 1, 0.0);
+  for (int c = 0; c < nC; ++c) { latC[h->newOf[MPASB200_CELL][c]] = g->latCell[c]; areaC[h->newOf[MPASB200_CELL][c]] = g->areaCell[c]; }
+  for (int v = 0; v < nV; ++v) latV[h->newOf[MPASB200_VERTEX][v]] = g->latVertex[v];
+  TDJ(J.latCell = t.up<double>(latC.data(), latC.size(), h->stream, &err)); TDJ(J.areaCell = t.up<double>(areaC.data(), areaC.size(), h->stream, &err));
+  TDJ(J.latVertex = t.up<double>(latV.data(), latV.size(), h->stream, &err));
+  const size_t plane = (size_t)J.nlat * L;
+  double* wk = nullptr;
+  TDJ(J.pp_t = t.out<double>(plane, &err)); TDJ(J.tt_t = t.out<double>(plane, &err)); TDJ(wk = t.out<double>(4 * plane, &err));
+#undef TDJ
+  { KTimer kt_(h, "k_jw_table"); k_jw_table<<<(unsigned)((J.nlat + 63) / 64), 64, 0, h->stream>>>(J, h->V, wk); h->launches++; }
+  { Cfg cf_ = cfg_for(h, nC); KTimer kt_(h, "k_jw_cell"); k_jw_cell<<<cf_.grid, cf_.block, 0, h->stream>>>(J, h->V); h->launches++; }
+  if (h->nEdges) { Cfg cf_ = cfg_for(h, h->nEdges); KTimer kt_(h, "k_jw_edge"); k_jw_edge<<<cf_.grid, cf_.block, 0, h->stream>>>(J, h->V); h->launches++; }
+  LAUNCH(k_jw_rw, nC, 0, h->V);
+  if (int rc = post_launch(h)) return rc;
+  CK(cudaStreamSynchronize(h->stream));        // the scratch goes away with `t`
+  return 0;
+}
 
 int mpasb200_rk_dynamics_substep_finish(mpasb200_t* h, int substep, int split) {
   REQUIRE_MESH();

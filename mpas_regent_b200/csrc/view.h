@@ -57,6 +57,14 @@ struct View {
   double* scr_rs; double* scr_ts;     // horizontal flux parts of rs/ts in the two-kernel acoustic step  [(nCells+1)][LP]
 };
 
+// tile lists of k_dt_edge_tile (kernels_tiles.cuh, laboratory builds); the handle holds one in every build so that its layout does not depend on the build
+struct EdgeTiles {
+  const int* cols;             // [tile][cap]  internal edge ids of the staged columns; the tile's own edges come first (slot = local index)
+  const int* ncols;            // [tile]
+  const unsigned char* slot;   // [edge][SP]   byte j = staged slot of edgesOnEdge[j], 255 = not staged (read from global memory)
+  int cap, SP, TE;
+};
+
 // scalar constants a task needs (filled on the host from MpasConfig + task arguments)
 struct DynTendParams {
   int rk_step; int mixing; int mix_full; int rayleigh_u; int visc4_on; int cam_on; int vmix_u_on; int vmix_t_on;

@@ -73,6 +73,8 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         "adv_coef_compression": ([H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], I),
         "couple_coef_3rd_order": ([H, D, C.c_void_p], I),
     }
+    if prefix == "mpasb200_":
+        sig["init_atm_case_jw"] = ([H, C.c_void_p], I)
     for name, (args, res) in sig.items():
         fn = getattr(lib, prefix + name)
         fn.argtypes, fn.restype = args, res
@@ -235,6 +237,13 @@ class TaskAPI:
         if adv_coefs_3rd is not None:
             assert adv_coefs_3rd.dtype == np.float64 and adv_coefs_3rd.flags.c_contiguous
         self._call("couple_coef_3rd_order", float(config_coef_3rd_order), None if adv_coefs_3rd is None else adv_coefs_3rd.ctypes.data)
+
+    def init_atm_case_jw(self, latCell: np.ndarray, areaCell: np.ndarray, latVertex: np.ndarray, n_lat_table: int = 0):
+        """vertical_init/init_atm_cases.rg:24-743 on the device (corrected reading = init_jw.py); geometry scaled to the sphere"""
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (latCell, areaCell, latVertex)]
+        assert a[0].shape == (self.dims.nCells,) and a[1].shape == (self.dims.nCells,) and a[2].shape == (self.dims.nVertices,)
+        geo = _abi.MpasJwGeometry(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, int(n_lat_table))
+        self._call("init_atm_case_jw", C.addressof(geo))
 
     def atm_rk_dynamics_substep_finish(self, dynamics_substep: int, dynamics_split: int):
         self._call("rk_dynamics_substep_finish", int(dynamics_substep), int(dynamics_split))

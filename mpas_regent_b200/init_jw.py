@@ -97,7 +97,7 @@ def vertical_grid(L: int, zt: float = 45000.0, strf: float = 1.5):
 
 
 def make_state(mesh_unit: Mesh, nVertLevels: int, policy: int = CORRECTED, m5: bool = True,
-               seed: int = SEED, diag_on_host: bool = True) -> HostState:
+               seed: int = SEED, diag_on_host: bool = True, keep_jw: bool = False) -> HostState:
     """Build every hot-path input.  ``m5`` = fill never-written fields (rule M5); with
     m5=False they stay zero (rule M1, the literal reading)."""
     L = nVertLevels
@@ -231,6 +231,11 @@ def make_state(mesh_unit: Mesh, nVertLevels: int, policy: int = CORRECTED, m5: b
     w = np.zeros((nC, L1))
     w[:, 1:L] = rw[:, 1:L] / (fzp[None, 1:L] * F["rho_zz"][:, 0:L - 1] + fzm[None, 1:L] * F["rho_zz"][:, 1:L])
     F["rw"], F["w"] = rw, w
+
+    if keep_jw:      # what init_atm_case_jw itself leaves in the regions (the device form, mpasb200_init_atm_case_jw, is checked against this)
+        st.extras["jw"] = {k: F[k].copy() for k in ("zgrid", "zz", "zxu", "rho_base", "pressure_p", "rho_p", "exner", "theta_m", "rtheta_p",
+                                                    "rho_zz", "u", "ru", "rw", "w")}
+        st.extras["jw"].update(theta_base=theta_base.copy(), zb=zb.copy())
 
     # ================= atm_core_init chain (atm_core.rg:22-42) =================
     sg = core_init.atm_compute_signs(mesh, policy, zb=zb, zb3=zb3, nlev1=L1)

@@ -232,6 +232,28 @@ def test_edge_tiles_bit_identical(grid2562, tiles, policy, levels):
         assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
 
 
+@pytest.mark.parametrize("policy", [_abi.INDEX_CORRECTED, _abi.INDEX_LITERAL], ids=["corrected", "literal"])
+@pytest.mark.parametrize("levels", [L_SMALL, 55], ids=lambda v: f"L{v}")
+def test_kernel_forms_bit_identical(grid2562, policy, levels):
+    """MpasConfig.kernel_forms selects alternative launch forms of the same arithmetic (bit 0: k_dt_cellC as a w launch and a theta
+    launch): every field keeps its bytes over two full steps and a mixing / Rayleigh variant of dyn_tend at rk_step 0."""
+    from mpas_regent_b200 import dynamics, init_jw
+    st = init_jw.make_state(grid2562, levels, policy)
+    outs = []
+    for forms in (0, 1):
+        g = dynamics.Dynamics(dynamics.dims_of(grid2562, levels), _abi.default_config(rkarg_policy=_abi.RKARG_STAGE_INDEX, index_policy=policy, kernel_forms=forms,
+                                                                                      config_v_mom_eddy_visc2=10.0, config_v_theta_eddy_visc2=10.0, config_h_mom_eddy_visc4=1e13, config_h_theta_eddy_visc4=1e13))
+        g.upload_mesh(st.static); g.upload_state(st.f, st.vert)
+        g.atm_compute_solve_diagnostics(False, -1)
+        for _ in range(2):
+            g.atm_srk3(DT)
+        g.atm_compute_dyn_tend(0, DT, config_rayleigh_damp_u=True)
+        outs.append(g.download_all())
+        g.close()
+    for n in outs[0]:
+        assert np.array_equal(outs[0][n], outs[1][n], equal_nan=True), n
+
+
 @pytest.mark.parametrize("mask", [0, 1, 2, 4, -1], ids=["plain", "dt_edge", "acoustic_gather", "theta_flux", "all"])
 def test_staged_gathers_bit_identical(grid2562, mask):
     """(laboratory build only; measured slower, profiles/r2_staged_gathers.md)  MpasConfig.gather_stage only changes HOW neighbour columns reach the arithmetic (cp.async into shared-memory slots
@@ -718,3 +740,36 @@ def test_mesh_only_init_producers_on_the_device(grid2562, grid642, policy, which
         assert np.array_equal(g.download_field(n), ora.download_field(n)), n
         assert np.array_equal(g.download_field(n), st.f[n]), n
     g.close(); ora.close()
+
+
+@pytest.mark.parametrize("which,levels", [("x1.2562", L_SMALL), ("icosa642", 55), ("icosa642", 10)], ids=["x1.2562_L26", "icosa642_L55", "icosa642_L10"])
+def test_init_atm_case_jw_on_the_device(grid2562, grid642, which, levels):
+    """init_atm_case_jw (vertical_init/init_atm_cases.rg:24-743) as device kernels -- the corrected reading,
+    compared field by field with the host generator (mpas_regent_b200/init_jw.py, what every parity test is fed by): 1e-12 of the
+    field's largest value (libm and the device differ in the last place of exp / pow / sin / cos; rw and w also in the order the
+    edge terms are summed), vertical-grid arrays included; then the whole atm_core_init chain on the device reproduces the inputs."""
+    from mpas_regent_b200 import dynamics, init_jw
+    mesh = grid2562 if which == "x1.2562" else grid642
+    st = init_jw.make_state(mesh, levels, _abi.INDEX_CORRECTED, m5=False, keep_jw=True)
+    g = dynamics.Dynamics(dynamics.dims_of(mesh, levels), _abi.default_config())
+    g.upload_mesh(st.static)
+    v = st.mesh.v
+    g.init_atm_case_jw(v["latCell"], v["areaCell"], v["latVertex"])
+    worst = {}
+    for n, ref in list(st.extras["jw"].items()) + [(k, st.vert[k]) for k in ("rdzw", "rdzu", "fzm", "fzp", "cf1", "cf2", "cf3")]:
+        a = g.download_field(n)
+        scale = np.abs(ref).max()
+        err = np.abs(a - ref).max()
+        worst[n] = err / scale if scale > 0 else err
+        assert np.isfinite(a).all(), n
+        assert err <= 1e-12 * scale if scale > 0 else err == 0.0, (n, err, scale)
+    assert not g.download_field("zb3").any()
+    # the rest of atm_core_init on the device: zb_cell, coupled diagnostics -> the state the host chain produces
+    g.atm_compute_zb_cell()
+    g.atm_init_coupled_diagnostics()
+    for n in ("zb_cell", "zb3_cell", "rho_zz", "ru", "rw", "rho_p", "rtheta_base", "rtheta_p", "exner", "exner_base", "pressure_p"):
+        a, ref = g.download_field(n), st.f[n]
+        scale = np.abs(ref).max()
+        assert np.abs(a - ref).max() <= 2e-12 * max(scale, 1e-300), (n, np.abs(a - ref).max(), scale)
+    print("worst relative deviations:", {k: f"{x:.1e}" for k, x in worst.items()})
+    g.close()
