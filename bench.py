@@ -522,6 +522,7 @@ def main():
             "step_hbm": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs_per_gpu": step_gbs / world,
                          "frac_of_peak": step_gbs / world / peak},
             "kernels_ms_per_step": {k: round(v[0] / k_steps, 4) for k, v in top},
+            "kernels_launches_per_step": {k: round(v[1] / k_steps, 2) for k, v in top},
             "e2e": e2e, "cpu_baseline": cpu, "check": check,
         }
         _emit(line)

@@ -303,6 +303,14 @@ int  mpasb200_adv_coef_compression(mpasb200_t *h, const MpasInitMesh *m, int32_t
  *                                     mpasb200_upload_mesh)                                                                        */
 int  mpasb200_couple_coef_3rd_order(mpasb200_t *h, double config_coef_3rd_order, double *adv_coefs_3rd);
 
+/* atm_compute_mesh_scaling            dynamics_tasks.rg:595-646: meshScalingDel2 / meshScalingDel4 [nEdges] (host arrays, caller's numbering)
+ *                                     from meshDensity [nCells] read through cellsOnEdge (m->cellsOnEdge, raw ids); 1.0 when
+ *                                     config_h_ScaleWithMesh is false.  The regional-relaxation factors are not on the hot path.   */
+int  mpasb200_compute_mesh_scaling(mpasb200_t *h, const MpasInitMesh *m, const double *meshDensity, int config_h_ScaleWithMesh,
+                                   double *meshScalingDel2, double *meshScalingDel4);
+/* atm_compute_damping_coefs           dynamics_tasks.rg:274-300: dss from zgrid (device fields) and meshDensity [nCells] (host, caller's
+ *                                     numbering); levels 0..nVertLevels-1; after mpasb200_upload_mesh.                                */
+int  mpasb200_compute_damping_coefs(mpasb200_t *h, const double *meshDensity, double config_zd, double config_xnutr);
 /* init_atm_case_jw                    vertical_init/init_atm_cases.rg:24-743 -- the Jablonowski-Williamson baroclinic-wave initial
  * state on the device, CORRECTED reading (the reference text indexes regions with swapped, out-of-range (level, cell) pairs and cannot
  * be restated literally; this is the formula-by-formula equivalent of the host generator mpas_regent_b200/init_jw.py, dry case, parity

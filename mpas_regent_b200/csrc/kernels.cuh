@@ -32,7 +32,7 @@
 #define LB_AC 3
 #endif
 #ifndef KDE_PREFETCH
-#define KDE_PREFETCH 0
+#define KDE_PREFETCH 1       /* measured: k_dt_edge 2.208 -> 2.135 ms/step on x1.163842 (profiles/r2_small_experiments.md) */
 #endif
 #ifndef LB_MISC
 #define LB_MISC 1
@@ -124,6 +124,12 @@ DI void prefetch_edge_rows(const View& V, long xa, int lane, const int* eoe) {
   (void)ix; (void)m1; (void)k1;
 #define G2(p, e) ld2((p), (size_t)(e) * LP + k0)                 /* the level pair of neighbour column e */
 #define G1(p, e, k_) ((p)[(size_t)(e) * LP + (k_)])
+// (Measured and removed, profiles/r2_small_experiments.md: taking the cell's OWN level pair from a register instead of gathering it
+// again in the edgesOnCell loops -- one of the two cells of every slot is the cell itself -- saves a third of those gathers and is
+// SLOWER: k_acoustic_gather 1.147 -> 1.237 ms/step, k_dt_cellA 0.357 -> 0.440, k_dt_cellB 0.267 -> 0.332 on x1.163842.)
+#ifndef AG_PACKED
+#define AG_PACKED 0
+#endif
 // values one level below / above the pair: (f[k0-1], f[k0]) and (f[k1], f[k1+1])
 DI D2 below(const double* p, size_t ix, int k0, D2 cur) { return mk(k0 > 0 ? p[ix - 1] : 0.0, cur.x); }
 DI D2 above(const double* p, size_t ix, int k0, int L, D2 cur) { return mk(cur.y, (k0 + 2 <= L) ? p[ix + 2] : 0.0); }
@@ -484,7 +490,7 @@ __global__ void k_dt_edge(const View V, const DynTendParams P) {
   if (m0) {
     cv = V.ecv[x];
 #if KDE_PREFETCH
-    // (laboratory variant) the loads of the kernel's tail -- own-column strips and the cell columns that depend only on `cv` -- are
+    // the loads of the kernel's tail -- own-column strips and the cell columns that depend only on `cv` -- are
     // requested into L2 now, one request per 128-byte line, so that they later cost an L2 round trip instead of a DRAM one
     if ((threadIdx.x & 7) == 0) {
       prefetch_l2(FLD(rho_edge) + ix); prefetch_l2(FLD(tend_u_euler) + ix); prefetch_l2(FLD(tend_ru_physics) + ix); prefetch_l2(FLD(pv_edge) + ix);
@@ -1015,6 +1021,21 @@ __global__ void k_acoustic_gather(const View V, double dts) {
   const double* ru_p = FLD(ru_p); const double* tm = FLD(theta_m);
   const double inva = V.invAreaCell[x];
   D2 rs = bc(0), ts = bc(0);
+#if AG_PACKED
+  if (V.signDvOnCell) {
+    // every lane of a column reads the same static row: each such load is an L1 wavefront per column in the warp, and they were 5 of
+    // the 8 loads per slot.  Packed at upload_mesh: {edge, cell1, cell2} in one 16-byte word and sign*dvEdge in one double (the sign
+    // is +-1 or 0, so (sign*dts)*dv and dts*(sign*dv) are the same double): 2 static loads per slot.
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {
+      const int4 id = V.slotIds[x * ME + i];
+      const D2 flux = dts * V.signDvOnCell[x * ME + i] * G2(ru_p, id.x) * inva;
+      rs -= flux;
+      ts -= flux * 0.5 * (G2(tm, id.z) + G2(tm, id.y));
+    }
+  } else
+#endif
+  {
 #pragma unroll 2
   for (int i = 0; i < n; ++i) {
     const int e = V.edgesOnCell[x * V.MEP + i];
@@ -1022,6 +1043,7 @@ __global__ void k_acoustic_gather(const View V, double dts) {
     const D2 flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G2(ru_p, e) * inva;
     rs -= flux;
     ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
+  }
   }
   st2m(V.scr_rs, ix, rs, m0, m1); st2m(V.scr_ts, ix, ts, m0, m1);
 }

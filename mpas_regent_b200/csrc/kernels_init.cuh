@@ -148,3 +148,41 @@ __global__ void k_zb3_level0(const View V, double c) {          // `cr[{iCell, 0
   if (x >= V.nCells) return;
   for (int j = 0; j < V.maxEdges; ++j) FLD(zb3_cell)[(size_t)j * V.cellSlot + (size_t)x * V.LP] *= c;
 }
+
+// atm_compute_mesh_scaling  :595-646 (the del2 / del4 factors; cellOne / cellTwo are cellsOnEdge)
+__global__ void k_mesh_scaling(const InitMeshDev M, const double* __restrict__ meshDensity, int scale_with_mesh,
+                               double* __restrict__ del2, double* __restrict__ del4) {
+  const int iEdge = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iEdge >= M.nE) return;
+  double a = 1.0, b = 1.0;
+  if (scale_with_mesh) {
+    const long c1 = im_R(M, M.cellsOnEdge[(size_t)iEdge * 2], M.nC), c2 = im_R(M, M.cellsOnEdge[(size_t)iEdge * 2 + 1], M.nC);
+    const double m = ((c1 < M.nC ? meshDensity[c1] : 0.0) + (c2 < M.nC ? meshDensity[c2] : 0.0)) / 2.0;
+    a = 1.0 / pow(m, 0.25); b = 1.0 / pow(m, 0.75);
+  }
+  del2[iEdge] = a; del4[iEdge] = b;
+}
+
+// atm_compute_damping_coefs  :274-300 on the device mirror; meshDensity in internal numbering
+__global__ void k_damping_coefs(const View V, const double* __restrict__ meshDensity, double config_zd, double config_xnutr) {
+  PAIR_THREAD(V.nCells)
+  if (!m0) return;
+  const double pii = acos(-1.0);
+  const double* zg = FLD(zgrid);
+  const double zt = zg[(size_t)x * LP + L];
+  const double md = pow(meshDensity[x], 0.25);
+  D2 out = bc(0.0);
+  for (int c = 0; c < 2; ++c) {
+    const int k = k0 + c;
+    if (k >= L) break;
+    const double z = 0.5 * (zg[ix + c] + zg[ix + c + 1]);
+    double d = 0.0;
+    if (z > config_zd) {
+      const double s = sin(0.5 * pii * (z - config_zd) / (zt - config_zd));
+      d = config_xnutr * (s * s);          // pow(x, 2.0)
+      d /= md;
+    }
+    if (c) out.y = d; else out.x = d;
+  }
+  st2m(FLD(dss), ix, out, m0, m1);
+}

@@ -1181,6 +1181,23 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
   UP_IDS(verticesOnCell, m->verticesOnCell, nC, ME, cNew, nV, vNew);
   UP_INT(kiteForCell, m->kiteForCell, nC, ME, cNew);
   UP_DBL(edgesOnCellSign, m->edgesOnCellSign, nC, ME, cNew);
+  {   // packed per-slot statics of k_acoustic_gather: ids in one 16-byte word, edgesOnCellSign * dvEdge in one double
+    const std::vector<int> eocC = build_ids(m->edgesOnCell, nC, ME, cNew, nE, eNew, pol);
+    const std::vector<int> coe = build_ids(m->cellsOnEdge, nE, 2, eNew, nC, cNew, pol);
+    const std::vector<double> dvE = build_vals<double, double>(m->dvEdge, nE, 1, eNew), sgn = build_vals<double, double>(m->edgesOnCellSign, nC, ME, cNew);
+    std::vector<int4> ids((size_t)(nC + 1) * ME);
+    std::vector<double> sdv((size_t)(nC + 1) * ME, 0.0);
+    bool exact = true;
+    for (size_t i = 0; i < ids.size(); ++i) {
+      const int e = eocC[i];
+      ids[i] = make_int4(e, coe[(size_t)e * 2], coe[(size_t)e * 2 + 1], 0);
+      sdv[i] = sgn[i] * dvE[e];
+      if (!(sgn[i] == 1.0 || sgn[i] == -1.0 || sgn[i] == 0.0)) exact = false;
+    }
+    if ((rc = dev_upload<int4>(h, &V.slotIds, ids))) return rc;
+    if (exact) { if ((rc = dev_upload<double>(h, &V.signDvOnCell, sdv))) return rc; }
+    else V.signDvOnCell = nullptr;      // a caller-supplied sign that is not +-1 / 0: the product would round differently -> plain loads
+  }
   UP_DBL(edgesOnCell_sign, m->edgesOnCell_sign, nC, ME, cNew);
   UP_DBL(invAreaCell, m->invAreaCell, nC, 1, cNew);
   UP_DBL(defc_a, m->defc_a, nC, ME, cNew);
@@ -1609,6 +1626,42 @@ int mpasb200_adv_coef_compression(mpasb200_t* h, const MpasInitMesh* m, int32_t*
   if (int rc = fetch(h, (int*)advCellsForEdge, d_adv, nE * NA)) return rc;
   if (int rc = fetch(h, adv_coefs, d_a, nE * NA)) return rc;
   if (int rc = fetch(h, adv_coefs_3rd, d_a3, nE * NA)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int mpasb200_compute_mesh_scaling(mpasb200_t* h, const MpasInitMesh* m, const double* meshDensity, int scale_with_mesh, double* del2, double* del4) {
+  if (!h || !m) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  if (!m->cellsOnEdge || !del2 || !del4 || (scale_with_mesh && !meshDensity)) return fail(h, MPASB200_EINVAL, "compute_mesh_scaling: cellsOnEdge, meshDensity and both outputs are required");
+  TempDev t; InitMeshDev M;
+  MpasInitMesh only; std::memset(&only, 0, sizeof(only)); only.cellsOnEdge = m->cellsOnEdge;
+  if (int rc = init_mesh_dev(h, &only, t, M)) return rc;
+  cudaError_t err = cudaSuccess;
+  const size_t nE = h->nEdges, nC = h->nCells;
+  double* d_md = nullptr; double* d2 = nullptr; double* d4 = nullptr;
+  TD(d_md = t.up<double>(meshDensity, nC, h->stream, &err)); TD(d2 = t.out<double>(nE, &err)); TD(d4 = t.out<double>(nE, &err));
+  if (nE) { KTimer kt_(h, "k_mesh_scaling"); k_mesh_scaling<<<(unsigned)((nE + 127) / 128), 128, 0, h->stream>>>(M, d_md, scale_with_mesh, d2, d4); h->launches++; }
+  if (int rc = post_launch(h)) return rc;
+  if (int rc = fetch(h, del2, d2, nE)) return rc;
+  if (int rc = fetch(h, del4, d4, nE)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int mpasb200_compute_damping_coefs(mpasb200_t* h, const double* meshDensity, double config_zd, double config_xnutr) {
+  REQUIRE_MESH();
+  if (!meshDensity) return fail(h, MPASB200_EINVAL, "compute_damping_coefs: meshDensity is required");
+  Entry en(h, -1);
+  TempDev t;
+  cudaError_t err = cudaSuccess;
+  std::vector<double> md((size_t)h->nCells + 1, 1.0);
+  for (int c = 0; c < h->nCells; ++c) md[h->newOf[MPASB200_CELL][c]] = meshDensity[c];
+  double* d_md = nullptr;
+  TD(d_md = t.up<double>(md.data(), md.size(), h->stream, &err));
+  LAUNCH(k_damping_coefs, h->nCells, 0, h->V, d_md, config_zd, config_xnutr);
+  if (int rc = post_launch(h)) return rc;
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }

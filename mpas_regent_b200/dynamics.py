@@ -72,6 +72,8 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         "compute_zb_cell": ([H], I),
         "adv_coef_compression": ([H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], I),
         "couple_coef_3rd_order": ([H, D, C.c_void_p], I),
+        "compute_mesh_scaling": ([H, C.c_void_p, C.c_void_p, I, C.c_void_p, C.c_void_p], I),
+        "compute_damping_coefs": ([H, C.c_void_p, D, D], I),
     }
     if prefix == "mpasb200_":
         sig["init_atm_case_jw"] = ([H, C.c_void_p], I)
@@ -237,6 +239,23 @@ class TaskAPI:
         if adv_coefs_3rd is not None:
             assert adv_coefs_3rd.dtype == np.float64 and adv_coefs_3rd.flags.c_contiguous
         self._call("couple_coef_3rd_order", float(config_coef_3rd_order), None if adv_coefs_3rd is None else adv_coefs_3rd.ctypes.data)
+
+    def atm_compute_mesh_scaling(self, mesh: Dict[str, np.ndarray], meshDensity: np.ndarray, config_h_ScaleWithMesh: bool = True):
+        """dynamics_tasks.rg:595-646 -> {meshScalingDel2, meshScalingDel4}"""
+        d = self.dims
+        m, keep = _abi.init_mesh_ptrs({"cellsOnEdge": mesh["cellsOnEdge"]}, d)
+        md = np.ascontiguousarray(meshDensity, dtype=np.float64)
+        out = dict(meshScalingDel2=np.zeros(d.nEdges), meshScalingDel4=np.zeros(d.nEdges))
+        self._call("compute_mesh_scaling", C.addressof(m), md.ctypes.data, int(bool(config_h_ScaleWithMesh)),
+                   out["meshScalingDel2"].ctypes.data, out["meshScalingDel4"].ctypes.data)
+        del keep
+        return out
+
+    def atm_compute_damping_coefs(self, meshDensity: np.ndarray, config_zd: float = 22000.0, config_xnutr: float = 0.2):
+        """dynamics_tasks.rg:274-300: zgrid -> dss (after upload_mesh)"""
+        md = np.ascontiguousarray(meshDensity, dtype=np.float64)
+        assert md.shape == (self.dims.nCells,)
+        self._call("compute_damping_coefs", md.ctypes.data, float(config_zd), float(config_xnutr))
 
     def init_atm_case_jw(self, latCell: np.ndarray, areaCell: np.ndarray, latVertex: np.ndarray, n_lat_table: int = 0):
         """vertical_init/init_atm_cases.rg:24-743 on the device (corrected reading = init_jw.py); geometry scaled to the sphere"""

@@ -233,9 +233,9 @@ def make_state(mesh_unit: Mesh, nVertLevels: int, policy: int = CORRECTED, m5: b
     F["rw"], F["w"] = rw, w
 
     if keep_jw:      # what init_atm_case_jw itself leaves in the regions (the device form, mpasb200_init_atm_case_jw, is checked against this)
-        st.extras["jw"] = {k: F[k].copy() for k in ("zgrid", "zz", "zxu", "rho_base", "pressure_p", "rho_p", "exner", "theta_m", "rtheta_p",
+        jw_snapshot = {k: F[k].copy() for k in ("zgrid", "zz", "zxu", "rho_base", "pressure_p", "rho_p", "exner", "theta_m", "rtheta_p",
                                                     "rho_zz", "u", "ru", "rw", "w")}
-        st.extras["jw"].update(theta_base=theta_base.copy(), zb=zb.copy())
+        jw_snapshot.update(theta_base=theta_base.copy(), zb=zb.copy())
 
     # ================= atm_core_init chain (atm_core.rg:22-42) =================
     sg = core_init.atm_compute_signs(mesh, policy, zb=zb, zb3=zb3, nlev1=L1)
@@ -340,6 +340,8 @@ def make_state(mesh_unit: Mesh, nVertLevels: int, policy: int = CORRECTED, m5: b
             F[k] = zero_e()
         coeffs = np.zeros((nC, MAX_EDGES, 3))
     st.extras = dict(coeffs_reconstruct=coeffs, theta_base=theta_base, zb=zb, zb3=zb3, deriv_two=deriv_two)
+    if keep_jw:
+        st.extras["jw"] = jw_snapshot
     # inputs of the device-side init chain (mpasb200_init_coupled_diagnostics / mpasb200_reconstruct_2d)
     S["lonCell"] = v["lonCell"]
     S["coeffs_reconstruct"] = coeffs

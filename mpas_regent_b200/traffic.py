@@ -95,6 +95,7 @@ K: Dict[str, Tuple[List[str], List[str]]] = {
                     ["rw", "rho_p", "rtheta_base", "rtheta_p", "exner", "exner_base", "pressure_p", "pressure_base"]),
     "k_reconstruct": (["u"], ["uReconstructX", "uReconstructY", "uReconstructZ", "uReconstructZonal", "uReconstructMeridional"]),
     "k_zb_cell": (["zb", "zb3"], ["zb_cell", "zb3_cell"]),          # atm_compute_signs, 3-D part (one-time)
+    "k_damping_coefs": (["zgrid"], ["dss"]),                        # atm_compute_damping_coefs (one-time)
     "k_jw_rw": (["zz", "ru", "rho_zz", "zb"], ["rw", "w"]),         # init_atm_case_jw (one-time)
     "k_setup_scalars": (["scalars"], ["scalars_old"]),
     "k_scalar_flux<NS>": (["ruAvg", "scalars"], ["scr_e"] * 8),

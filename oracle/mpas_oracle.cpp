@@ -512,6 +512,39 @@ int oracle_adv_coef_compression(oracle_t* o, const MpasInitMesh* m, int32_t* nAd
   return 0;
 }
 
+// atm_compute_mesh_scaling   dynamics_tasks.rg:595-646 (del2 / del4 factors)
+int oracle_compute_mesh_scaling(oracle_t* o, const MpasInitMesh* m, const double* meshDensity, int scale_with_mesh, double* del2, double* del4) {
+  if (!o || !m || !m->cellsOnEdge || !del2 || !del4) return MPASB200_EINVAL;
+  const RawMesh r = raw_of(o, m);
+  for (int iEdge = 0; iEdge < r.nE; ++iEdge) { del2[iEdge] = 1.0; del4[iEdge] = 1.0; }
+  if (scale_with_mesh)
+    for (int iEdge = 0; iEdge < r.nE; ++iEdge) {
+      const long c1 = r.R(m->cellsOnEdge[(size_t)iEdge * 2], r.nC), c2 = r.R(m->cellsOnEdge[(size_t)iEdge * 2 + 1], r.nC);
+      const double md = ((c1 < r.nC ? meshDensity[c1] : 0.0) + (c2 < r.nC ? meshDensity[c2] : 0.0)) / 2.0;
+      del2[iEdge] = 1.0 / pow(md, 0.25);
+      del4[iEdge] = 1.0 / pow(md, 0.75);
+    }
+  return 0;
+}
+
+// atm_compute_damping_coefs   dynamics_tasks.rg:274-300
+int oracle_compute_damping_coefs(oracle_t* o, const double* meshDensity, double config_zd, double config_xnutr) {
+  if (!o || !meshDensity) return MPASB200_EINVAL;
+  F3 zgrid = o->f(MPASB200_F_zgrid), dss = o->f(MPASB200_F_dss);
+  const double m1 = -1.0, pii = acos(m1), dx_scale_power = 1.0;
+  for (int iCell = 0; iCell < o->nCells; ++iCell)
+    for (int k = 0; k < o->L; ++k) {
+      dss(iCell, k) = 0.0;
+      const double zt = zgrid(iCell, o->L);
+      const double z = 0.5 * (zgrid(iCell, k) + zgrid(iCell, k + 1));
+      if (z > config_zd) {
+        dss(iCell, k) = config_xnutr * pow(sin(0.5 * pii * (z - config_zd) / (zt - config_zd)), 2.0);
+        dss(iCell, k) /= pow(meshDensity[iCell], (0.25 * dx_scale_power));
+      }
+    }
+  return 0;
+}
+
 // atm_couple_coef_3rd_order   dynamics_tasks.rg:303-325 (zb3_cell: `cr[{iCell, 0}]` is LEVEL 0 only)
 int oracle_couple_coef_3rd_order(oracle_t* o, double coef, double* adv_coefs_3rd) {
   if (adv_coefs_3rd) for (size_t i = 0; i < (size_t)o->nEdges * o->nAdv; ++i) adv_coefs_3rd[i] *= coef;

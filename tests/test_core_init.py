@@ -218,3 +218,31 @@ def test_oracle_init_producers_equal_host_producers(grid2562, grid642, policy, w
     assert np.array_equal(ora.download_field("zb3_cell"), zb3c_h)
     assert np.array_equal(a3, st.static["adv_coefs_3rd"]) and np.array_equal(ora.download_field("zb3_cell"), st.f["zb3_cell"])
     ora.close()
+
+
+@pytest.mark.parametrize("policy", [_abi.INDEX_CORRECTED, _abi.INDEX_LITERAL], ids=["corrected", "literal"])
+def test_oracle_mesh_scaling_and_damping_coefs_equal_host_producers(grid2562, policy):
+    """oracle_compute_mesh_scaling (dynamics_tasks.rg:595-646) and oracle_compute_damping_coefs (:274-300) against core_init.py on a
+    NON-uniform meshDensity (the bundled mesh is quasi-uniform: density 1 would make both trivial)."""
+    from mpas_regent_b200 import dynamics
+    from mpas_regent_b200.mesh import Mesh
+    from oracle.oracle import Oracle
+    L = 9
+    st = init_jw.make_state(grid2562, L, policy)
+    rng = np.random.default_rng(5)
+    md = rng.uniform(0.05, 1.0, grid2562.nCells)
+    mesh_d = Mesh(v={**st.mesh.v, "meshDensity": md}, partition=None, name="x")
+    ora = Oracle(dynamics.dims_of(grid2562, L), _abi.default_config(index_policy=policy))
+    ms_h = core_init.atm_compute_mesh_scaling(mesh_d, policy, True)
+    ms_o = ora.atm_compute_mesh_scaling({"cellsOnEdge": grid2562.v["cellsOnEdge"]}, md, True)
+    for k in ms_h:
+        assert np.allclose(ms_o[k], ms_h[k], rtol=1e-14, atol=0), k
+    one = ora.atm_compute_mesh_scaling({"cellsOnEdge": grid2562.v["cellsOnEdge"]}, md, False)
+    assert (one["meshScalingDel2"] == 1.0).all() and (one["meshScalingDel4"] == 1.0).all()
+    ora.upload_mesh(st.static)
+    ora.upload_field("zgrid", st.f["zgrid"])
+    ora.atm_compute_damping_coefs(md, 22000.0, 0.2)
+    dss_h = core_init.atm_compute_damping_coefs(st.f["zgrid"], md, L)
+    assert dss_h.max() > 0
+    assert np.allclose(ora.download_field("dss"), dss_h, rtol=1e-14, atol=0)
+    ora.close()
