@@ -126,9 +126,10 @@ DI void prefetch_edge_rows(const View& V, long xa, int lane, const int* eoe) {
 #define G1(p, e, k_) ((p)[(size_t)(e) * LP + (k_)])
 // (Measured and removed, profiles/r2_small_experiments.md: taking the cell's OWN level pair from a register instead of gathering it
 // again in the edgesOnCell loops -- one of the two cells of every slot is the cell itself -- saves a third of those gathers and is
-// SLOWER: k_acoustic_gather 1.147 -> 1.237 ms/step, k_dt_cellA 0.357 -> 0.440, k_dt_cellB 0.267 -> 0.332 on x1.163842.)
-#ifndef AG_PACKED
-#define AG_PACKED 0
+// SLOWER: k_acoustic_gather 1.147 -> 1.237 ms/step, k_dt_cellA 0.357 -> 0.440, k_dt_cellB 0.267 -> 0.332 on x1.163842.  So is packing
+// the per-slot statics of k_acoustic_gather into one 16-byte id word + one sign*dvEdge double: 1.151 -> 1.256.)
+#ifndef CELLC_PREFETCH
+#define CELLC_PREFETCH 0
 #endif
 // values one level below / above the pair: (f[k0-1], f[k0]) and (f[k1], f[k1+1])
 DI D2 below(const double* p, size_t ix, int k0, D2 cur) { return mk(k0 > 0 ? p[ix - 1] : 0.0, cur.x); }
@@ -697,6 +698,16 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
   const double* rw = FLD(rw);
   D2 w2 = bc(0.0), twe = bc(0.0), fzm = bc(0.0), fzp = bc(0.0), rdzu = bc(0.0), rdzw = bc(0.0), rw2 = bc(0.0), rwm = bc(0.0);
   if (m0) {
+#if CELLC_PREFETCH
+    // own-column strips this kernel reads late (behind its barriers): requested into L2 now, one request per 128-byte line
+    if ((threadIdx.x & 7) == 0) {
+      if (PART != 1) {
+        prefetch_l2(FLD(theta_m) + ix); prefetch_l2(FLD(theta_m_save) + ix); prefetch_l2(FLD(rw_save) + ix); prefetch_l2(FLD(rho_zz) + ix);
+        prefetch_l2(FLD(rt_diabatic_tend) + ix); prefetch_l2(FLD(tend_theta_euler) + ix); prefetch_l2(FLD(tend_rtheta_physics) + ix);
+      }
+      if (PART != 2 && !RK0) prefetch_l2(FLD(tend_w_euler) + ix);
+    }
+#endif
     fzm = ld2(FLD(fzm), k0); fzp = ld2(FLD(fzp), k0); rdzu = ld2(FLD(rdzu), k0); rdzw = ld2(FLD(rdzw), k0);
     rw2 = ld2(rw, ix); rwm = below(rw, ix, k0, rw2);
     if (PART != 2) {
@@ -1021,21 +1032,6 @@ __global__ void k_acoustic_gather(const View V, double dts) {
   const double* ru_p = FLD(ru_p); const double* tm = FLD(theta_m);
   const double inva = V.invAreaCell[x];
   D2 rs = bc(0), ts = bc(0);
-#if AG_PACKED
-  if (V.signDvOnCell) {
-    // every lane of a column reads the same static row: each such load is an L1 wavefront per column in the warp, and they were 5 of
-    // the 8 loads per slot.  Packed at upload_mesh: {edge, cell1, cell2} in one 16-byte word and sign*dvEdge in one double (the sign
-    // is +-1 or 0, so (sign*dts)*dv and dts*(sign*dv) are the same double): 2 static loads per slot.
-#pragma unroll 2
-    for (int i = 0; i < n; ++i) {
-      const int4 id = V.slotIds[x * ME + i];
-      const D2 flux = dts * V.signDvOnCell[x * ME + i] * G2(ru_p, id.x) * inva;
-      rs -= flux;
-      ts -= flux * 0.5 * (G2(tm, id.z) + G2(tm, id.y));
-    }
-  } else
-#endif
-  {
 #pragma unroll 2
   for (int i = 0; i < n; ++i) {
     const int e = V.edgesOnCell[x * V.MEP + i];
@@ -1043,7 +1039,6 @@ __global__ void k_acoustic_gather(const View V, double dts) {
     const D2 flux = V.edgesOnCellSign[x * ME + i] * dts * V.dvOnCell[x * ME + i] * G2(ru_p, e) * inva;
     rs -= flux;
     ts -= flux * 0.5 * (G2(tm, c2) + G2(tm, c1));
-  }
   }
   st2m(V.scr_rs, ix, rs, m0, m1); st2m(V.scr_ts, ix, ts, m0, m1);
 }

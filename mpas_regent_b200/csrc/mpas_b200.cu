@@ -1181,23 +1181,6 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
   UP_IDS(verticesOnCell, m->verticesOnCell, nC, ME, cNew, nV, vNew);
   UP_INT(kiteForCell, m->kiteForCell, nC, ME, cNew);
   UP_DBL(edgesOnCellSign, m->edgesOnCellSign, nC, ME, cNew);
-  {   // packed per-slot statics of k_acoustic_gather: ids in one 16-byte word, edgesOnCellSign * dvEdge in one double
-    const std::vector<int> eocC = build_ids(m->edgesOnCell, nC, ME, cNew, nE, eNew, pol);
-    const std::vector<int> coe = build_ids(m->cellsOnEdge, nE, 2, eNew, nC, cNew, pol);
-    const std::vector<double> dvE = build_vals<double, double>(m->dvEdge, nE, 1, eNew), sgn = build_vals<double, double>(m->edgesOnCellSign, nC, ME, cNew);
-    std::vector<int4> ids((size_t)(nC + 1) * ME);
-    std::vector<double> sdv((size_t)(nC + 1) * ME, 0.0);
-    bool exact = true;
-    for (size_t i = 0; i < ids.size(); ++i) {
-      const int e = eocC[i];
-      ids[i] = make_int4(e, coe[(size_t)e * 2], coe[(size_t)e * 2 + 1], 0);
-      sdv[i] = sgn[i] * dvE[e];
-      if (!(sgn[i] == 1.0 || sgn[i] == -1.0 || sgn[i] == 0.0)) exact = false;
-    }
-    if ((rc = dev_upload<int4>(h, &V.slotIds, ids))) return rc;
-    if (exact) { if ((rc = dev_upload<double>(h, &V.signDvOnCell, sdv))) return rc; }
-    else V.signDvOnCell = nullptr;      // a caller-supplied sign that is not +-1 / 0: the product would round differently -> plain loads
-  }
   UP_DBL(edgesOnCell_sign, m->edgesOnCell_sign, nC, ME, cNew);
   UP_DBL(invAreaCell, m->invAreaCell, nC, 1, cNew);
   UP_DBL(defc_a, m->defc_a, nC, ME, cNew);

@@ -32,8 +32,6 @@ struct View {
   const int* c1OnCell; const int* c2OnCell;            // [c][MEP]: cellsOnEdge[e][0/1] of the cell's slot-i edge
   const double* edgesOnCellSign; const double* edgesOnCell_sign; const double* invAreaCell; const double* cosLatCell;
   const double* dvOnCell; const double* invDcOnCell; const double* ms2OnCell; const double* ms4OnCell;   // [c][maxEdges]
-  const int4* slotIds;         // [c][maxEdges] {edgesOnCell, cell1, cell2 of that edge, 0}: one 16-byte load per slot (k_acoustic_gather)
-  const double* signDvOnCell;  // [c][maxEdges] edgesOnCellSign * dvEdge of the slot's edge (exact: the sign is +-1 or 0)
   const double* defc_a; const double* defc_b; const int* bdyMaskCell; const double* specZoneMaskCell;
   const unsigned char* isShared; const unsigned char* inCpr;
   const double* sinLatCell; const double* cosLonCell; const double* sinLonCell;   // host-evaluated (glibc), like cosLatCell
