@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--graph", type=int, default=0)
     ap.add_argument("--gather-stage", type=int, default=-1, help="MpasConfig.gather_stage bit mask (ablation: 0 = the plain gather kernels)")
     ap.add_argument("--edge-tiles", type=int, default=None, help="MpasConfig.edge_tiles (0 = plain k_dt_edge; 8 / 16 = tile-staged form)")
+    ap.add_argument("--timeline", default="", help="write the launch timeline of ONE step (both streams, rank 0) to this file and exit")
     ap.add_argument("--kernel-forms", type=int, default=None, help="MpasConfig.kernel_forms bit mask (1 = k_dt_cellC as two launches)")
     ap.add_argument("--acoustic", type=int, default=3, help="MpasConfig.acoustic_tma (3 = exact column-per-lane pipeline, 2 = affine sweep)")
     ap.add_argument("--physics", choices=("literal", "corrected"), default="literal",
@@ -346,6 +347,22 @@ def main():
         launches0 = g.launch_count
         sampler = ClockSampler(local_rank) if rank == 0 else None
         torch.cuda.synchronize(); barrier()
+        if args.timeline:
+            # one step with an event pair around every launch on both of the handle's streams: where the exchanges sit in time
+            g.enable_kernel_timing(2)
+            step()
+            if world > 1:
+                run.flush()
+            g.sync(); torch.cuda.synchronize()
+            tl = g.timeline()
+            g.enable_kernel_timing(False)
+            if rank == 0:
+                with open(args.timeline, "w") as fh:
+                    json.dump({"n_gpus": world, "mesh": nC, "levels": L, "rank": 0, "entries": tl}, fh)
+            barrier()
+            if world > 1:
+                dist.destroy_process_group()
+            return
         # ---- the timed region: K steps, nothing else on the stream (per-kernel events are a separate pass below) ----
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)

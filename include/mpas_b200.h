@@ -406,6 +406,10 @@ int  mpasb200_reset_timing(mpasb200_t *h);
 int  mpasb200_enable_kernel_timing(mpasb200_t *h, int on);
 int  mpasb200_reset_kernel_timing(mpasb200_t *h);
 int  mpasb200_kernel_time(mpasb200_t *h, int idx, const char **name, double *ms, int64_t *launches);
+/* enable_kernel_timing(h, 2) additionally keeps a TIMELINE: start and end of every launch (and of every NCCL send/recv group) in ms since
+ * the call, with the stream it ran on (0 = compute, 1 = the handle's communication stream) -- what shows the exchanges travelling
+ * under interior compute (profiles/r2_timeline_2gpu.md).  timeline_entry(idx) walks it (MPASB200_EINVAL past the end).          */
+int  mpasb200_timeline_entry(mpasb200_t *h, int idx, const char **name, double *t0_ms, double *t1_ms, int *stream);
 enum { MPASB200_T_SETUP = 0, MPASB200_T_MOIST, MPASB200_T_VERT_IMP, MPASB200_T_DYN_TEND, MPASB200_T_SMLSTEP,
        MPASB200_T_ACOUSTIC, MPASB200_T_DIVDAMP, MPASB200_T_RECOVER, MPASB200_T_DIAG, MPASB200_T_FINISH, MPASB200_T_SCALARS, MPASB200_T_COUNT };
 

@@ -129,7 +129,7 @@ DI void prefetch_edge_rows(const View& V, long xa, int lane, const int* eoe) {
 // SLOWER: k_acoustic_gather 1.147 -> 1.237 ms/step, k_dt_cellA 0.357 -> 0.440, k_dt_cellB 0.267 -> 0.332 on x1.163842.  So is packing
 // the per-slot statics of k_acoustic_gather into one 16-byte id word + one sign*dvEdge double: 1.151 -> 1.256.)
 #ifndef CELLC_PREFETCH
-#define CELLC_PREFETCH 0
+#define CELLC_PREFETCH 1     /* measured: k_dt_cellC<false> 1.392 -> 1.363 ms/step on x1.163842 (profiles/r2_small_experiments.md) */
 #endif
 // values one level below / above the pair: (f[k0-1], f[k0]) and (f[k1], f[k1+1])
 DI D2 below(const double* p, size_t ix, int k0, D2 cur) { return mk(k0 > 0 ? p[ix - 1] : 0.0, cur.x); }

@@ -86,7 +86,11 @@ struct mpasb200 {
   // per-kernel CUDA-event timing (bench / profiling aid): event pairs recorded around every launch
   bool ktiming = false;
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
-  struct Pending { int stat; cudaEvent_t a, b; };
+  struct Pending { int stat; cudaEvent_t a, b; bool comm; };
+  // timeline mode (mpasb200_enable_kernel_timing(h, 2)): start / end of every launch in ms since the mode was switched on, with its stream
+  bool ktimeline = false; cudaEvent_t ktl_base = nullptr;
+  struct TlEntry { int stat; float t0, t1; bool comm; };
+  std::vector<TlEntry> timeline;
   std::vector<Pending> pending;
   struct KStat { std::string name; double ms; int64_t n; };
   std::vector<KStat> kstats;
@@ -223,7 +227,7 @@ struct KTimer {      // brackets one launch with an event pair when kernel timin
     if (h->ktiming && !h->capturing) { id = kstat_id(h, name); a = pool_event(h); cudaEventRecord(a, h->stream); }
   }
   ~KTimer() {
-    if (a) { cudaEvent_t b = pool_event(h); cudaEventRecord(b, h->stream); h->pending.push_back({id, a, b}); }   // same stream as `a`: one LAUNCH
+    if (a) { cudaEvent_t b = pool_event(h); cudaEventRecord(b, h->stream); h->pending.push_back({id, a, b, h->comm_stream && h->stream == h->comm_stream}); }   // same stream as `a`: one LAUNCH
   }
 };
 void drain_kernel_times(mpasb200_t* h) {
@@ -233,6 +237,11 @@ void drain_kernel_times(mpasb200_t* h) {
     float ms = 0;
     if (cudaEventSynchronize(p.b) != cudaSuccess || cudaEventElapsedTime(&ms, p.a, p.b) != cudaSuccess) { cudaGetLastError(); continue; }
     h->kstats[p.stat].ms += ms; h->kstats[p.stat].n++;
+    if (h->ktimeline && h->ktl_base) {
+      float t0 = 0, t1 = 0;
+      if (cudaEventElapsedTime(&t0, h->ktl_base, p.a) == cudaSuccess && cudaEventElapsedTime(&t1, h->ktl_base, p.b) == cudaSuccess) h->timeline.push_back({p.stat, t0, t1, p.comm});
+      else cudaGetLastError();
+    }
   }
   h->pending.clear(); h->ev_used = 0;
 }
@@ -754,6 +763,7 @@ int dist_start(mpasb200_t* h, int kind, bool forked = false) {
   int rc = 0;
   for (auto& p : h->xplan[kind]) if ((rc = dist_pack_unpack(h, p, true))) break;
   if (!rc) {
+    KTimer kt_(h, "nccl_send_recv");
     int nrc = g_nccl.GroupStart();
     for (auto& p : h->xplan[kind]) {
       const mpasb200_t::Halo& H = h->halo[p.ent];
@@ -949,6 +959,7 @@ int mpasb200_destroy(mpasb200_t* h) {
   }
   if (h->up_stream) cudaStreamDestroy(h->up_stream);
   if (h->dn_stream) cudaStreamDestroy(h->dn_stream);
+  if (h->ktl_base) cudaEventDestroy(h->ktl_base);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -2002,6 +2013,27 @@ int mpasb200_enable_kernel_timing(mpasb200_t* h, int on) {
   cudaSetDevice(h->device);
   drain_kernel_times(h);
   h->ktiming = on != 0;
+  h->ktimeline = on == 2;
+  if (h->ktimeline) {          // the time origin of the timeline: now, on the compute stream
+    if (!h->ktl_base) cudaEventCreate(&h->ktl_base);
+    h->timeline.clear();
+    cudaEventRecord(h->ktl_base, h->stream);
+  }
+  return 0;
+}
+// timeline mode: entry idx (launch order per drain) -> kernel name, start / end in ms since mode 2 was switched on, stream (0 = compute,
+// 1 = the handle's communication stream).  MPASB200_EINVAL past the end.
+int mpasb200_timeline_entry(mpasb200_t* h, int idx, const char** name, double* t0_ms, double* t1_ms, int* stream) {
+  if (!h) return MPASB200_EINVAL;
+  std::unique_lock<std::mutex> lk(h->mu);
+  cudaSetDevice(h->device);
+  drain_kernel_times(h);
+  if (idx < 0 || idx >= (int)h->timeline.size()) return MPASB200_EINVAL;
+  const auto& e = h->timeline[idx];
+  if (name) *name = h->kstats[e.stat].name.c_str();
+  if (t0_ms) *t0_ms = e.t0;
+  if (t1_ms) *t1_ms = e.t1;
+  if (stream) *stream = e.comm ? 1 : 0;
   return 0;
 }
 int mpasb200_reset_kernel_timing(mpasb200_t* h) {

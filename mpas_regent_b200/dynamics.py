@@ -120,6 +120,8 @@ def _declare(lib, prefix: str, handle_t=C.c_void_p):
         lib.mpasb200_enable_kernel_timing.argtypes = [H, I]
         lib.mpasb200_reset_kernel_timing.argtypes = [H]
         lib.mpasb200_kernel_time.argtypes = [H, I, C.POINTER(C.c_char_p), C.POINTER(D), C.POINTER(C.c_int64)]
+        lib.mpasb200_timeline_entry.argtypes = [H, I, C.POINTER(C.c_char_p), C.POINTER(D), C.POINTER(D), C.POINTER(I)]
+        lib.mpasb200_timeline_entry.restype = I
         for n in ("enable_kernel_timing", "reset_kernel_timing", "kernel_time"):
             getattr(lib, "mpasb200_" + n).restype = I
         for n in ("upload_field_async", "download_field_async", "transfer_wait"):
@@ -508,8 +510,19 @@ class Dynamics(TaskAPI):
     def reset_timing(self):
         self._check(self._lib.mpasb200_reset_timing(self._h), "reset_timing")
 
-    def enable_kernel_timing(self, on: bool = True):
+    def enable_kernel_timing(self, on=True):
+        """on = 2 also keeps a timeline (see timeline())"""
         self._check(self._lib.mpasb200_enable_kernel_timing(self._h, int(on)), "enable_kernel_timing")
+
+    def timeline(self):
+        """[(kernel, start ms, end ms, stream)] since enable_kernel_timing(2); stream 0 = compute, 1 = communication"""
+        out, i = [], 0
+        while True:
+            nm, t0, t1, st = C.c_char_p(), C.c_double(), C.c_double(), C.c_int()
+            if self._lib.mpasb200_timeline_entry(self._h, i, C.byref(nm), C.byref(t0), C.byref(t1), C.byref(st)) != 0:
+                return out
+            out.append((nm.value.decode(), t0.value, t1.value, st.value))
+            i += 1
 
     def reset_kernel_timing(self):
         self._check(self._lib.mpasb200_reset_kernel_timing(self._h), "reset_kernel_timing")
