@@ -37,6 +37,29 @@
 #ifndef LB_MISC
 #define LB_MISC 1
 #endif
+// Stall-guided forms (profiles/r2_stall_profiles.md, GPU calls 18-20; x1.163842 x 55, ms per step, all bit-identical).  Adopted:
+//  * HOIST: loads whose latency sat in front of a barrier or at the head of a dependent chain -- the one-lane level-L reads of
+//    k_dt_edge / k_dt_cellC / k_vert_imp, the length of the edgesOnEdge row -- are requested at the top of the kernel and consumed
+//    where they were read before (k_dt_edge 2.139 -> 1.874 at the same 56 registers, k_dt_cellC<false> 1.259 -> 1.234, <true>
+//    0.614 -> 0.590, k_vert_imp 0.626 -> 0.584);
+//  * w_adv_curv leaves out the advection-coefficient loads whose values are multiplied by an exact 0.0 (k_dt_cellC<false>
+//    1.362 -> 1.259, k_dt_cellA 0.357 -> 0.322); slot 0 of k_diag_cell peeled, dcEdge from a per-(cell, slot) copy (0.411 -> 0.384);
+//  * cross-block prefetch of the index WORDS / ROWS of the block about one wave later (XPF_*): k_acoustic_gather 1.146 -> 1.102,
+//    k_dt_edge 1.868 -> 1.830, k_diag_cell, k_diag_edge, k_dt_edge_euler, k_dt_cellA/B -1 .. -4 %; k_dt_cellC and k_dt_theta_flux
+//    got slower with it (+0.6 %) and go without.
+// Measured and removed: the neighbour columns of 2..6 slots of a gather loop requested together (ptxas issues slot j+1's gathers
+// after slot j's arithmetic) -- k_dt_edge 2.11 .. 2.64, k_acoustic_gather 1.29 .. 1.96 against 1.148, k_dt_theta_flux 1.01 against
+// 0.756, k_diag_cell 0.46 .. 0.60 against 0.411: resident warps, not loads in flight per thread, carry these kernels; slot 0's statics
+// and columns peeled in front of the row length (k_acoustic_gather +4 %, k_dt_theta_flux +27 %, k_dt_edge +8 %); a last-edge static
+// for w_adv_curv (+1 %); prefetch.global.L1 instead of .L2 (no change); in-thread L2 prefetch of the columns a slot loop will
+// gather, lanes spread over slot x line (k_dt_edge +11 %, k_dt_theta_flux +9 %, k_acoustic_gather -0.8 %).
+#ifndef KDE_MAXREG
+#define KDE_MAXREG 56        /* the hoisted values would cost k_dt_edge a resident block (60 registers): capped, 8 bytes of spills */
+#endif
+// cross-block row prefetch of a cell kernel / an edge kernel (statics of the block about one wave later)
+#define XPF_CELL_ROWS() do { if (threadIdx.y < 2) prefetch_cell_rows(V, (long)x + (long)(PF_AHEAD + threadIdx.y * 4) * blockDim.y, threadIdx.x); } while (0)
+#define XPF_EDGE_WORDS() do { if (threadIdx.y == 0 && threadIdx.x < 3) { const long xa_ = (long)x + (long)PF_AHEAD * blockDim.y; \
+    if (xa_ < V.nEdges) { if (threadIdx.x == 0) prefetch_l2(V.ecv + xa_); if (threadIdx.x == 1) prefetch_l2(V.invDcEdge + xa_); if (threadIdx.x == 2) prefetch_l2(V.invDvEdge + xa_); } } } while (0)
 typedef double2 D2;
 
 DI D2 mk(double a, double b) { return make_double2(a, b); }
@@ -188,6 +211,9 @@ __global__ void k_vert_imp(const View V, double dtseps, double c2, double rcv, d
   }
   D2 zz = bc(0), zzm = bc(0), coftz = bc(0), cofwt = bc(0), cofwr = bc(0), cofwz = bc(0), gprev = bc(0);
   D2 rdzw2 = bc(0), rdzwm = bc(0);
+  double coftz_L = 0.0;                  // level L is never written: whatever the mirror holds (requested first, stored in front of the barrier)
+  if (inx && k0 == L) coftz_L = FLD(coftz)[ix];
+  if (inx && k1 == L) coftz_L = FLD(coftz)[ix + 1];
   if (m0) {
     const D2 fzm = ld2(FLD(fzm), k0), fzp = ld2(FLD(fzp), k0), rdzu = ld2(FLD(rdzu), k0);
     rdzw2 = ld2(FLD(rdzw), k0); rdzwm = below(FLD(rdzw), k0, k0, rdzw2);
@@ -208,8 +234,7 @@ __global__ void k_vert_imp(const View V, double dtseps, double c2, double rcv, d
     if (m1) { s_coftz[k1] = coftz.y; s_cofwt[k1] = cofwt.y; }
   }
   // level L is never written: whatever the mirror holds
-  if (inx && k0 == L) s_coftz[L] = FLD(coftz)[ix];
-  if (inx && k1 == L) s_coftz[L] = FLD(coftz)[ix + 1];
+  if (inx && (k0 == L || k1 == L)) s_coftz[L] = coftz_L;
   __syncthreads();
   if (!m0) return;
   st2m(FLD(coftz), ix, coftz, m0, m1); st2m(FLD(cofwt), ix, cofwt, m0, m1);
@@ -249,27 +274,41 @@ __global__ void k_diag_vertex(const View V) {      // vorticity :356-366, pv_ver
 }
 __global__ void k_diag_cell(const View V) {        // divergence :369-379 (s + u), ke :382-390
   PAIR_THREAD(V.nCells)
+  XPF_CELL_ROWS();
   if (!m0) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
   const double* u = FLD(u);
   D2 div = bc(0.0), kec = bc(0.0);
+  // slot 0's statics and column are requested together with the row length; dcEdge comes from the per-(cell, slot) copy
+  const double r = V.invAreaCell[x];
+  {
+    const int e = V.edgesOnCell[x * V.MEP];
+    const double dv = V.dvOnCell[x * ME], sg = V.edgesOnCellSign[x * ME], dc = V.dcOnCell[x * ME];
+    const D2 ue = G2(u, e);
+    if (n > 0) {
+      const double s = sg * dv;
+      div += s + ue;
+      const double efac = dc * dv;
+      kec += 0.25 * (efac * (ue * ue));
+    }
+  }
 #pragma unroll 2
-  for (int i = 0; i < n; ++i) {
+  for (int i = 1; i < n; ++i) {
     const int e = V.edgesOnCell[x * V.MEP + i];
     const double dv = V.dvOnCell[x * ME + i];
     const double s = V.edgesOnCellSign[x * ME + i] * dv;
     const D2 ue = G2(u, e);
     div += s + ue;
-    const double efac = V.dcEdge[e] * dv;
+    const double efac = V.dcOnCell[x * ME + i] * dv;
     kec += 0.25 * (efac * (ue * ue));               // ke_edge recomputed from u: same value as the stored field
   }
-  const double r = V.invAreaCell[x];
   st2m(FLD(divergence), ix, div * r, m0, m1);
   st2m(FLD(ke), ix, kec * r, m0, m1);
 }
 template <bool RECON_V>
 __global__ void k_diag_edge(const View V) {        // h_edge, ke_edge :346-353; v :431-438; pv_edge :449-451
   PAIR_THREAD(V.nEdges)
+  XPF_EDGE_WORDS();
   if (!m0) return;
   const int4 cv = V.ecv[x];
   const double* u = FLD(u); const double* h = FLD(h); const double* pvv = FLD(pv_vertex);
@@ -429,6 +468,7 @@ DI double vmix_u_at(double rho_e, double visc, double up, double uc, double um, 
 __global__ void k_dt_edge_euler(const View V, const DynTendParams P) {
   extern __shared__ double sm[];
   PAIR_THREAD(V.nEdges)
+  XPF_EDGE_WORDS();
   const int TS = LP + 2;
   double* s_um = sm + (size_t)threadIdx.y * TS;      // u_mix (vertical mixing of the perturbation from the initial state)
   const double* u = FLD(u);
@@ -480,7 +520,12 @@ __global__ void k_dt_edge_euler(const View V, const DynTendParams P) {
 }
 
 // u tendency  :958-1163 (tend_u_euler comes from k_dt_edge_euler at rk_step 0, from the previous stages otherwise)
-__global__ void k_dt_edge(const View V, const DynTendParams P) {
+#if KDE_MAXREG
+#define KDE_REGCAP __maxnreg__(KDE_MAXREG)
+#else
+#define KDE_REGCAP
+#endif
+__global__ void KDE_REGCAP k_dt_edge(const View V, const DynTendParams P) {
   extern __shared__ double sm[];
   PAIR_THREAD(V.nEdges)
   const int TS = LP + 2;
@@ -488,6 +533,24 @@ __global__ void k_dt_edge(const View V, const DynTendParams P) {
   const double* u = FLD(u);
   int4 cv = make_int4(0, 0, 0, 0);
   D2 u2 = bc(0.0), wduz = bc(0.0);
+  // requested first, consumed behind the barrier: level L of wduz (one lane; 6 % of the kernel's stall samples sat on this load in
+  // front of the barrier) and the length of the edgesOnEdge row; the row itself and its weights are asked into L2
+  double wduz_L = 0.0; int n_eoe = 0;
+  if (inx && k0 == L) wduz_L = FLD(wduz)[ix];
+  if (inx && k1 == L) wduz_L = FLD(wduz)[ix + 1];
+  if (threadIdx.y == 0 && threadIdx.x < 3) {       // the 16-byte words / row lengths of the block about one wave later: one line each
+    const long xa = (long)x + (long)PF_AHEAD * blockDim.y;
+    if (xa < V.nEdges) {
+      if (threadIdx.x == 0) prefetch_l2(V.ecv + xa);
+      if (threadIdx.x == 1) prefetch_l2(V.nEdgesOnEdge + xa);
+      if (threadIdx.x == 2) prefetch_l2(V.invDcEdge + xa);
+    }
+  }
+  if (m0) {
+    n_eoe = V.nEdgesOnEdge[x];
+    if (threadIdx.x == 1) { prefetch_l2(V.edgesOnEdge + (size_t)x * V.maxEdges2); prefetch_l2(V.edgesOnEdge + (size_t)x * V.maxEdges2 + V.maxEdges2 - 1); }
+    if (threadIdx.x == 2) { prefetch_l2(V.weightsOnEdge + (size_t)x * V.maxEdges2); prefetch_l2(V.weightsOnEdge + (size_t)x * V.maxEdges2 + V.maxEdges2 - 1); }
+  }
   if (m0) {
     cv = V.ecv[x];
 #if KDE_PREFETCH
@@ -502,7 +565,8 @@ __global__ void k_dt_edge(const View V, const DynTendParams P) {
 #endif
     u2 = ld2(u, ix);
     const double* rw = FLD(rw);
-    const D2 rwavg = 0.5 * (G2(rw, cv.x) + G2(rw, cv.y));
+    const D2 rw_a = G2(rw, cv.x), rw_b = G2(rw, cv.y);
+    const D2 rwavg = 0.5 * (rw_a + rw_b);
     const D2 fzm = ld2(FLD(fzm), k0), fzp = ld2(FLD(fzp), k0);
     const D2 um = (k0 >= 2) ? ld2(u, ix - 2) : bc(0.0);            // (u[k0-2], u[k0-1])
     const double up = (k0 + 2 <= L) ? u[ix + 2] : 0.0;             // u[k1+1]
@@ -511,8 +575,7 @@ __global__ void k_dt_edge(const View V, const DynTendParams P) {
     s_wduz[k0] = wduz.x; if (m1) s_wduz[k1] = wduz.y;
     st2m(FLD(wduz), ix, wduz, m0, m1);
   }
-  if (inx && k0 == L) s_wduz[L] = FLD(wduz)[ix];          // level L: never written, read as stored
-  if (inx && k1 == L) s_wduz[L] = FLD(wduz)[ix + 1];
+  if (inx && (k0 == L || k1 == L)) s_wduz[L] = wduz_L;    // level L: never written, read as stored
   __syncthreads();
   if (!m0) return;
   const D2 rho_e = ld2(FLD(rho_edge), ix);
@@ -523,7 +586,7 @@ __global__ void k_dt_edge(const View V, const DynTendParams P) {
   // (Q14); here it is added once, multiplied by nVertLevels (same value to O(L) ulp).
   D2 q = bc(0.0);
   {
-    const int ME2 = V.maxEdges2, n = V.nEdgesOnEdge[x];
+    const int ME2 = V.maxEdges2, n = n_eoe;
     const double* pv = FLD(pv_edge);
     const D2 pv_k = ld2(pv, ix);
     const double Ld = (double)L;
@@ -570,11 +633,15 @@ DI D2 w_adv_curv(const View& V, const DynTendParams& P, int x, int k0, size_t ix
     const D2 ru2 = G2(ru, e);
     const D2 rew = fm * ru2 + fp * below(ru, (size_t)e * LP + k0, k0, ru2);
     D2 fa = bc(0.0);
-    const int na = V.nAdvOnCell[x * ME + (n - 1)];
-    const size_t ab = ((size_t)x * ME + (n - 1)) * V.NAP;
-    for (int j = 0; j < na; ++j) {
-      const D2 sw = V.advCoefOnCell[ab + j] + sgn1(rew) * V.adv3OnCell[ab + j];
-      fa += sw * 0.0;          // cr.w was zeroed on levels < L just before (:1170-1172); the pad cell is zero too
+    // every term is (coefficient) * 0.0: with finite coefficients (checked once at upload_mesh) the sum is +0.0 exactly and the
+    // na coefficient loads -- 6 % of k_dt_cellC<false>'s stall samples -- are left out; a NaN / Inf coefficient takes the literal loop
+    if (!V.advFinite) {
+      const int na = V.nAdvOnCell[x * ME + (n - 1)];
+      const size_t ab = ((size_t)x * ME + (n - 1)) * V.NAP;
+      for (int j = 0; j < na; ++j) {
+        const D2 sw = V.advCoefOnCell[ab + j] + sgn1(rew) * V.adv3OnCell[ab + j];
+        fa += sw * 0.0;          // cr.w was zeroed on levels < L just before (:1170-1172); the pad cell is zero too
+      }
     }
     st2m(FLD(ru_edge_w), ix, rew, m0 && k0 > 0, m1);
     for (int i = 0; i < n; ++i) wv -= V.edgesOnCell_sign[x * ME + i] * rew * fa;                    // :1202
@@ -592,6 +659,7 @@ DI D2 w_adv_curv(const View& V, const DynTendParams& P, int x, int k0, size_t ix
 // rk_step == 0, cell pass A: w after advection+curvature (:1170-1218) and the first del^2 of theta (:1365-1382)
 __global__ void k_dt_cellA(const View V, const DynTendParams P) {
   PAIR_THREAD(V.nCells)
+  XPF_CELL_ROWS();
   if (!m0) return;
   st2m(FLD(w), ix, w_adv_curv(V, P, x, k0, ix, LP, m0, m1), m0, m1);
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
@@ -615,6 +683,7 @@ __global__ void k_dt_cellA(const View V, const DynTendParams P) {
 // rk_step == 0, cell pass B: first del^2 of w  :1231-1254  (needs pass A's w on neighbour cells)
 __global__ void k_dt_cellB(const View V, const DynTendParams P) {
   PAIR_THREAD(V.nCells)
+  XPF_CELL_ROWS();
   if (!m0) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
   const double* w = FLD(w); const double* kd = FLD(kdiff); const double* re = FLD(rho_edge);
@@ -697,6 +766,13 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
   const int n = inx ? V.nEdgesOnCell[x] : 0;
   const double* rw = FLD(rw);
   D2 w2 = bc(0.0), twe = bc(0.0), fzm = bc(0.0), fzp = bc(0.0), rdzu = bc(0.0), rdzw = bc(0.0), rw2 = bc(0.0), rwm = bc(0.0);
+  // level L of w / wdwz / wdtz (one lane per column) requested first, consumed in front of the barriers
+  double wL = 0.0, wdwzL = 0.0, wdtzL = 0.0;
+  if (inx && (k0 == L || k1 == L)) {
+    const size_t iL = ix + (k0 == L ? 0 : 1);
+    if (PART != 2) { wL = FLD(w)[iL]; wdwzL = FLD(wdwz)[iL]; }
+    if (PART != 1) wdtzL = FLD(wdtz)[iL];
+  }
   if (m0) {
 #if CELLC_PREFETCH
     // own-column strips this kernel reads late (behind its barriers): requested into L2 now, one request per 128-byte line
@@ -733,8 +809,7 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
     }
   }
   if (PART != 2) {
-  if (inx && k0 == L) { s_a[L] = FLD(w)[ix]; s_b[L] = FLD(wdwz)[ix]; }          // level L keeps its stored value
-  if (inx && k1 == L) { s_a[L] = FLD(w)[ix + 1]; s_b[L] = FLD(wdwz)[ix + 1]; }
+  if (inx && (k0 == L || k1 == L)) { s_a[L] = wL; s_b[L] = wdwzL; }             // level L keeps its stored value
   __syncthreads();
   D2 wdwz = bc(0.0);
   if (m0) {
@@ -812,8 +887,7 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
     s_a[k0] = wdtz.x; if (m1) s_a[k1] = wdtz.y;
     st2m(FLD(wdtz), ix, wdtz, m0, m1);
   }
-  if (inx && k0 == L) s_a[L] = FLD(wdtz)[ix];
-  if (inx && k1 == L) s_a[L] = FLD(wdtz)[ix + 1];
+  if (inx && (k0 == L || k1 == L)) s_a[L] = wdtzL;
   __syncthreads();
   if (!m0) return;
   const D2 rz = ld2(FLD(rho_zz), ix);
@@ -1026,11 +1100,12 @@ __global__ void __launch_bounds__(256, S0 ? LB_AC + 1 : LB_AC) k_acoustic(const 
 // rs_h / ts_h go to library scratch and are streamed by phase 2 as two more strips.
 __global__ void k_acoustic_gather(const View V, double dts) {
   PAIR_THREAD_R()
+  XPF_CELL_ROWS();                                  // rows of 8 cells span 2 lines
   if (!m0) return;
   if (V.specZoneMaskCell[x] != 0.0) return;
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
-  const double* ru_p = FLD(ru_p); const double* tm = FLD(theta_m);
   const double inva = V.invAreaCell[x];
+  const double* ru_p = FLD(ru_p); const double* tm = FLD(theta_m);
   D2 rs = bc(0), ts = bc(0);
 #pragma unroll 2
   for (int i = 0; i < n; ++i) {

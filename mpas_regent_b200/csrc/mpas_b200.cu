@@ -1164,6 +1164,20 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
     if ((rc = dev_upload<int>(h, &V.c1OnCell, c1))) return rc;
     if ((rc = dev_upload<int>(h, &V.c2OnCell, c2))) return rc;
     if ((rc = dev_upload<double>(h, &V.dvOnCell, dvS))) return rc;
+    {   // dcEdge of the slot-i edge (k_diag_cell: one dependent scalar load less) and the cell's LAST edge (w_adv_curv reads only that
+        // one: n -> id -> column becomes id -> column)
+      const std::vector<double> dcE2 = build_vals<double, double>(m->dcEdge, nE, 1, eNew);
+      const std::vector<int> nEoc = build_vals<int, int32_t>(m->nEdgesOnCell, nC, 1, cNew);
+      std::vector<double> dcS((size_t)(nC + 1) * ME, 0.0);
+      std::vector<int> lastE((size_t)nC + 1, nE);
+      for (int c = 0; c <= nC; ++c) {
+        for (int i = 0; i < ME; ++i) dcS[(size_t)c * ME + i] = dcE2[eocC[(size_t)c * ME + i]];
+        const int n = nEoc[c];
+        if (n > 0 && n <= ME) lastE[c] = eocC[(size_t)c * ME + (n - 1)];
+      }
+      if ((rc = dev_upload<double>(h, &V.dcOnCell, dcS))) return rc;
+      if ((rc = dev_upload<int>(h, &V.lastEdgeOnCell, lastE))) return rc;
+    }
     if ((rc = dev_upload<double>(h, &V.invDcOnCell, idcS))) return rc;
     if ((rc = dev_upload<double>(h, &V.ms2OnCell, ms2S))) return rc;
     if ((rc = dev_upload<double>(h, &V.ms4OnCell, ms4S))) return rc;
@@ -1171,6 +1185,12 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
     if ((rc = dev_upload<int>(h, &V.advCellOnCell, advS))) return rc;
     if ((rc = dev_upload<double>(h, &V.advCoefOnCell, acS))) return rc;
     if ((rc = dev_upload<double>(h, &V.adv3OnCell, a3S))) return rc;
+    {   // w_adv_curv multiplies every coefficient by an exact 0.0 (the reference's flux of a zeroed w): with finite coefficients the sum
+        // is +0.0 whatever they are, and the kernel may leave the loads out
+      bool fin = true;
+      for (size_t i = 0; i < acS.size() && fin; ++i) fin = std::fabs(acS[i]) <= 1e150 && std::fabs(a3S[i]) <= 1e150;   // false for NaN / Inf
+      V.advFinite = fin ? 1 : 0;
+    }
     // per-edge {cell1, cell2, vertex1, vertex2} in one 16-byte word, and the divergence-damping skip flag
     const std::vector<int> voe = build_ids(m->verticesOnEdge, nE, 2, eNew, nV, vNew, pol);
     const std::vector<unsigned char> shr = build_vals<unsigned char, uint8_t>(m->isShared, nC, 1, cNew);

@@ -32,6 +32,8 @@ struct View {
   const int* c1OnCell; const int* c2OnCell;            // [c][MEP]: cellsOnEdge[e][0/1] of the cell's slot-i edge
   const double* edgesOnCellSign; const double* edgesOnCell_sign; const double* invAreaCell; const double* cosLatCell;
   const double* dvOnCell; const double* invDcOnCell; const double* ms2OnCell; const double* ms4OnCell;   // [c][maxEdges]
+  const double* dcOnCell;      // [c][maxEdges]  dcEdge of the slot-i edge
+  const int* lastEdgeOnCell;   // [c]  edgesOnCell[c][nEdgesOnCell[c] - 1] (the pad edge when the cell has no edges)
   const double* defc_a; const double* defc_b; const int* bdyMaskCell; const double* specZoneMaskCell;
   const unsigned char* isShared; const unsigned char* inCpr;
   const double* sinLatCell; const double* cosLonCell; const double* sinLonCell;   // host-evaluated (glibc), like cosLatCell
@@ -39,6 +41,7 @@ struct View {
   const int* nAdvOnCell;       // [c][maxEdges]
   const int* advCellOnCell;    // [c][maxEdges][NAP]
   const double* advCoefOnCell; const double* adv3OnCell;   // [c][maxEdges][NAP]
+  int advFinite;               // every advection coefficient is finite and small enough that coef + coef_3rd cannot overflow (upload_mesh)
   // edge statics
   const int4* ecv;             // {cell1, cell2, vertex1, vertex2}
   const int* cellsOnEdge; const int* verticesOnEdge; const int* nEdgesOnEdge; const int* edgesOnEdge_ECP; const int* edgesOnEdge;

@@ -161,6 +161,39 @@ def test_vertical_mixing_branches(grid642):
         g.close(); ora.close()
 
 
+def test_nonfinite_advection_coefficient_takes_the_literal_loop(grid642):
+    """w_adv_curv multiplies every advection coefficient of the cell's last edge by an exact 0.0 (dynamics_tasks.rg:1170-1202): the
+    kernel leaves those loads out when upload_mesh found every coefficient finite.  One NaN and one Inf coefficient must bring the
+    literal loop back -- the NaN pattern they spread over w / tend_w / rw has to be the oracle's."""
+    from mpas_regent_b200 import dynamics, init_jw
+    from oracle.oracle import Oracle
+    L = 12
+    st = init_jw.make_state(grid642, L, _abi.INDEX_CORRECTED, m5=True)
+    static = dict(st.static)
+    ac = np.array(static["adv_coefs"], dtype=np.float64, copy=True); a3 = np.array(static["adv_coefs_3rd"], dtype=np.float64, copy=True)
+    n_adv = np.asarray(static["nAdvCellsForEdge"])
+    edges = np.flatnonzero(n_adv > 0)
+    ac[edges[::7], 0] = np.nan
+    a3[edges[3::11], 0] = np.inf
+    static["adv_coefs"], static["adv_coefs_3rd"] = ac, a3
+    cfg = _abi.default_config(index_policy=_abi.INDEX_CORRECTED, rkarg_policy=_abi.RKARG_STAGE_INDEX)
+    ora = Oracle(dynamics.dims_of(grid642, L), cfg)
+    g = dynamics.Dynamics(dynamics.dims_of(grid642, L), cfg)
+    for b in (ora, g):
+        b.upload_mesh(static)
+        b.upload_state(st.f, st.vert)
+        b.atm_compute_solve_diagnostics(False, -1)
+        b.atm_compute_dyn_tend(1, 600.0)            # rk_step > 0: k_dt_cellC<false> evaluates w_adv_curv; nothing else feeds w here
+    w = ora.download_field("w")
+    bad_cells = np.isnan(w).any(axis=1).sum()
+    assert 0 < bad_cells < w.shape[0], "the poisoned coefficients must reach w in some cells of the oracle, not all"
+    compare(g, ora, what="non-finite advection coefficients, one dyn_tend")
+    for b in (ora, g):
+        b.atm_srk3(600.0)
+    compare(g, ora, what="non-finite advection coefficients, full step")
+    g.close(); ora.close()
+
+
 def test_strided_region_layout(grid642):
     """upload/download with Legion-style byte strides (x-fastest instance): stride_x = 8, stride_k = 8*n."""
     import ctypes as C
