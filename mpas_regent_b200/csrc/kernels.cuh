@@ -37,7 +37,7 @@
 #ifndef LB_MISC
 #define LB_MISC 1
 #endif
-// Stall-guided forms (profiles/r2_stall_profiles.md, GPU calls 18-20; x1.163842 x 55, ms per step, all bit-identical).  Adopted:
+// Stall-guided forms (profiles/r2_stall_profiles.md, GPU calls 18-23; x1.163842 x 55, ms per step, all bit-identical).  Adopted:
 //  * HOIST: loads whose latency sat in front of a barrier or at the head of a dependent chain -- the one-lane level-L reads of
 //    k_dt_edge / k_dt_cellC / k_vert_imp, the length of the edgesOnEdge row -- are requested at the top of the kernel and consumed
 //    where they were read before (k_dt_edge 2.139 -> 1.874 at the same 56 registers, k_dt_cellC<false> 1.259 -> 1.234, <true>
@@ -46,13 +46,17 @@
 //    1.362 -> 1.259, k_dt_cellA 0.357 -> 0.322); slot 0 of k_diag_cell peeled, dcEdge from a per-(cell, slot) copy (0.411 -> 0.384);
 //  * cross-block prefetch of the index WORDS / ROWS of the block about one wave later (XPF_*): k_acoustic_gather 1.146 -> 1.102,
 //    k_dt_edge 1.868 -> 1.830, k_diag_cell, k_diag_edge, k_dt_edge_euler, k_dt_cellA/B -1 .. -4 %; k_dt_cellC and k_dt_theta_flux
-//    got slower with it (+0.6 %) and go without.
+//    got slower with it (+0.6 %) and go without;
+//  * static rows staged in shared memory by lane-distributed loads where a slot loop read several statics per slot: the advection
+//    row of k_dt_theta_flux (ids + coefficient pairs; 0.756 -> 0.615) and the theta-loop rows of k_dt_cellC<false> (1.236 -> 1.205);
+//    k_smlstep requests its two masks and the row length together (0.820 -> 0.799).
 // Measured and removed: the neighbour columns of 2..6 slots of a gather loop requested together (ptxas issues slot j+1's gathers
 // after slot j's arithmetic) -- k_dt_edge 2.11 .. 2.64, k_acoustic_gather 1.29 .. 1.96 against 1.148, k_dt_theta_flux 1.01 against
 // 0.756, k_diag_cell 0.46 .. 0.60 against 0.411: resident warps, not loads in flight per thread, carry these kernels; slot 0's statics
 // and columns peeled in front of the row length (k_acoustic_gather +4 %, k_dt_theta_flux +27 %, k_dt_edge +8 %); a last-edge static
 // for w_adv_curv (+1 %); prefetch.global.L1 instead of .L2 (no change); in-thread L2 prefetch of the columns a slot loop will
-// gather, lanes spread over slot x line (k_dt_edge +11 %, k_dt_theta_flux +9 %, k_acoustic_gather -0.8 %).
+// gather, lanes spread over slot x line (k_dt_edge +11 %, k_dt_theta_flux +9 %, k_acoustic_gather -0.8 %); the same row staging in
+// k_dt_edge (Coriolis row, +12 %), k_acoustic_gather (+10 %) and k_dt_cellC<true> (+8 %); an L2 prefetch of k_smlstep's own strips (+10 %).
 #ifndef KDE_MAXREG
 #define KDE_MAXREG 56        /* the hoisted values would cost k_dt_edge a resident block (60 registers): capped, 8 bytes of spills */
 #endif
@@ -713,27 +717,28 @@ __global__ void k_dt_cellB(const View V, const DynTendParams P) {
 // 2-ring gathers, and the gather lives in a kernel with a single level of index loads.
 __global__ void k_dt_theta_flux(const View V) {
   PAIR_THREAD(V.nEdges)
+  // the advection row of the column's edge -- ids and {adv_coefs, adv_coefs_3rd} pairs -- goes to shared memory, one entry per lane;
+  // the stencil loop reads them with broadcast LDS
+  extern __shared__ double sm[];
+  const int NAE = V.NAE;
+  double2* s_c = reinterpret_cast<double2*>(sm) + (size_t)threadIdx.y * NAE;
+  int* s_i = reinterpret_cast<int*>(reinterpret_cast<double2*>(sm) + (size_t)blockDim.y * NAE) + (size_t)threadIdx.y * NAE;
+  int na = 0; D2 ru2 = bc(0.0);
+  if (inx) {
+    na = V.nAdvCellsForEdge[x];
+    for (int j = threadIdx.x; j < NAE; j += blockDim.x) { s_i[j] = V.advCellE[(size_t)x * NAE + j]; s_c[j] = V.advCoefE[(size_t)x * NAE + j]; }
+  }
+  if (m0) ru2 = ld2(FLD(ru), ix);
+  __syncthreads();
   if (!m0) return;
   const double* tm = FLD(theta_m);
-  const int na = V.nAdvCellsForEdge[x];
-  const D2 sg = sgn1(ld2(FLD(ru), ix));
+  const D2 sg = sgn1(ru2);
   D2 fa = bc(0.0);
-  // per-edge advection rows repacked at upload_mesh: ids [e][NAE] (NAE a multiple of 4) and {adv_coefs, adv_coefs_3rd} pairs
-  // [e][NAE], so four ids come with one 128-bit load and a coefficient pair with one -- 14 wide loads instead of 30 scalar ones
-  // for a 10-cell stencil (every lane of a column reads the same address: each load is an L1 wavefront per column in the warp)
-  const int NAE = V.NAE;
-  const int4* idr = reinterpret_cast<const int4*>(V.advCellE + (size_t)x * NAE);
-  const double2* cr = V.advCoefE + (size_t)x * NAE;
-  for (int j0 = 0; j0 < na; j0 += 4) {
-    const int4 id = idr[j0 >> 2];
-    const int ids[4] = {id.x, id.y, id.z, id.w};
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-      if (j0 + t < na) {
-        const double2 c = cr[j0 + t];
-        const D2 sw = c.x + sg * c.y;
-        fa += sw * G2(tm, ids[t]);
-      }
+#pragma unroll 2
+  for (int j = 0; j < na; ++j) {
+    const double2 c = s_c[j];
+    const D2 sw = c.x + sg * c.y;
+    fa += sw * G2(tm, s_i[j]);
   }
   st2m(V.scr_flux, ix, fa, m0, m1);
 }
@@ -764,6 +769,20 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
   double* s_b = sm + (size_t)(blockDim.y + threadIdx.y) * TS;        // wdwz, later post-multiply w
   const int ME = V.maxEdges;
   const int n = inx ? V.nEdgesOnCell[x] : 0;
+  // the static rows of the theta loops -- ids {e, c1, c2}, edgesOnCell_sign, dvOnCell -- go to shared memory at the top, one slot per
+  // lane; the w pass's barriers make them visible and the loops read them with broadcast LDS (k_dt_cellC<false> 1.236 -> 1.205 ms per
+  // step on x1.163842; the rk_step == 0 form got slower with it, 0.591 -> 0.637, and keeps its global rows)
+  constexpr bool SROW = !RK0;
+  double* s_sg = sm + (size_t)2 * blockDim.y * TS + (size_t)threadIdx.y * 2 * ME; double* s_dv = s_sg + ME;
+  int* s_e = reinterpret_cast<int*>(sm + (size_t)2 * blockDim.y * (TS + ME)) + (size_t)threadIdx.y * 3 * ME;
+  if (SROW) {
+    if (inx && PART != 1)
+      for (int i = threadIdx.x; i < ME; i += blockDim.x) {
+        s_e[3 * i] = V.edgesOnCell[x * V.MEP + i]; s_e[3 * i + 1] = V.c1OnCell[x * V.MEP + i]; s_e[3 * i + 2] = V.c2OnCell[x * V.MEP + i];
+        s_sg[i] = V.edgesOnCell_sign[x * ME + i]; s_dv[i] = V.dvOnCell[x * ME + i];
+      }
+    if (PART == 2) __syncthreads();
+  }
   const double* rw = FLD(rw);
   D2 w2 = bc(0.0), twe = bc(0.0), fzm = bc(0.0), fzp = bc(0.0), rdzu = bc(0.0), rdzw = bc(0.0), rw2 = bc(0.0), rwm = bc(0.0);
   // level L of w / wdwz / wdtz (one lane per column) requested first, consumed in front of the barriers
@@ -862,10 +881,11 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
     D2 fa_last = bc(0.0);
 #pragma unroll 2
     for (int i = 0; i < n; ++i) {                                                                     // :1328-1344
-      const int e = V.edgesOnCell[x * V.MEP + i];
+      const int e = SROW ? s_e[3 * i] : V.edgesOnCell[x * V.MEP + i];
+      const double sg_i = SROW ? s_sg[i] : V.edgesOnCell_sign[x * ME + i];
       const D2 ru_e = G2(ru, e);
       const D2 fa = G2(V.scr_flux, e);              // flux_arr of this edge (k_dt_theta_flux)
-      tt -= V.edgesOnCell_sign[x * ME + i] * ru_e * fa;
+      tt -= sg_i * ru_e * fa;
       fa_last = fa;
     }
     if (n > 0) st2m(FLD(flux_arr), ix, fa_last, m0, m1);
@@ -873,10 +893,10 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
       const double* rus = FLD(ru_save);
 #pragma unroll 2
       for (int i = 0; i < n; ++i) {
-        const int e = V.edgesOnCell[x * V.MEP + i];
-        const int c1 = V.c1OnCell[x * V.MEP + i], c2 = V.c2OnCell[x * V.MEP + i];
-        const D2 flux = (V.edgesOnCell_sign[x * ME + i] * V.dvOnCell[x * ME + i]) * (G2(rus, e) - G2(ru, e)) * 0.5
-                        * (G2(tms, c2) + G2(tms, c1));
+        const int e = SROW ? s_e[3 * i] : V.edgesOnCell[x * V.MEP + i];
+        const int c1 = SROW ? s_e[3 * i + 1] : V.c1OnCell[x * V.MEP + i], c2 = SROW ? s_e[3 * i + 2] : V.c2OnCell[x * V.MEP + i];
+        const double sd_i = SROW ? s_sg[i] * s_dv[i] : V.edgesOnCell_sign[x * ME + i] * V.dvOnCell[x * ME + i];
+        const D2 flux = sd_i * (G2(rus, e) - G2(ru, e)) * 0.5 * (G2(tms, c2) + G2(tms, c1));
         tt -= flux;
       }
     }
@@ -941,8 +961,10 @@ __global__ void k_smlstep(const View V, int nRelaxZone) {
   const bool a0 = inx && k0 <= L, a1 = inx && k1 <= L;        // level L included
   (void)m0;
   if (!a0) return;
-  if (!V.inCpr[x] || V.bdyMaskCell[x] > nRelaxZone) return;
+  // the two masks and the row length are requested together (they were three dependent round trips: || and the early return)
+  const unsigned char in_cpr = V.inCpr[x]; const int bdy = V.bdyMaskCell[x];
   const int ME = V.maxEdges, n = V.nEdgesOnCell[x];
+  if (!in_cpr || bdy > nRelaxZone) return;
   const double* ut = FLD(u_tend); const double* zb = FLD(zb_cell); const double* zb3 = FLD(zb3_cell);
   const D2 fm = ld2(FLD(fzm), k0), fp = ld2(FLD(fzp), k0);
   D2 wv = ld2(FLD(w), ix);

@@ -283,6 +283,8 @@ bool staged_on(const mpasb200_t* h, int bit, size_t smem) { return (h->c.gather_
   } while (0)
 #endif
 size_t tile_bytes(const mpasb200_t* h, int tiles) { return (size_t)tiles * h->CPB * (h->LP + 2) * sizeof(double); }
+// dynamic shared memory of k_dt_theta_flux: the advection row of each column's edge (ids + coefficient pairs)
+#define TF_SMEM(h) ((size_t)(h)->CPB * (h)->V.NAE * (sizeof(double2) + sizeof(int)))
 
 #ifdef MPASB200_LAB
 // k_dt_edge_tile (kernels_tiles.cuh): compiled for at most ET_MAXT threads per block, ET_MINB resident blocks
@@ -403,7 +405,8 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
   P.omega2 = 2.0 * C.omega; P.gravity = C.gravity; P.del4u_div_factor = C.config_del4u_div_factor;
   P.rayleigh_levels = C.config_number_rayleigh_damp_u_levels;
   P.rayleigh_coef_inverse = 1.0 / ((double)(C.config_number_rayleigh_damp_u_levels) * (C.config_rayleigh_damp_u_timescale_days * 86400.0));
-  const size_t sm2 = tile_bytes(h, 2);
+  // two column tiles + the static rows of the theta loops (k_dt_cellC<false> stages them; the <true> form leaves the space unused)
+  const size_t sm2 = tile_bytes(h, 2) + (size_t)h->CPB * h->d.maxEdges * (2 * sizeof(double) + 3 * sizeof(int));
   const size_t sm_edge = staged_bytes(h, 20, 1), sm_flux = staged_bytes(h, 10, 0);
   if (rk_step == 0) {
     LAUNCH(k_dt_cell0<true>, h->nCells, 0, h->V, P, C.config_len_disp, cam_coef);
@@ -419,7 +422,7 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
     LAUNCH(k_dt_cellA, h->nCells, 0, h->V, P);
     LAUNCH(k_dt_cellB, h->nCells, 0, h->V, P);
     if (staged_on(h, GS_THETA_FLUX, sm_flux)) LAUNCH_STAGED(k_dt_theta_flux_s<10>, h->nEdges, sm_flux, h->V);
-    else LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
+    else LAUNCH(k_dt_theta_flux, h->nEdges, TF_SMEM(h), h->V);
     if (h->c.kernel_forms & 1) { LAUNCH((k_dt_cellC<true, 1>), h->nCells, sm2, h->V, P); LAUNCH((k_dt_cellC<true, 2>), h->nCells, sm2, h->V, P); }
     else LAUNCH(k_dt_cellC<true>, h->nCells, sm2, h->V, P);
   } else {
@@ -428,7 +431,7 @@ int t_dyn_tend(mpasb200_t* h, int rk_step, double dt, int mixing, double cam_coe
     else if (ET_ON(h)) launch_dt_edge(h, P);
     else LAUNCH(k_dt_edge, h->nEdges, tile_bytes(h, 1), h->V, P);
     if (staged_on(h, GS_THETA_FLUX, sm_flux)) LAUNCH_STAGED(k_dt_theta_flux_s<10>, h->nEdges, sm_flux, h->V);
-    else LAUNCH(k_dt_theta_flux, h->nEdges, 0, h->V);
+    else LAUNCH(k_dt_theta_flux, h->nEdges, TF_SMEM(h), h->V);
     if (h->c.kernel_forms & 1) { LAUNCH((k_dt_cellC<false, 1>), h->nCells, sm2, h->V, P); LAUNCH((k_dt_cellC<false, 2>), h->nCells, sm2, h->V, P); }
     else LAUNCH(k_dt_cellC<false>, h->nCells, sm2, h->V, P);
   }
