@@ -56,7 +56,8 @@
 // and columns peeled in front of the row length (k_acoustic_gather +4 %, k_dt_theta_flux +27 %, k_dt_edge +8 %); a last-edge static
 // for w_adv_curv (+1 %); prefetch.global.L1 instead of .L2 (no change); in-thread L2 prefetch of the columns a slot loop will
 // gather, lanes spread over slot x line (k_dt_edge +11 %, k_dt_theta_flux +9 %, k_acoustic_gather -0.8 %); the same row staging in
-// k_dt_edge (Coriolis row, +12 %), k_acoustic_gather (+10 %) and k_dt_cellC<true> (+8 %); an L2 prefetch of k_smlstep's own strips (+10 %).
+// k_dt_edge (Coriolis row, +12 %), k_acoustic_gather (+10 %) and k_dt_cellC<true> (+8 %); an L2 prefetch of k_smlstep's own strips (+10 %);
+// register caps that buy a resident block (k_acoustic_gather 48 / 40 registers: +3 % / +9 %, k_divdamp 48: +2 %).
 #ifndef KDE_MAXREG
 #define KDE_MAXREG 56        /* the hoisted values would cost k_dt_edge a resident block (60 registers): capped, 8 bytes of spills */
 #endif
@@ -92,6 +93,13 @@ DI double dmax(double a, double b) { return (a < b) ? b : a; }     // std::max
 DI D2 sel(bool c0, bool c1, D2 a, D2 b) { return mk(c0 ? a.x : b.x, c1 ? a.y : b.y); }
 DI D2 ld2(const double* p, size_t i) { return *reinterpret_cast<const D2*>(p + i); }
 DI void st2(double* p, size_t i, D2 v) { *reinterpret_cast<D2*>(p + i) = v; }
+// streaming forms for strips nobody reads again in this kernel: evict-first loads / stores leave L1 and L2 to the gathered columns
+DI D2 ld2s(const double* p, size_t i) { return __ldcs(reinterpret_cast<const D2*>(p + i)); }
+DI void st2s(double* p, size_t i, D2 v) { __stcs(reinterpret_cast<D2*>(p + i), v); }
+DI void st2ms(double* p, size_t i, D2 v, bool m0, bool m1) {
+  if (m0 && m1) st2s(p, i, v);
+  else { if (m0) __stcs(p + i, v.x); if (m1) __stcs(p + i + 1, v.y); }
+}
 // store the components whose mask is set (a pair that straddles the top level stores one double)
 DI void st2m(double* p, size_t i, D2 v, bool m0, bool m1) {
   if (m0 && m1) st2(p, i, v);
@@ -529,6 +537,9 @@ __global__ void k_dt_edge_euler(const View V, const DynTendParams P) {
 #else
 #define KDE_REGCAP
 #endif
+// read-once strips and outputs go through evict-first loads / stores (k_dt_edge 1.834 -> 1.816 ms per step on x1.163842)
+#define KDE_LD ld2s
+#define KDE_ST st2ms
 __global__ void KDE_REGCAP k_dt_edge(const View V, const DynTendParams P) {
   extern __shared__ double sm[];
   PAIR_THREAD(V.nEdges)
@@ -577,12 +588,12 @@ __global__ void KDE_REGCAP k_dt_edge(const View V, const DynTendParams P) {
     wduz.x = wduz_at(k0, L, rwavg.x, fzm.x, fzp.x, um.x, um.y, u2.x, u2.y);
     if (m1) wduz.y = wduz_at(k1, L, rwavg.y, fzm.y, fzp.y, um.y, u2.x, u2.y, up);
     s_wduz[k0] = wduz.x; if (m1) s_wduz[k1] = wduz.y;
-    st2m(FLD(wduz), ix, wduz, m0, m1);
+    KDE_ST(FLD(wduz), ix, wduz, m0, m1);
   }
   if (inx && (k0 == L || k1 == L)) s_wduz[L] = wduz_L;    // level L: never written, read as stored
   __syncthreads();
   if (!m0) return;
-  const D2 rho_e = ld2(FLD(rho_edge), ix);
+  const D2 rho_e = KDE_LD(FLD(rho_edge), ix);
   const double invDc = V.invDcEdge[x];
   const D2 wduz_p = mk(s_wduz[k1], m1 ? s_wduz[k1 + 1] : 0.0);
   D2 tend_u = -ld2(FLD(rdzw), k0) * (wduz_p - wduz);                                                // :987
@@ -603,7 +614,7 @@ __global__ void KDE_REGCAP k_dt_edge(const View V, const DynTendParams P) {
       q += Ld * (V.weightsOnEdge[x * ME2 + j] * G2(u, eoe) * workpv);
     }
   }
-  st2m(FLD(q), ix, q, m0, m1);
+  KDE_ST(FLD(q), ix, q, m0, m1);
   const double* ke = FLD(ke); const double* hd = FLD(h_divergence); const double* w = FLD(w);
   tend_u += rho_e * (q - (G2(ke, cv.y) - G2(ke, cv.x)) * invDc) - u2 * 0.5 * (G2(hd, cv.x) + G2(hd, cv.y));   // :1005-1007
   {
@@ -613,14 +624,14 @@ __global__ void KDE_REGCAP k_dt_edge(const View V, const DynTendParams P) {
     tend_u -= (P.omega2 * V.cosAngleEdge[x] * V.cosLatEdge[x] * rho_e * 0.25 * wsum)
               - (u2 * 0.25 * wsum * rho_e * P.inv_r_earth);                                        // :1011-1017
   }
-  const D2 tue = ld2(FLD(tend_u_euler), ix);
+  const D2 tue = KDE_LD(FLD(tend_u_euler), ix);
   if (P.rayleigh_u) {                                                                               // :1152-1159
     const int lim = L - P.rayleigh_levels + 1;
     if (k0 > lim) tend_u.x -= rho_e.x * u2.x * ((double)((double)k0 - (L - P.rayleigh_levels)) * P.rayleigh_coef_inverse);
     if (k1 > lim) tend_u.y -= rho_e.y * u2.y * ((double)((double)k1 - (L - P.rayleigh_levels)) * P.rayleigh_coef_inverse);
   }
-  tend_u += tue + ld2(FLD(tend_ru_physics), ix);                                                    // :1162
-  st2m(FLD(tend_u), ix, tend_u, m0, m1);
+  tend_u += tue + KDE_LD(FLD(tend_ru_physics), ix);                                                   // :1162
+  KDE_ST(FLD(tend_u), ix, tend_u, m0, m1);
 }
 
 // horizontal advection + curvature part of the w tendency  :1170-1218  (value of cr.w before mixing);
@@ -760,6 +771,9 @@ DI double wdtz_at(int k, int L, double rws, double rw, double fzm, double fzp, d
 // final cell pass: w (:1256-1322) and theta (:1328-1479)
 // PART 0: both passes in one launch; 1: the w pass alone; 2: the theta pass alone.  The two passes share only `rw` (one unit re-read):
 // launched separately each needs fewer registers and fewer barriers than the fused kernel (64 registers with 80-96 B of spills).
+// read-once strips and outputs go through evict-first loads / stores (k_dt_cellC<false> 1.201 -> 1.179, <true> 0.591 -> 0.583)
+#define CC_LD ld2s
+#define CC_ST st2ms
 template <bool RK0, int PART = 0>
 __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_dt_cellC(const View V, const DynTendParams P) {
   extern __shared__ double sm[];
@@ -835,7 +849,7 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
     wdwz.x = wdwz_at(k0, L, rw2.x, rwm.x, s_a);
     if (m1) wdwz.y = wdwz_at(k1, L, rw2.y, rwm.y, s_a);
     s_b[k0] = wdwz.x; if (m1) s_b[k1] = wdwz.y;
-    st2m(FLD(wdwz), ix, wdwz, m0, m1);
+    CC_ST(FLD(wdwz), ix, wdwz, m0, m1);
   }
   __syncthreads();
   D2 wdwz_p = bc(0.0);
@@ -867,9 +881,9 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
       }
     }
     if (!RK0) { const D2 t = ld2(FLD(tend_w_euler), ix); twe = mk(k0 > 0 ? t.x : 0.0, t.y); }
-    if (RK0) st2m(FLD(tend_w_euler), ix, twe, m0, m1);
+    if (RK0) CC_ST(FLD(tend_w_euler), ix, twe, m0, m1);
     w2 = mk(k0 > 0 ? w2.x + twe.x : w2.x, w2.y + twe.y);                                            // :1320
-    st2m(FLD(w), ix, w2, m0, m1);
+    CC_ST(FLD(w), ix, w2, m0, m1);
   }
   }
   if (PART == 1) return;
@@ -888,7 +902,7 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
       tt -= sg_i * ru_e * fa;
       fa_last = fa;
     }
-    if (n > 0) st2m(FLD(flux_arr), ix, fa_last, m0, m1);
+    if (n > 0) CC_ST(FLD(flux_arr), ix, fa_last, m0, m1);
     if (P.rk_step > 0) {                                                                              // :1347-1360
       const double* rus = FLD(ru_save);
 #pragma unroll 2
@@ -900,12 +914,12 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
         tt -= flux;
       }
     }
-    const D2 tm2 = ld2(tm, ix), tms2 = ld2(tms, ix), rws2 = ld2(FLD(rw_save), ix);
+    const D2 tm2 = ld2(tm, ix), tms2 = ld2(tms, ix), rws2 = CC_LD(FLD(rw_save), ix);
     const D2 tmm = below(tm, ix, k0, tm2), tmsm = below(tms, ix, k0, tms2);
     wdtz.x = wdtz_at(k0, L, rws2.x, rw2.x, fzm.x, fzp.x, tms2.x, tmsm.x, tm2.x, tmm.x);
     if (m1) wdtz.y = wdtz_at(k1, L, rws2.y, rw2.y, fzm.y, fzp.y, tms2.y, tmsm.y, tm2.y, tmm.y);
     s_a[k0] = wdtz.x; if (m1) s_a[k1] = wdtz.y;
-    st2m(FLD(wdtz), ix, wdtz, m0, m1);
+    CC_ST(FLD(wdtz), ix, wdtz, m0, m1);
   }
   if (inx && (k0 == L || k1 == L)) s_a[L] = wdtzL;
   __syncthreads();
@@ -913,9 +927,9 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
   const D2 rz = ld2(FLD(rho_zz), ix);
   const D2 wdtz_p = mk(s_a[k1], m1 ? s_a[k1 + 1] : 0.0);
   tt *= V.invAreaCell[x] - rdzw * (wdtz_p - wdtz);                                                   // :1423
-  st2m(FLD(tend_rtheta_adv), ix, tt, m0, m1);
-  st2m(FLD(rthdynten), ix, tt / rz, m0, m1);
-  tt += rz * ld2(FLD(rt_diabatic_tend), ix);
+  CC_ST(FLD(tend_rtheta_adv), ix, tt, m0, m1);
+  CC_ST(FLD(rthdynten), ix, tt / rz, m0, m1);
+  tt += rz * CC_LD(FLD(rt_diabatic_tend), ix);
   D2 tte = ld2(FLD(tend_theta_euler), ix);
   if (RK0) {
     if (P.visc4_on) {                                                                                 // :1384-1399
@@ -946,10 +960,10 @@ __global__ void __launch_bounds__(256, PART == 0 ? LB_CELLC : LB_CELLC_SPLIT) k_
         if (c) tte.y += add; else tte.x += add;
       }
     }
-    st2m(FLD(tend_theta_euler), ix, tte, m0, m1);
+    CC_ST(FLD(tend_theta_euler), ix, tte, m0, m1);
   }
-  tt += tte + ld2(FLD(tend_rtheta_physics), ix);                                                      // :1478
-  st2m(FLD(tend_theta), ix, tt, m0, m1);
+  tt += tte + CC_LD(FLD(tend_rtheta_physics), ix);                                                      // :1478
+  CC_ST(FLD(tend_theta), ix, tt, m0, m1);
 }
 
 // ============================================================================================
@@ -1441,7 +1455,10 @@ __global__ void __launch_bounds__(128, 5) k_acoustic_tma(const View V, const AcP
 //     128-bit loads and the movers' 128-bit loads/stores are all bank-conflict free.
 // 32 recurrences advance per sweeper instruction, two blocks are resident per SM, and while the
 // sweeper works on chunk j the copies of chunk j+1 are in flight: the kernel is bound by the strips, not by the chain.
-enum { AL_KC = 8, AL_COLS = 32, AL_NMOV = 96, AL_NOUT = 5 };
+#ifndef AL_NMOV
+#define AL_NMOV 160           /* mover threads: 5 warps (3 -> 5: k_acoustic_lane<false> 1.610 -> 1.586, <true> 1.133 -> 1.093 ms/step on x1.163842; 2 warps: 1.837 / 1.233) */
+#endif
+enum { AL_KC = 8, AL_COLS = 32, AL_NOUT = 5 };
 DI void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 DI void cp_async_arrive_noinc(uint64_t* bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 DI void cp_async_16(void* dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory"); }
@@ -1542,11 +1559,19 @@ __global__ void __launch_bounds__(32 + AL_NMOV, 2) k_acoustic_lane(const View V,
         if (!S0) { rho_o = LDP(AF_rho_pp); rt_o = LDP(AF_rtheta_pp); rwp = LDP(AF_rw_p); wwo = LDP(AF_wwAvg); rwpn = LDP(NS16 + 1); }
 #undef LDP
         D2 rho_n = bc(0.0), rt_n = bc(0.0), rw_n = bc(0.0), ww_n = bc(0.0);
+#ifdef AL_ABLATE_SWEEP      /* measurement only: the sweeper moves data but skips the arithmetic (results are wrong) */
+        if (false)
+#else
         if (on && k0 < L)
+#endif
           ac_level(k0, spec, S0, dts, epssm, resm, s_v[k0], s_v[LP + k0], s_v[2 * LP + k0], s_v[3 * LP + k0], tr.x, tm.x, w2.x, cz.x, czn.x,
                    cwz.x, cwr.x, cwt.x, at.x, al.x, zz.x, rws.x, rwv.x, ds.x, rz.x, rsh.x, tsh.x, rho_o.x, rt_o.x, rwp.x, rwpn.x, wwo.x, cr,
                    rho_n.x, rt_n.x, rw_n.x, ww_n.x);
+#ifdef AL_ABLATE_SWEEP
+        if (false)
+#else
         if (on && k0 + 1 < L)
+#endif
           ac_level(k0 + 1, spec, S0, dts, epssm, resm, s_v[k0 + 1], s_v[LP + k0 + 1], s_v[2 * LP + k0 + 1], s_v[3 * LP + k0 + 1], tr.y, tm.y, w2.y,
                    cz.y, czn.y, cwz.y, cwr.y, cwt.y, at.y, al.y, zz.y, rws.y, rwv.y, ds.y, rz.y, rsh.y, tsh.y, rho_o.y, rt_o.y, rwp.y, rwpn.y,
                    wwo.y, cr, rho_n.y, rt_n.y, rw_n.y, ww_n.y);
