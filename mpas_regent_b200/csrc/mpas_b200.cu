@@ -1175,19 +1175,12 @@ int mpasb200_upload_mesh(mpasb200_t* h, const MpasMeshPtrs* m) {
     if ((rc = dev_upload<int>(h, &V.c1OnCell, c1))) return rc;
     if ((rc = dev_upload<int>(h, &V.c2OnCell, c2))) return rc;
     if ((rc = dev_upload<double>(h, &V.dvOnCell, dvS))) return rc;
-    {   // dcEdge of the slot-i edge (k_diag_cell: one dependent scalar load less) and the cell's LAST edge (w_adv_curv reads only that
-        // one: n -> id -> column becomes id -> column)
+    {   // dcEdge of the slot-i edge (k_diag_cell: one dependent scalar load less)
       const std::vector<double> dcE2 = build_vals<double, double>(m->dcEdge, nE, 1, eNew);
-      const std::vector<int> nEoc = build_vals<int, int32_t>(m->nEdgesOnCell, nC, 1, cNew);
       std::vector<double> dcS((size_t)(nC + 1) * ME, 0.0);
-      std::vector<int> lastE((size_t)nC + 1, nE);
-      for (int c = 0; c <= nC; ++c) {
+      for (int c = 0; c <= nC; ++c)
         for (int i = 0; i < ME; ++i) dcS[(size_t)c * ME + i] = dcE2[eocC[(size_t)c * ME + i]];
-        const int n = nEoc[c];
-        if (n > 0 && n <= ME) lastE[c] = eocC[(size_t)c * ME + (n - 1)];
-      }
       if ((rc = dev_upload<double>(h, &V.dcOnCell, dcS))) return rc;
-      if ((rc = dev_upload<int>(h, &V.lastEdgeOnCell, lastE))) return rc;
     }
     if ((rc = dev_upload<double>(h, &V.invDcOnCell, idcS))) return rc;
     if ((rc = dev_upload<double>(h, &V.ms2OnCell, ms2S))) return rc;

@@ -33,7 +33,6 @@ struct View {
   const double* edgesOnCellSign; const double* edgesOnCell_sign; const double* invAreaCell; const double* cosLatCell;
   const double* dvOnCell; const double* invDcOnCell; const double* ms2OnCell; const double* ms4OnCell;   // [c][maxEdges]
   const double* dcOnCell;      // [c][maxEdges]  dcEdge of the slot-i edge
-  const int* lastEdgeOnCell;   // [c]  edgesOnCell[c][nEdgesOnCell[c] - 1] (the pad edge when the cell has no edges)
   const double* defc_a; const double* defc_b; const int* bdyMaskCell; const double* specZoneMaskCell;
   const unsigned char* isShared; const unsigned char* inCpr;
   const double* sinLatCell; const double* cosLonCell; const double* sinLonCell;   // host-evaluated (glibc), like cosLatCell
