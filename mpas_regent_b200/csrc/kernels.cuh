@@ -1446,7 +1446,7 @@ __global__ void __launch_bounds__(128, 5) k_acoustic_tma(const View V, const AcP
 //   * warp 0, the SWEEPER: lane = column.  It walks the levels strictly in the reference's order (the body of
 //     k_acoustic_column, bit-identical to the oracle) with the recurrence state in registers, reading its inputs two
 //     levels at a time (one 128-bit shared-memory load per field) and writing its five outputs the same way.
-//   * warps 1..3, the MOVERS: stream the 20 (16 at small_step 0) input fields of the tile, chunk by chunk of 8 levels, from
+//   * warps 1..5, the MOVERS (AL_NMOV threads): stream the 20 (16 at small_step 0) input fields of the tile, chunk by chunk of 8 levels, from
 //     global memory into a two-stage shared-memory ring with cp.async (16 bytes per lane, 64 contiguous bytes per column
 //     and field; the two fields read one level ahead -- coftz(k+1), rw_p(k+1) -- come as 8-byte copies of the shifted
 //     strip), and write the finished chunks back with 128-bit stores.
