@@ -100,7 +100,7 @@ class Exchanger:
         raise NotImplementedError
 
 
-class InProcessExchanger:
+class InProcessExchanger(Exchanger):
     """All ranks live in one process (tests, and the single-GPU emulation of an N-rank run): ghost columns are
     copied owner -> holder through download_field / upload_field."""
 
